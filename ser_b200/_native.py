@@ -1,0 +1,254 @@
+"""ctypes binding of libser_b200.so (the C ABI declared in include/ser_b200.h).
+
+This is the only place the package touches native code.  There is no CPU fallback: if the
+library is missing or no CUDA device is visible every compute call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import threading
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "libser_b200.so"
+
+FLAG_MFCC, FLAG_CHROMA, FLAG_MEL, FLAG_CONTRAST, FLAG_TONNETZ = 1, 2, 4, 8, 16
+FLAG_ALL = 31
+
+OUT_SOFTMAX, OUT_LOGISTIC = 0, 1
+
+# every symbol include/ser_b200.h declares: (restype, argtypes)
+_P = c_void_p
+SIGNATURES: dict[str, tuple] = {
+    "serb_version": (c_char_p, []),
+    "serb_device_count": (c_int, []),
+    "serb_ctx_create": (c_int, [c_int, POINTER(_P)]),
+    "serb_ctx_destroy": (None, [_P]),
+    "serb_last_error": (c_char_p, [_P]),
+    "serb_feature_dim": (c_int, [c_uint32]),
+    "serb_features_device": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P, _P]),
+    "serb_features_host": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P]),
+    "serb_mlp_load": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32]),
+    "serb_mlp_n_classes": (c_int, [_P]),
+    "serb_mlp_predict_host": (c_int, [_P, _P, c_int64, _P, _P]),
+    "serb_mlp_predict_device": (c_int, [_P, _P, c_int64, _P, _P, _P]),
+    "serb_infer_host": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P, _P, _P]),
+    "serb_prepare_pcm16_host": (c_int, [_P, _P, c_int64, _P]),
+    "serb_prepare_pcm16_device": (c_int, [_P, _P, c_int64, _P, _P]),
+    "serb_debug_filterbank": (c_int, [c_int32, c_int32, c_int32, c_int32, _P]),
+    "serb_debug_stft_host": (c_int, [_P, _P, c_int64, _P, c_int64]),
+    "serb_debug_last_tuning": (c_int, [_P, _P, c_int64]),
+    "serb_debug_launch_count": (c_int64, [_P]),
+    "serb_debug_last_compute_ms": (c_float, [_P]),
+    "serb_debug_set_profile": (c_int, [_P, c_int32]),
+    "serb_debug_kernel_ms": (c_int, [_P, c_int32, _P, _P]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class ParameterError(Exception):
+    """Counterpart of librosa.util.exceptions.ParameterError raised by the reference path
+    (e.g. spectral_contrast's Nyquist check, ser/_internal/utils/dsp.py:127-136)."""
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libser_b200.so once; raises RuntimeError with build instructions if it is absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m ser_b200.build` "
+                "(ser_b200 has no CPU fallback)"
+            )
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here means header and library disagree
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def _ptr(array: np.ndarray | None):
+    return None if array is None else array.ctypes.data_as(c_void_p)
+
+
+def _raise(lib, ctx, code: int) -> None:
+    message = lib.serb_last_error(ctx)
+    text = message.decode("utf-8", "replace") if message else f"ser_b200 error {code}"
+    if code == -5:
+        raise ParameterError(text)
+    if code < 0:
+        raise ValueError(text)
+    raise RuntimeError(text)
+
+
+class Context:
+    """One libser_b200 context (one CUDA device).  Thread-safe; calls are serialised natively."""
+
+    def __init__(self, device: int = 0) -> None:
+        self._lib = load_library()
+        handle = c_void_p()
+        code = self._lib.serb_ctx_create(int(device), ctypes.byref(handle))
+        if code != 0:
+            _raise(self._lib, None, code)
+        self._handle = handle
+        self.device = int(device)
+        self._mlp_classes: int = 0
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.serb_ctx_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self) -> None:  # pragma: no cover - interpreter shutdown ordering
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code: int) -> None:
+        if code != 0:
+            _raise(self._lib, self._handle, code)
+
+    # ---- features ------------------------------------------------------------------------
+    def features_host(self, wave: np.ndarray, starts: np.ndarray, lengths: np.ndarray,
+                      sample_rate: int, flag_bits: int) -> np.ndarray:
+        """Ragged batch over a host waveform -> (n_clips, dim) float32."""
+        wave = np.ascontiguousarray(wave, dtype=np.float32)
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        dim = self._lib.serb_feature_dim(flag_bits)
+        out = np.empty((starts.size, dim), dtype=np.float32)
+        self._check(self._lib.serb_features_host(
+            self._handle, _ptr(wave), wave.size, _ptr(starts), _ptr(lengths), starts.size,
+            int(sample_rate), int(flag_bits), _ptr(out)))
+        return out
+
+    def features_device(self, d_wave_ptr: int, n_wave: int, starts: np.ndarray, lengths: np.ndarray,
+                        sample_rate: int, flag_bits: int, d_out_ptr: int, stream: int = 0) -> None:
+        """Device pointers in, device pointer out; enqueues on ``stream`` (0 = the context's)."""
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        self._check(self._lib.serb_features_device(
+            self._handle, c_void_p(d_wave_ptr), int(n_wave), _ptr(starts), _ptr(lengths), starts.size,
+            int(sample_rate), int(flag_bits), c_void_p(d_out_ptr), c_void_p(stream)))
+
+    # ---- classifier ----------------------------------------------------------------------
+    def mlp_load(self, mean, scale, w1, b1, w2, b2, out_activation: int) -> None:
+        arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, scale, w1, b1, w2, b2)]
+        n_in, n_hidden = arrays[2].shape
+        n_out = arrays[4].shape[1]
+        self._check(self._lib.serb_mlp_load(self._handle, n_in, n_hidden, n_out,
+                                            *[_ptr(a) for a in arrays], int(out_activation)))
+        self._mlp_classes = self._lib.serb_mlp_n_classes(self._handle)
+
+    @property
+    def mlp_n_classes(self) -> int:
+        return self._mlp_classes
+
+    def mlp_predict_host(self, x: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = x.shape[0]
+        proba = np.empty((n, max(self._mlp_classes, 1)), dtype=np.float64)
+        labels = np.empty(n, dtype=np.int32)
+        self._check(self._lib.serb_mlp_predict_host(self._handle, _ptr(x), n, _ptr(proba), _ptr(labels)))
+        return proba, labels
+
+    def mlp_predict_device(self, d_x_ptr: int, n: int, d_proba_ptr: int, d_label_ptr: int, stream: int = 0) -> None:
+        self._check(self._lib.serb_mlp_predict_device(self._handle, c_void_p(d_x_ptr), int(n),
+                                                      c_void_p(d_proba_ptr), c_void_p(d_label_ptr),
+                                                      c_void_p(stream)))
+
+    def infer_host(self, wave: np.ndarray, starts: np.ndarray, lengths: np.ndarray, sample_rate: int,
+                   flag_bits: int, *, want_features: bool = True):
+        wave = np.ascontiguousarray(wave, dtype=np.float32)
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        n = starts.size
+        dim = self._lib.serb_feature_dim(flag_bits)
+        feats = np.empty((n, dim), dtype=np.float32) if want_features else None
+        proba = np.empty((n, max(self._mlp_classes, 1)), dtype=np.float64)
+        labels = np.empty(n, dtype=np.int32)
+        self._check(self._lib.serb_infer_host(
+            self._handle, _ptr(wave), wave.size, _ptr(starts), _ptr(lengths), n, int(sample_rate),
+            int(flag_bits), _ptr(feats), _ptr(proba), _ptr(labels)))
+        return feats, proba, labels
+
+    # ---- audio prep ----------------------------------------------------------------------
+    def prepare_pcm16_host(self, pcm: np.ndarray) -> np.ndarray:
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        out = np.empty(pcm.size, dtype=np.float32)
+        self._check(self._lib.serb_prepare_pcm16_host(self._handle, _ptr(pcm), pcm.size, _ptr(out)))
+        return out
+
+    # ---- introspection -------------------------------------------------------------------
+    def debug_stft_host(self, wave: np.ndarray) -> np.ndarray:
+        wave = np.ascontiguousarray(wave, dtype=np.float32)
+        n_cols = 1 + wave.size // 512
+        out = np.empty((n_cols, 1025), dtype=np.float32)
+        self._check(self._lib.serb_debug_stft_host(self._handle, _ptr(wave), wave.size, _ptr(out), n_cols))
+        return out
+
+    def debug_last_tuning(self, n_clips: int) -> np.ndarray:
+        out = np.empty(n_clips, dtype=np.int32)
+        self._check(self._lib.serb_debug_last_tuning(self._handle, _ptr(out), n_clips))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.serb_debug_launch_count(self._handle))
+
+    def set_profile(self, enabled: bool) -> None:
+        self._check(self._lib.serb_debug_set_profile(self._handle, 1 if enabled else 0))
+
+    def kernel_ms(self) -> dict[str, tuple[float, int]]:
+        """{kernel: (total device ms, launches)} since set_profile(True)."""
+        out = {}
+        for kind, name in enumerate(("stft", "tuning", "proj", "pool", "short", "mlp")):
+            ms = c_double(0.0)
+            n = c_int64(0)
+            self._check(self._lib.serb_debug_kernel_ms(self._handle, kind, ctypes.byref(ms), ctypes.byref(n)))
+            out[name] = (float(ms.value), int(n.value))
+        return out
+
+    def last_compute_ms(self) -> float:
+        return float(self._lib.serb_debug_last_compute_ms(self._handle))
+
+
+def debug_filterbank(kind: int, sample_rate: int, n_fft: int, tuning_index: int = 50) -> np.ndarray:
+    """Host-side tables of the library (no GPU needed): 0 mel, 1 chroma, 2 DCT, 3 Hann."""
+    lib = load_library()
+    n_bins = 1 + n_fft // 2
+    shape = {0: (128, n_bins), 1: (12, n_bins), 2: (40, 128), 3: (n_fft,)}[kind]
+    out = np.empty(shape, dtype=np.float32)
+    code = lib.serb_debug_filterbank(kind, int(sample_rate), int(n_fft), int(tuning_index), _ptr(out))
+    if code != 0:
+        raise ValueError(f"serb_debug_filterbank failed with {code}")
+    return out
+
+
+def device_count() -> int:
+    return int(load_library().serb_device_count())
+
+
+_contexts: dict[int, Context] = {}
+_contexts_lock = threading.Lock()
+
+
+def get_context(device: int = 0) -> Context:
+    """Lazily created per-device context (CUDA is never touched at import time, so fork-based
+    callers such as the reference's mp.Pool path stay safe: ser/_internal/data/data_loader.py:378)."""
+    with _contexts_lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _contexts[device] = ctx
+        return ctx

@@ -1,0 +1,820 @@
+// C ABI of libser_b200.so (see include/ser_b200.h): context, chunked launch chains, staging.
+#include "../../include/ser_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "filterbanks.h"
+#include "kernels.h"
+
+namespace {
+
+using namespace serb;
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+        // grow geometrically so repeated calls with slowly growing sizes do not thrash
+        size_t want = std::max(need, bytes + bytes / 2);
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) { want = need; e = cudaMalloc(&ptr, want); }
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct SrTables {
+    int sample_rate = 0;
+    DevBuf chroma_banks;   // [100][1025][12] float
+    DevBuf mel_start, mel_count, mel_offset, mel_weights, mel_points;
+    int mel_nnz = 0;
+    int kmin = 0, kmax = 0, peak_cap = 0;
+};
+
+struct Mlp {
+    bool loaded = false;
+    int n_in = 0, n_hidden = 0, n_out = 0, n_classes = 0, out_activation = 0;
+    DevBuf mean, scale, w1, b1, w2, b2;
+};
+
+}  // namespace
+
+struct serb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> piece_events;
+    std::mutex mu;
+    std::string err;
+    long long launches = 0;
+    int chunk_cols = 12288;
+    float last_ms = 0.f;
+    bool timed = false;
+
+    DevBuf edges, dct;
+    std::map<int, SrTables> sr_tables;
+    Mlp mlp;
+
+    // scratch, reused by every chunk so it stays L2 resident
+    DevBuf spill, logmel, tile_mel, tile_lmax, tile_chroma, peaks, peak_count;
+    DevBuf clips, short_clips, tuning, short_tuning, status;
+    // host-entry staging
+    DevBuf wave, out, proba, labels, x64, pcm, pcm_max;
+    std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
+    std::vector<int> last_short_rows;
+    long long last_n_clips = 0;
+    bool last_had_chroma = false;
+
+    // optional per-kernel timing (serb_debug_set_profile): event pairs around every launch
+    bool profile = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+    long long prof_n[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(serb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+int fail_cuda(serb_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, SERB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define SERB_CUDA(ctx, call)                                          \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);    \
+    } while (0)
+
+// kinds: 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp
+struct ProfScope {
+    serb_ctx* ctx; int kind; cudaStream_t stream; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(serb_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), stream(s) {
+        if (!ctx->profile) return;
+        auto take = [&]() {
+            cudaEvent_t ev = nullptr;
+            if (!ctx->prof_pool.empty()) { ev = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+            else cudaEventCreate(&ev);
+            return ev;
+        };
+        a = take(); b = take();
+        cudaEventRecord(a, stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, stream);
+        ctx->prof_recs.push_back({kind, a, b});
+    }
+};
+
+template <typename T>
+int upload(serb_ctx* ctx, DevBuf& buf, const T* host, size_t count, cudaStream_t stream) {
+    SERB_CUDA(ctx, buf.reserve(std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) SERB_CUDA(ctx, cudaMemcpyAsync(buf.ptr, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return SERB_OK;
+}
+
+int get_sr_tables(serb_ctx* ctx, int sr, SrTables** out) {
+    auto it = ctx->sr_tables.find(sr);
+    if (it != ctx->sr_tables.end()) { *out = &it->second; return SERB_OK; }
+    SrTables& t = ctx->sr_tables[sr];
+    t.sample_rate = sr;
+    // mel (sparse CSR)
+    std::vector<float> dense;
+    mel_filterbank(sr, kNFft, dense);
+    MelSparse ms;
+    mel_sparse(dense, kNBins, ms);
+    if (ms.weights.size() > 2304) return fail(ctx, SERB_ERR_UNSUPPORTED, "mel filterbank has more non-zeros than the kernel stages");
+    t.mel_nnz = static_cast<int>(ms.weights.size());
+    int rc;
+    if ((rc = upload(ctx, t.mel_start, ms.start.data(), ms.start.size(), ctx->stream))) return rc;
+    if ((rc = upload(ctx, t.mel_count, ms.count.data(), ms.count.size(), ctx->stream))) return rc;
+    if ((rc = upload(ctx, t.mel_offset, ms.offset.data(), ms.offset.size(), ctx->stream))) return rc;
+    if ((rc = upload(ctx, t.mel_weights, ms.weights.data(), ms.weights.size(), ctx->stream))) return rc;
+    std::vector<double> pts;
+    mel_points(sr, pts);
+    if ((rc = upload(ctx, t.mel_points, pts.data(), pts.size(), ctx->stream))) return rc;
+    // chroma banks, one per tuning-histogram bin, transposed to [bin][12]
+    std::vector<float> banks(static_cast<size_t>(kNTunings) * kNBins * 12);
+    std::vector<float> w;
+    for (int i = 0; i < kNTunings; ++i) {
+        chroma_filterbank(sr, kNFft, tuning_edge(i), w);
+        float* dst = banks.data() + static_cast<size_t>(i) * kNBins * 12;
+        for (int c = 0; c < 12; ++c)
+            for (int k = 0; k < kNBins; ++k) dst[k * 12 + c] = w[static_cast<size_t>(c) * kNBins + k];
+    }
+    if ((rc = upload(ctx, t.chroma_banks, banks.data(), banks.size(), ctx->stream))) return rc;
+    // piptrack band: fmin <= k * (1 / (n_fft * (1/sr))) < min(4000, sr/2)
+    const double val = 1.0 / (static_cast<double>(kNFft) * (1.0 / static_cast<double>(sr)));
+    const double fmax = std::min(4000.0, static_cast<double>(sr) / 2.0);
+    int kmin = kNBins, kmax = 0;
+    for (int k = 0; k < kNBins; ++k) {
+        const double f = k * val;
+        if (f >= 150.0 && f < fmax) { kmin = std::min(kmin, k); kmax = std::max(kmax, k + 1); }
+    }
+    if (kmin >= kmax) { kmin = 1; kmax = 1; }
+    kmin = std::max(kmin, 1);
+    kmax = std::min(kmax, kNBins - 1);
+    t.kmin = kmin;
+    t.kmax = kmax;
+    t.peak_cap = std::max(1, (kmax - kmin + 1) / 2 + 1);
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    *out = &t;
+    return SERB_OK;
+}
+
+struct Offsets { int dim, mfcc, chroma, mel, contrast, tonnetz; };
+Offsets make_offsets(uint32_t flags) {
+    Offsets o{0, -1, -1, -1, -1, -1};
+    if (flags & SERB_FLAG_MFCC) { o.mfcc = o.dim; o.dim += 40; }
+    if (flags & SERB_FLAG_CHROMA) { o.chroma = o.dim; o.dim += 12; }
+    if (flags & SERB_FLAG_MEL) { o.mel = o.dim; o.dim += 128; }
+    if (flags & SERB_FLAG_CONTRAST) { o.contrast = o.dim; o.dim += 7; }
+    if (flags & SERB_FLAG_TONNETZ) { o.tonnetz = o.dim; o.dim += 6; }
+    return o;
+}
+
+struct Chunk { int clip_lo, clip_hi, n_cols, n_tiles; long long max_end; };
+
+// Validates the request and splits it into the main path (n_fft = 2048) and short clips.
+int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* lengths, long long n_clips,
+         int sr, uint32_t flags, std::vector<ClipDev>& main_clips, std::vector<ShortClip>& short_clips,
+         std::vector<Chunk>& chunks) {
+    if (sr <= 0) return fail(ctx, SERB_ERR_SAMPLE_RATE, "Sample rate must be a positive integer.");
+    if (n_clips < 0 || (n_clips > 0 && (!starts || !lengths))) return fail(ctx, SERB_ERR_INVALID_ARG, "bad clip arrays");
+    if (flags & ~SERB_FLAG_ALL) return fail(ctx, SERB_ERR_INVALID_ARG, "unknown feature flag bits");
+    if ((flags & SERB_FLAG_CONTRAST) && !(6400.0 < 0.5 * sr))
+        return fail(ctx, SERB_ERR_NYQUIST, "Frequency band exceeds Nyquist. Reduce either fmin or n_bands.");
+    if (flags & SERB_FLAG_TONNETZ)
+        return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz group is not implemented in this build");
+    Chunk cur{0, 0, 0, 0, 0};
+    for (long long i = 0; i < n_clips; ++i) {
+        const long long s = starts[i], len = lengths[i];
+        if (len <= 0) return fail(ctx, SERB_ERR_EMPTY, "Audio contains no samples.");
+        if (s < 0 || s + len > n_wave || len > 0x7fffffffLL)
+            return fail(ctx, SERB_ERR_INVALID_ARG, "clip " + std::to_string(i) + " lies outside the waveform buffer");
+        if (len < kNFft) {
+            short_clips.push_back(ShortClip{s, static_cast<int>(len), static_cast<int>(i)});
+            continue;
+        }
+        ClipDev c{};
+        c.start = s;
+        c.length = static_cast<int>(len);
+        c.n_cols = 1 + static_cast<int>(len / kHop);
+        c.out_row = static_cast<int>(i);
+        const int tiles = (c.n_cols + kColsPerTile - 1) / kColsPerTile;
+        if (cur.clip_hi > cur.clip_lo && cur.n_cols + c.n_cols > ctx->chunk_cols) {
+            chunks.push_back(cur);
+            cur = Chunk{cur.clip_hi, cur.clip_hi, 0, 0, 0};
+        }
+        c.col_base = cur.n_cols;
+        c.tile_base = cur.n_tiles;
+        cur.n_cols += c.n_cols;
+        cur.n_tiles += tiles;
+        cur.max_end = std::max(cur.max_end, s + len);
+        cur.clip_hi += 1;
+        main_clips.push_back(c);
+    }
+    if (cur.clip_hi > cur.clip_lo) chunks.push_back(cur);
+    return SERB_OK;
+}
+
+// Enqueues the whole launch chain on `stream`.  before_chunk(max_end) lets the host entry make
+// the stream wait for the H2D piece that holds the chunk's last sample.
+template <typename BeforeChunk>
+int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int64_t* starts,
+                 const int64_t* lengths, long long n_clips, int sr, uint32_t flags, float* d_out,
+                 cudaStream_t stream, BeforeChunk before_chunk) {
+    std::vector<ClipDev> main_clips;
+    std::vector<ShortClip> short_clips;
+    std::vector<Chunk> chunks;
+    int rc = plan(ctx, n_wave, starts, lengths, n_clips, sr, flags, main_clips, short_clips, chunks);
+    if (rc) return rc;
+    ctx->last_n_clips = n_clips;
+    ctx->last_had_chroma = (flags & SERB_FLAG_CHROMA) != 0;
+    ctx->last_tuning_rows.clear();
+    ctx->last_short_rows.clear();
+    const Offsets off = make_offsets(flags);
+    if (n_clips == 0 || off.dim == 0) return SERB_OK;
+    if (off.contrast >= 0 && off.dim == 7 && main_clips.empty() && short_clips.empty()) return SERB_OK;
+
+    SrTables* tab = nullptr;
+    if ((rc = get_sr_tables(ctx, sr, &tab))) return rc;
+    const bool want_chroma = off.chroma >= 0;
+    const bool want_mel = off.mel >= 0 || off.mfcc >= 0;
+
+    int max_cols = 0, max_tiles = 0, max_clips = 0;
+    for (const Chunk& c : chunks) {
+        max_cols = std::max(max_cols, c.n_cols);
+        max_tiles = std::max(max_tiles, c.n_tiles);
+        max_clips = std::max(max_clips, c.clip_hi - c.clip_lo);
+    }
+    if (!chunks.empty()) {
+        SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(max_cols) * kSpillStride * sizeof(float)));
+        SERB_CUDA(ctx, ctx->logmel.reserve(static_cast<size_t>(max_cols) * 128 * sizeof(float)));
+        SERB_CUDA(ctx, ctx->tile_mel.reserve(static_cast<size_t>(max_tiles) * 128 * sizeof(float)));
+        SERB_CUDA(ctx, ctx->tile_lmax.reserve(static_cast<size_t>(max_tiles) * sizeof(float)));
+        SERB_CUDA(ctx, ctx->tile_chroma.reserve(static_cast<size_t>(max_tiles) * 12 * sizeof(float)));
+        if (want_chroma) {
+            SERB_CUDA(ctx, ctx->peaks.reserve(static_cast<size_t>(max_cols) * tab->peak_cap * sizeof(float2)));
+            SERB_CUDA(ctx, ctx->peak_count.reserve(static_cast<size_t>(max_cols) * sizeof(int)));
+        }
+        SERB_CUDA(ctx, ctx->tuning.reserve(main_clips.size() * sizeof(int)));
+        if ((rc = upload(ctx, ctx->clips, main_clips.data(), main_clips.size(), stream))) return rc;
+        for (const ClipDev& c : main_clips) ctx->last_tuning_rows.push_back(c.out_row);
+    }
+    SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
+    SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), stream));
+
+    if (ctx->timed) SERB_CUDA(ctx, cudaEventRecord(ctx->ev_start, stream));
+    for (const Chunk& c : chunks) {
+        before_chunk(c.max_end);
+        const ClipDev* d_clips = ctx->clips.as<ClipDev>() + c.clip_lo;
+        const int nc = c.clip_hi - c.clip_lo;
+        StftParams sp{};
+        sp.wave = d_wave;
+        sp.clips = d_clips;
+        sp.n_clips = nc;
+        sp.spill = ctx->spill.as<float>();
+        sp.do_peaks = want_chroma ? 1 : 0;
+        sp.kmin = tab->kmin;
+        sp.kmax = tab->kmax;
+        sp.peak_cap = tab->peak_cap;
+        sp.peaks = ctx->peaks.as<float2>();
+        sp.peak_count = ctx->peak_count.as<int>();
+        sp.sr_over_nfft_num = static_cast<double>(sr);
+        sp.status = ctx->status.as<int>();
+        { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
+        ctx->launches += 1;
+        int* d_tuning = ctx->tuning.as<int>() + c.clip_lo;
+        if (want_chroma) {
+            TuneParams tp{};
+            tp.clips = d_clips;
+            tp.peaks = sp.peaks;
+            tp.peak_count = sp.peak_count;
+            tp.peak_cap = tab->peak_cap;
+            tp.bins_per_octave = 12;
+            tp.edges = ctx->edges.as<double>();
+            tp.tuning_idx = d_tuning;
+            { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream)); }
+            ctx->launches += 1;
+        }
+        ProjParams pp{};
+        pp.clips = d_clips;
+        pp.n_clips = nc;
+        pp.spill = sp.spill;
+        pp.do_mel = want_mel ? 1 : 0;
+        pp.mel_start = tab->mel_start.as<int>();
+        pp.mel_count = tab->mel_count.as<int>();
+        pp.mel_offset = tab->mel_offset.as<int>();
+        pp.mel_weights = tab->mel_weights.as<float>();
+        pp.mel_nnz = tab->mel_nnz;
+        pp.logmel = ctx->logmel.as<float>();
+        pp.tile_mel = ctx->tile_mel.as<float>();
+        pp.tile_lmax = ctx->tile_lmax.as<float>();
+        pp.do_chroma = want_chroma ? 1 : 0;
+        pp.chroma_banks = tab->chroma_banks.as<float>();
+        pp.tuning_idx = d_tuning;
+        pp.tile_chroma = ctx->tile_chroma.as<float>();
+        if (want_mel || want_chroma) {
+            { ProfScope ps(ctx, 2, stream); SERB_CUDA(ctx, launch_proj(pp, c.n_tiles, stream)); }
+            ctx->launches += 1;
+        }
+        PoolParams qp{};
+        qp.clips = d_clips;
+        qp.logmel = pp.logmel;
+        qp.tile_mel = pp.tile_mel;
+        qp.tile_lmax = pp.tile_lmax;
+        qp.tile_chroma = pp.tile_chroma;
+        qp.dct = ctx->dct.as<double>();
+        qp.out = d_out;
+        qp.dim = off.dim;
+        qp.off_mfcc = off.mfcc;
+        qp.off_chroma = off.chroma;
+        qp.off_mel = off.mel;
+        qp.off_contrast = off.contrast;
+        { ProfScope ps(ctx, 3, stream); SERB_CUDA(ctx, launch_pool(qp, nc, stream)); }
+        ctx->launches += 1;
+    }
+    if (!short_clips.empty()) {
+        long long max_end = 0;
+        for (const ShortClip& s : short_clips) {
+            max_end = std::max(max_end, s.start + s.length);
+            ctx->last_short_rows.push_back(s.out_row);
+        }
+        before_chunk(max_end);
+        if ((rc = upload(ctx, ctx->short_clips, short_clips.data(), short_clips.size(), stream))) return rc;
+        SERB_CUDA(ctx, ctx->short_tuning.reserve(short_clips.size() * sizeof(int)));
+        ShortParams hp{};
+        hp.wave = d_wave;
+        hp.clips = ctx->short_clips.as<ShortClip>();
+        hp.sample_rate = sr;
+        hp.mel_points = tab->mel_points.as<double>();
+        hp.edges = ctx->edges.as<double>();
+        hp.dct = ctx->dct.as<double>();
+        hp.out = d_out;
+        hp.dim = off.dim;
+        hp.off_mfcc = off.mfcc;
+        hp.off_chroma = off.chroma;
+        hp.off_mel = off.mel;
+        hp.off_contrast = off.contrast;
+        hp.tuning_idx = ctx->short_tuning.as<int>();
+        hp.status = ctx->status.as<int>();
+        { ProfScope ps(ctx, 4, stream); SERB_CUDA(ctx, launch_short(hp, static_cast<int>(short_clips.size()), stream)); }
+        ctx->launches += 1;
+    }
+    if (ctx->timed) SERB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, stream));
+    return SERB_OK;
+}
+
+int check_status(serb_ctx* ctx, cudaStream_t stream) {
+    int status = 0;
+    SERB_CUDA(ctx, cudaMemcpyAsync(&status, ctx->status.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (status & 1) return fail(ctx, SERB_ERR_NOT_FINITE, "Audio buffer is not finite everywhere.");
+    return SERB_OK;
+}
+
+// host waveform -> ctx->wave in pieces on the copy stream; returns a functor making `stream`
+// wait for the piece holding sample (max_end - 1)
+struct PieceWaiter {
+    serb_ctx* ctx;
+    cudaStream_t stream;
+    long long piece;
+    int n_pieces;
+    int waited = -1;
+    void operator()(long long max_end) {
+        if (n_pieces == 0) return;
+        int idx = static_cast<int>(std::min<long long>((std::max<long long>(max_end, 1) - 1) / piece, n_pieces - 1));
+        if (idx > waited) {
+            cudaStreamWaitEvent(stream, ctx->piece_events[idx], 0);
+            waited = idx;
+        }
+    }
+};
+
+int stage_wave(serb_ctx* ctx, const float* h_wave, long long n_wave, PieceWaiter& waiter) {
+    SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
+    const long long piece = 8LL << 20;  // samples per piece (32 MiB)
+    const int n_pieces = static_cast<int>((n_wave + piece - 1) / piece);
+    while (static_cast<int>(ctx->piece_events.size()) < n_pieces) {
+        cudaEvent_t ev;
+        SERB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->piece_events.push_back(ev);
+    }
+    // the previous call's kernels may still read ctx->wave
+    SERB_CUDA(ctx, cudaEventRecord(ctx->ev_done, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
+    for (int i = 0; i < n_pieces; ++i) {
+        const long long lo = i * piece, hi = std::min(n_wave, lo + piece);
+        SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.as<float>() + lo, h_wave + lo, (hi - lo) * sizeof(float),
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+        SERB_CUDA(ctx, cudaEventRecord(ctx->piece_events[i], ctx->copy_stream));
+    }
+    waiter = PieceWaiter{ctx, ctx->stream, piece, n_pieces};
+    return SERB_OK;
+}
+
+int mlp_run(serb_ctx* ctx, const float* d_x32, const double* d_x64, long long n, double* d_proba,
+            int* d_label, cudaStream_t stream) {
+    if (!ctx->mlp.loaded) return fail(ctx, SERB_ERR_NO_MODEL, "no classifier loaded (call serb_mlp_load)");
+    MlpParams p{};
+    const Mlp& m = ctx->mlp;
+    p.n_in = m.n_in; p.n_hidden = m.n_hidden; p.n_out = m.n_out; p.n_classes = m.n_classes;
+    p.out_activation = m.out_activation;
+    p.mean = m.mean.as<double>(); p.scale = m.scale.as<double>();
+    p.w1 = m.w1.as<double>(); p.b1 = m.b1.as<double>(); p.w2 = m.w2.as<double>(); p.b2 = m.b2.as<double>();
+    p.x32 = d_x32; p.x64 = d_x64; p.n = n; p.proba = d_proba; p.label = d_label;
+    { ProfScope ps(ctx, 5, stream); SERB_CUDA(ctx, launch_mlp(p, stream)); }
+    if (n > 0) ctx->launches += 1;
+    return SERB_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* serb_version(void) { return "ser_b200 0.1.0 (sm_100a)"; }
+
+int serb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* serb_last_error(const serb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int serb_feature_dim(uint32_t flag_bits) { return make_offsets(flag_bits & SERB_FLAG_ALL).dim; }
+
+int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
+    if (!out_ctx) return fail(nullptr, SERB_ERR_INVALID_ARG, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SERB_ERR_NO_DEVICE, "no CUDA device available: ser_b200 has no CPU fallback");
+    }
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(nullptr, SERB_ERR_INVALID_ARG, "device ordinal out of range");
+    if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return fail_cuda(nullptr, e, "cudaSetDevice");
+    serb_ctx* ctx = new serb_ctx();
+    ctx->device = device_ordinal;
+    if (const char* env = std::getenv("SERB_CHUNK_COLS")) {
+        const int v = std::atoi(env);
+        if (v >= 64) ctx->chunk_cols = v;
+    }
+    ctx->timed = true;
+#define CREATE_CHECK(call)                                                                     \
+    do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { int rc2 = fail_cuda(nullptr, e2, #call); delete ctx; return rc2; } } while (0)
+    CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_CHECK(cudaEventCreate(&ctx->ev_start));
+    CREATE_CHECK(cudaEventCreate(&ctx->ev_stop));
+    CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+    CREATE_CHECK(configure_stft());
+    CREATE_CHECK(configure_proj());
+    CREATE_CHECK(configure_short());
+    std::vector<double> edges(101), dct;
+    for (int i = 0; i <= 100; ++i) edges[i] = tuning_edge(i);
+    dct_matrix(dct);
+    CREATE_CHECK(ctx->edges.reserve(edges.size() * sizeof(double)));
+    CREATE_CHECK(cudaMemcpy(ctx->edges.ptr, edges.data(), edges.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CREATE_CHECK(ctx->dct.reserve(dct.size() * sizeof(double)));
+    CREATE_CHECK(cudaMemcpy(ctx->dct.ptr, dct.data(), dct.size() * sizeof(double), cudaMemcpyHostToDevice));
+#undef CREATE_CHECK
+    *out_ctx = ctx;
+    return SERB_OK;
+}
+
+void serb_ctx_destroy(serb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (DevBuf* b : {&ctx->edges, &ctx->dct, &ctx->spill, &ctx->logmel, &ctx->tile_mel, &ctx->tile_lmax,
+                      &ctx->tile_chroma, &ctx->peaks, &ctx->peak_count, &ctx->clips, &ctx->short_clips,
+                      &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
+                      &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->mlp.mean, &ctx->mlp.scale,
+                      &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2})
+        b->release();
+    for (auto& kv : ctx->sr_tables) {
+        SrTables& t = kv.second;
+        for (DevBuf* b : {&t.chroma_banks, &t.mel_start, &t.mel_count, &t.mel_offset, &t.mel_weights, &t.mel_points})
+            b->release();
+    }
+    for (cudaEvent_t ev : ctx->piece_events) cudaEventDestroy(ev);
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    cudaEventDestroy(ctx->ev_done);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int serb_features_device(serb_ctx* ctx, const float* d_wave, int64_t n_wave, const int64_t* starts,
+                         const int64_t* lengths, int64_t n_clips, int32_t sample_rate, uint32_t flag_bits,
+                         float* d_out, void* stream) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_clips > 0 && (!d_wave || !d_out)) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL device buffer");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return run_features(ctx, d_wave, n_wave, starts, lengths, n_clips, sample_rate, flag_bits, d_out, s,
+                        [](long long) {});
+}
+
+int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const int64_t* starts,
+                       const int64_t* lengths, int64_t n_clips, int32_t sample_rate, uint32_t flag_bits,
+                       float* h_out) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_clips > 0 && (!h_wave || !h_out)) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+    const int dim = serb_feature_dim(flag_bits);
+    PieceWaiter waiter{ctx, ctx->stream, 1, 0};
+    int rc = stage_wave(ctx, h_wave, n_wave, waiter);
+    if (rc) return rc;
+    SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
+    rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
+                      ctx->out.as<float>(), ctx->stream, waiter);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+    if (n_clips > 0 && dim > 0)
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.ptr, static_cast<size_t>(n_clips) * dim * sizeof(float),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_clips > 0 && dim > 0) return check_status(ctx, ctx->stream);
+    return SERB_OK;
+}
+
+int serb_mlp_load(serb_ctx* ctx, int32_t n_in, int32_t n_hidden, int32_t n_out, const double* mean,
+                  const double* scale, const double* w1, const double* b1, const double* w2, const double* b2,
+                  int32_t out_activation) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_in <= 0 || n_hidden <= 0 || n_out <= 0 || !mean || !scale || !w1 || !b1 || !w2 || !b2)
+        return fail(ctx, SERB_ERR_INVALID_ARG, "bad classifier shapes");
+    if (out_activation != SERB_OUT_SOFTMAX && out_activation != SERB_OUT_LOGISTIC)
+        return fail(ctx, SERB_ERR_INVALID_ARG, "unsupported output activation");
+    if (mlp_smem_bytes(n_in, n_hidden, n_out) > 200 * 1024)
+        return fail(ctx, SERB_ERR_UNSUPPORTED, "classifier too wide for the fused kernel");
+    Mlp& m = ctx->mlp;
+    m.loaded = false;
+    int rc;
+    if ((rc = upload(ctx, m.mean, mean, n_in, ctx->stream))) return rc;
+    if ((rc = upload(ctx, m.scale, scale, n_in, ctx->stream))) return rc;
+    if ((rc = upload(ctx, m.w1, w1, static_cast<size_t>(n_in) * n_hidden, ctx->stream))) return rc;
+    if ((rc = upload(ctx, m.b1, b1, n_hidden, ctx->stream))) return rc;
+    if ((rc = upload(ctx, m.w2, w2, static_cast<size_t>(n_hidden) * n_out, ctx->stream))) return rc;
+    if ((rc = upload(ctx, m.b2, b2, n_out, ctx->stream))) return rc;
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SERB_CUDA(ctx, configure_mlp(n_in, n_hidden, n_out));
+    m.n_in = n_in; m.n_hidden = n_hidden; m.n_out = n_out; m.out_activation = out_activation;
+    m.n_classes = (out_activation == SERB_OUT_LOGISTIC && n_out == 1) ? 2 : n_out;
+    m.loaded = true;
+    return SERB_OK;
+}
+
+int serb_mlp_n_classes(const serb_ctx* ctx) { return (ctx && ctx->mlp.loaded) ? ctx->mlp.n_classes : 0; }
+
+int serb_mlp_predict_device(serb_ctx* ctx, const float* d_x, int64_t n, double* d_proba, int32_t* d_label_index,
+                            void* stream) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n < 0 || (n > 0 && (!d_x || !d_proba || !d_label_index))) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL buffer");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return mlp_run(ctx, d_x, nullptr, n, d_proba, d_label_index, s);
+}
+
+int serb_mlp_predict_host(serb_ctx* ctx, const double* h_x, int64_t n, double* h_proba, int32_t* h_label_index) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->mlp.loaded) return fail(ctx, SERB_ERR_NO_MODEL, "no classifier loaded (call serb_mlp_load)");
+    if (n < 0 || (n > 0 && (!h_x || !h_proba || !h_label_index))) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL buffer");
+    if (n == 0) return SERB_OK;
+    const Mlp& m = ctx->mlp;
+    SERB_CUDA(ctx, ctx->x64.reserve(static_cast<size_t>(n) * m.n_in * sizeof(double)));
+    SERB_CUDA(ctx, ctx->proba.reserve(static_cast<size_t>(n) * m.n_classes * sizeof(double)));
+    SERB_CUDA(ctx, ctx->labels.reserve(static_cast<size_t>(n) * sizeof(int)));
+    SERB_CUDA(ctx, cudaMemcpyAsync(ctx->x64.ptr, h_x, static_cast<size_t>(n) * m.n_in * sizeof(double),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    int rc = mlp_run(ctx, nullptr, ctx->x64.as<double>(), n, ctx->proba.as<double>(), ctx->labels.as<int>(), ctx->stream);
+    if (rc) return rc;
+    SERB_CUDA(ctx, cudaMemcpyAsync(h_proba, ctx->proba.ptr, static_cast<size_t>(n) * m.n_classes * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(h_label_index, ctx->labels.ptr, static_cast<size_t>(n) * sizeof(int),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SERB_OK;
+}
+
+int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const int64_t* starts,
+                    const int64_t* lengths, int64_t n_clips, int32_t sample_rate, uint32_t flag_bits,
+                    float* h_features, double* h_proba, int32_t* h_label_index) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->mlp.loaded) return fail(ctx, SERB_ERR_NO_MODEL, "no classifier loaded (call serb_mlp_load)");
+    if (n_clips > 0 && (!h_wave || !h_proba || !h_label_index)) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+    const int dim = serb_feature_dim(flag_bits);
+    const Mlp& m = ctx->mlp;
+    if (dim != m.n_in)
+        return fail(ctx, SERB_ERR_INVALID_ARG,
+                    "Feature vector size mismatch for loaded model. Expected " + std::to_string(m.n_in) +
+                        ", got [" + std::to_string(dim) + "].");
+    PieceWaiter waiter{ctx, ctx->stream, 1, 0};
+    int rc = stage_wave(ctx, h_wave, n_wave, waiter);
+    if (rc) return rc;
+    SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
+    SERB_CUDA(ctx, ctx->proba.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * m.n_classes, 1) * sizeof(double)));
+    SERB_CUDA(ctx, ctx->labels.reserve(std::max<size_t>(static_cast<size_t>(n_clips), 1) * sizeof(int)));
+    rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
+                      ctx->out.as<float>(), ctx->stream, waiter);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+    if (n_clips == 0) return SERB_OK;
+    rc = mlp_run(ctx, ctx->out.as<float>(), nullptr, n_clips, ctx->proba.as<double>(), ctx->labels.as<int>(), ctx->stream);
+    if (rc) return rc;
+    if (h_features)
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_features, ctx->out.ptr, static_cast<size_t>(n_clips) * dim * sizeof(float),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(h_proba, ctx->proba.ptr, static_cast<size_t>(n_clips) * m.n_classes * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(h_label_index, ctx->labels.ptr, static_cast<size_t>(n_clips) * sizeof(int),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_status(ctx, ctx->stream);
+}
+
+int serb_prepare_pcm16_device(serb_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out, void* stream) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n < 0 || (n > 0 && (!d_pcm || !d_out))) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL buffer");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    SERB_CUDA(ctx, ctx->pcm_max.reserve(sizeof(int)));
+    SERB_CUDA(ctx, launch_prepare_pcm16(d_pcm, n, ctx->pcm_max.as<int>(), d_out, s));
+    if (n > 0) ctx->launches += 2;
+    return SERB_OK;
+}
+
+int serb_prepare_pcm16_host(serb_ctx* ctx, const int16_t* h_pcm, int64_t n, float* h_out) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n < 0 || (n > 0 && (!h_pcm || !h_out))) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL buffer");
+    if (n == 0) return SERB_OK;
+    SERB_CUDA(ctx, ctx->pcm.reserve(static_cast<size_t>(n) * sizeof(int16_t)));
+    SERB_CUDA(ctx, ctx->pcm_max.reserve(sizeof(int)));
+    SERB_CUDA(ctx, ctx->wave.reserve(static_cast<size_t>(n) * sizeof(float) + 64));
+    SERB_CUDA(ctx, cudaMemcpyAsync(ctx->pcm.ptr, h_pcm, static_cast<size_t>(n) * sizeof(int16_t),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    SERB_CUDA(ctx, launch_prepare_pcm16(ctx->pcm.as<short>(), n, ctx->pcm_max.as<int>(), ctx->wave.as<float>(), ctx->stream));
+    ctx->launches += 2;
+    SERB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->wave.ptr, static_cast<size_t>(n) * sizeof(float),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SERB_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------
+int serb_debug_filterbank(int32_t kind, int32_t sample_rate, int32_t n_fft, int32_t tuning_index, float* out) {
+    if (!out || n_fft < 2) return SERB_ERR_INVALID_ARG;
+    if (kind == 0) {
+        if (sample_rate <= 0) return SERB_ERR_SAMPLE_RATE;
+        std::vector<float> w;
+        mel_filterbank(sample_rate, n_fft, w);
+        std::memcpy(out, w.data(), w.size() * sizeof(float));
+    } else if (kind == 1) {
+        if (sample_rate <= 0) return SERB_ERR_SAMPLE_RATE;
+        if (tuning_index < 0 || tuning_index >= kNTunings) return SERB_ERR_INVALID_ARG;
+        std::vector<float> w;
+        chroma_filterbank(sample_rate, n_fft, tuning_edge(tuning_index), w);
+        std::memcpy(out, w.data(), w.size() * sizeof(float));
+    } else if (kind == 2) {
+        std::vector<double> d;
+        dct_matrix(d);
+        for (size_t i = 0; i < d.size(); ++i) out[i] = static_cast<float>(d[i]);
+    } else if (kind == 3) {
+        std::vector<double> w;
+        hann_periodic(n_fft, w);
+        for (size_t i = 0; i < w.size(); ++i) out[i] = static_cast<float>(w[i]);
+    } else {
+        return SERB_ERR_INVALID_ARG;
+    }
+    return SERB_OK;
+}
+
+int serb_debug_stft_host(serb_ctx* ctx, const float* h_wave, int64_t n, float* h_out, int64_t n_cols) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!h_wave || !h_out || n < kNFft || n > 0x7fffffffLL) return fail(ctx, SERB_ERR_INVALID_ARG, "need one clip of >= 2048 samples");
+    ClipDev c{};
+    c.start = 0; c.length = static_cast<int>(n); c.n_cols = 1 + static_cast<int>(n / kHop);
+    if (n_cols != c.n_cols) return fail(ctx, SERB_ERR_INVALID_ARG, "n_cols must be 1 + n / 512");
+    const int tiles = (c.n_cols + kColsPerTile - 1) / kColsPerTile;
+    SERB_CUDA(ctx, ctx->wave.reserve(static_cast<size_t>(n) * sizeof(float) + 64));
+    SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(c.n_cols) * kSpillStride * sizeof(float)));
+    SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
+    SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.ptr, h_wave, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = upload(ctx, ctx->clips, &c, 1, ctx->stream);
+    if (rc) return rc;
+    StftParams sp{};
+    sp.wave = ctx->wave.as<float>();
+    sp.clips = ctx->clips.as<ClipDev>();
+    sp.n_clips = 1;
+    sp.spill = ctx->spill.as<float>();
+    sp.status = ctx->status.as<int>();
+    SERB_CUDA(ctx, launch_stft(sp, tiles, ctx->stream));
+    ctx->launches += 1;
+    SERB_CUDA(ctx, cudaMemcpy2DAsync(h_out, kNBins * sizeof(float), ctx->spill.ptr, kSpillStride * sizeof(float),
+                                     kNBins * sizeof(float), c.n_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SERB_OK;
+}
+
+int serb_debug_last_tuning(serb_ctx* ctx, int32_t* h_out, int64_t n_clips) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!h_out || n_clips != ctx->last_n_clips) return fail(ctx, SERB_ERR_INVALID_ARG, "n_clips differs from the last features call");
+    for (long long i = 0; i < n_clips; ++i) h_out[i] = -1;
+    if (!ctx->last_had_chroma) return SERB_OK;
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int> tmp(ctx->last_tuning_rows.size());
+    if (!tmp.empty()) {
+        SERB_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->tuning.ptr, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) h_out[ctx->last_tuning_rows[i]] = tmp[i];
+    }
+    tmp.resize(ctx->last_short_rows.size());
+    if (!tmp.empty()) {
+        SERB_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->short_tuning.ptr, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) h_out[ctx->last_short_rows[i]] = tmp[i];
+    }
+    return SERB_OK;
+}
+
+int64_t serb_debug_launch_count(const serb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int serb_debug_set_profile(serb_ctx* ctx, int32_t enabled) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->profile = enabled != 0;
+    for (int i = 0; i < 6; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+    return SERB_OK;
+}
+
+int serb_debug_kernel_ms(serb_ctx* ctx, int32_t kind, double* total_ms, int64_t* n_launches) {
+    if (!ctx || kind < 0 || kind >= 6 || !total_ms || !n_launches) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (auto& rec : ctx->prof_recs) {
+        float ms = 0.f;
+        SERB_CUDA(ctx, cudaEventSynchronize(rec.b));
+        SERB_CUDA(ctx, cudaEventElapsedTime(&ms, rec.a, rec.b));
+        ctx->prof_ms[rec.kind] += ms;
+        ctx->prof_n[rec.kind] += 1;
+        ctx->prof_pool.push_back(rec.a);
+        ctx->prof_pool.push_back(rec.b);
+    }
+    ctx->prof_recs.clear();
+    *total_ms = ctx->prof_ms[kind];
+    *n_launches = ctx->prof_n[kind];
+    return SERB_OK;
+}
+
+float serb_debug_last_compute_ms(serb_ctx* ctx) {
+    if (!ctx) return -1.f;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(ctx->ev_stop) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// K2 tuning estimation, K3 mel + chroma projections, K4 per-clip pooling + DCT.
+//
+// Reference arithmetic replaced (librosa 0.11.0 via ser/_internal/utils/dsp.py):
+//   K2  librosa.estimate_tuning / pitch_tuning                dsp.py:113-118 (inside chroma_stft)
+//   K3  librosa.feature.melspectrogram + power_to_db          dsp.py:106-111, 120-125
+//       librosa.feature.chroma_stft (filterbank product, L-inf column normalisation)
+//   K4  np.mean(..., axis=1) per group, top_db clip against the clip-global maximum,
+//       scipy.fftpack.dct(type=2, norm="ortho")[:40]           dsp.py:107, 114, 121
+// (SURVEY.md Appendix A.2-A.6).
+#include "common.cuh"
+#include "kernels.h"
+#include <cfloat>
+
+namespace serb {
+
+// =========================================================================================
+// K2: tuning.  One CTA per clip.  Exact median of the peak magnitudes by 4-pass radix
+// select on the float bit patterns, then the 100-bin residual histogram of the peaks at or
+// above the median and its first arg-max.
+// =========================================================================================
+constexpr int kTuneThreads = 256;
+
+
+__device__ __forceinline__ unsigned key_of(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float value_of(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// k-th smallest (0-based) magnitude of the clip; every thread returns the same value.
+__device__ float select_rank(const TuneParams& p, const ClipDev& clip, long long rank, unsigned* hist,
+                             unsigned* shared_prefix, long long* shared_rank) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kTuneThreads / 32;
+    unsigned prefix = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += kTuneThreads) hist[i] = 0;
+        __syncthreads();
+        for (int t = warp; t < clip.n_cols; t += n_warps) {
+            const long long col = static_cast<long long>(clip.col_base) + t;
+            const int cnt = p.peak_count[col];
+            const float2* src = p.peaks + col * p.peak_cap;
+            for (int i = lane; i < cnt; i += 32) {
+                const unsigned key = key_of(src[i].x);
+                const bool match = (pass == 0) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+                if (match) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long r = rank;
+            unsigned b = 0;
+            for (; b < 256; ++b) {
+                const unsigned c = hist[b];
+                if (r < static_cast<long long>(c)) break;
+                r -= c;
+            }
+            *shared_prefix = prefix | (b << shift);
+            *shared_rank = r;
+        }
+        __syncthreads();
+        prefix = *shared_prefix;
+        rank = *shared_rank;
+        __syncthreads();
+    }
+    return value_of(prefix);
+}
+
+__global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix;
+    __shared__ long long s_rank;
+    __shared__ long long s_total;
+    __shared__ int counts[100];
+    const ClipDev clip = p.clips[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kTuneThreads / 32;
+
+    if (threadIdx.x == 0) s_total = 0;
+    for (int i = threadIdx.x; i < 100; i += kTuneThreads) counts[i] = 0;
+    __syncthreads();
+    long long local = 0;
+    for (int t = threadIdx.x; t < clip.n_cols; t += kTuneThreads)
+        local += p.peak_count[static_cast<long long>(clip.col_base) + t];
+    if (local) atomicAdd(reinterpret_cast<unsigned long long*>(&s_total), static_cast<unsigned long long>(local));
+    __syncthreads();
+    const long long n = s_total;
+    if (n == 0) {
+        // pitch_tuning on an empty set returns 0.0 == np.linspace(-0.5, 0.5, 101)[50]
+        if (threadIdx.x == 0) p.tuning_idx[blockIdx.x] = 50;
+        return;
+    }
+    // np.median: mean of the two middle order statistics (float32 arithmetic) when n is even
+    float thr;
+    if (n & 1) {
+        thr = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank);
+    } else {
+        const float a = select_rank(p, clip, n / 2 - 1, hist, &s_prefix, &s_rank);
+        const float b = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank);
+        thr = __fmul_rn(__fadd_rn(a, b), 0.5f);
+    }
+    const float bpo = static_cast<float>(p.bins_per_octave);
+    for (int t = warp; t < clip.n_cols; t += n_warps) {
+        const long long col = static_cast<long long>(clip.col_base) + t;
+        const int cnt = p.peak_count[col];
+        const float2* src = p.peaks + col * p.peak_cap;
+        for (int i = lane; i < cnt; i += 32) {
+            const float2 pk = src[i];
+            if (!(pk.x >= thr) || !(pk.y > 0.f)) continue;
+            // residual = mod(bpo * log2(f / 27.5), 1.0) in float32, folded to [-0.5, 0.5)
+            const float q = __fdiv_rn(pk.y, 27.5f);
+            const float l2 = static_cast<float>(log2(static_cast<double>(q)));
+            float r = fmodf(__fmul_rn(bpo, l2), 1.0f);
+            if (r < 0.f) r += 1.0f;
+            if (r >= 0.5f) r = __fsub_rn(r, 1.0f);
+            // np.histogram with explicit float64 edges: edges[i] <= r < edges[i+1]
+            const double rd = static_cast<double>(r);
+            int bin = static_cast<int>(floor((rd + 0.5) * 100.0));
+            bin = max(0, min(99, bin));
+            while (bin > 0 && rd < p.edges[bin]) --bin;
+            while (bin < 99 && rd >= p.edges[bin + 1]) ++bin;
+            atomicAdd(&counts[bin], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0, best_count = counts[0];
+        for (int i = 1; i < 100; ++i)
+            if (counts[i] > best_count) { best_count = counts[i]; best = i; }
+        p.tuning_idx[blockIdx.x] = best;
+    }
+}
+
+cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream) {
+    if (n_clips <= 0) return cudaSuccess;
+    tuning_kernel<<<n_clips, kTuneThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// =========================================================================================
+// K3: mel (sparse Slaney triangles) and chroma (dense 12 x 1025, bank picked by the clip's
+// tuning) projections of one tile of 16 columns, as shared-memory fp32 contractions with
+// the |X| tile transposed to [bin][column] so every thread register-tiles over columns.
+// =========================================================================================
+constexpr int kProjThreads = 256;
+constexpr int kSsmPitch = 20;  // floats per bin row: 16 columns + 4 pad -> conflict-free LDS.128
+
+
+struct ProjSmem {
+    float s[kNBins * kSsmPitch];       // 82000 B
+    float red[20 * 12 * 16];           // chroma split-K partials, 15360 B
+    float raw[12 * 16];
+    float melw[2304];                  // sparse mel weights (<= 2304 non-zeros)
+    int mstart[128], mcount[128], moffset[129];
+    float melsum[2][128];
+    float wmax[kProjThreads / 32];
+};
+
+__global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
+    const int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const int tid = threadIdx.x;
+    const int ci = find_clip_by_tile(p.clips, p.n_clips, tile);
+    const ClipDev clip = p.clips[ci];
+    const int t0 = (tile - clip.tile_base) * kColsPerTile;
+    const int n_valid = min(kColsPerTile, clip.n_cols - t0);
+
+    // ---- stage the |X| tile, transposed to [bin][column] ----
+    for (int j = 0; j < kColsPerTile; ++j) {
+        if (j < n_valid) {
+            const float* row = p.spill + (static_cast<long long>(clip.col_base) + t0 + j) * kSpillStride;
+            for (int f = tid; f < kNBins; f += kProjThreads) sm.s[f * kSsmPitch + j] = row[f];
+        } else {
+            for (int f = tid; f < kNBins; f += kProjThreads) sm.s[f * kSsmPitch + j] = 0.0f;
+        }
+    }
+    if (p.do_mel) {
+        for (int i = tid; i < p.mel_nnz; i += kProjThreads) sm.melw[i] = p.mel_weights[i];
+        for (int i = tid; i < 128; i += kProjThreads) { sm.mstart[i] = p.mel_start[i]; sm.mcount[i] = p.mel_count[i]; }
+        for (int i = tid; i < 129; i += kProjThreads) sm.moffset[i] = p.mel_offset[i];
+    }
+    __syncthreads();
+
+    // ---- chroma: raw[c][t] = sum_f W[c][f] |X|[f][t] ----
+    if (p.do_chroma) {
+        const float* bank = p.chroma_banks + static_cast<size_t>(p.tuning_idx[ci]) * (kNBins * 12);
+        if (tid < 240) {
+            const int cg = tid % 3, tg = (tid / 3) & 3, ks = tid / 12;
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            const int f_lo = ks * 52, f_hi = min(kNBins, f_lo + 52);
+            for (int f = f_lo; f < f_hi; ++f) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(bank + f * 12 + 4 * cg));
+                const float4 x = *reinterpret_cast<const float4*>(&sm.s[f * kSsmPitch + 4 * tg]);
+                acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
+                acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
+                acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
+                acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
+                acc[2][0] = fmaf(w.z, x.x, acc[2][0]); acc[2][1] = fmaf(w.z, x.y, acc[2][1]);
+                acc[2][2] = fmaf(w.z, x.z, acc[2][2]); acc[2][3] = fmaf(w.z, x.w, acc[2][3]);
+                acc[3][0] = fmaf(w.w, x.x, acc[3][0]); acc[3][1] = fmaf(w.w, x.y, acc[3][1]);
+                acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) sm.red[(ks * 12 + 4 * cg + a) * 16 + 4 * tg + b] = acc[a][b];
+        }
+        __syncthreads();
+        if (tid < 192) {
+            float total = 0.f;
+            for (int ks = 0; ks < 20; ++ks) total += sm.red[ks * 192 + tid];
+            sm.raw[tid] = total;  // [c][t]
+        }
+        __syncthreads();
+        // util.normalize(norm=inf, axis=-2): divide each column by its maximum (float64 quotient)
+        if (tid < 16) {
+            float length = 0.f;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.raw[c * 16 + tid]));
+            const double len = (length < FLT_MIN) ? 1.0 : static_cast<double>(length);
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+                sm.raw[c * 16 + tid] = static_cast<float>(static_cast<double>(sm.raw[c * 16 + tid]) / len);
+        }
+        __syncthreads();
+        if (tid < 12) {
+            float total = 0.f;
+            for (int t = 0; t < n_valid; ++t) total += sm.raw[tid * 16 + t];
+            p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
+        }
+        __syncthreads();
+    }
+
+    // ---- mel power + log-mel ----
+    if (p.do_mel) {
+        // power = |X| * |X| in float32 (np.abs(D) ** 2.0), in place
+        for (int i = tid; i < kNBins * kSsmPitch; i += kProjThreads) { const float v = sm.s[i]; sm.s[i] = v * v; }
+        __syncthreads();
+        const int m = tid & 127, g = tid >> 7;
+        float acc[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+        const int start = sm.mstart[m], count = sm.mcount[m];
+        const float* w = sm.melw + sm.moffset[m];
+        for (int i = 0; i < count; ++i) {
+            const float wi = w[i];
+            const float4 a = *reinterpret_cast<const float4*>(&sm.s[(start + i) * kSsmPitch + 8 * g]);
+            const float4 b = *reinterpret_cast<const float4*>(&sm.s[(start + i) * kSsmPitch + 8 * g + 4]);
+            acc[0] = fmaf(wi, a.x, acc[0]); acc[1] = fmaf(wi, a.y, acc[1]);
+            acc[2] = fmaf(wi, a.z, acc[2]); acc[3] = fmaf(wi, a.w, acc[3]);
+            acc[4] = fmaf(wi, b.x, acc[4]); acc[5] = fmaf(wi, b.y, acc[5]);
+            acc[6] = fmaf(wi, b.z, acc[6]); acc[7] = fmaf(wi, b.w, acc[7]);
+        }
+        float msum = 0.f, lmax = -FLT_MAX;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int j = 8 * g + b;
+            if (j < n_valid) {
+                msum += acc[b];
+                // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
+                const float lm = 10.0f * log10f(fmaxf(1e-10f, acc[b]));
+                p.logmel[(static_cast<long long>(clip.col_base) + t0 + j) * 128 + m] = lm;
+                lmax = fmaxf(lmax, lm);
+            }
+        }
+        sm.melsum[g][m] = msum;
+        lmax = warp_max(lmax);
+        if ((tid & 31) == 0) sm.wmax[tid >> 5] = lmax;
+        __syncthreads();
+        if (tid < 128) p.tile_mel[static_cast<long long>(tile) * 128 + tid] = sm.melsum[0][tid] + sm.melsum[1][tid];
+        if (tid == 0) {
+            float v = sm.wmax[0];
+            for (int i = 1; i < kProjThreads / 32; ++i) v = fmaxf(v, sm.wmax[i]);
+            p.tile_lmax[tile] = v;
+        }
+    }
+}
+
+cudaError_t configure_proj() {
+    return cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(ProjSmem)));
+}
+
+cudaError_t launch_proj(const ProjParams& p, int n_tiles, cudaStream_t stream) {
+    if (n_tiles <= 0) return cudaSuccess;
+    proj_kernel<<<n_tiles, kProjThreads, sizeof(ProjSmem), stream>>>(p, n_tiles);
+    return cudaGetLastError();
+}
+
+// =========================================================================================
+// K4: per-clip pooling.  mean over columns of every group, MFCC via the DCT of the mean of
+// the top_db-clipped log-mel (DCT and mean commute), output assembled in the reference's
+// group order.
+// =========================================================================================
+
+__global__ void __launch_bounds__(128) pool_kernel(PoolParams p) {
+    __shared__ double meanlog[128];
+    __shared__ float s_thr;
+    const ClipDev clip = p.clips[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int n_tiles = (clip.n_cols + kColsPerTile - 1) / kColsPerTile;
+    const double inv_t = 1.0 / static_cast<double>(clip.n_cols);
+    float* out = p.out + static_cast<long long>(clip.out_row) * p.dim;
+
+    if (p.off_mfcc >= 0) {
+        if (tid < 32) {
+            float v = -FLT_MAX;
+            for (int i = tid; i < n_tiles; i += 32) v = fmaxf(v, p.tile_lmax[clip.tile_base + i]);
+            v = warp_max(v);
+            // np.maximum(log_spec, log_spec.max() - top_db) with top_db = 80.0, float32
+            if (tid == 0) s_thr = __fsub_rn(v, 80.0f);
+        }
+        __syncthreads();
+        const float thr = s_thr;
+        double acc = 0.0;
+        const float* src = p.logmel + static_cast<long long>(clip.col_base) * 128 + tid;
+        for (int t = 0; t < clip.n_cols; ++t) acc += static_cast<double>(fmaxf(src[static_cast<long long>(t) * 128], thr));
+        meanlog[tid] = acc * inv_t;
+        __syncthreads();
+        if (tid < 40) {
+            const double* d = p.dct + tid * 128;
+            double v = 0.0;
+            for (int m = 0; m < 128; ++m) v = fma(d[m], meanlog[m], v);
+            out[p.off_mfcc + tid] = static_cast<float>(v);
+        }
+    }
+    if (p.off_mel >= 0) {
+        double acc = 0.0;
+        for (int i = 0; i < n_tiles; ++i) acc += static_cast<double>(p.tile_mel[static_cast<long long>(clip.tile_base + i) * 128 + tid]);
+        out[p.off_mel + tid] = static_cast<float>(acc * inv_t);
+    }
+    if (p.off_chroma >= 0 && tid < 12) {
+        double acc = 0.0;
+        for (int i = 0; i < n_tiles; ++i) acc += static_cast<double>(p.tile_chroma[static_cast<long long>(clip.tile_base + i) * 12 + tid]);
+        out[p.off_chroma + tid] = static_cast<float>(acc * inv_t);
+    }
+    if (p.off_contrast >= 0 && tid < 7) out[p.off_contrast + tid] = 0.0f;
+}
+
+cudaError_t launch_pool(const PoolParams& p, int n_clips, cudaStream_t stream) {
+    if (n_clips <= 0) return cudaSuccess;
+    pool_kernel<<<n_clips, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace serb

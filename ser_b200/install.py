@@ -1,0 +1,103 @@
+"""Drop-in installation behind the reference's fast-profile seams.
+
+``install()`` swaps the CUDA implementations into an importable jsugg/ser checkout at the
+exact attributes the reference resolves at call time:
+
+=====================================================================  =========================================
+reference attribute                                                    replaced by
+=====================================================================  =========================================
+ser._internal.utils.dsp.extract_feature_from_signal                    ser_b200.dsp.extract_feature_from_signal
+ser._internal.features.feature_extractor._extract_feature_from_signal  (same; it is a from-import alias)
+ser._internal.repr.handcrafted.HandcraftedBackend.encode_sequence      one ragged-batch GPU call per recording
+ser._internal.models.fast_path.predict_emotions_detailed_with_model    ser_b200.fast_path (fused CUDA MLP)
+ser._internal.models.emotion_model._fast_predict_emotions_detailed_with_model  (same; from-import alias)
+=====================================================================  =========================================
+
+``ser.api.infer``, ``ser --file``, ``ser --train`` and ``run_fast_inference`` keep their
+signatures; the registry hook ``"handcrafted"`` still resolves
+``ser._internal.runtime.fast_inference.run_fast_inference`` by module path
+(ser/_internal/runtime/backend_hooks.py:56-59) and reaches the patched functions through it.
+``uninstall()`` restores the originals.
+"""
+
+from __future__ import annotations
+
+import importlib
+from typing import Any
+
+from . import dsp as _dsp
+from . import fast_path as _fast_path
+from .handcrafted import frame_bounds
+
+_originals: list[tuple[Any, str, Any]] = []
+
+
+def _swap(owner: Any, name: str, value: Any) -> None:
+    _originals.append((owner, name, getattr(owner, name)))
+    setattr(owner, name, value)
+
+
+def _make_encode_sequence(encoded_sequence_type, device: int):
+    def encode_sequence(self, audio, sample_rate):
+        import numpy as np
+
+        if sample_rate <= 0:
+            raise ValueError("sample_rate must be a positive integer.")
+        if audio.ndim != 1:
+            raise ValueError("audio must be mono (1D array).")
+        if audio.size == 0:
+            raise ValueError("audio must contain at least one sample.")
+        wave = np.ascontiguousarray(audio, dtype=np.float32)
+        if not bool(np.all(np.isfinite(wave))):
+            raise ValueError("Audio buffer is not finite everywhere.")
+        starts, ends = frame_bounds(wave.size, sample_rate, self._frame_size_seconds,
+                                    self._frame_stride_seconds)
+        if starts.size == 0:
+            raise ValueError("Could not extract handcrafted features from provided audio.")
+        rows = _dsp.extract_features_ragged(wave, starts, ends - starts, sample_rate,
+                                            feature_flags=self._feature_flags, device=device)
+        return encoded_sequence_type(
+            embeddings=rows.astype(np.float32, copy=False),
+            frame_start_seconds=starts.astype(np.float64) / float(sample_rate),
+            frame_end_seconds=ends.astype(np.float64) / float(sample_rate),
+            backend_id=self.backend_id,
+        )
+
+    return encode_sequence
+
+
+def install(device: int = 0) -> list[str]:
+    """Patches the importable reference package in place; returns the patched attribute names."""
+    if _originals:
+        return [f"{getattr(o, '__name__', o)}.{n}" for o, n, _ in _originals]
+    ref_dsp = importlib.import_module("ser._internal.utils.dsp")
+    ref_features = importlib.import_module("ser._internal.features.feature_extractor")
+    ref_handcrafted = importlib.import_module("ser._internal.repr.handcrafted")
+    ref_backend = importlib.import_module("ser._internal.repr.backend")
+    ref_fast_path = importlib.import_module("ser._internal.models.fast_path")
+    ref_emotion_model = importlib.import_module("ser._internal.models.emotion_model")
+
+    def extract_feature_from_signal(audio, sample_rate, *, feature_flags=None):
+        return _dsp.extract_feature_from_signal(audio, sample_rate, feature_flags=feature_flags, device=device)
+
+    def predict_emotions_detailed_with_model(file, *, model, expected_feature_size, output_schema_version,
+                                             extract_feature_frames_fn, logger):
+        return _fast_path.predict_emotions_detailed_with_model(
+            file, model=model, expected_feature_size=expected_feature_size,
+            output_schema_version=output_schema_version,
+            extract_feature_frames_fn=extract_feature_frames_fn, logger=logger, device=device)
+
+    _swap(ref_dsp, "extract_feature_from_signal", extract_feature_from_signal)
+    _swap(ref_features, "_extract_feature_from_signal", extract_feature_from_signal)
+    _swap(ref_handcrafted.HandcraftedBackend, "encode_sequence",
+          _make_encode_sequence(ref_backend.EncodedSequence, device))
+    _swap(ref_fast_path, "predict_emotions_detailed_with_model", predict_emotions_detailed_with_model)
+    _swap(ref_emotion_model, "_fast_predict_emotions_detailed_with_model", predict_emotions_detailed_with_model)
+    return [f"{getattr(o, '__name__', o)}.{n}" for o, n, _ in _originals]
+
+
+def uninstall() -> None:
+    """Restores every attribute ``install`` replaced."""
+    while _originals:
+        owner, name, value = _originals.pop()
+        setattr(owner, name, value)
