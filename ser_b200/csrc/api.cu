@@ -63,7 +63,7 @@ struct serb_ctx {
     std::mutex mu;
     std::string err;
     long long launches = 0;
-    int chunk_cols = 12288;
+    int chunk_cols = 131072;
     float last_ms = 0.f;
     bool timed = false;
 

@@ -29,30 +29,40 @@ __device__ __forceinline__ float value_of(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// k-th smallest (0-based) magnitude of the clip; every thread returns the same value.
+constexpr int kTuneCache = 10240;   // peak magnitudes cached in shared memory (40 KB)
+
+// k-th smallest (0-based) key; every thread returns the same value.  Keys come from the
+// shared-memory cache when the clip's peaks fit, else from the global peak lists.
 __device__ float select_rank(const TuneParams& p, const ClipDev& clip, long long rank, unsigned* hist,
-                             unsigned* shared_prefix, long long* shared_rank) {
+                             unsigned* shared_prefix, long long* shared_rank, const float* cache, int n_cached) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kTuneThreads / 32;
     unsigned prefix = 0;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
+        const unsigned hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
         for (int i = threadIdx.x; i < 256; i += kTuneThreads) hist[i] = 0;
         __syncthreads();
-        for (int t = warp; t < clip.n_cols; t += n_warps) {
-            const long long col = static_cast<long long>(clip.col_base) + t;
-            const int cnt = p.peak_count[col];
-            const float2* src = p.peaks + col * p.peak_cap;
-            for (int i = lane; i < cnt; i += 32) {
-                const unsigned key = key_of(src[i].x);
-                const bool match = (pass == 0) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
-                if (match) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        if (cache) {
+            for (int i = threadIdx.x; i < n_cached; i += kTuneThreads) {
+                const unsigned key = key_of(cache[i]);
+                if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        } else {
+            for (int t = warp; t < clip.n_cols; t += n_warps) {
+                const long long col = static_cast<long long>(clip.col_base) + t;
+                const int cnt = p.peak_count[col];
+                const float2* src = p.peaks + col * p.peak_cap;
+                for (int i = lane; i < cnt; i += 32) {
+                    const unsigned key = key_of(src[i].x);
+                    if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
             }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             long long r = rank;
             unsigned b = 0;
-            for (; b < 256; ++b) {
+            for (; b < 255; ++b) {
                 const unsigned c = hist[b];
                 if (r < static_cast<long long>(c)) break;
                 r -= c;
@@ -69,15 +79,17 @@ __device__ float select_rank(const TuneParams& p, const ClipDev& clip, long long
 }
 
 __global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
+    __shared__ float cache[kTuneCache];
     __shared__ unsigned hist[256];
     __shared__ unsigned s_prefix;
     __shared__ long long s_rank;
     __shared__ long long s_total;
+    __shared__ int s_cursor;
     __shared__ int counts[100];
     const ClipDev clip = p.clips[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kTuneThreads / 32;
 
-    if (threadIdx.x == 0) s_total = 0;
+    if (threadIdx.x == 0) { s_total = 0; s_cursor = 0; }
     for (int i = threadIdx.x; i < 100; i += kTuneThreads) counts[i] = 0;
     __syncthreads();
     long long local = 0;
@@ -91,13 +103,30 @@ __global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
         if (threadIdx.x == 0) p.tuning_idx[blockIdx.x] = 50;
         return;
     }
+    const bool cached = n <= kTuneCache;
+    if (cached) {
+        // gather the magnitudes once; their order is irrelevant to the order statistics
+        for (int t = warp; t < clip.n_cols; t += n_warps) {
+            const long long col = static_cast<long long>(clip.col_base) + t;
+            const int cnt = p.peak_count[col];
+            if (cnt == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_cursor, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const float2* src = p.peaks + col * p.peak_cap;
+            for (int i = lane; i < cnt; i += 32) cache[base + i] = src[i].x;
+        }
+        __syncthreads();
+    }
+    const float* keys = cached ? cache : nullptr;
+    const int n_cached = static_cast<int>(cached ? n : 0);
     // np.median: mean of the two middle order statistics (float32 arithmetic) when n is even
     float thr;
     if (n & 1) {
-        thr = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank);
+        thr = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank, keys, n_cached);
     } else {
-        const float a = select_rank(p, clip, n / 2 - 1, hist, &s_prefix, &s_rank);
-        const float b = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank);
+        const float a = select_rank(p, clip, n / 2 - 1, hist, &s_prefix, &s_rank, keys, n_cached);
+        const float b = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank, keys, n_cached);
         thr = __fmul_rn(__fadd_rn(a, b), 0.5f);
     }
     const float bpo = static_cast<float>(p.bins_per_octave);
@@ -169,12 +198,19 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
     const int n_valid = min(kColsPerTile, clip.n_cols - t0);
 
     // ---- stage the |X| tile, transposed to [bin][column] ----
-    for (int j = 0; j < kColsPerTile; ++j) {
-        if (j < n_valid) {
-            const float* row = p.spill + (static_cast<long long>(clip.col_base) + t0 + j) * kSpillStride;
-            for (int f = tid; f < kNBins; f += kProjThreads) sm.s[f * kSsmPitch + j] = row[f];
-        } else {
-            for (int f = tid; f < kNBins; f += kProjThreads) sm.s[f * kSsmPitch + j] = 0.0f;
+    // 16 independent coalesced loads in flight per thread (one per column), then four
+    // conflict-free 16-byte shared stores into the thread's own bin row.
+    {
+        const float* base = p.spill + (static_cast<long long>(clip.col_base) + t0) * kSpillStride;
+        for (int f = tid; f < kNBins; f += kProjThreads) {
+            float v[kColsPerTile];
+#pragma unroll
+            for (int j = 0; j < kColsPerTile; ++j)
+                v[j] = (j < n_valid) ? __ldg(base + static_cast<long long>(j) * kSpillStride + f) : 0.0f;
+            float4* dst = reinterpret_cast<float4*>(&sm.s[f * kSsmPitch]);
+#pragma unroll
+            for (int q = 0; q < kColsPerTile / 4; ++q)
+                dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
     }
     if (p.do_mel) {
@@ -300,11 +336,16 @@ cudaError_t launch_proj(const ProjParams& p, int n_tiles, cudaStream_t stream) {
 // group order.
 // =========================================================================================
 
-__global__ void __launch_bounds__(128) pool_kernel(PoolParams p) {
+constexpr int kPoolSlices = 4;
+constexpr int kPoolThreads = 128 * kPoolSlices;
+
+__global__ void __launch_bounds__(kPoolThreads) pool_kernel(PoolParams p) {
+    __shared__ double part[kPoolSlices][128];
     __shared__ double meanlog[128];
     __shared__ float s_thr;
     const ClipDev clip = p.clips[blockIdx.x];
     const int tid = threadIdx.x;
+    const int m = tid & 127, slice = tid >> 7;
     const int n_tiles = (clip.n_cols + kColsPerTile - 1) / kColsPerTile;
     const double inv_t = 1.0 / static_cast<double>(clip.n_cols);
     float* out = p.out + static_cast<long long>(clip.out_row) * p.dim;
@@ -319,34 +360,54 @@ __global__ void __launch_bounds__(128) pool_kernel(PoolParams p) {
         }
         __syncthreads();
         const float thr = s_thr;
+        // each time slice sums its columns in a fixed order; slices are then added in order
         double acc = 0.0;
-        const float* src = p.logmel + static_cast<long long>(clip.col_base) * 128 + tid;
-        for (int t = 0; t < clip.n_cols; ++t) acc += static_cast<double>(fmaxf(src[static_cast<long long>(t) * 128], thr));
-        meanlog[tid] = acc * inv_t;
+        const float* src = p.logmel + static_cast<long long>(clip.col_base) * 128 + m;
+        int t = slice;
+        for (; t + 3 * kPoolSlices < clip.n_cols; t += 4 * kPoolSlices) {
+            const float a0 = src[static_cast<long long>(t) * 128];
+            const float a1 = src[static_cast<long long>(t + kPoolSlices) * 128];
+            const float a2 = src[static_cast<long long>(t + 2 * kPoolSlices) * 128];
+            const float a3 = src[static_cast<long long>(t + 3 * kPoolSlices) * 128];
+            acc += static_cast<double>(fmaxf(a0, thr));
+            acc += static_cast<double>(fmaxf(a1, thr));
+            acc += static_cast<double>(fmaxf(a2, thr));
+            acc += static_cast<double>(fmaxf(a3, thr));
+        }
+        for (; t < clip.n_cols; t += kPoolSlices) acc += static_cast<double>(fmaxf(src[static_cast<long long>(t) * 128], thr));
+        part[slice][m] = acc;
+        __syncthreads();
+        if (tid < 128) {
+            double total = 0.0;
+#pragma unroll
+            for (int s2 = 0; s2 < kPoolSlices; ++s2) total += part[s2][tid];
+            meanlog[tid] = total * inv_t;
+        }
         __syncthreads();
         if (tid < 40) {
             const double* d = p.dct + tid * 128;
             double v = 0.0;
-            for (int m = 0; m < 128; ++m) v = fma(d[m], meanlog[m], v);
+            for (int k = 0; k < 128; ++k) v = fma(d[k], meanlog[k], v);
             out[p.off_mfcc + tid] = static_cast<float>(v);
         }
     }
-    if (p.off_mel >= 0) {
+    if (p.off_mel >= 0 && tid < 128) {
         double acc = 0.0;
         for (int i = 0; i < n_tiles; ++i) acc += static_cast<double>(p.tile_mel[static_cast<long long>(clip.tile_base + i) * 128 + tid]);
         out[p.off_mel + tid] = static_cast<float>(acc * inv_t);
     }
-    if (p.off_chroma >= 0 && tid < 12) {
+    if (p.off_chroma >= 0 && tid >= 128 && tid < 140) {
+        const int c = tid - 128;
         double acc = 0.0;
-        for (int i = 0; i < n_tiles; ++i) acc += static_cast<double>(p.tile_chroma[static_cast<long long>(clip.tile_base + i) * 12 + tid]);
-        out[p.off_chroma + tid] = static_cast<float>(acc * inv_t);
+        for (int i = 0; i < n_tiles; ++i) acc += static_cast<double>(p.tile_chroma[static_cast<long long>(clip.tile_base + i) * 12 + c]);
+        out[p.off_chroma + c] = static_cast<float>(acc * inv_t);
     }
-    if (p.off_contrast >= 0 && tid < 7) out[p.off_contrast + tid] = 0.0f;
+    if (p.off_contrast >= 0 && tid >= 160 && tid < 167) out[p.off_contrast + tid - 160] = 0.0f;
 }
 
 cudaError_t launch_pool(const PoolParams& p, int n_clips, cudaStream_t stream) {
     if (n_clips <= 0) return cudaSuccess;
-    pool_kernel<<<n_clips, 128, 0, stream>>>(p);
+    pool_kernel<<<n_clips, kPoolThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

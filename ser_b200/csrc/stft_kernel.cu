@@ -5,8 +5,8 @@
 //   librosa.piptrack (inside chroma_stft -> estimate_tuning)  ser/_internal/utils/dsp.py:113-118
 // (librosa 0.11.0 semantics: SURVEY.md Appendix A.1, A.6).
 //
-// Layout: one CTA per tile of 16 consecutive STFT columns of one clip.  The tile's
-// 9728 samples are staged once in shared memory by a TMA bulk copy (cp.async.bulk ->
+// Layout: one CTA per 8 consecutive STFT columns of one clip (half a projection tile), two
+// CTAs resident per SM.  The CTA's 5632 samples are staged once in shared memory by a TMA bulk copy (cp.async.bulk ->
 // UBLKCP) signalling an mbarrier; zero padding of the centred STFT is a shared-memory
 // fill.  Each warp then owns whole columns: a 2048-point real FFT is done as a 1024-point
 // complex FFT split 32 x 32 across the 32 lanes -- two register-resident 32-point DFTs
@@ -20,11 +20,13 @@ namespace serb {
 
 constexpr int kStftWarps = 8;
 constexpr int kStftThreads = kStftWarps * 32;
+constexpr int kStftCols = 8;                                    // columns per CTA: one per warp
+constexpr int kStftSamples = (kStftCols - 1) * kHop + kNFft;    // 5632 staged samples
 constexpr int kBufPitch = 33;  // float2 pitch of the per-warp 32x32 transpose buffer
 
 
 struct StftSmem {
-    float wave[kTileSamples];                       // 38912 B
+    float wave[kStftSamples];                       // 22528 B
     float2 tw[32][32];                              // W_1024^(k1*n2): [k1][n2], 8192 B
     float2 buf[kStftWarps][32 * kBufPitch];         // per-warp transpose / |X| staging
     unsigned long long bar;
@@ -39,7 +41,7 @@ __device__ __forceinline__ void stage_tile(StftSmem& sm, const float* __restrict
                                            long long clip_start, int clip_len, int s0) {
     // shared index i <-> clip sample s0 + i ; valid when 0 <= s0 + i < clip_len
     const int lo = max(0, -s0);
-    const int hi = min(kTileSamples, clip_len - s0);
+    const int hi = min(kStftSamples, clip_len - s0);
     const float* src = wave + clip_start + s0;  // src[i] is the sample for shared index i
     const int tid = threadIdx.x;
     const bool aligned = (((clip_start + s0 + lo) & 3LL) == 0) && ((lo & 3) == 0);
@@ -63,7 +65,7 @@ __device__ __forceinline__ void stage_tile(StftSmem& sm, const float* __restrict
     // everything the bulk copy does not cover: zero padding and the unaligned remainder
     for (int i = tid; i < lo; i += kStftThreads) sm.wave[i] = 0.0f;
     for (int i = bulk_end + tid; i < hi; i += kStftThreads) sm.wave[i] = __ldg(src + i);
-    for (int i = max(hi, 0) + tid; i < kTileSamples; i += kStftThreads) sm.wave[i] = 0.0f;
+    for (int i = max(hi, 0) + tid; i < kStftSamples; i += kStftThreads) sm.wave[i] = 0.0f;
     if (bytes > 0) {
         uint32_t done = 0;
         while (!done) {
@@ -80,11 +82,13 @@ __device__ __forceinline__ void stage_tile(StftSmem& sm, const float* __restrict
 }
 
 // ---- one STFT column per warp -----------------------------------------------------------
-// On return S[k2] = |X[lane + 32 k2]| and s_nyq = |X[1024]| (valid in lane 0).
-__device__ __forceinline__ void column_fft(const float* __restrict__ frame, const float2 (*tw)[32],
-                                           float2* __restrict__ buf, int lane,
-                                           float wc0, float ws0, float wc1, float ws1,
-                                           float tc, float ts, float (&S)[32], float& s_nyq) {
+// Writes |X[k]|, k = 0..1024, to row[] (global spill) and to the warp's staging buffer (as
+// floats, aliasing buf, which is free once the transpose has been read back); returns the
+// lane's running maximum of |X|.
+__device__ __forceinline__ float column_fft(const float* __restrict__ frame, const float2 (*tw)[32],
+                                            float2* __restrict__ buf, int lane,
+                                            float wc0, float ws0, float wc1, float ws1,
+                                            float tc, float ts, float* __restrict__ row) {
     float2 v[32];
     // load z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane, times the periodic Hann window
     // w[j] = 0.5 - 0.5 cos(2 pi j / 2048), j = 64 n1 + 2 lane (+1):
@@ -116,7 +120,8 @@ __device__ __forceinline__ void column_fft(const float* __restrict__ frame, cons
 
     // real-input split: X[k] = E + W_2048^k O, E = (Z[k] + conj Z[M-k]) / 2, O = -i (Z[k] - conj Z[M-k]) / 2
     const int src = (32 - lane) & 31;
-    s_nyq = 0.0f;
+    float* sbuf = reinterpret_cast<float*>(buf);
+    float cmax = 0.0f;
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) {
         float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
@@ -133,12 +138,19 @@ __device__ __forceinline__ void column_fft(const float* __restrict__ frame, cons
         const float wx = fmaf(c, ox, s * oy);
         const float wy = fmaf(c, oy, -s * ox);
         const float xr = ex + wx, xi = ey + wy;
-        S[k2] = sqrtf(fmaf(xr, xr, xi * xi));
-        if (k2 == 0) {
+        const float mag = sqrtf(fmaf(xr, xr, xi * xi));
+        row[lane + 32 * k2] = mag;
+        sbuf[lane + 32 * k2] = mag;
+        cmax = fmaxf(cmax, mag);
+        if (k2 == 0 && lane == 0) {
             const float nr = ex - wx, ni = ey - wy;
-            s_nyq = sqrtf(fmaf(nr, nr, ni * ni));
+            const float nyq = sqrtf(fmaf(nr, nr, ni * ni));
+            row[1024] = nyq;
+            sbuf[1024] = nyq;
+            cmax = fmaxf(cmax, nyq);
         }
     }
+    return cmax;
 }
 
 // ---- piptrack on one column (librosa.piptrack) -------------------
@@ -182,14 +194,16 @@ __device__ __forceinline__ void column_peaks(const float* __restrict__ sbuf, flo
     if (lane == 0) p.peak_count[col] = min(n_found, p.peak_cap);
 }
 
-__global__ void __launch_bounds__(kStftThreads, 1) stft_kernel(StftParams p, int n_tiles) {
+__global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(StftParams p, int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
-    const int tile = blockIdx.x;
+    // blockIdx.x enumerates half tiles: two 8-column CTAs per 16-column projection tile
+    const int tile = blockIdx.x >> 1;
     if (tile >= n_tiles) return;
     const int ci = find_clip_by_tile(p.clips, p.n_clips, tile);
     const ClipDev clip = p.clips[ci];
-    const int t0 = (tile - clip.tile_base) * kColsPerTile;
+    const int t0 = (tile - clip.tile_base) * kColsPerTile + (blockIdx.x & 1) * kStftCols;
+    if (t0 >= clip.n_cols) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // W_1024^(k1 * n2) table (accurate sincospi, once per CTA)
@@ -202,7 +216,7 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_kernel(StftParams p, int
     stage_tile(sm, p.wave, clip.start, clip.length, t0 * kHop - kNFft / 2);
     {   // dsp.py:94 "Audio buffer is not finite everywhere." -> status bit 0, reported by the host entry
         int bad = 0;
-        for (int i = threadIdx.x; i < kTileSamples; i += kStftThreads) bad |= !isfinite(sm.wave[i]);
+        for (int i = threadIdx.x; i < kStftSamples; i += kStftThreads) bad |= !isfinite(sm.wave[i]);
         if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(p.status, 1);
     }
 
@@ -213,33 +227,16 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_kernel(StftParams p, int
     sincospif(static_cast<float>(lane) * (2.0f / 2048.0f), &ts, &tc);
 
     float2* buf = sm.buf[warp];
-    for (int j = warp; j < kColsPerTile; j += kStftWarps) {
-        const int t = t0 + j;
-        if (t >= clip.n_cols) break;
+    const int t = t0 + warp;
+    if (t < clip.n_cols) {
         const long long col = static_cast<long long>(clip.col_base) + t;
-        float S[32];
-        float s_nyq;
-        column_fft(sm.wave + j * kHop, sm.tw, buf, lane, wc0, ws0, wc1, ws1, tc, ts, S, s_nyq);
-        float* row = p.spill + col * kSpillStride;
-        float* sbuf = reinterpret_cast<float*>(buf);
-        float cmax = 0.f;
-#pragma unroll
-        for (int k2 = 0; k2 < 32; ++k2) {
-            row[lane + 32 * k2] = S[k2];
-            sbuf[lane + 32 * k2] = S[k2];
-            cmax = fmaxf(cmax, S[k2]);
-        }
-        if (lane == 0) {
-            row[1024] = s_nyq;
-            sbuf[1024] = s_nyq;
-            cmax = fmaxf(cmax, s_nyq);
-        }
+        float cmax = column_fft(sm.wave + warp * kHop, sm.tw, buf, lane, wc0, ws0, wc1, ws1, tc, ts,
+                                p.spill + col * kSpillStride);
         if (p.do_peaks) {
             cmax = warp_max(cmax);
             __syncwarp();
-            column_peaks(sbuf, cmax, lane, p, col);
+            column_peaks(reinterpret_cast<const float*>(buf), cmax, lane, p, col);
         }
-        __syncwarp();
     }
 }
 
@@ -250,7 +247,7 @@ cudaError_t configure_stft() {
 
 cudaError_t launch_stft(const StftParams& p, int n_tiles, cudaStream_t stream) {
     if (n_tiles <= 0) return cudaSuccess;
-    stft_kernel<<<n_tiles, kStftThreads, sizeof(StftSmem), stream>>>(p, n_tiles);
+    stft_kernel<<<2 * n_tiles, kStftThreads, sizeof(StftSmem), stream>>>(p, n_tiles);
     return cudaGetLastError();
 }
 
