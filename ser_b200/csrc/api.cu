@@ -67,7 +67,7 @@ struct serb_ctx {
     float last_ms = 0.f;
     bool timed = false;
 
-    DevBuf edges, dct;
+    DevBuf edges, dct, tables, tile_clip;
     std::map<int, SrTables> sr_tables;
     Mlp mlp;
 
@@ -270,7 +270,8 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         max_clips = std::max(max_clips, c.clip_hi - c.clip_lo);
     }
     if (!chunks.empty()) {
-        SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(max_cols) * kSpillStride * sizeof(float)));
+        SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(max_tiles) * 2 * kHalfTileFloats * sizeof(float)));
+        SERB_CUDA(ctx, ctx->tile_clip.reserve(static_cast<size_t>(max_tiles) * sizeof(int)));
         SERB_CUDA(ctx, ctx->logmel.reserve(static_cast<size_t>(max_cols) * 128 * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_mel.reserve(static_cast<size_t>(max_tiles) * 128 * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_lmax.reserve(static_cast<size_t>(max_tiles) * sizeof(float)));
@@ -291,10 +292,14 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         before_chunk(c.max_end);
         const ClipDev* d_clips = ctx->clips.as<ClipDev>() + c.clip_lo;
         const int nc = c.clip_hi - c.clip_lo;
+        SERB_CUDA(ctx, launch_expand_tiles(d_clips, nc, ctx->tile_clip.as<int>(), stream));
+        ctx->launches += 1;
         StftParams sp{};
         sp.wave = d_wave;
         sp.clips = d_clips;
         sp.n_clips = nc;
+        sp.tile_clip = ctx->tile_clip.as<int>();
+        sp.tables = ctx->tables.as<float2>();
         sp.spill = ctx->spill.as<float>();
         sp.do_peaks = want_chroma ? 1 : 0;
         sp.kmin = tab->kmin;
@@ -322,6 +327,7 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         ProjParams pp{};
         pp.clips = d_clips;
         pp.n_clips = nc;
+        pp.tile_clip = sp.tile_clip;
         pp.spill = sp.spill;
         pp.do_mel = want_mel ? 1 : 0;
         pp.mel_start = tab->mel_start.as<int>();
@@ -500,6 +506,24 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
     dct_matrix(dct);
     CREATE_CHECK(ctx->edges.reserve(edges.size() * sizeof(double)));
     CREATE_CHECK(cudaMemcpy(ctx->edges.ptr, edges.data(), edges.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        // FFT twiddles: W_1024^(k1 n2) as (cos, -sin) [32][32], then W_2048^k as (cos, sin) [1024]
+        std::vector<float> tables(2 * 2048);
+        const double pi = 3.14159265358979323846;
+        for (int k1 = 0; k1 < 32; ++k1)
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const double a = 2.0 * pi * static_cast<double>((k1 * n2) & 1023) / 1024.0;
+                tables[2 * (k1 * 32 + n2)] = static_cast<float>(std::cos(a));
+                tables[2 * (k1 * 32 + n2) + 1] = static_cast<float>(-std::sin(a));
+            }
+        for (int k = 0; k < 1024; ++k) {
+            const double a = 2.0 * pi * static_cast<double>(k) / 2048.0;
+            tables[2048 + 2 * k] = static_cast<float>(std::cos(a));
+            tables[2048 + 2 * k + 1] = static_cast<float>(std::sin(a));
+        }
+        CREATE_CHECK(ctx->tables.reserve(tables.size() * sizeof(float)));
+        CREATE_CHECK(cudaMemcpy(ctx->tables.ptr, tables.data(), tables.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     CREATE_CHECK(ctx->dct.reserve(dct.size() * sizeof(double)));
     CREATE_CHECK(cudaMemcpy(ctx->dct.ptr, dct.data(), dct.size() * sizeof(double), cudaMemcpyHostToDevice));
 #undef CREATE_CHECK
@@ -512,7 +536,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    for (DevBuf* b : {&ctx->edges, &ctx->dct, &ctx->spill, &ctx->logmel, &ctx->tile_mel, &ctx->tile_lmax,
+    for (DevBuf* b : {&ctx->edges, &ctx->dct, &ctx->tables, &ctx->tile_clip, &ctx->spill, &ctx->logmel, &ctx->tile_mel, &ctx->tile_lmax,
                       &ctx->tile_chroma, &ctx->peaks, &ctx->peak_count, &ctx->clips, &ctx->short_clips,
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->mlp.mean, &ctx->mlp.scale,
@@ -737,23 +761,32 @@ int serb_debug_stft_host(serb_ctx* ctx, const float* h_wave, int64_t n, float* h
     if (n_cols != c.n_cols) return fail(ctx, SERB_ERR_INVALID_ARG, "n_cols must be 1 + n / 512");
     const int tiles = (c.n_cols + kColsPerTile - 1) / kColsPerTile;
     SERB_CUDA(ctx, ctx->wave.reserve(static_cast<size_t>(n) * sizeof(float) + 64));
-    SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(c.n_cols) * kSpillStride * sizeof(float)));
+    SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(tiles) * 2 * kHalfTileFloats * sizeof(float)));
+    SERB_CUDA(ctx, ctx->tile_clip.reserve(static_cast<size_t>(tiles) * sizeof(int)));
     SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
     SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
     SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.ptr, h_wave, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     int rc = upload(ctx, ctx->clips, &c, 1, ctx->stream);
     if (rc) return rc;
+    SERB_CUDA(ctx, launch_expand_tiles(ctx->clips.as<ClipDev>(), 1, ctx->tile_clip.as<int>(), ctx->stream));
     StftParams sp{};
     sp.wave = ctx->wave.as<float>();
     sp.clips = ctx->clips.as<ClipDev>();
     sp.n_clips = 1;
+    sp.tile_clip = ctx->tile_clip.as<int>();
+    sp.tables = ctx->tables.as<float2>();
     sp.spill = ctx->spill.as<float>();
     sp.status = ctx->status.as<int>();
     SERB_CUDA(ctx, launch_stft(sp, tiles, ctx->stream));
-    ctx->launches += 1;
-    SERB_CUDA(ctx, cudaMemcpy2DAsync(h_out, kNBins * sizeof(float), ctx->spill.ptr, kSpillStride * sizeof(float),
-                                     kNBins * sizeof(float), c.n_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->launches += 2;
+    // un-interleave the [half tile][bin][8] spill on the host
+    std::vector<float> raw(static_cast<size_t>(tiles) * 2 * kHalfTileFloats);
+    SERB_CUDA(ctx, cudaMemcpyAsync(raw.data(), ctx->spill.ptr, raw.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < c.n_cols; ++t) {
+        const float* block = raw.data() + static_cast<size_t>(t / kHalfTileCols) * kHalfTileFloats;
+        for (int k = 0; k < kNBins; ++k) h_out[static_cast<size_t>(t) * kNBins + k] = block[k * kHalfTileCols + (t % kHalfTileCols)];
+    }
     return SERB_OK;
 }
 

@@ -8,9 +8,10 @@ namespace serb {
 constexpr int kNFft = 2048;          // librosa default, dsp.py:96 n_fft = min(len, 2048)
 constexpr int kHop = 512;            // n_fft // 4 (stft) == melspectrogram's hop_length
 constexpr int kNBins = 1025;         // 1 + n_fft / 2
-constexpr int kSpillStride = 1032;   // S row pitch in floats (16-byte multiple)
-constexpr int kColsPerTile = 16;     // STFT columns one CTA handles
-constexpr int kTileSamples = (kColsPerTile - 1) * kHop + kNFft;  // 9728 staged samples
+constexpr int kColsPerTile = 16;     // STFT columns per projection tile
+constexpr int kHalfTileCols = 8;     // STFT columns per STFT CTA (half a projection tile)
+// |X| spill: one block per half tile, rows of 8 columns: [half tile][bin 0..1024][8]
+constexpr int kHalfTileFloats = kNBins * kHalfTileCols;          // 8200 floats = 32800 B
 
 // One clip of the ragged batch, chunk-relative bookkeeping included.
 struct ClipDev {
@@ -23,15 +24,6 @@ struct ClipDev {
     int pad_;
 };
 
-// binary search: largest c with tile_base[c] <= tile  (clips sorted by tile_base)
-__device__ __forceinline__ int find_clip_by_tile(const ClipDev* __restrict__ clips, int n, int tile) {
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (clips[mid].tile_base <= tile) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -11,7 +11,9 @@ struct StftParams {
     const float* wave;
     const ClipDev* clips;
     int n_clips;
-    float* spill;            // [cols][kSpillStride]  |X|
+    const int* tile_clip;    // [tiles] clip index of every 16-column tile
+    const float2* tables;    // W_1024^(k1 n2) [32][32] then W_2048^k [1024] as (cos, sin)
+    float* spill;            // [half tiles][1025][8]  |X|
     int do_peaks;            // piptrack wanted (chroma enabled)
     int kmin, kmax;          // bins with 150 <= f < min(4000, sr/2):  kmin <= k < kmax
     int peak_cap;            // slots per column
@@ -21,6 +23,7 @@ struct StftParams {
     int* status;             // bit 0: a non-finite sample was staged
 };
 cudaError_t configure_stft();
+cudaError_t launch_expand_tiles(const ClipDev* clips, int n_clips, int* tile_clip, cudaStream_t stream);
 cudaError_t launch_stft(const StftParams& p, int n_tiles, cudaStream_t stream);
 
 // ---- K2/K3/K4 proj_kernels.cu ------------------------------------------------------------
@@ -38,7 +41,8 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 struct ProjParams {
     const ClipDev* clips;
     int n_clips;
-    const float* spill;        // [cols][kSpillStride]
+    const int* tile_clip;      // [tiles]
+    const float* spill;        // [half tiles][1025][8]
     int do_mel;                // mel or mfcc requested
     const int* mel_start;      // [128]
     const int* mel_count;      // [128]

@@ -169,22 +169,26 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 
 // =========================================================================================
 // K3: mel (sparse Slaney triangles) and chroma (dense 12 x 1025, bank picked by the clip's
-// tuning) projections of one tile of 16 columns, as shared-memory fp32 contractions with
-// the |X| tile transposed to [bin][column] so every thread register-tiles over columns.
+// tuning) projections of one tile of 16 columns, as shared-memory fp32 contractions.  The
+// STFT kernel spills |X| as [bin][8 columns] rows, so one TMA bulk copy stages the tile and
+// every thread register-tiles over 4 or 8 columns with 16-byte shared loads.
 // =========================================================================================
 constexpr int kProjThreads = 256;
-constexpr int kSsmPitch = 20;  // floats per bin row: 16 columns + 4 pad -> conflict-free LDS.128
-
 
 struct ProjSmem {
-    float s[kNBins * kSsmPitch];       // 82000 B
+    float s[2 * kHalfTileFloats];      // [half][bin][8 columns], 65600 B, filled by one TMA bulk copy
     float red[20 * 12 * 16];           // chroma split-K partials, 15360 B
     float raw[12 * 16];
     float melw[2304];                  // sparse mel weights (<= 2304 non-zeros)
     int mstart[128], mcount[128], moffset[129];
     float melsum[2][128];
     float wmax[kProjThreads / 32];
+    unsigned long long bar;
 };
+
+__device__ __forceinline__ uint32_t proj_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 
 __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -192,31 +196,40 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
     const int tile = blockIdx.x;
     if (tile >= n_tiles) return;
     const int tid = threadIdx.x;
-    const int ci = find_clip_by_tile(p.clips, p.n_clips, tile);
+    const int ci = p.tile_clip[tile];
     const ClipDev clip = p.clips[ci];
     const int t0 = (tile - clip.tile_base) * kColsPerTile;
     const int n_valid = min(kColsPerTile, clip.n_cols - t0);
 
-    // ---- stage the |X| tile, transposed to [bin][column] ----
-    // 16 independent coalesced loads in flight per thread (one per column), then four
-    // conflict-free 16-byte shared stores into the thread's own bin row.
-    {
-        const float* base = p.spill + (static_cast<long long>(clip.col_base) + t0) * kSpillStride;
-        for (int f = tid; f < kNBins; f += kProjThreads) {
-            float v[kColsPerTile];
-#pragma unroll
-            for (int j = 0; j < kColsPerTile; ++j)
-                v[j] = (j < n_valid) ? __ldg(base + static_cast<long long>(j) * kSpillStride + f) : 0.0f;
-            float4* dst = reinterpret_cast<float4*>(&sm.s[f * kSsmPitch]);
-#pragma unroll
-            for (int q = 0; q < kColsPerTile / 4; ++q)
-                dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
+    // ---- stage the |X| tile: both half-tile blocks are contiguous in the spill -> one bulk copy ----
+    const uint32_t bar = proj_smem_u32(&sm.bar);
+    constexpr uint32_t tile_bytes = 2 * kHalfTileFloats * sizeof(float);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float* src = p.spill + static_cast<long long>(tile) * (2 * kHalfTileFloats);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(proj_smem_u32(&sm.s[0])), "l"(src), "r"(tile_bytes), "r"(bar) : "memory");
     }
     if (p.do_mel) {
         for (int i = tid; i < p.mel_nnz; i += kProjThreads) sm.melw[i] = p.mel_weights[i];
         for (int i = tid; i < 128; i += kProjThreads) { sm.mstart[i] = p.mel_start[i]; sm.mcount[i] = p.mel_count[i]; }
         for (int i = tid; i < 129; i += kProjThreads) sm.moffset[i] = p.mel_offset[i];
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(bar) : "memory");
+        }
     }
     __syncthreads();
 
@@ -231,9 +244,12 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
             const int f_lo = ks * 52, f_hi = min(kNBins, f_lo + 52);
+            const float* xs = &sm.s[(tg >> 1) * kHalfTileFloats + 4 * (tg & 1)];
+            const float* ws = bank + 4 * cg;
+#pragma unroll 4
             for (int f = f_lo; f < f_hi; ++f) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(bank + f * 12 + 4 * cg));
-                const float4 x = *reinterpret_cast<const float4*>(&sm.s[f * kSsmPitch + 4 * tg]);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(ws + f * 12));
+                const float4 x = *reinterpret_cast<const float4*>(xs + f * kHalfTileCols);
                 acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
                 acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
                 acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
@@ -251,6 +267,7 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
         __syncthreads();
         if (tid < 192) {
             float total = 0.f;
+#pragma unroll
             for (int ks = 0; ks < 20; ++ks) total += sm.red[ks * 192 + tid];
             sm.raw[tid] = total;  // [c][t]
         }
@@ -271,28 +288,27 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
             for (int t = 0; t < n_valid; ++t) total += sm.raw[tid * 16 + t];
             p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
         }
-        __syncthreads();
     }
 
     // ---- mel power + log-mel ----
     if (p.do_mel) {
-        // power = |X| * |X| in float32 (np.abs(D) ** 2.0), in place
-        for (int i = tid; i < kNBins * kSsmPitch; i += kProjThreads) { const float v = sm.s[i]; sm.s[i] = v * v; }
-        __syncthreads();
-        const int m = tid & 127, g = tid >> 7;
+        const int m = tid & 127, g = tid >> 7;     // band, half tile (8 columns)
         float acc[8];
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[b] = 0.f;
         const int start = sm.mstart[m], count = sm.mcount[m];
         const float* w = sm.melw + sm.moffset[m];
+        const float* xs = &sm.s[g * kHalfTileFloats + start * kHalfTileCols];
+#pragma unroll 2
         for (int i = 0; i < count; ++i) {
             const float wi = w[i];
-            const float4 a = *reinterpret_cast<const float4*>(&sm.s[(start + i) * kSsmPitch + 8 * g]);
-            const float4 b = *reinterpret_cast<const float4*>(&sm.s[(start + i) * kSsmPitch + 8 * g + 4]);
-            acc[0] = fmaf(wi, a.x, acc[0]); acc[1] = fmaf(wi, a.y, acc[1]);
-            acc[2] = fmaf(wi, a.z, acc[2]); acc[3] = fmaf(wi, a.w, acc[3]);
-            acc[4] = fmaf(wi, b.x, acc[4]); acc[5] = fmaf(wi, b.y, acc[5]);
-            acc[6] = fmaf(wi, b.z, acc[6]); acc[7] = fmaf(wi, b.w, acc[7]);
+            const float4 a = *reinterpret_cast<const float4*>(xs + i * kHalfTileCols);
+            const float4 b = *reinterpret_cast<const float4*>(xs + i * kHalfTileCols + 4);
+            // power = |X| * |X| in float32 (np.abs(D) ** 2.0)
+            acc[0] = fmaf(wi, a.x * a.x, acc[0]); acc[1] = fmaf(wi, a.y * a.y, acc[1]);
+            acc[2] = fmaf(wi, a.z * a.z, acc[2]); acc[3] = fmaf(wi, a.w * a.w, acc[3]);
+            acc[4] = fmaf(wi, b.x * b.x, acc[4]); acc[5] = fmaf(wi, b.y * b.y, acc[5]);
+            acc[6] = fmaf(wi, b.z * b.z, acc[6]); acc[7] = fmaf(wi, b.w * b.w, acc[7]);
         }
         float msum = 0.f, lmax = -FLT_MAX;
 #pragma unroll
