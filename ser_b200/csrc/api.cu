@@ -270,7 +270,7 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         max_clips = std::max(max_clips, c.clip_hi - c.clip_lo);
     }
     if (!chunks.empty()) {
-        SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(max_tiles) * 2 * kHalfTileFloats * sizeof(float)));
+        SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(max_cols) * kSpillStride * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_clip.reserve(static_cast<size_t>(max_tiles) * sizeof(int)));
         SERB_CUDA(ctx, ctx->logmel.reserve(static_cast<size_t>(max_cols) * 128 * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_mel.reserve(static_cast<size_t>(max_tiles) * 128 * sizeof(float)));
@@ -761,7 +761,7 @@ int serb_debug_stft_host(serb_ctx* ctx, const float* h_wave, int64_t n, float* h
     if (n_cols != c.n_cols) return fail(ctx, SERB_ERR_INVALID_ARG, "n_cols must be 1 + n / 512");
     const int tiles = (c.n_cols + kColsPerTile - 1) / kColsPerTile;
     SERB_CUDA(ctx, ctx->wave.reserve(static_cast<size_t>(n) * sizeof(float) + 64));
-    SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(tiles) * 2 * kHalfTileFloats * sizeof(float)));
+    SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(c.n_cols) * kSpillStride * sizeof(float)));
     SERB_CUDA(ctx, ctx->tile_clip.reserve(static_cast<size_t>(tiles) * sizeof(int)));
     SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
     SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
@@ -779,14 +779,9 @@ int serb_debug_stft_host(serb_ctx* ctx, const float* h_wave, int64_t n, float* h
     sp.status = ctx->status.as<int>();
     SERB_CUDA(ctx, launch_stft(sp, tiles, ctx->stream));
     ctx->launches += 2;
-    // un-interleave the [half tile][bin][8] spill on the host
-    std::vector<float> raw(static_cast<size_t>(tiles) * 2 * kHalfTileFloats);
-    SERB_CUDA(ctx, cudaMemcpyAsync(raw.data(), ctx->spill.ptr, raw.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpy2DAsync(h_out, kNBins * sizeof(float), ctx->spill.ptr, kSpillStride * sizeof(float),
+                                     kNBins * sizeof(float), c.n_cols, cudaMemcpyDeviceToHost, ctx->stream));
     SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int t = 0; t < c.n_cols; ++t) {
-        const float* block = raw.data() + static_cast<size_t>(t / kHalfTileCols) * kHalfTileFloats;
-        for (int k = 0; k < kNBins; ++k) h_out[static_cast<size_t>(t) * kNBins + k] = block[k * kHalfTileCols + (t % kHalfTileCols)];
-    }
     return SERB_OK;
 }
 

@@ -8,10 +8,9 @@ namespace serb {
 constexpr int kNFft = 2048;          // librosa default, dsp.py:96 n_fft = min(len, 2048)
 constexpr int kHop = 512;            // n_fft // 4 (stft) == melspectrogram's hop_length
 constexpr int kNBins = 1025;         // 1 + n_fft / 2
+constexpr int kSpillStride = 1032;   // |X| spill row pitch in floats: [column][1032], 16-byte multiple
 constexpr int kColsPerTile = 16;     // STFT columns per projection tile
-constexpr int kHalfTileCols = 8;     // STFT columns per STFT CTA (half a projection tile)
-// |X| spill: one block per half tile, rows of 8 columns: [half tile][bin 0..1024][8]
-constexpr int kHalfTileFloats = kNBins * kHalfTileCols;          // 8200 floats = 32800 B
+constexpr int kHalfTileCols = 8;     // STFT columns per STFT work item (half a projection tile)
 
 // One clip of the ragged batch, chunk-relative bookkeeping included.
 struct ClipDev {

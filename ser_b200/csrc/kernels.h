@@ -13,7 +13,7 @@ struct StftParams {
     int n_clips;
     const int* tile_clip;    // [tiles] clip index of every 16-column tile
     const float2* tables;    // W_1024^(k1 n2) [32][32] then W_2048^k [1024] as (cos, sin)
-    float* spill;            // [half tiles][1025][8]  |X|
+    float* spill;            // [cols][kSpillStride]  |X|
     int do_peaks;            // piptrack wanted (chroma enabled)
     int kmin, kmax;          // bins with 150 <= f < min(4000, sr/2):  kmin <= k < kmax
     int peak_cap;            // slots per column
@@ -42,7 +42,7 @@ struct ProjParams {
     const ClipDev* clips;
     int n_clips;
     const int* tile_clip;      // [tiles]
-    const float* spill;        // [half tiles][1025][8]
+    const float* spill;        // [cols][kSpillStride]
     int do_mel;                // mel or mfcc requested
     const int* mel_start;      // [128]
     const int* mel_count;      // [128]

@@ -170,18 +170,20 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 // =========================================================================================
 // K3: mel (sparse Slaney triangles) and chroma (dense 12 x 1025, bank picked by the clip's
 // tuning) projections of one tile of 16 columns, as shared-memory fp32 contractions.  The
-// STFT kernel spills |X| as [bin][8 columns] rows, so one TMA bulk copy stages the tile and
-// every thread register-tiles over 4 or 8 columns with 16-byte shared loads.
+// tile's |X| rows are staged by TMA bulk copies (one per column); chroma is a split-K
+// 4 x 4 register-tiled product, mel a per-(column, band) sparse dot product with the bands
+// dealt round-robin so every thread sums the same number of non-zeros.
 // =========================================================================================
 constexpr int kProjThreads = 256;
+constexpr int kRowPitch = 1028;   // floats per staged column row: 16-byte multiple, = 4 (mod 32 banks)
 
 struct ProjSmem {
-    float s[2 * kHalfTileFloats];      // [half][bin][8 columns], 65600 B, filled by one TMA bulk copy
-    float red[20 * 12 * 16];           // chroma split-K partials, 15360 B
+    float s[kColsPerTile][kRowPitch];  // |X| rows of the tile, one TMA bulk copy per column, 65792 B
+    float red[20 * 12 * 16];           // chroma split-K partials; reused for mel power [16][128]
+    float lm[kColsPerTile][128];       // log-mel staging for coalesced stores
     float raw[12 * 16];
     float melw[2304];                  // sparse mel weights (<= 2304 non-zeros)
     int mstart[128], mcount[128], moffset[129];
-    float melsum[2][128];
     float wmax[kProjThreads / 32];
     unsigned long long bar;
 };
@@ -200,22 +202,27 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
     const ClipDev clip = p.clips[ci];
     const int t0 = (tile - clip.tile_base) * kColsPerTile;
     const int n_valid = min(kColsPerTile, clip.n_cols - t0);
+    const long long col0 = static_cast<long long>(clip.col_base) + t0;
 
-    // ---- stage the |X| tile: both half-tile blocks are contiguous in the spill -> one bulk copy ----
+    // ---- stage the tile's |X| rows: one TMA bulk copy per existing column ----
     const uint32_t bar = proj_smem_u32(&sm.bar);
-    constexpr uint32_t tile_bytes = 2 * kHalfTileFloats * sizeof(float);
+    constexpr uint32_t row_bytes = kRowPitch * sizeof(float);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-        const float* src = p.spill + static_cast<long long>(tile) * (2 * kHalfTileFloats);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            ::"r"(proj_smem_u32(&sm.s[0])), "l"(src), "r"(tile_bytes), "r"(bar) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * n_valid) : "memory");
+        for (int j = 0; j < n_valid; ++j) {
+            const float* src = p.spill + (col0 + j) * kSpillStride;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(proj_smem_u32(&sm.s[j][0])), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+        }
     }
+    for (int j = n_valid; j < kColsPerTile; ++j)
+        for (int f = tid; f < kRowPitch; f += kProjThreads) sm.s[j][f] = 0.0f;
     if (p.do_mel) {
         for (int i = tid; i < p.mel_nnz; i += kProjThreads) sm.melw[i] = p.mel_weights[i];
         for (int i = tid; i < 128; i += kProjThreads) { sm.mstart[i] = p.mel_start[i]; sm.mcount[i] = p.mel_count[i]; }
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
     }
     __syncthreads();
 
-    // ---- chroma: raw[c][t] = sum_f W[c][f] |X|[f][t] ----
+    // ---- chroma: raw[c][t] = sum_f W[c][f] |X|[f][t], split over 20 bin slices ----
     if (p.do_chroma) {
         const float* bank = p.chroma_banks + static_cast<size_t>(p.tuning_idx[ci]) * (kNBins * 12);
         if (tid < 240) {
@@ -244,20 +251,20 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
             const int f_lo = ks * 52, f_hi = min(kNBins, f_lo + 52);
-            const float* xs = &sm.s[(tg >> 1) * kHalfTileFloats + 4 * (tg & 1)];
+            const float* x0 = &sm.s[4 * tg][0];
             const float* ws = bank + 4 * cg;
 #pragma unroll 4
             for (int f = f_lo; f < f_hi; ++f) {
                 const float4 w = __ldg(reinterpret_cast<const float4*>(ws + f * 12));
-                const float4 x = *reinterpret_cast<const float4*>(xs + f * kHalfTileCols);
-                acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
-                acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
-                acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
-                acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
-                acc[2][0] = fmaf(w.z, x.x, acc[2][0]); acc[2][1] = fmaf(w.z, x.y, acc[2][1]);
-                acc[2][2] = fmaf(w.z, x.z, acc[2][2]); acc[2][3] = fmaf(w.z, x.w, acc[2][3]);
-                acc[3][0] = fmaf(w.w, x.x, acc[3][0]); acc[3][1] = fmaf(w.w, x.y, acc[3][1]);
-                acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
+                const float xa = x0[f], xb = x0[kRowPitch + f], xc = x0[2 * kRowPitch + f], xd = x0[3 * kRowPitch + f];
+                acc[0][0] = fmaf(w.x, xa, acc[0][0]); acc[0][1] = fmaf(w.x, xb, acc[0][1]);
+                acc[0][2] = fmaf(w.x, xc, acc[0][2]); acc[0][3] = fmaf(w.x, xd, acc[0][3]);
+                acc[1][0] = fmaf(w.y, xa, acc[1][0]); acc[1][1] = fmaf(w.y, xb, acc[1][1]);
+                acc[1][2] = fmaf(w.y, xc, acc[1][2]); acc[1][3] = fmaf(w.y, xd, acc[1][3]);
+                acc[2][0] = fmaf(w.z, xa, acc[2][0]); acc[2][1] = fmaf(w.z, xb, acc[2][1]);
+                acc[2][2] = fmaf(w.z, xc, acc[2][2]); acc[2][3] = fmaf(w.z, xd, acc[2][3]);
+                acc[3][0] = fmaf(w.w, xa, acc[3][0]); acc[3][1] = fmaf(w.w, xb, acc[3][1]);
+                acc[3][2] = fmaf(w.w, xc, acc[3][2]); acc[3][3] = fmaf(w.w, xd, acc[3][3]);
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -288,45 +295,45 @@ __global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int
             for (int t = 0; t < n_valid; ++t) total += sm.raw[tid * 16 + t];
             p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
         }
+        __syncthreads();   // red is reused below
     }
 
-    // ---- mel power + log-mel ----
+    // ---- mel power + log-mel: thread = (column, band group), bands bg, bg+16, ... (balanced) ----
     if (p.do_mel) {
-        const int m = tid & 127, g = tid >> 7;     // band, half tile (8 columns)
-        float acc[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[b] = 0.f;
-        const int start = sm.mstart[m], count = sm.mcount[m];
-        const float* w = sm.melw + sm.moffset[m];
-        const float* xs = &sm.s[g * kHalfTileFloats + start * kHalfTileCols];
-#pragma unroll 2
-        for (int i = 0; i < count; ++i) {
-            const float wi = w[i];
-            const float4 a = *reinterpret_cast<const float4*>(xs + i * kHalfTileCols);
-            const float4 b = *reinterpret_cast<const float4*>(xs + i * kHalfTileCols + 4);
-            // power = |X| * |X| in float32 (np.abs(D) ** 2.0)
-            acc[0] = fmaf(wi, a.x * a.x, acc[0]); acc[1] = fmaf(wi, a.y * a.y, acc[1]);
-            acc[2] = fmaf(wi, a.z * a.z, acc[2]); acc[3] = fmaf(wi, a.w * a.w, acc[3]);
-            acc[4] = fmaf(wi, b.x * b.x, acc[4]); acc[5] = fmaf(wi, b.y * b.y, acc[5]);
-            acc[6] = fmaf(wi, b.z * b.z, acc[6]); acc[7] = fmaf(wi, b.w * b.w, acc[7]);
-        }
-        float msum = 0.f, lmax = -FLT_MAX;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int j = 8 * g + b;
-            if (j < n_valid) {
-                msum += acc[b];
-                // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
-                const float lm = 10.0f * log10f(fmaxf(1e-10f, acc[b]));
-                p.logmel[(static_cast<long long>(clip.col_base) + t0 + j) * 128 + m] = lm;
-                lmax = fmaxf(lmax, lm);
+        const int col = tid & 15, bg = tid >> 4;
+        const float* x = &sm.s[col][0];
+        float* melp = sm.red;   // [16][128]
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const int m = bg + 16 * j;
+            const int start = sm.mstart[m], count = sm.mcount[m];
+            const float* w = sm.melw + sm.moffset[m];
+            float acc = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < count; ++i) {
+                const float v = x[start + i];
+                acc = fmaf(w[i], v * v, acc);   // power = |X| * |X| in float32 (np.abs(D) ** 2.0)
             }
+            melp[col * 128 + m] = acc;
+            // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
+            sm.lm[col][m] = 10.0f * log10f(fmaxf(1e-10f, acc));
         }
-        sm.melsum[g][m] = msum;
+        __syncthreads();
+        // coalesced write-out of the valid columns' log-mel rows, tile maximum, tile mel sums
+        float lmax = -FLT_MAX;
+        for (int i = tid; i < n_valid * 128; i += kProjThreads) {
+            const float v = sm.lm[i >> 7][i & 127];
+            p.logmel[col0 * 128 + i] = v;
+            lmax = fmaxf(lmax, v);
+        }
         lmax = warp_max(lmax);
         if ((tid & 31) == 0) sm.wmax[tid >> 5] = lmax;
+        if (tid < 128) {
+            float total = 0.f;
+            for (int t = 0; t < n_valid; ++t) total += melp[t * 128 + tid];
+            p.tile_mel[static_cast<long long>(tile) * 128 + tid] = total;
+        }
         __syncthreads();
-        if (tid < 128) p.tile_mel[static_cast<long long>(tile) * 128 + tid] = sm.melsum[0][tid] + sm.melsum[1][tid];
         if (tid == 0) {
             float v = sm.wmax[0];
             for (int i = 1; i < kProjThreads / 32; ++i) v = fmaxf(v, sm.wmax[i]);

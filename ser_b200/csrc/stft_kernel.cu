@@ -5,15 +5,15 @@
 //   librosa.piptrack (inside chroma_stft -> estimate_tuning)  ser/_internal/utils/dsp.py:113-118
 // (librosa 0.11.0 semantics: SURVEY.md Appendix A.1, A.6).
 //
-// Layout: one CTA per 8 consecutive STFT columns of one clip (half a projection tile), two
-// CTAs resident per SM.  The CTA's 5632 samples and the two twiddle tables are staged in
-// shared memory by TMA bulk copies (cp.async.bulk -> UBLKCP) signalling one mbarrier; the
-// zero padding of the centred STFT is a shared-memory fill.  Each warp owns one column: the
-// 2048-point real FFT is a 1024-point complex FFT split 32 x 32 across the 32 lanes -- two
-// register-resident 32-point DFTs around one shared-memory transpose -- followed by the
-// real-input split, which pairs lane l with lane 32-l through warp shuffles.  The CTA then
-// writes its |X| block to the spill as [bin][8 columns] rows (32 bytes per thread, fully
-// coalesced), the layout the projection kernel register-tiles over; peaks are compacted per
+// Persistent kernel: two CTAs of 8 warps per SM walk the list of half tiles (8 consecutive
+// STFT columns of one clip).  A half tile's 5632 samples are staged in shared memory by a TMA
+// bulk copy (cp.async.bulk -> UBLKCP) signalling an mbarrier; the copy for the NEXT half tile
+// is issued as soon as every warp has pulled its frame into registers, so it lands while the
+// FFTs run.  Zero padding of the centred STFT is a shared-memory fill.  Each warp owns one
+// column: the 2048-point real FFT is a 1024-point complex FFT split 32 x 32 across the 32
+// lanes -- two register-resident 32-point DFTs around one shared-memory transpose -- followed
+// by the real-input split, which pairs lane l with lane 32-l through warp shuffles.  |X| goes
+// to the spill (row-major [column][1032], coalesced 128-byte stores); peaks are compacted per
 // column with a warp ballot.
 #include "fft.cuh"
 #include "kernels.h"
@@ -22,16 +22,29 @@ namespace serb {
 
 constexpr int kStftWarps = 8;
 constexpr int kStftThreads = kStftWarps * 32;
-constexpr int kStftCols = kHalfTileCols;                        // columns per CTA: one per warp
+constexpr int kStftCols = kHalfTileCols;                        // columns per work item: one per warp
 constexpr int kStftSamples = (kStftCols - 1) * kHop + kNFft;    // 5632 staged samples
 constexpr int kBufPitch = 33;  // float2 pitch of the per-warp 32x32 transpose buffer
+
+// What one work item needs; produced one iteration ahead by thread 0.
+struct ItemDesc {
+    const float* src;    // src[i] is the sample for shared index i
+    int lo, hi;          // valid shared indices [lo, hi)
+    int bulk_end;        // [lo, bulk_end) arrives by TMA, [bulk_end, hi) by plain loads
+    int n_here;          // columns of this half tile that exist (0 = nothing to do)
+    long long col0;      // spill / peak column of the first one
+};
 
 struct StftSmem {
     float wave[kStftSamples];                       // 22528 B
     float2 tw[32][32];                              // W_1024^(k1*n2): [k1][n2]
     float2 tw2[1024];                               // W_2048^k, k < 1024 (real-input split)
     float2 buf[kStftWarps][32 * kBufPitch];         // per-warp transpose buffer, then |X| staging
-    unsigned long long bar;
+    ItemDesc desc[2];
+    ItemDesc next;                                  // thread 0's look-ahead descriptor
+    float4 win[32];                                 // per-lane window angles (cos, sin) x 2
+    int bad;
+    unsigned long long bar_wave, bar_tables;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -42,71 +55,54 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
-// ---- staging: TMA bulk copies of the tables and the valid samples, zero fill of the rest ----
-__device__ __forceinline__ void stage_tile(StftSmem& sm, const float* __restrict__ wave,
-                                           const float2* __restrict__ tables,
-                                           long long clip_start, int clip_len, int s0) {
-    // shared index i <-> clip sample s0 + i ; valid when 0 <= s0 + i < clip_len
-    const int lo = max(0, -s0);
-    const int hi = min(kStftSamples, clip_len - s0);
-    const float* src = wave + clip_start + s0;  // src[i] is the sample for shared index i
-    const int tid = threadIdx.x;
-    const bool aligned = (((clip_start + s0 + lo) & 3LL) == 0) && ((lo & 3) == 0);
-    int bulk_end = lo;
-    if (aligned && hi - lo >= 4) bulk_end = lo + ((hi - lo) & ~3);
-    const uint32_t wave_bytes = static_cast<uint32_t>(bulk_end - lo) * 4u;
-    constexpr uint32_t table_bytes = 2 * 1024 * sizeof(float2);
-    const uint32_t bar = smem_u32(&sm.bar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"(wave_bytes + table_bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            ::"r"(smem_u32(&sm.tw[0][0])), "l"(tables), "r"(table_bytes), "r"(bar) : "memory");
-        if (wave_bytes > 0)
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                ::"r"(smem_u32(&sm.wave[lo])), "l"(src + lo), "r"(wave_bytes), "r"(bar) : "memory");
-    }
-    // everything the bulk copy does not cover: zero padding and the unaligned remainder
-    for (int i = tid; i < lo; i += kStftThreads) sm.wave[i] = 0.0f;
-    for (int i = bulk_end + tid; i < hi; i += kStftThreads) sm.wave[i] = __ldg(src + i);
-    for (int i = max(hi, 0) + tid; i < kStftSamples; i += kStftThreads) sm.wave[i] = 0.0f;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
-    __syncthreads();
+}
+
+__device__ __forceinline__ ItemDesc make_desc(const StftParams& p, int item, int n_items) {
+    ItemDesc d;
+    d.src = nullptr; d.lo = 0; d.hi = 0; d.bulk_end = 0; d.n_here = 0; d.col0 = 0;
+    if (item >= n_items) return d;
+    const int tile = item >> 1;
+    const ClipDev clip = p.clips[p.tile_clip[tile]];
+    const int t0 = (tile - clip.tile_base) * kColsPerTile + (item & 1) * kStftCols;
+    if (t0 >= clip.n_cols) return d;
+    const int s0 = t0 * kHop - kNFft / 2;       // shared index i <-> clip sample s0 + i
+    d.n_here = min(kStftCols, clip.n_cols - t0);
+    d.col0 = static_cast<long long>(clip.col_base) + t0;
+    d.lo = max(0, -s0);
+    d.hi = min(kStftSamples, clip.length - s0);
+    d.src = p.wave + clip.start + s0;
+    const bool aligned = (((clip.start + s0 + d.lo) & 3LL) == 0) && ((d.lo & 3) == 0);
+    d.bulk_end = d.lo;
+    if (aligned && d.hi - d.lo >= 4) d.bulk_end = d.lo + ((d.hi - d.lo) & ~3);
+    return d;
+}
+
+// thread 0: arm the barrier and start the bulk copy of the item's aligned part (possibly empty)
+__device__ __forceinline__ void issue_wave_copy(StftSmem& sm, const ItemDesc& d) {
+    const uint32_t bar = smem_u32(&sm.bar_wave);
+    const uint32_t bytes = static_cast<uint32_t>(d.bulk_end - d.lo) * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    if (bytes > 0)
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(&sm.wave[d.lo])), "l"(d.src + d.lo), "r"(bytes), "r"(bar) : "memory");
 }
 
 // ---- one STFT column per warp -----------------------------------------------------------
-// Leaves |X[k]|, k = 0..1024, in the warp's staging buffer (floats aliasing buf, free once the
-// transpose has been read back) and returns the lane's running maximum of |X|.
-__device__ __forceinline__ float column_fft(const float* __restrict__ frame, const float2 (*tw)[32],
+// v[] holds the windowed frame z[32 n1 + lane].  Writes |X[k]|, k = 0..1024, to row[] (global
+// spill) and to the warp's staging buffer; returns the lane's running maximum of |X|.
+__device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[32],
                                             const float2* __restrict__ tw2, float2* __restrict__ buf,
-                                            int lane, float wc0, float ws0, float wc1, float ws1) {
-    float2 v[32];
-    // load z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane, times the periodic Hann window
-    // w[j] = 0.5 - 0.5 cos(2 pi j / 2048), j = 64 n1 + 2 lane (+1):
-    // cos(a + t) = cos a cos t - sin a sin t with a = 2 pi n1 / 32 (immediates), t per lane.
-#pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) {
-        const float2 x = *reinterpret_cast<const float2*>(frame + 64 * n1 + 2 * lane);
-        const float ca = cos32(n1), sa = sin32(n1);
-        const float w0 = fmaf(-0.5f * ca, wc0, fmaf(0.5f * sa, ws0, 0.5f));
-        const float w1 = fmaf(-0.5f * ca, wc1, fmaf(0.5f * sa, ws1, 0.5f));
-        v[n1] = make_float2(x.x * w0, x.y * w1);
-    }
+                                            int lane, float* __restrict__ row) {
     fft32(v);  // over n1 -> index k1
     // twiddle W_1024^(lane * k1), transpose through shared memory
 #pragma unroll
@@ -141,11 +137,13 @@ __device__ __forceinline__ float column_fft(const float* __restrict__ frame, con
         const float wy = fmaf(w.x, oy, -w.y * ox);
         const float xr = ex + wx, xi = ey + wy;
         const float mag = 0.5f * sqrt_approx(fmaf(xr, xr, xi * xi));
+        row[lane + 32 * k2] = mag;
         sbuf[lane + 32 * k2] = mag;
         cmax = fmaxf(cmax, mag);
         if (k2 == 0 && lane == 0) {
             const float nr = ex - wx, ni = ey - wy;
             const float nyq = 0.5f * sqrt_approx(fmaf(nr, nr, ni * ni));
+            row[1024] = nyq;
             sbuf[1024] = nyq;
             cmax = fmaxf(cmax, nyq);
         }
@@ -197,55 +195,86 @@ __device__ __forceinline__ void column_peaks(const float* __restrict__ sbuf, flo
 __global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(StftParams p, int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
-    // blockIdx.x enumerates half tiles: two 8-column CTAs per 16-column projection tile
-    const int tile = blockIdx.x >> 1;
-    if (tile >= n_tiles) return;
-    const int ci = p.tile_clip[tile];
-    const ClipDev clip = p.clips[ci];
-    const int t0 = (tile - clip.tile_base) * kColsPerTile + (blockIdx.x & 1) * kStftCols;
-    float4* block = reinterpret_cast<float4*>(p.spill + static_cast<long long>(blockIdx.x) * kHalfTileFloats);
-    if (t0 >= clip.n_cols) {
-        // the projection kernel bulk-loads both halves of a tile: keep the unused half defined
-        for (int i = threadIdx.x; i < kHalfTileFloats / 4; i += kStftThreads) block[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = 2 * n_tiles;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int item = blockIdx.x;
+    if (item >= n_items) return;
 
-    stage_tile(sm, p.wave, p.tables, clip.start, clip.length, t0 * kHop - kNFft / 2);
-    {   // dsp.py:94 "Audio buffer is not finite everywhere." -> status bit 0, reported by the host entry
-        int bad = 0;
-        for (int i = threadIdx.x; i < kStftSamples; i += kStftThreads) bad |= !isfinite(sm.wave[i]);
-        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(p.status, 1);
+    // ---- prologue: barriers, twiddle tables and the first item's samples by TMA ----
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_wave)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_tables)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        constexpr uint32_t table_bytes = 2 * 1024 * sizeof(float2);
+        const uint32_t bt = smem_u32(&sm.bar_tables);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bt), "r"(table_bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(&sm.tw[0][0])), "l"(p.tables), "r"(table_bytes), "r"(bt) : "memory");
+        sm.desc[0] = make_desc(p, item, n_items);
+        issue_wave_copy(sm, sm.desc[0]);
+        sm.next = make_desc(p, item + gridDim.x, n_items);
     }
-
-    // per-lane window angles
-    float ws0, wc0, ws1, wc1;
-    sincospif(static_cast<float>(2 * lane) * (2.0f / 2048.0f), &ws0, &wc0);
-    sincospif(static_cast<float>(2 * lane + 1) * (2.0f / 2048.0f), &ws1, &wc1);
+    // per-lane window angles: w[j] = 0.5 - 0.5 cos(2 pi j / 2048), j = 64 n1 + 2 lane (+1)
+    if (tid < 32) {
+        float ws0, wc0, ws1, wc1;
+        sincospif(static_cast<float>(2 * tid) * (2.0f / 2048.0f), &ws0, &wc0);
+        sincospif(static_cast<float>(2 * tid + 1) * (2.0f / 2048.0f), &ws1, &wc1);
+        sm.win[tid] = make_float4(wc0, ws0, wc1, ws1);
+    }
+    if (tid == 32) sm.bad = 0;
+    __syncthreads();
+    mbar_wait(smem_u32(&sm.bar_tables), 0);
 
     float2* buf = sm.buf[warp];
-    float* sbuf = reinterpret_cast<float*>(buf);
-    const int t = t0 + warp;
-    if (t < clip.n_cols) {
-        float cmax = column_fft(sm.wave + warp * kHop, sm.tw, sm.tw2, buf, lane, wc0, ws0, wc1, ws1);
-        if (p.do_peaks) {
-            cmax = warp_max(cmax);
-            __syncwarp();
-            column_peaks(sbuf, cmax, lane, p, static_cast<long long>(clip.col_base) + t);
+    for (int it = 0; item < n_items; ++it, item += gridDim.x) {
+        const ItemDesc d = sm.desc[it & 1];
+        // what the bulk copy does not cover: zero padding and the unaligned remainder
+        for (int i = tid; i < d.lo; i += kStftThreads) sm.wave[i] = 0.0f;
+        for (int i = d.bulk_end + tid; i < d.hi; i += kStftThreads) sm.wave[i] = __ldg(d.src + i);
+        for (int i = max(d.hi, 0) + tid; i < kStftSamples; i += kStftThreads) sm.wave[i] = 0.0f;
+        mbar_wait(smem_u32(&sm.bar_wave), it & 1);
+        __syncthreads();
+
+        // frame -> registers: z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane, times the Hann window;
+        // cos(a + t) = cos a cos t - sin a sin t with a = 2 pi n1 / 32 (immediates), t per lane
+        float2 v[32];
+        const bool active = warp < d.n_here;
+        if (active) {
+            const float* frame = sm.wave + warp * kHop;
+            const float4 wa = sm.win[lane];
+            const float wc0 = wa.x, ws0 = wa.y, wc1 = wa.z, ws1 = wa.w;
+            int bad = 0;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const float2 x = *reinterpret_cast<const float2*>(frame + 64 * n1 + 2 * lane);
+                bad |= !isfinite(x.x) | !isfinite(x.y);   // dsp.py:94 finite check, folded into the load
+                const float ca = cos32(n1), sa = sin32(n1);
+                const float w0 = fmaf(-0.5f * ca, wc0, fmaf(0.5f * sa, ws0, 0.5f));
+                const float w1 = fmaf(-0.5f * ca, wc1, fmaf(0.5f * sa, ws1, 0.5f));
+                v[n1] = make_float2(x.x * w0, x.y * w1);
+            }
+            if (bad) sm.bad = 1;
         }
-    } else {
-        for (int i = lane; i < kNBins; i += 32) sbuf[i] = 0.0f;
+        if (tid == 0) sm.desc[(it + 1) & 1] = sm.next;   // published by the barrier below
+        __syncthreads();   // every warp holds its frame: the wave buffer may be refilled
+        if (tid == 0) {
+            if (item + gridDim.x < n_items) issue_wave_copy(sm, sm.next);
+            sm.next = make_desc(p, item + 2 * gridDim.x, n_items);
+        }
+        if (active) {
+            const long long col = d.col0 + warp;
+            float cmax = column_fft(v, sm.tw, sm.tw2, buf, lane, p.spill + col * kSpillStride);
+            if (p.do_peaks) {
+                cmax = warp_max(cmax);
+                __syncwarp();
+                column_peaks(reinterpret_cast<const float*>(buf), cmax, lane, p, col);
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
-    // spill block [bin][8 columns]: each thread gathers one bin from the 8 warp buffers
-    // (conflict-free: consecutive lanes, consecutive bins) and stores 32 contiguous bytes
-    for (int k = threadIdx.x; k < kNBins; k += kStftThreads) {
-        float c[kStftCols];
-#pragma unroll
-        for (int w = 0; w < kStftCols; ++w) c[w] = reinterpret_cast<const float*>(sm.buf[w])[k];
-        block[2 * k] = make_float4(c[0], c[1], c[2], c[3]);
-        block[2 * k + 1] = make_float4(c[4], c[5], c[6], c[7]);
-    }
+    if (tid == 0 && sm.bad) atomicOr(p.status, 1);
 }
 
 // one thread per clip: tile_clip[tile] = clip index, for every 16-column tile of the clip
@@ -263,14 +292,24 @@ cudaError_t launch_expand_tiles(const ClipDev* clips, int n_clips, int* tile_cli
     return cudaGetLastError();
 }
 
+static int g_stft_grid = 0;
+
 cudaError_t configure_stft() {
-    return cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(sizeof(StftSmem)));
+    cudaError_t e = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(StftSmem)));
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel, kStftThreads, sizeof(StftSmem))) != cudaSuccess) return e;
+    g_stft_grid = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
 }
 
 cudaError_t launch_stft(const StftParams& p, int n_tiles, cudaStream_t stream) {
     if (n_tiles <= 0) return cudaSuccess;
-    stft_kernel<<<2 * n_tiles, kStftThreads, sizeof(StftSmem), stream>>>(p, n_tiles);
+    const int grid = (2 * n_tiles < g_stft_grid || g_stft_grid <= 0) ? 2 * n_tiles : g_stft_grid;
+    stft_kernel<<<grid, kStftThreads, sizeof(StftSmem), stream>>>(p, n_tiles);
     return cudaGetLastError();
 }
 
