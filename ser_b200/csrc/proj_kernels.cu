@@ -169,187 +169,254 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 
 // =========================================================================================
 // K3: mel (sparse Slaney triangles) and chroma (dense 12 x 1025, bank picked by the clip's
-// tuning) projections of one tile of 16 columns, as shared-memory fp32 contractions.  The
-// tile's |X| rows are staged by TMA bulk copies (one per column); chroma is a split-K
-// 4 x 4 register-tiled product, mel a per-(column, band) sparse dot product with the bands
-// dealt round-robin so every thread sums the same number of non-zeros.
+// tuning) projections as shared-memory fp32 contractions.
+//
+// Persistent, warp-specialised kernel: one CTA of 16 warps per SM walks a contiguous range of
+// 16-column tiles.  Thread 0 keeps a two-stage ring of |X| tiles full with TMA bulk copies
+// (one per column row, cp.async.bulk -> UBLKCP, mbarrier completion) and reloads the clip's
+// chroma bank into shared memory when the clip changes.  Warps 0-8 do the chroma product
+// (split-K over 24 bin slices, 4 chroma x 4 columns register tile, deterministic slice
+// reduction, per-column L-inf normalisation); warps 9-15 do mel at the same time (thread =
+// (column, band group), bands dealt round-robin so all threads sum equally many non-zeros),
+// power_to_db, and the coalesced log-mel write-out.  The two groups meet only at the
+// end-of-tile barrier.
 // =========================================================================================
-constexpr int kProjThreads = 256;
+constexpr int kProjWarps = 16;
+constexpr int kProjThreads = kProjWarps * 32;
+constexpr int kChromaThreads = 288;                 // warps 0..8: 24 bin slices x 3 chroma groups x 4 column groups
+constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 9..15: 16 columns x 14 band groups
+constexpr int kChromaSlices = 24;
+constexpr int kSliceBins = 43;                      // 24 * 43 = 1032 >= 1025
+constexpr int kMelGroups = kMelThreads / 16;        // 14
 constexpr int kRowPitch = 1028;   // floats per staged column row: 16-byte multiple, = 4 (mod 32 banks)
 
 struct ProjSmem {
-    float s[kColsPerTile][kRowPitch];  // |X| rows of the tile, one TMA bulk copy per column, 65792 B
-    float red[20 * 12 * 16];           // chroma split-K partials; reused for mel power [16][128]
-    float lm[kColsPerTile][128];       // log-mel staging for coalesced stores
-    float raw[12 * 16];
-    float melw[2304];                  // sparse mel weights (<= 2304 non-zeros)
+    float s[2][kColsPerTile][kRowPitch];   // two-stage ring of |X| tiles, 131584 B
+    float w[kNBins * 12];                  // chroma bank of the current clip, [bin][12], 49200 B
+    float red[kChromaSlices * 192];        // chroma split-K partials
+    float melp[kColsPerTile][128];         // mel power of the tile
+    float lm[kColsPerTile][128];           // log-mel staging for coalesced stores
+    float raw[192];
+    float melw[2304];                      // sparse mel weights (<= 2304 non-zeros)
     int mstart[128], mcount[128], moffset[129];
-    float wmax[kProjThreads / 32];
-    unsigned long long bar;
+    float wmax[8];
+    unsigned long long bar_tile[2], bar_bank;
 };
 
 __device__ __forceinline__ uint32_t proj_smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void proj_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
-__global__ void __launch_bounds__(kProjThreads, 2) proj_kernel(ProjParams p, int n_tiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
-    const int tile = blockIdx.x;
-    if (tile >= n_tiles) return;
-    const int tid = threadIdx.x;
-    const int ci = p.tile_clip[tile];
-    const ClipDev clip = p.clips[ci];
+// thread 0: start the bulk copies of one tile's existing column rows into ring stage `stage`
+__device__ __forceinline__ void proj_issue_tile(ProjSmem& sm, const ProjParams& p, int tile, int stage) {
+    const ClipDev clip = p.clips[p.tile_clip[tile]];
     const int t0 = (tile - clip.tile_base) * kColsPerTile;
     const int n_valid = min(kColsPerTile, clip.n_cols - t0);
     const long long col0 = static_cast<long long>(clip.col_base) + t0;
-
-    // ---- stage the tile's |X| rows: one TMA bulk copy per existing column ----
-    const uint32_t bar = proj_smem_u32(&sm.bar);
+    const uint32_t bar = proj_smem_u32(&sm.bar_tile[stage]);
     constexpr uint32_t row_bytes = kRowPitch * sizeof(float);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * n_valid) : "memory");
+    for (int j = 0; j < n_valid; ++j) {
+        const float* src = p.spill + (col0 + j) * kSpillStride;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(proj_smem_u32(&sm.s[stage][j][0])), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    // contiguous tile range of this CTA (consecutive tiles mostly share a clip and hence a bank)
+    const int tile_lo = static_cast<int>(static_cast<long long>(n_tiles) * blockIdx.x / gridDim.x);
+    const int tile_hi = static_cast<int>(static_cast<long long>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
+    if (tile_lo >= tile_hi) return;
+
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_tile[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_tile[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_bank)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * n_valid) : "memory");
-        for (int j = 0; j < n_valid; ++j) {
-            const float* src = p.spill + (col0 + j) * kSpillStride;
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                ::"r"(proj_smem_u32(&sm.s[j][0])), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
-        }
-    }
-    for (int j = n_valid; j < kColsPerTile; ++j)
-        for (int f = tid; f < kRowPitch; f += kProjThreads) sm.s[j][f] = 0.0f;
     if (p.do_mel) {
         for (int i = tid; i < p.mel_nnz; i += kProjThreads) sm.melw[i] = p.mel_weights[i];
         for (int i = tid; i < 128; i += kProjThreads) { sm.mstart[i] = p.mel_start[i]; sm.mcount[i] = p.mel_count[i]; }
         for (int i = tid; i < 129; i += kProjThreads) sm.moffset[i] = p.mel_offset[i];
     }
-    {
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done) : "r"(bar) : "memory");
-        }
-    }
+    // rows of columns that do not exist are never copied: keep them finite
+    for (int i = tid; i < 2 * kColsPerTile * kRowPitch; i += kProjThreads) (&sm.s[0][0][0])[i] = 0.0f;
     __syncthreads();
-
-    // ---- chroma: raw[c][t] = sum_f W[c][f] |X|[f][t], split over 20 bin slices ----
-    if (p.do_chroma) {
-        const float* bank = p.chroma_banks + static_cast<size_t>(p.tuning_idx[ci]) * (kNBins * 12);
-        if (tid < 240) {
-            const int cg = tid % 3, tg = (tid / 3) & 3, ks = tid / 12;
-            float acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-            const int f_lo = ks * 52, f_hi = min(kNBins, f_lo + 52);
-            const float* x0 = &sm.s[4 * tg][0];
-            const float* ws = bank + 4 * cg;
-#pragma unroll 4
-            for (int f = f_lo; f < f_hi; ++f) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(ws + f * 12));
-                const float xa = x0[f], xb = x0[kRowPitch + f], xc = x0[2 * kRowPitch + f], xd = x0[3 * kRowPitch + f];
-                acc[0][0] = fmaf(w.x, xa, acc[0][0]); acc[0][1] = fmaf(w.x, xb, acc[0][1]);
-                acc[0][2] = fmaf(w.x, xc, acc[0][2]); acc[0][3] = fmaf(w.x, xd, acc[0][3]);
-                acc[1][0] = fmaf(w.y, xa, acc[1][0]); acc[1][1] = fmaf(w.y, xb, acc[1][1]);
-                acc[1][2] = fmaf(w.y, xc, acc[1][2]); acc[1][3] = fmaf(w.y, xd, acc[1][3]);
-                acc[2][0] = fmaf(w.z, xa, acc[2][0]); acc[2][1] = fmaf(w.z, xb, acc[2][1]);
-                acc[2][2] = fmaf(w.z, xc, acc[2][2]); acc[2][3] = fmaf(w.z, xd, acc[2][3]);
-                acc[3][0] = fmaf(w.w, xa, acc[3][0]); acc[3][1] = fmaf(w.w, xb, acc[3][1]);
-                acc[3][2] = fmaf(w.w, xc, acc[3][2]); acc[3][3] = fmaf(w.w, xd, acc[3][3]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) sm.red[(ks * 12 + 4 * cg + a) * 16 + 4 * tg + b] = acc[a][b];
-        }
-        __syncthreads();
-        if (tid < 192) {
-            float total = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 20; ++ks) total += sm.red[ks * 192 + tid];
-            sm.raw[tid] = total;  // [c][t]
-        }
-        __syncthreads();
-        // util.normalize(norm=inf, axis=-2): divide each column by its maximum (float64 quotient)
-        if (tid < 16) {
-            float length = 0.f;
-#pragma unroll
-            for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.raw[c * 16 + tid]));
-            const double len = (length < FLT_MIN) ? 1.0 : static_cast<double>(length);
-#pragma unroll
-            for (int c = 0; c < 12; ++c)
-                sm.raw[c * 16 + tid] = static_cast<float>(static_cast<double>(sm.raw[c * 16 + tid]) / len);
-        }
-        __syncthreads();
-        if (tid < 12) {
-            float total = 0.f;
-            for (int t = 0; t < n_valid; ++t) total += sm.raw[tid * 16 + t];
-            p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
-        }
-        __syncthreads();   // red is reused below
+    if (tid == 0) {
+        // generic-proxy zero fill above must be ordered before the async-proxy bulk writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        proj_issue_tile(sm, p, tile_lo, 0);
     }
 
-    // ---- mel power + log-mel: thread = (column, band group), bands bg, bg+16, ... (balanced) ----
-    if (p.do_mel) {
-        const int col = tid & 15, bg = tid >> 4;
-        const float* x = &sm.s[col][0];
-        float* melp = sm.red;   // [16][128]
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const int m = bg + 16 * j;
-            const int start = sm.mstart[m], count = sm.mcount[m];
-            const float* w = sm.melw + sm.moffset[m];
-            float acc = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < count; ++i) {
-                const float v = x[start + i];
-                acc = fmaf(w[i], v * v, acc);   // power = |X| * |X| in float32 (np.abs(D) ** 2.0)
-            }
-            melp[col * 128 + m] = acc;
-            // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
-            sm.lm[col][m] = 10.0f * log10f(fmaxf(1e-10f, acc));
-        }
-        __syncthreads();
-        // coalesced write-out of the valid columns' log-mel rows, tile maximum, tile mel sums
-        float lmax = -FLT_MAX;
-        for (int i = tid; i < n_valid * 128; i += kProjThreads) {
-            const float v = sm.lm[i >> 7][i & 127];
-            p.logmel[col0 * 128 + i] = v;
-            lmax = fmaxf(lmax, v);
-        }
-        lmax = warp_max(lmax);
-        if ((tid & 31) == 0) sm.wmax[tid >> 5] = lmax;
-        if (tid < 128) {
-            float total = 0.f;
-            for (int t = 0; t < n_valid; ++t) total += melp[t * 128 + tid];
-            p.tile_mel[static_cast<long long>(tile) * 128 + tid] = total;
-        }
-        __syncthreads();
+    int bank_loaded = -1;     // tuning index whose bank sits in sm.w (uniform across the CTA)
+    int bank_phase = 0;
+    for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
+        const int stage = it & 1;
+        const int ci = p.tile_clip[tile];
+        const ClipDev clip = p.clips[ci];
+        const int t0 = (tile - clip.tile_base) * kColsPerTile;
+        const int n_valid = min(kColsPerTile, clip.n_cols - t0);
+        const long long col0 = static_cast<long long>(clip.col_base) + t0;
+        const int want_bank = p.do_chroma ? p.tuning_idx[ci] : -1;
+        const bool new_bank = want_bank != bank_loaded;
+
         if (tid == 0) {
-            float v = sm.wmax[0];
-            for (int i = 1; i < kProjThreads / 32; ++i) v = fmaxf(v, sm.wmax[i]);
-            p.tile_lmax[tile] = v;
+            // the other ring stage and sm.w were released by the barrier that ended the previous tile
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tile + 1 < tile_hi) proj_issue_tile(sm, p, tile + 1, stage ^ 1);
+            if (new_bank) {
+                constexpr uint32_t bank_bytes = kNBins * 12 * sizeof(float);
+                const uint32_t bb = proj_smem_u32(&sm.bar_bank);
+                const float* src = p.chroma_banks + static_cast<size_t>(want_bank) * (kNBins * 12);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(bank_bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                    ::"r"(proj_smem_u32(&sm.w[0])), "l"(src), "r"(bank_bytes), "r"(bb) : "memory");
+            }
         }
+        proj_mbar_wait(proj_smem_u32(&sm.bar_tile[stage]), (it >> 1) & 1);
+
+        if (tid < kChromaThreads) {
+            // ================= chroma: raw[c][t] = sum_f W[c][f] |X|[f][t] =================
+            if (p.do_chroma) {
+                if (new_bank) proj_mbar_wait(proj_smem_u32(&sm.bar_bank), bank_phase & 1);
+                const int cg = tid % 3, tg = (tid / 3) & 3, ks = tid / 12;
+                float acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                const int f_lo = ks * kSliceBins, f_hi = min(kNBins, f_lo + kSliceBins);
+                const float* x0 = &sm.s[stage][4 * tg][0];
+                const float* ws = &sm.w[4 * cg];
+#pragma unroll 4
+                for (int f = f_lo; f < f_hi; ++f) {
+                    const float4 w = *reinterpret_cast<const float4*>(ws + f * 12);
+                    const float xa = x0[f], xb = x0[kRowPitch + f], xc = x0[2 * kRowPitch + f], xd = x0[3 * kRowPitch + f];
+                    acc[0][0] = fmaf(w.x, xa, acc[0][0]); acc[0][1] = fmaf(w.x, xb, acc[0][1]);
+                    acc[0][2] = fmaf(w.x, xc, acc[0][2]); acc[0][3] = fmaf(w.x, xd, acc[0][3]);
+                    acc[1][0] = fmaf(w.y, xa, acc[1][0]); acc[1][1] = fmaf(w.y, xb, acc[1][1]);
+                    acc[1][2] = fmaf(w.y, xc, acc[1][2]); acc[1][3] = fmaf(w.y, xd, acc[1][3]);
+                    acc[2][0] = fmaf(w.z, xa, acc[2][0]); acc[2][1] = fmaf(w.z, xb, acc[2][1]);
+                    acc[2][2] = fmaf(w.z, xc, acc[2][2]); acc[2][3] = fmaf(w.z, xd, acc[2][3]);
+                    acc[3][0] = fmaf(w.w, xa, acc[3][0]); acc[3][1] = fmaf(w.w, xb, acc[3][1]);
+                    acc[3][2] = fmaf(w.w, xc, acc[3][2]); acc[3][3] = fmaf(w.w, xd, acc[3][3]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) sm.red[(ks * 12 + 4 * cg + a) * 16 + 4 * tg + b] = acc[a][b];
+                named_barrier(1, kChromaThreads);
+                if (tid < 192) {
+                    float total = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kChromaSlices; ++k) total += sm.red[k * 192 + tid];
+                    sm.raw[tid] = total;  // [c][t]
+                }
+                named_barrier(1, kChromaThreads);
+                // util.normalize(norm=inf, axis=-2): divide each column by its maximum (float64 quotient)
+                if (tid < 16) {
+                    float length = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.raw[c * 16 + tid]));
+                    const double len = (length < FLT_MIN) ? 1.0 : static_cast<double>(length);
+#pragma unroll
+                    for (int c = 0; c < 12; ++c)
+                        sm.raw[c * 16 + tid] = static_cast<float>(static_cast<double>(sm.raw[c * 16 + tid]) / len);
+                }
+                named_barrier(1, kChromaThreads);
+                if (tid < 12) {
+                    float total = 0.f;
+                    for (int t = 0; t < n_valid; ++t) total += sm.raw[tid * 16 + t];
+                    p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
+                }
+            }
+        } else if (p.do_mel) {
+            // ================= mel power + log-mel =================
+            const int mt = tid - kChromaThreads;
+            const int col = mt & 15, bg = mt >> 4;
+            const float* x = &sm.s[stage][col][0];
+            for (int m = bg; m < 128; m += kMelGroups) {
+                const int count = sm.mcount[m];
+                const float* w = sm.melw + sm.moffset[m];
+                const float* xs = x + sm.mstart[m];
+                float acc = 0.f;
+                int i = 0;
+                for (; i + 4 <= count; i += 4) {
+                    const float v0 = xs[i], v1 = xs[i + 1], v2 = xs[i + 2], v3 = xs[i + 3];
+                    // power = |X| * |X| in float32 (np.abs(D) ** 2.0), summed in bin order
+                    acc = fmaf(w[i], v0 * v0, acc);
+                    acc = fmaf(w[i + 1], v1 * v1, acc);
+                    acc = fmaf(w[i + 2], v2 * v2, acc);
+                    acc = fmaf(w[i + 3], v3 * v3, acc);
+                }
+                for (; i < count; ++i) { const float v = xs[i]; acc = fmaf(w[i], v * v, acc); }
+                sm.melp[col][m] = acc;
+                // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
+                sm.lm[col][m] = 10.0f * log10f(fmaxf(1e-10f, acc));
+            }
+            named_barrier(2, kMelThreads);
+            // coalesced write-out of the existing columns' log-mel rows, tile maximum, tile mel sums
+            float lmax = -FLT_MAX;
+            for (int i = mt; i < n_valid * 128; i += kMelThreads) {
+                const float v = sm.lm[i >> 7][i & 127];
+                p.logmel[col0 * 128 + i] = v;
+                lmax = fmaxf(lmax, v);
+            }
+            lmax = warp_max(lmax);
+            if ((mt & 31) == 0) sm.wmax[mt >> 5] = lmax;
+            if (mt < 128) {
+                float total = 0.f;
+                for (int t = 0; t < n_valid; ++t) total += sm.melp[t][mt];
+                p.tile_mel[static_cast<long long>(tile) * 128 + mt] = total;
+            }
+            named_barrier(2, kMelThreads);
+            if (mt == 0) {
+                float v = sm.wmax[0];
+                for (int i = 1; i < kMelThreads / 32; ++i) v = fmaxf(v, sm.wmax[i]);
+                p.tile_lmax[tile] = v;
+            }
+        }
+        if (new_bank) { bank_loaded = want_bank; bank_phase += 1; }
+        __syncthreads();   // both groups are done with this ring stage (and with sm.w)
     }
 }
 
+static int g_proj_grid = 0;
+
 cudaError_t configure_proj() {
-    return cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(sizeof(ProjSmem)));
+    cudaError_t e = cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(ProjSmem)));
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    g_proj_grid = sms;
+    return cudaSuccess;
 }
 
 cudaError_t launch_proj(const ProjParams& p, int n_tiles, cudaStream_t stream) {
     if (n_tiles <= 0) return cudaSuccess;
-    proj_kernel<<<n_tiles, kProjThreads, sizeof(ProjSmem), stream>>>(p, n_tiles);
+    const int grid = (n_tiles < g_proj_grid || g_proj_grid <= 0) ? n_tiles : g_proj_grid;
+    proj_kernel<<<grid, kProjThreads, sizeof(ProjSmem), stream>>>(p, n_tiles);
     return cudaGetLastError();
 }
 
