@@ -171,36 +171,37 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 // K3: mel (sparse Slaney triangles) and chroma (dense 12 x 1025, bank picked by the clip's
 // tuning) projections as shared-memory fp32 contractions.
 //
-// Persistent, warp-specialised kernel: one CTA of 16 warps per SM walks a contiguous range of
-// 16-column tiles.  Thread 0 keeps a two-stage ring of |X| tiles full with TMA bulk copies
-// (one per column row, cp.async.bulk -> UBLKCP, mbarrier completion) and reloads the clip's
-// chroma bank into shared memory when the clip changes.  Warps 0-8 do the chroma product
-// (split-K over 24 bin slices, 4 chroma x 4 columns register tile, deterministic slice
-// reduction, per-column L-inf normalisation); warps 9-15 do mel at the same time (thread =
-// (column, band group), bands dealt round-robin so all threads sum equally many non-zeros),
-// power_to_db, and the coalesced log-mel write-out.  The two groups meet only at the
-// end-of-tile barrier.
+// Persistent, warp-specialised kernel: one CTA of 12 warps per SM walks a contiguous range of
+// 16-column tiles.  Thread 0 stages each tile's |X| rows with TMA bulk copies (one per column,
+// cp.async.bulk -> UBLKCP, mbarrier completion) and reloads the clip's chroma bank into shared
+// memory when the tuning changes.  All warps transpose the staged rows to [bin][column]
+// (pitch 20 floats, so 16-byte loads over 4 columns are bank-conflict free); the copy of the
+// NEXT tile is issued right after the transpose and lands while the products run.  Warps 0-7
+// then do the chroma product (split-K over 20 bin slices, 4 chroma x 4 columns register tile,
+// deterministic slice reduction, per-column L-inf normalisation) while warps 8-11 do mel
+// (thread = (4 bands, 4 columns), bands paired short-with-long so all lanes sum about the same
+// number of non-zeros), power_to_db and the log-mel write-out.
 // =========================================================================================
-constexpr int kProjWarps = 16;
+constexpr int kProjWarps = 12;
 constexpr int kProjThreads = kProjWarps * 32;
-constexpr int kChromaThreads = 288;                 // warps 0..8: 24 bin slices x 3 chroma groups x 4 column groups
-constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 9..15: 16 columns x 14 band groups
-constexpr int kChromaSlices = 24;
-constexpr int kSliceBins = 43;                      // 24 * 43 = 1032 >= 1025
-constexpr int kMelGroups = kMelThreads / 16;        // 14
-constexpr int kRowPitch = 1028;   // floats per staged column row: 16-byte multiple, = 4 (mod 32 banks)
+constexpr int kChromaThreads = 256;                 // warps 0..7 (240 active): 20 bin slices x 3 chroma groups x 4 column groups
+constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 8..11: 32 band sets x 4 column groups
+constexpr int kChromaSlices = 20;
+constexpr int kSliceBins = 52;                      // 20 * 52 = 1040 >= 1025
+constexpr int kRowPitch = 1028;   // floats per staged column row (16-byte multiple)
+constexpr int kTPitch = 20;       // floats per transposed bin row: 16 columns + 4 pad
 
 struct ProjSmem {
-    float s[2][kColsPerTile][kRowPitch];   // two-stage ring of |X| tiles, 131584 B
+    float raw[kColsPerTile][kRowPitch];    // TMA landing zone: |X| rows of one tile, 65792 B
+    float t[kNBins * kTPitch];             // the same tile as [bin][column], 82000 B
     float w[kNBins * 12];                  // chroma bank of the current clip, [bin][12], 49200 B
-    float red[kChromaSlices * 192];        // chroma split-K partials
-    float melp[kColsPerTile][128];         // mel power of the tile
-    float lm[kColsPerTile][128];           // log-mel staging for coalesced stores
-    float raw[192];
+    float red[kChromaSlices * 192];        // chroma split-K partials, 15360 B
+    float chr[192];
     float melw[2304];                      // sparse mel weights (<= 2304 non-zeros)
     int mstart[128], mcount[128], moffset[129];
-    float wmax[8];
-    unsigned long long bar_tile[2], bar_bank;
+    float melsum[4][128];                  // per column-group partial sums of mel power
+    float wmax[4];
+    unsigned long long bar_tile, bar_bank;
 };
 
 __device__ __forceinline__ uint32_t proj_smem_u32(const void* p) {
@@ -220,20 +221,21 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// thread 0: start the bulk copies of one tile's existing column rows into ring stage `stage`
-__device__ __forceinline__ void proj_issue_tile(ProjSmem& sm, const ProjParams& p, int tile, int stage) {
+// thread 0: start the bulk copies of one tile's existing column rows
+__device__ __forceinline__ void proj_issue_tile(ProjSmem& sm, const ProjParams& p, int tile) {
     const ClipDev clip = p.clips[p.tile_clip[tile]];
     const int t0 = (tile - clip.tile_base) * kColsPerTile;
     const int n_valid = min(kColsPerTile, clip.n_cols - t0);
     const long long col0 = static_cast<long long>(clip.col_base) + t0;
-    const uint32_t bar = proj_smem_u32(&sm.bar_tile[stage]);
+    const uint32_t bar = proj_smem_u32(&sm.bar_tile);
     constexpr uint32_t row_bytes = kRowPitch * sizeof(float);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * n_valid) : "memory");
     for (int j = 0; j < n_valid; ++j) {
         const float* src = p.spill + (col0 + j) * kSpillStride;
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            ::"r"(proj_smem_u32(&sm.s[stage][j][0])), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+            ::"r"(proj_smem_u32(&sm.raw[j][0])), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
     }
 }
 
@@ -247,8 +249,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
     if (tile_lo >= tile_hi) return;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_tile[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_tile[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_tile)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(proj_smem_u32(&sm.bar_bank)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -257,19 +258,12 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         for (int i = tid; i < 128; i += kProjThreads) { sm.mstart[i] = p.mel_start[i]; sm.mcount[i] = p.mel_count[i]; }
         for (int i = tid; i < 129; i += kProjThreads) sm.moffset[i] = p.mel_offset[i];
     }
-    // rows of columns that do not exist are never copied: keep them finite
-    for (int i = tid; i < 2 * kColsPerTile * kRowPitch; i += kProjThreads) (&sm.s[0][0][0])[i] = 0.0f;
     __syncthreads();
-    if (tid == 0) {
-        // generic-proxy zero fill above must be ordered before the async-proxy bulk writes
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        proj_issue_tile(sm, p, tile_lo, 0);
-    }
+    if (tid == 0) proj_issue_tile(sm, p, tile_lo);
 
     int bank_loaded = -1;     // tuning index whose bank sits in sm.w (uniform across the CTA)
     int bank_phase = 0;
     for (int tile = tile_lo, it = 0; tile < tile_hi; ++tile, ++it) {
-        const int stage = it & 1;
         const int ci = p.tile_clip[tile];
         const ClipDev clip = p.clips[ci];
         const int t0 = (tile - clip.tile_base) * kColsPerTile;
@@ -278,125 +272,139 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         const int want_bank = p.do_chroma ? p.tuning_idx[ci] : -1;
         const bool new_bank = want_bank != bank_loaded;
 
-        if (tid == 0) {
-            // the other ring stage and sm.w were released by the barrier that ended the previous tile
+        if (tid == 0 && new_bank) {
+            // sm.w was released by the barrier that ended the previous tile
+            constexpr uint32_t bank_bytes = kNBins * 12 * sizeof(float);
+            const uint32_t bb = proj_smem_u32(&sm.bar_bank);
+            const float* src = p.chroma_banks + static_cast<size_t>(want_bank) * (kNBins * 12);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (tile + 1 < tile_hi) proj_issue_tile(sm, p, tile + 1, stage ^ 1);
-            if (new_bank) {
-                constexpr uint32_t bank_bytes = kNBins * 12 * sizeof(float);
-                const uint32_t bb = proj_smem_u32(&sm.bar_bank);
-                const float* src = p.chroma_banks + static_cast<size_t>(want_bank) * (kNBins * 12);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(bank_bytes) : "memory");
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                    ::"r"(proj_smem_u32(&sm.w[0])), "l"(src), "r"(bank_bytes), "r"(bb) : "memory");
-            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(bank_bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(proj_smem_u32(&sm.w[0])), "l"(src), "r"(bank_bytes), "r"(bb) : "memory");
         }
-        proj_mbar_wait(proj_smem_u32(&sm.bar_tile[stage]), (it >> 1) & 1);
+        proj_mbar_wait(proj_smem_u32(&sm.bar_tile), it & 1);
+
+        // ---- transpose raw[column][bin] -> t[bin][column]: conflict-free loads and 16-byte stores ----
+        for (int i = tid; i < kNBins * 4; i += kProjThreads) {
+            const int q = i / kNBins, f = i - q * kNBins;   // column quad, bin
+            float4 v;
+            v.x = (4 * q + 0 < n_valid) ? sm.raw[4 * q + 0][f] : 0.0f;
+            v.y = (4 * q + 1 < n_valid) ? sm.raw[4 * q + 1][f] : 0.0f;
+            v.z = (4 * q + 2 < n_valid) ? sm.raw[4 * q + 2][f] : 0.0f;
+            v.w = (4 * q + 3 < n_valid) ? sm.raw[4 * q + 3][f] : 0.0f;
+            *reinterpret_cast<float4*>(&sm.t[f * kTPitch + 4 * q]) = v;
+        }
+        __syncthreads();
+        if (tid == 0 && tile + 1 < tile_hi) proj_issue_tile(sm, p, tile + 1);   // lands during the products
 
         if (tid < kChromaThreads) {
             // ================= chroma: raw[c][t] = sum_f W[c][f] |X|[f][t] =================
             if (p.do_chroma) {
                 if (new_bank) proj_mbar_wait(proj_smem_u32(&sm.bar_bank), bank_phase & 1);
-                const int cg = tid % 3, tg = (tid / 3) & 3, ks = tid / 12;
-                float acc[4][4];
+                if (tid < 240) {
+                    const int cg = tid % 3, tg = (tid / 3) & 3, ks = tid / 12;
+                    float acc[4][4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-                const int f_lo = ks * kSliceBins, f_hi = min(kNBins, f_lo + kSliceBins);
-                const float* x0 = &sm.s[stage][4 * tg][0];
-                const float* ws = &sm.w[4 * cg];
+                        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                    const int f_lo = ks * kSliceBins, f_hi = min(kNBins, f_lo + kSliceBins);
+                    const float* xs = &sm.t[4 * tg];
+                    const float* ws = &sm.w[4 * cg];
 #pragma unroll 4
-                for (int f = f_lo; f < f_hi; ++f) {
-                    const float4 w = *reinterpret_cast<const float4*>(ws + f * 12);
-                    const float xa = x0[f], xb = x0[kRowPitch + f], xc = x0[2 * kRowPitch + f], xd = x0[3 * kRowPitch + f];
-                    acc[0][0] = fmaf(w.x, xa, acc[0][0]); acc[0][1] = fmaf(w.x, xb, acc[0][1]);
-                    acc[0][2] = fmaf(w.x, xc, acc[0][2]); acc[0][3] = fmaf(w.x, xd, acc[0][3]);
-                    acc[1][0] = fmaf(w.y, xa, acc[1][0]); acc[1][1] = fmaf(w.y, xb, acc[1][1]);
-                    acc[1][2] = fmaf(w.y, xc, acc[1][2]); acc[1][3] = fmaf(w.y, xd, acc[1][3]);
-                    acc[2][0] = fmaf(w.z, xa, acc[2][0]); acc[2][1] = fmaf(w.z, xb, acc[2][1]);
-                    acc[2][2] = fmaf(w.z, xc, acc[2][2]); acc[2][3] = fmaf(w.z, xd, acc[2][3]);
-                    acc[3][0] = fmaf(w.w, xa, acc[3][0]); acc[3][1] = fmaf(w.w, xb, acc[3][1]);
-                    acc[3][2] = fmaf(w.w, xc, acc[3][2]); acc[3][3] = fmaf(w.w, xd, acc[3][3]);
+                    for (int f = f_lo; f < f_hi; ++f) {
+                        const float4 w = *reinterpret_cast<const float4*>(ws + f * 12);
+                        const float4 x = *reinterpret_cast<const float4*>(xs + f * kTPitch);
+                        acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
+                        acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
+                        acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
+                        acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
+                        acc[2][0] = fmaf(w.z, x.x, acc[2][0]); acc[2][1] = fmaf(w.z, x.y, acc[2][1]);
+                        acc[2][2] = fmaf(w.z, x.z, acc[2][2]); acc[2][3] = fmaf(w.z, x.w, acc[2][3]);
+                        acc[3][0] = fmaf(w.w, x.x, acc[3][0]); acc[3][1] = fmaf(w.w, x.y, acc[3][1]);
+                        acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) sm.red[(ks * 12 + 4 * cg + a) * 16 + 4 * tg + b] = acc[a][b];
                 }
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) sm.red[(ks * 12 + 4 * cg + a) * 16 + 4 * tg + b] = acc[a][b];
                 named_barrier(1, kChromaThreads);
                 if (tid < 192) {
                     float total = 0.f;
 #pragma unroll
                     for (int k = 0; k < kChromaSlices; ++k) total += sm.red[k * 192 + tid];
-                    sm.raw[tid] = total;  // [c][t]
+                    sm.chr[tid] = total;  // [c][t]
                 }
                 named_barrier(1, kChromaThreads);
                 // util.normalize(norm=inf, axis=-2): divide each column by its maximum (float64 quotient)
                 if (tid < 16) {
                     float length = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.raw[c * 16 + tid]));
+                    for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.chr[c * 16 + tid]));
                     const double len = (length < FLT_MIN) ? 1.0 : static_cast<double>(length);
 #pragma unroll
                     for (int c = 0; c < 12; ++c)
-                        sm.raw[c * 16 + tid] = static_cast<float>(static_cast<double>(sm.raw[c * 16 + tid]) / len);
+                        sm.chr[c * 16 + tid] = static_cast<float>(static_cast<double>(sm.chr[c * 16 + tid]) / len);
                 }
                 named_barrier(1, kChromaThreads);
                 if (tid < 12) {
                     float total = 0.f;
-                    for (int t = 0; t < n_valid; ++t) total += sm.raw[tid * 16 + t];
+                    for (int t = 0; t < n_valid; ++t) total += sm.chr[tid * 16 + t];
                     p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
                 }
             }
         } else if (p.do_mel) {
             // ================= mel power + log-mel =================
             const int mt = tid - kChromaThreads;
-            const int col = mt & 15, bg = mt >> 4;
-            const float* x = &sm.s[stage][col][0];
-            for (int m = bg; m < 128; m += kMelGroups) {
+            const int bs = mt & 31, qg = mt >> 5;      // band set, column quad (one warp per quad)
+            float lmax = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // short bands paired with long ones: {bs, 63 - bs, 64 + bs, 127 - bs}
+                const int m = (j == 0) ? bs : (j == 1) ? 63 - bs : (j == 2) ? 64 + bs : 127 - bs;
                 const int count = sm.mcount[m];
                 const float* w = sm.melw + sm.moffset[m];
-                const float* xs = x + sm.mstart[m];
-                float acc = 0.f;
-                int i = 0;
-                for (; i + 4 <= count; i += 4) {
-                    const float v0 = xs[i], v1 = xs[i + 1], v2 = xs[i + 2], v3 = xs[i + 3];
+                const float* xs = &sm.t[sm.mstart[m] * kTPitch + 4 * qg];
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+                for (int i = 0; i < count; ++i) {
+                    const float wi = w[i];
+                    const float4 x = *reinterpret_cast<const float4*>(xs + i * kTPitch);
                     // power = |X| * |X| in float32 (np.abs(D) ** 2.0), summed in bin order
-                    acc = fmaf(w[i], v0 * v0, acc);
-                    acc = fmaf(w[i + 1], v1 * v1, acc);
-                    acc = fmaf(w[i + 2], v2 * v2, acc);
-                    acc = fmaf(w[i + 3], v3 * v3, acc);
+                    a0 = fmaf(wi, x.x * x.x, a0); a1 = fmaf(wi, x.y * x.y, a1);
+                    a2 = fmaf(wi, x.z * x.z, a2); a3 = fmaf(wi, x.w * x.w, a3);
                 }
-                for (; i < count; ++i) { const float v = xs[i]; acc = fmaf(w[i], v * v, acc); }
-                sm.melp[col][m] = acc;
-                // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
-                sm.lm[col][m] = 10.0f * log10f(fmaxf(1e-10f, acc));
-            }
-            named_barrier(2, kMelThreads);
-            // coalesced write-out of the existing columns' log-mel rows, tile maximum, tile mel sums
-            float lmax = -FLT_MAX;
-            for (int i = mt; i < n_valid * 128; i += kMelThreads) {
-                const float v = sm.lm[i >> 7][i & 127];
-                p.logmel[col0 * 128 + i] = v;
-                lmax = fmaxf(lmax, v);
+                const float acc[4] = {a0, a1, a2, a3};
+                float s4 = 0.f;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int col = 4 * qg + b;
+                    if (col < n_valid) {
+                        s4 += acc[b];
+                        // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
+                        const float lmv = 10.0f * log10f(fmaxf(1e-10f, acc[b]));
+                        p.logmel[(col0 + col) * 128 + m] = lmv;
+                        lmax = fmaxf(lmax, lmv);
+                    }
+                }
+                sm.melsum[qg][m] = s4;
             }
             lmax = warp_max(lmax);
-            if ((mt & 31) == 0) sm.wmax[mt >> 5] = lmax;
-            if (mt < 128) {
-                float total = 0.f;
-                for (int t = 0; t < n_valid; ++t) total += sm.melp[t][mt];
-                p.tile_mel[static_cast<long long>(tile) * 128 + mt] = total;
-            }
+            if (bs == 0) sm.wmax[qg] = lmax;
             named_barrier(2, kMelThreads);
-            if (mt == 0) {
-                float v = sm.wmax[0];
-                for (int i = 1; i < kMelThreads / 32; ++i) v = fmaxf(v, sm.wmax[i]);
-                p.tile_lmax[tile] = v;
+            {
+                // tile sums in column order: ((q0 + q1) + q2) + q3
+                const int m = mt;
+                p.tile_mel[static_cast<long long>(tile) * 128 + m] =
+                    ((sm.melsum[0][m] + sm.melsum[1][m]) + sm.melsum[2][m]) + sm.melsum[3][m];
+                if (mt == 0)
+                    p.tile_lmax[tile] = fmaxf(fmaxf(sm.wmax[0], sm.wmax[1]), fmaxf(sm.wmax[2], sm.wmax[3]));
             }
         }
         if (new_bank) { bank_loaded = want_bank; bank_phase += 1; }
-        __syncthreads();   // both groups are done with this ring stage (and with sm.w)
+        __syncthreads();   // both groups are done with sm.t (and sm.w)
     }
 }
 
