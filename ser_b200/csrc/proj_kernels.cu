@@ -171,21 +171,21 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 // K3: mel (sparse Slaney triangles) and chroma (dense 12 x 1025, bank picked by the clip's
 // tuning) projections as shared-memory fp32 contractions.
 //
-// Persistent, warp-specialised kernel: one CTA of 12 warps per SM walks a contiguous range of
+// Persistent, warp-specialised kernel: one CTA of 16 warps per SM walks a contiguous range of
 // 16-column tiles.  Thread 0 stages each tile's |X| rows with TMA bulk copies (one per column,
 // cp.async.bulk -> UBLKCP, mbarrier completion) and reloads the clip's chroma bank into shared
 // memory when the tuning changes.  All warps transpose the staged rows to [bin][column]
 // (pitch 20 floats, so 16-byte loads over 4 columns are bank-conflict free); the copy of the
 // NEXT tile is issued right after the transpose and lands while the products run.  Warps 0-7
 // then do the chroma product (split-K over 20 bin slices, 4 chroma x 4 columns register tile,
-// deterministic slice reduction, per-column L-inf normalisation) while warps 8-11 do mel
-// (thread = (4 bands, 4 columns), bands paired short-with-long so all lanes sum about the same
+// deterministic slice reduction, per-column L-inf normalisation) while warps 8-15 do mel
+// (thread = (4 bands, 2 columns), bands paired short-with-long so all lanes sum about the same
 // number of non-zeros), power_to_db and the log-mel write-out.
 // =========================================================================================
-constexpr int kProjWarps = 12;
+constexpr int kProjWarps = 16;
 constexpr int kProjThreads = kProjWarps * 32;
 constexpr int kChromaThreads = 256;                 // warps 0..7 (240 active): 20 bin slices x 3 chroma groups x 4 column groups
-constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 8..11: 32 band sets x 4 column groups
+constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 8..15: 32 band sets x 8 column pairs
 constexpr int kChromaSlices = 20;
 constexpr int kSliceBins = 52;                      // 20 * 52 = 1040 >= 1025
 constexpr int kRowPitch = 1028;   // floats per staged column row (16-byte multiple)
@@ -199,8 +199,8 @@ struct ProjSmem {
     float chr[192];
     float melw[2304];                      // sparse mel weights (<= 2304 non-zeros)
     int mstart[128], mcount[128], moffset[129];
-    float melsum[4][128];                  // per column-group partial sums of mel power
-    float wmax[4];
+    float melsum[8][128];                  // per column-pair partial sums of mel power
+    float wmax[8];
     unsigned long long bar_tile, bar_bank;
 };
 
@@ -286,14 +286,19 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         proj_mbar_wait(proj_smem_u32(&sm.bar_tile), it & 1);
 
         // ---- transpose raw[column][bin] -> t[bin][column]: conflict-free loads and 16-byte stores ----
-        for (int i = tid; i < kNBins * 4; i += kProjThreads) {
-            const int q = i / kNBins, f = i - q * kNBins;   // column quad, bin
-            float4 v;
-            v.x = (4 * q + 0 < n_valid) ? sm.raw[4 * q + 0][f] : 0.0f;
-            v.y = (4 * q + 1 < n_valid) ? sm.raw[4 * q + 1][f] : 0.0f;
-            v.z = (4 * q + 2 < n_valid) ? sm.raw[4 * q + 2][f] : 0.0f;
-            v.w = (4 * q + 3 < n_valid) ? sm.raw[4 * q + 3][f] : 0.0f;
-            *reinterpret_cast<float4*>(&sm.t[f * kTPitch + 4 * q]) = v;
+        {
+            // thread = (bin lane, column quad); 4 quads x 128 bin lanes
+            const int q = tid >> 7;
+            const float* r0 = &sm.raw[4 * q][0];
+            const bool v0 = 4 * q + 0 < n_valid, v1 = 4 * q + 1 < n_valid, v2 = 4 * q + 2 < n_valid, v3 = 4 * q + 3 < n_valid;
+            for (int f = tid & 127; f < kNBins; f += 128) {
+                float4 v;
+                v.x = v0 ? r0[f] : 0.0f;
+                v.y = v1 ? r0[kRowPitch + f] : 0.0f;
+                v.z = v2 ? r0[2 * kRowPitch + f] : 0.0f;
+                v.w = v3 ? r0[3 * kRowPitch + f] : 0.0f;
+                *reinterpret_cast<float4*>(&sm.t[f * kTPitch + 4 * q]) = v;
+            }
         }
         __syncthreads();
         if (tid == 0 && tile + 1 < tile_hi) proj_issue_tile(sm, p, tile + 1);   // lands during the products
@@ -358,49 +363,55 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         } else if (p.do_mel) {
             // ================= mel power + log-mel =================
             const int mt = tid - kChromaThreads;
-            const int bs = mt & 31, qg = mt >> 5;      // band set, column quad (one warp per quad)
+            const int bs = mt & 31, pg = mt >> 5;      // band set, column pair (one warp per pair)
+            const int c0 = 2 * pg, c1 = 2 * pg + 1;
             float lmax = -FLT_MAX;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 // short bands paired with long ones: {bs, 63 - bs, 64 + bs, 127 - bs}
                 const int m = (j == 0) ? bs : (j == 1) ? 63 - bs : (j == 2) ? 64 + bs : 127 - bs;
-                const int count = sm.mcount[m];
                 const float* w = sm.melw + sm.moffset[m];
-                const float* xs = &sm.t[sm.mstart[m] * kTPitch + 4 * qg];
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < count; ++i) {
-                    const float wi = w[i];
-                    const float4 x = *reinterpret_cast<const float4*>(xs + i * kTPitch);
+                const float* w_end = w + sm.mcount[m];
+                const float* xs = &sm.t[sm.mstart[m] * kTPitch + c0];
+                float a0 = 0.f, a1 = 0.f;
+                for (; w < w_end; ++w, xs += kTPitch) {
+                    const float wi = *w;
+                    const float2 x = *reinterpret_cast<const float2*>(xs);
                     // power = |X| * |X| in float32 (np.abs(D) ** 2.0), summed in bin order
-                    a0 = fmaf(wi, x.x * x.x, a0); a1 = fmaf(wi, x.y * x.y, a1);
-                    a2 = fmaf(wi, x.z * x.z, a2); a3 = fmaf(wi, x.w * x.w, a3);
+                    a0 = fmaf(wi, x.x * x.x, a0);
+                    a1 = fmaf(wi, x.y * x.y, a1);
                 }
-                const float acc[4] = {a0, a1, a2, a3};
-                float s4 = 0.f;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int col = 4 * qg + b;
-                    if (col < n_valid) {
-                        s4 += acc[b];
-                        // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)) in float32
-                        const float lmv = 10.0f * log10f(fmaxf(1e-10f, acc[b]));
-                        p.logmel[(col0 + col) * 128 + m] = lmv;
-                        lmax = fmaxf(lmax, lmv);
-                    }
+                float s2 = 0.f;
+                // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)); log10 via the MUFU log2
+                // (absolute error < 1e-6 dB, far below float32 resolution at these magnitudes)
+                if (c0 < n_valid) {
+                    s2 += a0;
+                    const float lmv = 3.01029995663981195f * __log2f(fmaxf(1e-10f, a0));
+                    p.logmel[(col0 + c0) * 128 + m] = lmv;
+                    lmax = fmaxf(lmax, lmv);
                 }
-                sm.melsum[qg][m] = s4;
+                if (c1 < n_valid) {
+                    s2 += a1;
+                    const float lmv = 3.01029995663981195f * __log2f(fmaxf(1e-10f, a1));
+                    p.logmel[(col0 + c1) * 128 + m] = lmv;
+                    lmax = fmaxf(lmax, lmv);
+                }
+                sm.melsum[pg][m] = s2;
             }
             lmax = warp_max(lmax);
-            if (bs == 0) sm.wmax[qg] = lmax;
+            if (bs == 0) sm.wmax[pg] = lmax;
             named_barrier(2, kMelThreads);
-            {
-                // tile sums in column order: ((q0 + q1) + q2) + q3
-                const int m = mt;
-                p.tile_mel[static_cast<long long>(tile) * 128 + m] =
-                    ((sm.melsum[0][m] + sm.melsum[1][m]) + sm.melsum[2][m]) + sm.melsum[3][m];
-                if (mt == 0)
-                    p.tile_lmax[tile] = fmaxf(fmaxf(sm.wmax[0], sm.wmax[1]), fmaxf(sm.wmax[2], sm.wmax[3]));
+            if (mt < 128) {
+                // tile sums in column order
+                float total = sm.melsum[0][mt];
+#pragma unroll
+                for (int g = 1; g < 8; ++g) total += sm.melsum[g][mt];
+                p.tile_mel[static_cast<long long>(tile) * 128 + mt] = total;
+            } else if (mt == 128) {
+                float v = sm.wmax[0];
+#pragma unroll
+                for (int g = 1; g < 8; ++g) v = fmaxf(v, sm.wmax[g]);
+                p.tile_lmax[tile] = v;
             }
         }
         if (new_bank) { bank_loaded = want_bank; bank_phase += 1; }
