@@ -336,28 +336,28 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
                         for (int b = 0; b < 4; ++b) sm.red[(ks * 12 + 4 * cg + a) * 16 + 4 * tg + b] = acc[a][b];
                 }
                 named_barrier(1, kChromaThreads);
+                float mine = 0.f;
                 if (tid < 192) {
-                    float total = 0.f;
 #pragma unroll
-                    for (int k = 0; k < kChromaSlices; ++k) total += sm.red[k * 192 + tid];
-                    sm.chr[tid] = total;  // [c][t]
+                    for (int k = 0; k < kChromaSlices; ++k) mine += sm.red[k * 192 + tid];
+                    sm.chr[tid] = mine;  // [c][t]
                 }
                 named_barrier(1, kChromaThreads);
-                // util.normalize(norm=inf, axis=-2): divide each column by its maximum (float64 quotient)
-                if (tid < 16) {
+                // util.normalize(norm=inf, axis=-2): divide each column by its maximum (float64 quotient);
+                // one division per thread, then the columns of the tile are summed in order
+                if (tid < 192) {
+                    const int t = tid & 15;
                     float length = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.chr[c * 16 + tid]));
+                    for (int c = 0; c < 12; ++c) length = fmaxf(length, fabsf(sm.chr[c * 16 + t]));
                     const double len = (length < FLT_MIN) ? 1.0 : static_cast<double>(length);
-#pragma unroll
-                    for (int c = 0; c < 12; ++c)
-                        sm.chr[c * 16 + tid] = static_cast<float>(static_cast<double>(sm.chr[c * 16 + tid]) / len);
-                }
-                named_barrier(1, kChromaThreads);
-                if (tid < 12) {
+                    float v = static_cast<float>(static_cast<double>(mine) / len);
+                    if (t >= n_valid) v = 0.0f;
+                    // sum over the 16 columns held by 16 consecutive lanes, in column order
                     float total = 0.f;
-                    for (int t = 0; t < n_valid; ++t) total += sm.chr[tid * 16 + t];
-                    p.tile_chroma[static_cast<long long>(tile) * 12 + tid] = total;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) total += __shfl_sync(0xffffffffu, v, (threadIdx.x & 16) + j);
+                    if (t == 0) p.tile_chroma[static_cast<long long>(tile) * 12 + (tid >> 4)] = total;
                 }
             }
         } else if (p.do_mel) {
