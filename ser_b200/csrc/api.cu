@@ -272,7 +272,7 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
     if (!chunks.empty()) {
         SERB_CUDA(ctx, ctx->spill.reserve(static_cast<size_t>(max_cols) * kSpillStride * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_clip.reserve(static_cast<size_t>(max_tiles) * sizeof(int)));
-        SERB_CUDA(ctx, ctx->logmel.reserve(static_cast<size_t>(max_cols) * 128 * sizeof(float)));
+        SERB_CUDA(ctx, ctx->logmel.reserve(static_cast<size_t>(max_tiles) * 128 * kColsPerTile * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_mel.reserve(static_cast<size_t>(max_tiles) * 128 * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_lmax.reserve(static_cast<size_t>(max_tiles) * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_chroma.reserve(static_cast<size_t>(max_tiles) * 12 * sizeof(float)));

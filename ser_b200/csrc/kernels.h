@@ -49,7 +49,7 @@ struct ProjParams {
     const int* mel_offset;     // [129]
     const float* mel_weights;  // nnz
     int mel_nnz;
-    float* logmel;             // [cols][128]
+    float* logmel;             // [tiles][128][16]
     float* tile_mel;           // [tiles][128]  sum of mel power over the tile's columns
     float* tile_lmax;          // [tiles]       max of logmel over the tile
     int do_chroma;
@@ -62,7 +62,7 @@ cudaError_t launch_proj(const ProjParams& p, int n_tiles, cudaStream_t stream);
 
 struct PoolParams {
     const ClipDev* clips;
-    const float* logmel;       // [cols][128]
+    const float* logmel;       // [tiles][128][16]
     const float* tile_mel;     // [tiles][128]
     const float* tile_lmax;    // [tiles]
     const float* tile_chroma;  // [tiles][12]

@@ -179,13 +179,14 @@ cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream)
 // NEXT tile is issued right after the transpose and lands while the products run.  Warps 0-7
 // then do the chroma product (split-K over 20 bin slices, 4 chroma x 4 columns register tile,
 // deterministic slice reduction, per-column L-inf normalisation) while warps 8-15 do mel
-// (thread = (4 bands, 2 columns), bands paired short-with-long so all lanes sum about the same
-// number of non-zeros), power_to_db and the log-mel write-out.
+// (thread = (column, 8 bands); the 16 lanes of a half warp read one 64-byte bin row, and bands
+// are dealt short-with-long so every thread sums about the same number of non-zeros),
+// power_to_db and the log-mel write-out ([tile][band][16 columns]).
 // =========================================================================================
 constexpr int kProjWarps = 16;
 constexpr int kProjThreads = kProjWarps * 32;
 constexpr int kChromaThreads = 256;                 // warps 0..7 (240 active): 20 bin slices x 3 chroma groups x 4 column groups
-constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 8..15: 32 band sets x 8 column pairs
+constexpr int kMelThreads = kProjThreads - kChromaThreads;   // warps 8..15: 16 columns x 16 band sets
 constexpr int kChromaSlices = 20;
 constexpr int kSliceBins = 52;                      // 20 * 52 = 1040 >= 1025
 constexpr int kRowPitch = 1028;   // floats per staged column row (16-byte multiple)
@@ -199,7 +200,6 @@ struct ProjSmem {
     float chr[192];
     float melw[2304];                      // sparse mel weights (<= 2304 non-zeros)
     int mstart[128], mcount[128], moffset[129];
-    float melsum[8][128];                  // per column-pair partial sums of mel power
     float wmax[8];
     unsigned long long bar_tile, bar_bank;
 };
@@ -363,51 +363,42 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         } else if (p.do_mel) {
             // ================= mel power + log-mel =================
             const int mt = tid - kChromaThreads;
-            const int bs = mt & 31, pg = mt >> 5;      // band set, column pair (one warp per pair)
-            const int c0 = 2 * pg, c1 = 2 * pg + 1;
+            const int col = mt & 15, bs = mt >> 4;      // column, band set (two band sets per warp)
+            const bool col_ok = col < n_valid;
+            float* lm_tile = p.logmel + static_cast<long long>(tile) * (128 * kColsPerTile);
             float lmax = -FLT_MAX;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // short bands paired with long ones: {bs, 63 - bs, 64 + bs, 127 - bs}
-                const int m = (j == 0) ? bs : (j == 1) ? 63 - bs : (j == 2) ? 64 + bs : 127 - bs;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                // bands dealt short-with-long: {bs, 31-bs, 32+bs, 63-bs, 64+bs, 95-bs, 96+bs, 127-bs}
+                const int m = (j & 1) ? (32 * (j >> 1) + 31 - bs) : (32 * (j >> 1) + bs);
                 const float* w = sm.melw + sm.moffset[m];
                 const float* w_end = w + sm.mcount[m];
-                const float* xs = &sm.t[sm.mstart[m] * kTPitch + c0];
-                float a0 = 0.f, a1 = 0.f;
-                for (; w < w_end; ++w, xs += kTPitch) {
-                    const float wi = *w;
-                    const float2 x = *reinterpret_cast<const float2*>(xs);
+                const float* xs = &sm.t[sm.mstart[m] * kTPitch + col];
+                float acc = 0.f;
+                for (; w + 2 <= w_end; w += 2, xs += 2 * kTPitch) {
+                    const float x0 = xs[0], x1 = xs[kTPitch];
                     // power = |X| * |X| in float32 (np.abs(D) ** 2.0), summed in bin order
-                    a0 = fmaf(wi, x.x * x.x, a0);
-                    a1 = fmaf(wi, x.y * x.y, a1);
+                    acc = fmaf(w[0], x0 * x0, acc);
+                    acc = fmaf(w[1], x1 * x1, acc);
                 }
-                float s2 = 0.f;
+                if (w < w_end) { const float x0 = xs[0]; acc = fmaf(w[0], x0 * x0, acc); }
                 // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)); log10 via the MUFU log2
                 // (absolute error < 1e-6 dB, far below float32 resolution at these magnitudes)
-                if (c0 < n_valid) {
-                    s2 += a0;
-                    const float lmv = 3.01029995663981195f * __log2f(fmaxf(1e-10f, a0));
-                    p.logmel[(col0 + c0) * 128 + m] = lmv;
-                    lmax = fmaxf(lmax, lmv);
-                }
-                if (c1 < n_valid) {
-                    s2 += a1;
-                    const float lmv = 3.01029995663981195f * __log2f(fmaxf(1e-10f, a1));
-                    p.logmel[(col0 + c1) * 128 + m] = lmv;
-                    lmax = fmaxf(lmax, lmv);
-                }
-                sm.melsum[pg][m] = s2;
+                const float lmv = 3.01029995663981195f * __log2f(fmaxf(1e-10f, acc));
+                lm_tile[m * kColsPerTile + col] = lmv;
+                if (col_ok) lmax = fmaxf(lmax, lmv);
+                // tile sum over the 16 columns (half warp), fixed tree order; missing columns hold 0
+                float tsum = acc;
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 8);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+                if (col == 0) p.tile_mel[static_cast<long long>(tile) * 128 + m] = tsum;
             }
             lmax = warp_max(lmax);
-            if (bs == 0) sm.wmax[pg] = lmax;
+            if ((mt & 31) == 0) sm.wmax[mt >> 5] = lmax;
             named_barrier(2, kMelThreads);
-            if (mt < 128) {
-                // tile sums in column order
-                float total = sm.melsum[0][mt];
-#pragma unroll
-                for (int g = 1; g < 8; ++g) total += sm.melsum[g][mt];
-                p.tile_mel[static_cast<long long>(tile) * 128 + mt] = total;
-            } else if (mt == 128) {
+            if (mt == 0) {
                 float v = sm.wmax[0];
 #pragma unroll
                 for (int g = 1; g < 8; ++g) v = fmaxf(v, sm.wmax[g]);
@@ -469,21 +460,20 @@ __global__ void __launch_bounds__(kPoolThreads) pool_kernel(PoolParams p) {
         }
         __syncthreads();
         const float thr = s_thr;
-        // each time slice sums its columns in a fixed order; slices are then added in order
+        // log-mel is stored [tile][band][16 columns]; each slice takes every 4th tile of the clip,
+        // sums its columns in order, and the slices are then added in order
         double acc = 0.0;
-        const float* src = p.logmel + static_cast<long long>(clip.col_base) * 128 + m;
-        int t = slice;
-        for (; t + 3 * kPoolSlices < clip.n_cols; t += 4 * kPoolSlices) {
-            const float a0 = src[static_cast<long long>(t) * 128];
-            const float a1 = src[static_cast<long long>(t + kPoolSlices) * 128];
-            const float a2 = src[static_cast<long long>(t + 2 * kPoolSlices) * 128];
-            const float a3 = src[static_cast<long long>(t + 3 * kPoolSlices) * 128];
-            acc += static_cast<double>(fmaxf(a0, thr));
-            acc += static_cast<double>(fmaxf(a1, thr));
-            acc += static_cast<double>(fmaxf(a2, thr));
-            acc += static_cast<double>(fmaxf(a3, thr));
+        const float* src = p.logmel + static_cast<long long>(clip.tile_base) * (128 * kColsPerTile) + m * kColsPerTile;
+        for (int tl = slice; tl < n_tiles; tl += kPoolSlices) {
+            const float4* row = reinterpret_cast<const float4*>(src + static_cast<long long>(tl) * (128 * kColsPerTile));
+            const float4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
+            const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                                 q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+            const int n_here = min(kColsPerTile, clip.n_cols - tl * kColsPerTile);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < n_here) acc += static_cast<double>(fmaxf(v[j], thr));
         }
-        for (; t < clip.n_cols; t += kPoolSlices) acc += static_cast<double>(fmaxf(src[static_cast<long long>(t) * 128], thr));
         part[slice][m] = acc;
         __syncthreads();
         if (tid < 128) {
