@@ -144,7 +144,7 @@ int get_sr_tables(serb_ctx* ctx, int sr, SrTables** out) {
     mel_filterbank(sr, kNFft, dense);
     MelSparse ms;
     mel_sparse(dense, kNBins, ms);
-    if (ms.weights.size() > 2304) return fail(ctx, SERB_ERR_UNSUPPORTED, "mel filterbank has more non-zeros than the kernel stages");
+    if (ms.weights.size() > 2560) return fail(ctx, SERB_ERR_UNSUPPORTED, "mel filterbank has more non-zeros than the kernel stages");
     t.mel_nnz = static_cast<int>(ms.weights.size());
     int rc;
     if ((rc = upload(ctx, t.mel_start, ms.start.data(), ms.start.size(), ctx->stream))) return rc;

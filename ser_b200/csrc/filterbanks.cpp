@@ -144,12 +144,16 @@ void mel_sparse(const std::vector<float>& dense, int n_bins, MelSparse& out) {
                 last = k;
             }
         }
-        out.offset[m] = static_cast<int32_t>(out.weights.size());
+        out.offset[m] = static_cast<int32_t>(out.weights.size());   // always a multiple of 4
         if (first >= 0) {
             out.start[m] = first;
-            out.count[m] = last - first + 1;
-            for (int k = first; k <= last; ++k)
-                out.weights.push_back(dense[static_cast<size_t>(m) * n_bins + k]);
+            // padded with zero weights to a multiple of 4 so the kernel reads 16-byte groups; the
+            // padding may index up to 3 bins past the last one (the kernel keeps 3 zero rows there)
+            const int n = last - first + 1;
+            const int padded = (n + 3) / 4 * 4;
+            out.count[m] = padded;
+            for (int k = first; k < first + padded; ++k)
+                out.weights.push_back(k <= last ? dense[static_cast<size_t>(m) * n_bins + k] : 0.0f);
         }
     }
     out.offset[kNMels] = static_cast<int32_t>(out.weights.size());

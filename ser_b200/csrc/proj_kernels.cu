@@ -194,11 +194,11 @@ constexpr int kTPitch = 20;       // floats per transposed bin row: 16 columns +
 
 struct ProjSmem {
     float raw[kColsPerTile][kRowPitch];    // TMA landing zone: |X| rows of one tile, 65792 B
-    float t[kNBins * kTPitch];             // the same tile as [bin][column], 82000 B
+    float t[(kNBins + 3) * kTPitch];       // the same tile as [bin][column] + 3 zero rows, 82240 B
     float w[kNBins * 12];                  // chroma bank of the current clip, [bin][12], 49200 B
     float red[kChromaSlices * 192];        // chroma split-K partials, 15360 B
     float chr[192];
-    float melw[2304];                      // sparse mel weights (<= 2304 non-zeros)
+    float melw[2560];                      // sparse mel weights, 4-padded per band (<= 2560)
     int mstart[128], mcount[128], moffset[129];
     float wmax[8];
     unsigned long long bar_tile, bar_bank;
@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         for (int i = tid; i < 128; i += kProjThreads) { sm.mstart[i] = p.mel_start[i]; sm.mcount[i] = p.mel_count[i]; }
         for (int i = tid; i < 129; i += kProjThreads) sm.moffset[i] = p.mel_offset[i];
     }
+    for (int i = tid; i < 3 * kTPitch; i += kProjThreads) sm.t[kNBins * kTPitch + i] = 0.0f;   // padding rows
     __syncthreads();
     if (tid == 0) proj_issue_tile(sm, p, tile_lo);
 
@@ -268,7 +269,6 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
         const ClipDev clip = p.clips[ci];
         const int t0 = (tile - clip.tile_base) * kColsPerTile;
         const int n_valid = min(kColsPerTile, clip.n_cols - t0);
-        const long long col0 = static_cast<long long>(clip.col_base) + t0;
         const int want_bank = p.do_chroma ? p.tuning_idx[ci] : -1;
         const bool new_bank = want_bank != bank_loaded;
 
@@ -371,17 +371,19 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_kernel(ProjParams p, int
             for (int j = 0; j < 8; ++j) {
                 // bands dealt short-with-long: {bs, 31-bs, 32+bs, 63-bs, 64+bs, 95-bs, 96+bs, 127-bs}
                 const int m = (j & 1) ? (32 * (j >> 1) + 31 - bs) : (32 * (j >> 1) + bs);
-                const float* w = sm.melw + sm.moffset[m];
-                const float* w_end = w + sm.mcount[m];
+                const float4* w = reinterpret_cast<const float4*>(sm.melw + sm.moffset[m]);
+                const float4* w_end = w + (sm.mcount[m] >> 2);     // counts are padded to multiples of 4
                 const float* xs = &sm.t[sm.mstart[m] * kTPitch + col];
                 float acc = 0.f;
-                for (; w + 2 <= w_end; w += 2, xs += 2 * kTPitch) {
-                    const float x0 = xs[0], x1 = xs[kTPitch];
+                for (; w < w_end; ++w, xs += 4 * kTPitch) {
+                    const float4 wi = *w;
+                    const float x0 = xs[0], x1 = xs[kTPitch], x2 = xs[2 * kTPitch], x3 = xs[3 * kTPitch];
                     // power = |X| * |X| in float32 (np.abs(D) ** 2.0), summed in bin order
-                    acc = fmaf(w[0], x0 * x0, acc);
-                    acc = fmaf(w[1], x1 * x1, acc);
+                    acc = fmaf(wi.x, x0 * x0, acc);
+                    acc = fmaf(wi.y, x1 * x1, acc);
+                    acc = fmaf(wi.z, x2 * x2, acc);
+                    acc = fmaf(wi.w, x3 * x3, acc);
                 }
-                if (w < w_end) { const float x0 = xs[0]; acc = fmaf(w[0], x0 * x0, acc); }
                 // power_to_db(ref=1, amin=1e-10): 10 * log10(max(1e-10, S)); log10 via the MUFU log2
                 // (absolute error < 1e-6 dB, far below float32 resolution at these magnitudes)
                 const float lmv = 3.01029995663981195f * __log2f(fmaxf(1e-10f, acc));
