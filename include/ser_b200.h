@@ -145,6 +145,23 @@ int serb_debug_filterbank(int32_t kind, int32_t sample_rate, int32_t n_fft, int3
 int serb_debug_stft_host(serb_ctx* ctx, const float* h_wave, int64_t n, float* h_out, int64_t n_cols);
 /* per-clip tuning index (0..99) chosen by the last serb_features_* call; -1 if chroma was off */
 int serb_debug_last_tuning(serb_ctx* ctx, int32_t* h_out, int64_t n_clips);
+/* intermediates of the tonnetz chain for ONE clip (any pointer may be NULL): h_yharm
+ * [max(n, 512)] = librosa.effects.harmonic(y); tuning_index = estimate_tuning(harmonic, 36 bins per
+ * octave) as a bin 0..99; h_cqmag [cq_cols x 252] = |cqt| / sqrt(length), rows = columns; h_tonnetz6. */
+int serb_debug_tonnetz_stages(serb_ctx* ctx, const float* h_wave, int64_t n, int32_t sample_rate,
+                              float* h_yharm, int32_t* tuning_index, float* h_cqmag,
+                              int64_t cq_capacity_rows, int32_t* cq_cols, float* h_tonnetz6);
+/* constant-Q plan of the tonnetz chain at one sample rate: out10 = {status (0 ok, 1 Nyquist,
+ * 2 unsupported), early downsampling factor, top-octave hop, n_fft of octaves 0..6}. Host only. */
+int serb_debug_cqt_plan(int32_t sample_rate, int32_t* out10);
+/* sparsified FFT-domain wavelet basis of one octave (0 = top) for tuning index 0..99:
+ * out_basis [36 x (1 + n_fft/2) x 2] complex64 (may be NULL), out_scale36 = 1/sqrt(length) per
+ * row (may be NULL).  Host only. */
+int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis,
+                         float* out_scale36);
+/* decimation filter (soxr_hq stand-in) for an integer factor 2..8; returns the tap count
+ * (> 0) and, when out is non-NULL and capacity suffices, the taps.  Host only. */
+int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity);
 /* kernels launched by this context since creation */
 int64_t serb_debug_launch_count(const serb_ctx* ctx);
 /* per-kernel CUDA-event timing: kinds 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp.

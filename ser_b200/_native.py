@@ -17,6 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libser_b200.so"
 
 FLAG_MFCC, FLAG_CHROMA, FLAG_MEL, FLAG_CONTRAST, FLAG_TONNETZ = 1, 2, 4, 8, 16
 FLAG_ALL = 31
+HAS_TONNETZ = True   # the tonnetz chain (harmonic + chroma_cqt) is implemented by this build
 
 OUT_SOFTMAX, OUT_LOGISTIC = 0, 1
 
@@ -41,6 +42,10 @@ SIGNATURES: dict[str, tuple] = {
     "serb_debug_filterbank": (c_int, [c_int32, c_int32, c_int32, c_int32, _P]),
     "serb_debug_stft_host": (c_int, [_P, _P, c_int64, _P, c_int64]),
     "serb_debug_last_tuning": (c_int, [_P, _P, c_int64]),
+    "serb_debug_tonnetz_stages": (c_int, [_P, _P, c_int64, c_int32, _P, _P, _P, c_int64, _P, _P]),
+    "serb_debug_cqt_plan": (c_int, [c_int32, _P]),
+    "serb_debug_cqt_basis": (c_int, [c_int32, c_int32, c_int32, _P, _P]),
+    "serb_debug_decimation_taps": (c_int, [c_int32, _P, c_int32]),
     "serb_debug_launch_count": (c_int64, [_P]),
     "serb_debug_last_compute_ms": (c_float, [_P]),
     "serb_debug_set_profile": (c_int, [_P, c_int32]),
@@ -202,6 +207,23 @@ class Context:
         self._check(self._lib.serb_debug_last_tuning(self._handle, _ptr(out), n_clips))
         return out
 
+    def debug_tonnetz_stages(self, wave: np.ndarray, sample_rate: int) -> dict:
+        """Intermediates of the tonnetz chain for one clip: harmonic signal, tuning bin (36 bins per
+        octave), scaled constant-Q magnitudes [columns][252], tonnetz means."""
+        wave = np.ascontiguousarray(wave, dtype=np.float32)
+        plen = max(wave.size, 512)
+        yharm = np.empty(plen, dtype=np.float32)
+        cap = 4 + plen // 256
+        cqmag = np.empty((cap, 252), dtype=np.float32)
+        tuning = c_int32(-1)
+        cq_cols = c_int32(0)
+        ton = np.empty(6, dtype=np.float32)
+        self._check(self._lib.serb_debug_tonnetz_stages(
+            self._handle, _ptr(wave), wave.size, int(sample_rate), _ptr(yharm), ctypes.byref(tuning),
+            _ptr(cqmag), cap, ctypes.byref(cq_cols), _ptr(ton)))
+        return {"yharm": yharm, "tuning_index": int(tuning.value), "cqmag": cqmag[: cq_cols.value].copy(),
+                "tonnetz": ton}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.serb_debug_launch_count(self._handle))
@@ -212,7 +234,7 @@ class Context:
     def kernel_ms(self) -> dict[str, tuple[float, int]]:
         """{kernel: (total device ms, launches)} since set_profile(True)."""
         out = {}
-        for kind, name in enumerate(("stft", "tuning", "proj", "pool", "short", "mlp")):
+        for kind, name in enumerate(("stft", "tuning", "proj", "pool", "short", "mlp", "hpss", "istft", "cqt")):
             ms = c_double(0.0)
             n = c_int64(0)
             self._check(self._lib.serb_debug_kernel_ms(self._handle, kind, ctypes.byref(ms), ctypes.byref(n)))
@@ -232,6 +254,37 @@ def debug_filterbank(kind: int, sample_rate: int, n_fft: int, tuning_index: int 
     code = lib.serb_debug_filterbank(kind, int(sample_rate), int(n_fft), int(tuning_index), _ptr(out))
     if code != 0:
         raise ValueError(f"serb_debug_filterbank failed with {code}")
+    return out
+
+
+def debug_cqt_plan(sample_rate: int) -> dict:
+    """Constant-Q plan of the tonnetz chain at one sample rate (host only)."""
+    out = np.zeros(10, dtype=np.int32)
+    code = load_library().serb_debug_cqt_plan(int(sample_rate), _ptr(out))
+    if code != 0:
+        raise ValueError(f"serb_debug_cqt_plan failed with {code}")
+    return {"status": int(out[0]), "early_factor": int(out[1]), "hop0": int(out[2]), "n_fft": [int(v) for v in out[3:]]}
+
+
+def debug_cqt_basis(sample_rate: int, tuning_index: int, octave: int) -> tuple[np.ndarray, np.ndarray]:
+    """(sparsified FFT-domain basis [36][1 + n_fft/2] complex64, 1/sqrt(length) [36]) of one octave."""
+    plan = debug_cqt_plan(sample_rate)
+    n_bins = 1 + plan["n_fft"][octave] // 2
+    basis = np.zeros((36, n_bins, 2), dtype=np.float32)
+    scale = np.zeros(36, dtype=np.float32)
+    code = load_library().serb_debug_cqt_basis(int(sample_rate), int(tuning_index), int(octave), _ptr(basis), _ptr(scale))
+    if code != 0:
+        raise ValueError(f"serb_debug_cqt_basis failed with {code}")
+    return basis[..., 0] + 1j * basis[..., 1], scale
+
+
+def debug_decimation_taps(factor: int) -> np.ndarray:
+    lib = load_library()
+    n = lib.serb_debug_decimation_taps(int(factor), None, 0)
+    if n <= 0:
+        raise ValueError(f"serb_debug_decimation_taps failed with {n}")
+    out = np.zeros(n, dtype=np.float64)
+    lib.serb_debug_decimation_taps(int(factor), _ptr(out), n)
     return out
 
 

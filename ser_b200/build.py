@@ -23,13 +23,16 @@ LIB_PATH = PKG_DIR / "libser_b200.so"
 
 SOURCES = [
     "filterbanks.cpp",
+    "cqt_tables.cpp",
     "stft_kernel.cu",
     "proj_kernels.cu",
     "short_kernel.cu",
+    "hpss_kernels.cu",
+    "cqt_kernels.cu",
     "mlp_kernel.cu",
     "api.cu",
 ]
-HEADERS = ["common.cuh", "fft.cuh", "kernels.h", "filterbanks.h", "../../include/ser_b200.h"]
+HEADERS = ["common.cuh", "fft.cuh", "kernels.h", "filterbanks.h", "cqt_tables.h", "../../include/ser_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -9,9 +9,11 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
+#include "cqt_tables.h"
 #include "filterbanks.h"
 #include "kernels.h"
 
@@ -44,6 +46,11 @@ struct SrTables {
     DevBuf mel_start, mel_count, mel_offset, mel_weights, mel_points;
     int mel_nnz = 0;
     int kmin = 0, kmax = 0, peak_cap = 0;
+    // tonnetz chain (built on first use)
+    bool cqt_ready = false;
+    CqtPlan plan;
+    DevBuf cq_rows, cq_vals, early_taps;
+    int n_early_taps = 0;
 };
 
 struct Mlp {
@@ -53,6 +60,8 @@ struct Mlp {
 };
 
 }  // namespace
+
+constexpr int kProfKinds = 10;
 
 struct serb_ctx {
     int device = 0;
@@ -76,6 +85,11 @@ struct serb_ctx {
     DevBuf clips, short_clips, tuning, short_tuning, status;
     // host-entry staging
     DevBuf wave, out, proba, labels, x64, pcm, pcm_max;
+    // tonnetz chain
+    DevBuf hann_sq, cq_twiddles;
+    DevBuf cspec, harm, perc, frames, yharm, yoct, cqmag;
+    DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
+    int ton_chunk_cols = 65536;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
     std::vector<int> last_short_rows;
     long long last_n_clips = 0;
@@ -86,8 +100,8 @@ struct serb_ctx {
     struct ProfRec { int kind; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[6] = {0, 0, 0, 0, 0, 0};
-    long long prof_n[6] = {0, 0, 0, 0, 0, 0};
+    double prof_ms[kProfKinds] = {};
+    long long prof_n[kProfKinds] = {};
 };
 
 namespace {
@@ -106,7 +120,8 @@ int fail_cuda(serb_ctx* ctx, cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);    \
     } while (0)
 
-// kinds: 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp
+// kinds: 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss medians, 7 istft + overlap-add,
+// 8 decimation + constant-Q + tonnetz
 struct ProfScope {
     serb_ctx* ctx; int kind; cudaStream_t stream; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(serb_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), stream(s) {
@@ -178,6 +193,7 @@ int get_sr_tables(serb_ctx* ctx, int sr, SrTables** out) {
     t.kmin = kmin;
     t.kmax = kmax;
     t.peak_cap = std::max(1, (kmax - kmin + 1) / 2 + 1);
+    cqt_plan(sr, t.plan);
     SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     *out = &t;
     return SERB_OK;
@@ -205,8 +221,6 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
     if (flags & ~SERB_FLAG_ALL) return fail(ctx, SERB_ERR_INVALID_ARG, "unknown feature flag bits");
     if ((flags & SERB_FLAG_CONTRAST) && !(6400.0 < 0.5 * sr))
         return fail(ctx, SERB_ERR_NYQUIST, "Frequency band exceeds Nyquist. Reduce either fmin or n_bands.");
-    if (flags & SERB_FLAG_TONNETZ)
-        return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz group is not implemented in this build");
     Chunk cur{0, 0, 0, 0, 0};
     for (long long i = 0; i < n_clips; ++i) {
         const long long s = starts[i], len = lengths[i];
@@ -236,6 +250,249 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
         main_clips.push_back(c);
     }
     if (cur.clip_hi > cur.clip_lo) chunks.push_back(cur);
+    return SERB_OK;
+}
+
+// ---- tonnetz chain -------------------------------------------------------------------------
+int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
+    if (tab->cqt_ready) return SERB_OK;
+    const CqtPlan& plan = tab->plan;
+    // 100 tuning-indexed sparse bases, built in parallel on the host (float64 FFTs)
+    std::vector<CqRow> rows(static_cast<size_t>(kNTunings) * kCqtBins);
+    std::vector<float> vals(static_cast<size_t>(kNTunings) * kCqtBins * kCqtRowCap * 2);
+    std::vector<int> ok(kNTunings, 1);
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> workers;
+    for (unsigned w = 0; w < hw; ++w)
+        workers.emplace_back([&, w]() {
+            CqtBank bank;
+            for (int t = static_cast<int>(w); t < kNTunings; t += static_cast<int>(hw)) {
+                ok[t] = cqt_bank(plan, t, bank) ? 1 : 0;
+                for (int r = 0; r < kCqtBins; ++r) {
+                    const CqtRow& src = bank.rows[r];
+                    rows[static_cast<size_t>(t) * kCqtBins + r] = CqRow{src.start, src.count, src.scale, src.bin};
+                }
+                std::memcpy(vals.data() + static_cast<size_t>(t) * kCqtBins * kCqtRowCap * 2, bank.vals.data(),
+                            bank.vals.size() * sizeof(float));
+            }
+        });
+    for (std::thread& th : workers) th.join();
+    for (int t = 0; t < kNTunings; ++t)
+        if (!ok[t]) return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz: a constant-Q basis row is wider than the kernel stages");
+    int rc;
+    if ((rc = upload(ctx, tab->cq_rows, rows.data(), rows.size(), ctx->stream))) return rc;
+    if ((rc = upload(ctx, tab->cq_vals, vals.data(), vals.size(), ctx->stream))) return rc;
+    std::vector<float> taps32;
+    if (plan.early_factor > 2) {
+        std::vector<double> taps;
+        decimation_taps(plan.early_factor, taps);
+        const double sc = std::sqrt(static_cast<double>(plan.early_factor));
+        for (double t : taps) taps32.push_back(static_cast<float>(t * sc));
+        tab->n_early_taps = static_cast<int>(taps32.size());
+        if ((rc = upload(ctx, tab->early_taps, taps32.data(), taps32.size(), ctx->stream))) return rc;
+    }
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tab->cqt_ready = true;
+    return SERB_OK;
+}
+
+struct TonChunk {
+    int clip_lo, clip_hi, n_cols, n_tiles, n_segs, cq_rows, max_len0, max_cq_cols;
+    long long max_end, total0;
+};
+
+// librosa.effects.harmonic + librosa.feature.tonnetz for every clip of the request (any length),
+// written to out[row][off_tonnetz .. +6)
+template <typename BeforeChunk>
+int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const int64_t* lengths,
+                long long n_clips, int sr, SrTables* tab, const Offsets& off, float* d_out,
+                cudaStream_t stream, BeforeChunk before_chunk) {
+    const CqtPlan& plan = tab->plan;
+    if (plan.status == 1) return fail(ctx, SERB_ERR_NYQUIST, plan.message);
+    if (plan.status != 0) return fail(ctx, SERB_ERR_UNSUPPORTED, plan.message);
+    int rc = get_cqt_tables(ctx, tab);
+    if (rc) return rc;
+    const int fe = plan.early_factor;
+
+    std::vector<TonClip> clips(n_clips);
+    std::vector<ClipDev> clips_a(n_clips), clips_b(n_clips);
+    std::vector<int2> segs;
+    std::vector<TonChunk> chunks;
+    std::vector<int> seg_begin;   // first segment of every chunk
+    TonChunk cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    seg_begin.push_back(0);
+    for (long long i = 0; i < n_clips; ++i) {
+        const long long len = lengths[i];
+        const long long plen = std::max<long long>(len, 512);          // dsp.py:38-45 _pad_audio_for_fft
+        const int n_cols = 1 + static_cast<int>(plen / kHop);
+        const int tiles = (n_cols + kColsPerTile - 1) / kColsPerTile;
+        if (cur.clip_hi > cur.clip_lo && cur.n_cols + n_cols > ctx->ton_chunk_cols) {
+            chunks.push_back(cur);
+            seg_begin.push_back(static_cast<int>(segs.size()));
+            cur = TonChunk{cur.clip_hi, cur.clip_hi, 0, 0, 0, 0, 0, 0, 0, 0};
+        }
+        const long long len0 = (plen + fe - 1) / fe;
+        if (len0 > (65535LL * 1024)) return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz: clip too long for one launch");
+        TonClip& c = clips[i];
+        c.off0 = cur.total0;
+        c.hoff = cur.total0 * fe;
+        c.length = static_cast<int>(plen);
+        c.n_cols = n_cols;
+        c.col_base = cur.n_cols;
+        c.tile_base = cur.n_tiles;
+        c.len0 = static_cast<int>(len0);
+        int cq = 0x7fffffff, ln = c.len0;
+        for (int l = 0; l < kCqOctaves; ++l) {
+            cq = std::min(cq, 1 + ln / (plan.hop0 >> l));
+            ln = (ln + 1) >> 1;
+        }
+        c.cq_cols = cq;
+        c.cq_base = cur.cq_rows;
+        c.out_row = static_cast<int>(i);
+        ClipDev& a = clips_a[i];
+        a = ClipDev{};
+        a.start = starts[i]; a.length = static_cast<int>(len); a.n_cols = n_cols;
+        a.col_base = c.col_base; a.tile_base = c.tile_base; a.out_row = c.out_row;
+        ClipDev& b = clips_b[i];
+        b = a;
+        b.start = c.hoff; b.length = c.length;
+        for (int t0 = 0; t0 < n_cols; t0 += kHarmSeg) segs.push_back(make_int2(static_cast<int>(i) - cur.clip_lo, t0));
+        cur.total0 += (len0 + 127) / 128 * 128;
+        cur.n_cols += n_cols;
+        cur.n_tiles += tiles;
+        cur.n_segs = static_cast<int>(segs.size()) - seg_begin.back();
+        cur.cq_rows += cq;
+        cur.max_len0 = std::max(cur.max_len0, c.len0);
+        cur.max_cq_cols = std::max(cur.max_cq_cols, cq);
+        cur.max_end = std::max(cur.max_end, starts[i] + len);
+        cur.clip_hi += 1;
+    }
+    if (cur.clip_hi > cur.clip_lo) chunks.push_back(cur);
+
+    int max_cols = 0, max_tiles = 0, max_cq = 0;
+    long long max_total0 = 0;
+    for (const TonChunk& c : chunks) {
+        max_cols = std::max(max_cols, c.n_cols);
+        max_tiles = std::max(max_tiles, c.n_tiles);
+        max_cq = std::max(max_cq, c.cq_rows);
+        max_total0 = std::max(max_total0, c.total0);
+    }
+    const size_t col_f = static_cast<size_t>(max_cols) * kSpillStride;
+    SERB_CUDA(ctx, ctx->spill.reserve(col_f * sizeof(float)));
+    SERB_CUDA(ctx, ctx->cspec.reserve(col_f * sizeof(float2)));
+    SERB_CUDA(ctx, ctx->harm.reserve(col_f * sizeof(float)));
+    SERB_CUDA(ctx, ctx->perc.reserve(col_f * sizeof(float)));
+    SERB_CUDA(ctx, ctx->frames.reserve(static_cast<size_t>(max_cols) * kNFft * sizeof(float)));
+    SERB_CUDA(ctx, ctx->yharm.reserve((static_cast<size_t>(max_total0) * fe + 64) * sizeof(float)));
+    SERB_CUDA(ctx, ctx->yoct.reserve((static_cast<size_t>(max_total0) * 2 + 64) * sizeof(float)));
+    SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(max_cq) * kCqBins * sizeof(float)));
+    SERB_CUDA(ctx, ctx->ton_tile_clip.reserve(static_cast<size_t>(max_tiles) * sizeof(int)));
+    SERB_CUDA(ctx, ctx->peaks.reserve(static_cast<size_t>(max_cols) * tab->peak_cap * sizeof(float2)));
+    SERB_CUDA(ctx, ctx->peak_count.reserve(static_cast<size_t>(max_cols) * sizeof(int)));
+    SERB_CUDA(ctx, ctx->ton_tuning.reserve(static_cast<size_t>(n_clips) * sizeof(int)));
+    if ((rc = upload(ctx, ctx->ton_clips, clips.data(), clips.size(), stream))) return rc;
+    if ((rc = upload(ctx, ctx->ton_clips_a, clips_a.data(), clips_a.size(), stream))) return rc;
+    if ((rc = upload(ctx, ctx->ton_clips_b, clips_b.data(), clips_b.size(), stream))) return rc;
+    if ((rc = upload(ctx, ctx->ton_segs, segs.data(), segs.size(), stream))) return rc;
+    // the pageable host vectors above must outlive their async copies
+    SERB_CUDA(ctx, cudaStreamSynchronize(stream));
+
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const TonChunk& c = chunks[ci];
+        before_chunk(c.max_end);
+        const int nc = c.clip_hi - c.clip_lo;
+        const TonClip* d_clips = ctx->ton_clips.as<TonClip>() + c.clip_lo;
+        const ClipDev* d_a = ctx->ton_clips_a.as<ClipDev>() + c.clip_lo;
+        const ClipDev* d_b = ctx->ton_clips_b.as<ClipDev>() + c.clip_lo;
+        int* d_tuning = ctx->ton_tuning.as<int>() + c.clip_lo;
+        SERB_CUDA(ctx, launch_expand_tiles(d_a, nc, ctx->ton_tile_clip.as<int>(), stream));
+        ctx->launches += 1;
+        // 1. complex STFT of the clip
+        StftParams sp{};
+        sp.wave = d_wave;
+        sp.clips = d_a;
+        sp.n_clips = nc;
+        sp.tile_clip = ctx->ton_tile_clip.as<int>();
+        sp.tables = ctx->tables.as<float2>();
+        sp.spill = ctx->spill.as<float>();
+        sp.cspill = ctx->cspec.as<float2>();
+        sp.do_peaks = 0;
+        sp.kmin = tab->kmin; sp.kmax = tab->kmax; sp.peak_cap = tab->peak_cap;
+        sp.peaks = ctx->peaks.as<float2>();
+        sp.peak_count = ctx->peak_count.as<int>();
+        sp.sr_over_nfft_num = static_cast<double>(sr);
+        sp.status = ctx->status.as<int>();
+        { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
+        ctx->launches += 1;
+        // 2. HPSS medians
+        HpssParams hp{};
+        hp.clips = d_clips;
+        hp.segs = ctx->ton_segs.as<int2>() + seg_begin[ci];
+        hp.mag = ctx->spill.as<float>();
+        hp.harm = ctx->harm.as<float>();
+        hp.perc = ctx->perc.as<float>();
+        { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_medians(hp, c.n_segs, c.n_cols, stream)); }
+        ctx->launches += 2;
+        // 3. soft mask + inverse STFT + overlap-add
+        IstftParams ip{};
+        ip.cspec = ctx->cspec.as<float2>();
+        ip.harm = hp.harm;
+        ip.perc = hp.perc;
+        ip.tables = ctx->tables.as<float2>();
+        ip.frames = ctx->frames.as<float>();
+        OlaParams op{};
+        op.clips = d_clips;
+        op.tile_clip = ctx->ton_tile_clip.as<int>();
+        op.frames = ip.frames;
+        op.hann_sq = ctx->hann_sq.as<double>();
+        op.yharm = ctx->yharm.as<float>();
+        {
+            ProfScope ps(ctx, 7, stream);
+            SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream));
+            SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream));
+        }
+        ctx->launches += 2;
+        // 4. tuning of the harmonic signal (36 bins per octave)
+        sp.wave = ctx->yharm.as<float>();
+        sp.clips = d_b;
+        sp.cspill = nullptr;
+        sp.do_peaks = 1;
+        { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
+        TuneParams tp{};
+        tp.clips = d_b;
+        tp.peaks = sp.peaks;
+        tp.peak_count = sp.peak_count;
+        tp.peak_cap = tab->peak_cap;
+        tp.bins_per_octave = 36;
+        tp.edges = ctx->edges.as<double>();
+        tp.tuning_idx = d_tuning;
+        { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream)); }
+        ctx->launches += 2;
+        // 5. decimations, constant-Q, chroma, tonnetz
+        CqtParams qp{};
+        qp.clips = d_clips;
+        qp.n_clips = nc;
+        qp.tuning_idx = d_tuning;
+        qp.yharm = ctx->yharm.as<float>();
+        qp.yoct = ctx->yoct.as<float>();
+        long long base = 0;
+        for (int l = 0; l < kCqOctaves; ++l) { qp.level_base[l] = base; base += c.total0 >> l; }
+        qp.early_factor = fe;
+        qp.hop0 = plan.hop0;
+        for (int l = 0; l < kCqOctaves; ++l) qp.n_fft[l] = plan.n_fft[l];
+        qp.early_taps = tab->early_taps.as<float>();
+        qp.n_early_taps = tab->n_early_taps;
+        qp.rows = tab->cq_rows.as<CqRow>();
+        qp.vals = tab->cq_vals.as<float2>();
+        qp.twiddles = ctx->cq_twiddles.as<float2>();
+        qp.cqmag = ctx->cqmag.as<float>();
+        qp.out = d_out;
+        qp.dim = off.dim;
+        qp.off_tonnetz = off.tonnetz;
+        qp.max_len0 = c.max_len0;
+        qp.max_cq_cols = c.max_cq_cols;
+        { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_cqt_chain(qp, stream, &ctx->launches)); }
+    }
     return SERB_OK;
 }
 
@@ -389,6 +646,10 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         { ProfScope ps(ctx, 4, stream); SERB_CUDA(ctx, launch_short(hp, static_cast<int>(short_clips.size()), stream)); }
         ctx->launches += 1;
     }
+    if (off.tonnetz >= 0) {
+        rc = run_tonnetz(ctx, d_wave, starts, lengths, n_clips, sr, tab, off, d_out, stream, before_chunk);
+        if (rc) return rc;
+    }
     if (ctx->timed) SERB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, stream));
     return SERB_OK;
 }
@@ -501,6 +762,36 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
     CREATE_CHECK(configure_stft());
     CREATE_CHECK(configure_proj());
     CREATE_CHECK(configure_short());
+    CREATE_CHECK(configure_hpss());
+    {
+        std::vector<double> taps, hsq;
+        decimation_taps(2, taps);
+        if (static_cast<int>(taps.size()) != kDecTaps2) {
+            delete ctx;
+            return fail(nullptr, SERB_ERR_UNSUPPORTED, "factor-2 decimation filter length differs from the compiled kernel");
+        }
+        std::vector<float> taps32(taps.size());
+        for (size_t i = 0; i < taps.size(); ++i) taps32[i] = static_cast<float>(taps[i] * std::sqrt(2.0));
+        CREATE_CHECK(configure_cqt(taps32.data()));
+        hann_squared_2048(hsq);
+        CREATE_CHECK(ctx->hann_sq.reserve(hsq.size() * sizeof(double)));
+        CREATE_CHECK(cudaMemcpy(ctx->hann_sq.ptr, hsq.data(), hsq.size() * sizeof(double), cudaMemcpyHostToDevice));
+        // constant-Q FFT twiddles: W_N^j = (cos, -sin) for N = 128..1024, then (cos, sin) 2 pi k / (2N)
+        std::vector<float> tw;
+        const double pi = 3.14159265358979323846;
+        for (int n = 128; n <= 1024; n *= 2)
+            for (int j = 0; j < n; ++j) {
+                tw.push_back(static_cast<float>(std::cos(2.0 * pi * j / n)));
+                tw.push_back(static_cast<float>(-std::sin(2.0 * pi * j / n)));
+            }
+        for (int n = 128; n <= 1024; n *= 2)
+            for (int k = 0; k < n; ++k) {
+                tw.push_back(static_cast<float>(std::cos(2.0 * pi * k / (2.0 * n))));
+                tw.push_back(static_cast<float>(std::sin(2.0 * pi * k / (2.0 * n))));
+            }
+        CREATE_CHECK(ctx->cq_twiddles.reserve(tw.size() * sizeof(float)));
+        CREATE_CHECK(cudaMemcpy(ctx->cq_twiddles.ptr, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     std::vector<double> edges(101), dct;
     for (int i = 0; i <= 100; ++i) edges[i] = tuning_edge(i);
     dct_matrix(dct);
@@ -540,11 +831,15 @@ void serb_ctx_destroy(serb_ctx* ctx) {
                       &ctx->tile_chroma, &ctx->peaks, &ctx->peak_count, &ctx->clips, &ctx->short_clips,
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->mlp.mean, &ctx->mlp.scale,
-                      &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2})
+                      &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles,
+                      &ctx->cspec, &ctx->harm, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag,
+                      &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
+                      &ctx->ton_tile_clip})
         b->release();
     for (auto& kv : ctx->sr_tables) {
         SrTables& t = kv.second;
-        for (DevBuf* b : {&t.chroma_banks, &t.mel_start, &t.mel_count, &t.mel_offset, &t.mel_weights, &t.mel_points})
+        for (DevBuf* b : {&t.chroma_banks, &t.mel_start, &t.mel_count, &t.mel_offset, &t.mel_weights, &t.mel_points,
+                          &t.cq_rows, &t.cq_vals, &t.early_taps})
             b->release();
     }
     for (cudaEvent_t ev : ctx->piece_events) cudaEventDestroy(ev);
@@ -806,18 +1101,98 @@ int serb_debug_last_tuning(serb_ctx* ctx, int32_t* h_out, int64_t n_clips) {
     return SERB_OK;
 }
 
+int serb_debug_tonnetz_stages(serb_ctx* ctx, const float* h_wave, int64_t n, int32_t sample_rate, float* h_yharm,
+                              int32_t* tuning_index, float* h_cqmag, int64_t cq_capacity_rows, int32_t* cq_cols,
+                              float* h_tonnetz6) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!h_wave || n <= 0 || n > 0x7fffffffLL) return fail(ctx, SERB_ERR_INVALID_ARG, "need one non-empty clip");
+    if (sample_rate <= 0) return fail(ctx, SERB_ERR_SAMPLE_RATE, "Sample rate must be a positive integer.");
+    SrTables* tab = nullptr;
+    int rc = get_sr_tables(ctx, sample_rate, &tab);
+    if (rc) return rc;
+    SERB_CUDA(ctx, ctx->wave.reserve(static_cast<size_t>(n) * sizeof(float) + 64));
+    SERB_CUDA(ctx, ctx->out.reserve(6 * sizeof(float)));
+    SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
+    SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.ptr, h_wave, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t start = 0, length = n;
+    Offsets off{6, -1, -1, -1, -1, 0};
+    rc = run_tonnetz(ctx, ctx->wave.as<float>(), &start, &length, 1, sample_rate, tab, off, ctx->out.as<float>(),
+                     ctx->stream, [](long long) {});
+    if (rc) return rc;
+    const long long plen = std::max<long long>(n, 512);
+    int cq = 0x7fffffff;
+    {
+        long long ln = (plen + tab->plan.early_factor - 1) / tab->plan.early_factor;
+        for (int l = 0; l < kCqOctaves; ++l) { cq = std::min<long long>(cq, 1 + ln / (tab->plan.hop0 >> l)); ln = (ln + 1) >> 1; }
+    }
+    if (cq_cols) *cq_cols = cq;
+    if (h_yharm) SERB_CUDA(ctx, cudaMemcpyAsync(h_yharm, ctx->yharm.ptr, static_cast<size_t>(plen) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (tuning_index) SERB_CUDA(ctx, cudaMemcpyAsync(tuning_index, ctx->ton_tuning.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_cqmag) {
+        if (cq_capacity_rows < cq) return fail(ctx, SERB_ERR_INVALID_ARG, "cqmag capacity too small");
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_cqmag, ctx->cqmag.ptr, static_cast<size_t>(cq) * kCqBins * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (h_tonnetz6) SERB_CUDA(ctx, cudaMemcpyAsync(h_tonnetz6, ctx->out.ptr, 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SERB_OK;
+}
+
+int serb_debug_cqt_plan(int32_t sample_rate, int32_t* out10) {
+    if (!out10 || sample_rate <= 0) return SERB_ERR_INVALID_ARG;
+    CqtPlan plan;
+    cqt_plan(sample_rate, plan);
+    out10[0] = plan.status;
+    out10[1] = plan.early_factor;
+    out10[2] = plan.hop0;
+    for (int i = 0; i < kCqtOctaves; ++i) out10[3 + i] = plan.n_fft[i];
+    return SERB_OK;
+}
+
+int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis, float* out_scale36) {
+    if (sample_rate <= 0 || tuning_index < 0 || tuning_index >= kNTunings || octave < 0 || octave >= kCqtOctaves)
+        return SERB_ERR_INVALID_ARG;
+    CqtPlan plan;
+    cqt_plan(sample_rate, plan);
+    if (plan.status != 0) return SERB_ERR_UNSUPPORTED;
+    if (out_basis) {
+        std::vector<float> dense;
+        cqt_basis_dense(plan, tuning_index, octave, dense);
+        std::memcpy(out_basis, dense.data(), dense.size() * sizeof(float));
+    }
+    if (out_scale36) {
+        CqtBank bank;
+        if (!cqt_bank(plan, tuning_index, bank)) return SERB_ERR_UNSUPPORTED;
+        for (int j = 0; j < kCqtBpo; ++j) out_scale36[j] = bank.rows[static_cast<size_t>(octave) * kCqtBpo + j].scale;
+    }
+    return SERB_OK;
+}
+
+int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity) {
+    if (factor < 2 || factor > 8) return SERB_ERR_INVALID_ARG;
+    std::vector<double> taps;
+    decimation_taps(factor, taps);
+    if (out) {
+        if (capacity < static_cast<int32_t>(taps.size())) return SERB_ERR_INVALID_ARG;
+        std::memcpy(out, taps.data(), taps.size() * sizeof(double));
+    }
+    return static_cast<int>(taps.size());
+}
+
 int64_t serb_debug_launch_count(const serb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int serb_debug_set_profile(serb_ctx* ctx, int32_t enabled) {
     if (!ctx) return SERB_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->profile = enabled != 0;
-    for (int i = 0; i < 6; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+    for (int i = 0; i < kProfKinds; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
     return SERB_OK;
 }
 
 int serb_debug_kernel_ms(serb_ctx* ctx, int32_t kind, double* total_ms, int64_t* n_launches) {
-    if (!ctx || kind < 0 || kind >= 6 || !total_ms || !n_launches) return SERB_ERR_INVALID_ARG;
+    if (!ctx || kind < 0 || kind >= kProfKinds || !total_ms || !n_launches) return SERB_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     SERB_CUDA(ctx, cudaSetDevice(ctx->device));
     for (auto& rec : ctx->prof_recs) {

@@ -1,0 +1,346 @@
+// Tonnetz chain, second half: librosa.feature.tonnetz(y=harmonic, sr) for a ragged batch.
+//
+// Replaces ser/_internal/utils/dsp.py:140-143
+//   tonnetz(y) = Phi @ l1norm(chroma_cqt(y)),  chroma_cqt = linf_norm(cq_to_chroma @ |cqt(y)|)
+// with cqt = 252 bins, 36 per octave, 7 octaves, hop 512, fmin = C1 * 2^(tuning/36), computed
+// the way librosa 0.11.0 does (oracle/shim/librosa/core.py vqt):
+// per octave a rectangular-window STFT of the (recursively half-band decimated) signal times a
+// sparsified FFT-domain wavelet basis.
+//
+// decimate2_kernel   factor-2 FIR decimation (381-tap Kaiser stand-in for soxr_hq, x sqrt 2):
+//                    polyphase split in shared memory, 4 outputs per thread, taps as
+//                    constant-bank FFMA operands (fully unrolled)
+// decimate_any_kernel  early downsampling by 4 / 8 (sample rates >= 64 kHz), plain
+// cqt_kernel<R>      n_fft = 64 R real FFT per column (32 / R columns per warp, register DFTs
+//                    around one shared-memory transpose), sparse complex rows, |.| / sqrt(len)
+// tonnetz_kernel     cq_to_chroma fold, L-inf and L1 normalisation, 6 x 12 projection (fp64),
+//                    mean over columns
+#include <cfloat>
+
+#include "fft.cuh"
+#include "kernels.h"
+
+namespace serb {
+
+__constant__ float c_taps2[384];   // h[k] * sqrt(2), k < 381
+
+namespace {
+
+__device__ __forceinline__ int level_length(int len0, int level) {
+    int n = len0;
+    for (int i = 0; i < level; ++i) n = (n + 1) >> 1;
+    return n;
+}
+// level -1 = the full-rate harmonic signal; level 0 aliases it when there is no early downsampling
+__device__ __forceinline__ const float* level_ptr(const CqtParams& p, const TonClip& c, int level) {
+    if (level < 0 || (level == 0 && p.early_factor == 1)) return p.yharm + c.hoff;
+    return p.yoct + p.level_base[level] + (c.off0 >> level);
+}
+
+}  // namespace
+
+// ---- factor-2 decimation -----------------------------------------------------------------
+constexpr int kDecTile = 1024;               // outputs per CTA
+constexpr int kDecHalo = 96;                 // polyphase samples staged before the tile
+constexpr int kDecSpan = kDecTile + 192;     // polyphase samples staged per phase
+
+template <int E_MAX, int TAP0>
+__device__ __forceinline__ void fir_phase(const float* __restrict__ xs, int t, float (&acc)[4]) {
+    // acc[r] += h[TAP0 - 2 e] * xs[4 t + r + e], e = 1 .. E_MAX
+#pragma unroll
+    for (int g = 0; g <= (E_MAX + 3) / 4; ++g) {
+        const float4 q = *reinterpret_cast<const float4*>(xs + 4 * t + 4 * g);
+        const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int e = 4 * g + c - r;
+                if (e >= 1 && e <= E_MAX) acc[r] = fmaf(c_taps2[TAP0 - 2 * e], v[c], acc[r]);
+            }
+    }
+}
+
+// src_level -1: yharm -> level 0 (early downsampling by 2); otherwise level l -> l + 1
+__global__ void __launch_bounds__(256) decimate2_kernel(CqtParams p, int src_level) {
+    __shared__ __align__(16) float xe[kDecSpan];
+    __shared__ __align__(16) float xo[kDecSpan];
+    const TonClip clip = p.clips[blockIdx.x];
+    const int len_in = src_level < 0 ? clip.length : level_length(clip.len0, src_level);
+    const int len_out = (len_in + 1) >> 1;
+    const int mb = blockIdx.y * kDecTile;
+    if (mb >= len_out) return;
+    const float* src = level_ptr(p, clip, src_level);
+    float* dst = p.yoct + p.level_base[src_level + 1] + (clip.off0 >> (src_level + 1));
+    for (int q = threadIdx.x; q < kDecSpan; q += 256) {
+        const int i = 2 * (mb - kDecHalo + q);
+        float a = 0.0f, b = 0.0f;
+        if (i >= 0 && i + 1 < len_in) {
+            const float2 v = *reinterpret_cast<const float2*>(src + i);
+            a = v.x; b = v.y;
+        } else {
+            if (i >= 0 && i < len_in) a = src[i];
+            if (i + 1 >= 0 && i + 1 < len_in) b = src[i + 1];
+        }
+        xe[q] = a;
+        xo[q] = b;
+    }
+    __syncthreads();
+    // out[m] = sum_j h[2j] xe[m + 95 - j] + sum_j h[2j+1] xo[m + 94 - j]   (half = 190)
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    fir_phase<191, 382>(xe, threadIdx.x, acc);   // tap 2 (191 - e)
+    fir_phase<190, 381>(xo, threadIdx.x, acc);   // tap 2 (190 - e) + 1
+    const int m = mb + 4 * threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (m + r < len_out) dst[m + r] = acc[r];
+}
+
+// yharm -> level 0 for early factors 4 and 8 (taps pre-scaled by sqrt(factor))
+__global__ void __launch_bounds__(256) decimate_any_kernel(CqtParams p) {
+    const TonClip clip = p.clips[blockIdx.x];
+    const int f = p.early_factor;
+    const int half = (p.n_early_taps - 1) / 2;
+    const float* src = p.yharm + clip.hoff;
+    float* dst = p.yoct + p.level_base[0] + clip.off0;
+    for (int m = blockIdx.y * 256 + threadIdx.x; m < clip.len0; m += gridDim.y * 256) {
+        const int centre = f * m + half;
+        const int k_lo = max(0, centre - (clip.length - 1));
+        const int k_hi = min(p.n_early_taps - 1, centre);
+        float acc = 0.0f;
+        for (int k = k_lo; k <= k_hi; ++k) acc = fmaf(p.early_taps[k], src[centre - k], acc);
+        dst[m] = acc;
+    }
+}
+
+// ---- constant-Q response of one octave ---------------------------------------------------
+__device__ __forceinline__ void fft16(float2* v) {
+    // n = 4a + b, k = k2 + 4 k1
+#pragma unroll
+    for (int b = 0; b < 4; ++b) fft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+#pragma unroll
+    for (int k2 = 1; k2 < 4; ++k2)
+#pragma unroll
+        for (int b = 1; b < 4; ++b)
+            v[4 * k2 + b] = cmul_conj_tw(v[4 * k2 + b], cos32(2 * b * k2), sin32(2 * b * k2));
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) fft4(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
+    float2 t[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2)
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) t[k2 + 4 * k1] = v[4 * k2 + k1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = t[i];
+}
+
+template <int R>
+__device__ __forceinline__ void fft_small(float2* v) {
+    if constexpr (R == 4) fft4(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 8) fft8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    else fft16(v);
+}
+
+constexpr int kCqtWarps = 4;
+
+// R complex points per lane per column; N = 32 R complex = n_fft / 2; G = 32 / R columns per warp
+template <int R>
+__global__ void __launch_bounds__(kCqtWarps * 32) cqt_kernel(CqtParams p, int octave) {
+    constexpr int G = 32 / R;
+    constexpr int N = 32 * R;
+    __shared__ float2 sbuf[kCqtWarps][32 * 33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TonClip clip = p.clips[blockIdx.x];
+    const int t_first = (blockIdx.y * kCqtWarps + warp) * G;
+    if (t_first >= clip.cq_cols) return;      // warps are independent: no CTA barrier below
+    const int tuning = p.tuning_idx[blockIdx.x];
+    const float* sig = level_ptr(p, clip, octave);
+    const int len = level_length(clip.len0, octave);
+    const int hop = p.hop0 >> octave;
+    const float2* twa = p.twiddles + (N - 128);            // W_N^j = (cos, -sin)
+    const float2* twb = p.twiddles + 1920 + (N - 128);     // (cos, sin) 2 pi k / (2N)
+    float2* buf = sbuf[warp];
+
+    // frames (rectangular window, centred, zero padded): z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane
+    float2 v[32];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int base = (t_first + g) * hop - N;
+#pragma unroll
+        for (int n1 = 0; n1 < R; ++n1) {
+            const int i = base + 2 * (32 * n1 + lane);
+            float a = 0.0f, b = 0.0f;
+            if (i >= 0 && i < len) a = sig[i];
+            if (i + 1 >= 0 && i + 1 < len) b = sig[i + 1];
+            v[g * R + n1] = make_float2(a, b);
+        }
+    }
+    // step A: R-point DFTs over n1 (per column), twiddle W_N^(lane k1), transpose
+    if constexpr (R == 32) {
+        fft32(v);
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) fft_small<R>(v + g * R);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1) {
+            float2 y = v[g * R + k1];
+            if (k1 > 0) {
+                const float2 w = twa[lane * k1];
+                y = make_float2(fmaf(y.x, w.x, -y.y * w.y), fmaf(y.x, w.y, y.y * w.x));
+            }
+            buf[(g * R + k1) * 33 + lane] = y;
+        }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[lane * 33 + n2];
+    __syncwarp();
+    // step B: 32-point DFT over n2; lane = (column g2, k1): v[k2] = Z[k1 + R k2]
+    fft32(v);
+    const int g2 = lane / R, k1 = lane % R;
+    const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
+    float2* xs = buf + g2 * (N + 1);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+        float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
+        float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
+        if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
+        const float ax = v[k2].x, ay = v[k2].y;
+        const float ex = ax + px, ey = ay - py;
+        const float ox = ay + py, oy = px - ax;        // -i (A - conj P)
+        const int k = k1 + R * k2;
+        const float2 w = twb[k];
+        const float wx = fmaf(w.x, ox, w.y * oy);
+        const float wy = fmaf(w.x, oy, -w.y * ox);
+        xs[k] = make_float2(0.5f * (ex + wx), 0.5f * (ey + wy));
+        if (k2 == 0 && k1 == 0) xs[N] = make_float2(0.5f * (ex - wx), 0.5f * (ey - wy));
+    }
+    __syncwarp();
+    // sparse basis rows: C[r] = sum_c B[r][c] X[start + c]
+    const size_t bank = (static_cast<size_t>(tuning) * kCqOctaves + octave) * kCqRows;
+    for (int i = lane; i < kCqRows * G; i += 32) {
+        const int g = i / kCqRows, r = i % kCqRows;
+        const int t = t_first + g;
+        if (t >= clip.cq_cols) continue;
+        const CqRow row = p.rows[bank + r];
+        const float2* b = p.vals + (bank + r) * kCqRowCap;
+        const float2* x = buf + g * (N + 1) + row.start;
+        float cr = 0.0f, ci = 0.0f;
+        for (int c = 0; c < row.count; ++c) {
+            const float2 bv = b[c], xv = x[c];
+            cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
+            ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
+        }
+        p.cqmag[(static_cast<size_t>(clip.cq_base) + t) * kCqBins + row.bin] = sqrtf(fmaf(cr, cr, ci * ci)) * row.scale;
+    }
+}
+
+// ---- chroma fold + tonnetz ---------------------------------------------------------------
+__global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
+    __shared__ float mags[4][256];
+    __shared__ double phi[6][12];
+    __shared__ double part[4][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TonClip clip = p.clips[blockIdx.x];
+    if (threadIdx.x < 72) {
+        // librosa.feature.tonnetz: phi = R * cos(pi * V), V = outer(scale, 0..11), even rows - 0.5
+        const int q = threadIdx.x / 12, c = threadIdx.x % 12;
+        const double scale = (q < 2) ? 7.0 / 6.0 : (q < 4) ? 3.0 / 2.0 : 2.0 / 3.0;
+        double vv = scale * static_cast<double>(c);
+        if ((q & 1) == 0) vv -= 0.5;
+        phi[q][c] = ((q < 4) ? 1.0 : 0.5) * cospi(vv);
+    }
+    __syncthreads();
+    double acc = 0.0;   // lanes 0..5: running sum of tonnetz row `lane`
+    for (int t = warp; t < clip.cq_cols; t += 4) {
+        const float* row = p.cqmag + (static_cast<size_t>(clip.cq_base) + t) * kCqBins;
+        for (int i = lane; i < kCqBins; i += 32) mags[warp][i] = row[i];
+        __syncwarp();
+        // filters.cq_to_chroma(252, bins_per_octave=36): chroma c <- bins 36 o + ((3c - 1 + j) mod 36)
+        float ch = 0.0f;
+        if (lane < 12) {
+            for (int o = 0; o < kCqOctaves; ++o)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ch += mags[warp][36 * o + (3 * lane - 1 + j + 36) % 36];
+        }
+        __syncwarp();
+        // util.normalize(norm=inf) then util.normalize(norm=1): float32 values, float64 lengths
+        float mx = ch;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        // lanes 12..15 hold 0, which never wins a max of non-negative values
+        double len_inf = static_cast<double>(mx);
+        if (len_inf < static_cast<double>(FLT_MIN)) len_inf = 1.0;
+        const float cn = static_cast<float>(static_cast<double>(ch) / len_inf);
+        double l1 = static_cast<double>(cn);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        if (l1 < static_cast<double>(FLT_MIN)) l1 = 1.0;
+        const float c1 = static_cast<float>(static_cast<double>(cn) / l1);
+        double proj = 0.0;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const double cv = static_cast<double>(__shfl_sync(0xffffffffu, c1, c));
+            if (lane < 6) proj = fma(phi[lane][c], cv, proj);
+        }
+        acc += proj;
+    }
+    if (lane < 6) part[warp][lane] = acc;
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const double total = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+        p.out[static_cast<size_t>(clip.out_row) * p.dim + p.off_tonnetz + threadIdx.x] =
+            static_cast<float>(total / static_cast<double>(clip.cq_cols));
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------
+cudaError_t configure_cqt(const float* taps2_scaled) {
+    return cudaMemcpyToSymbol(c_taps2, taps2_scaled, kDecTaps2 * sizeof(float));
+}
+
+template <int R>
+static void launch_cqt_octave(const CqtParams& p, int octave, cudaStream_t stream) {
+    constexpr int G = 32 / R;
+    const int groups = (p.max_cq_cols + G - 1) / G;
+    dim3 grid(p.n_clips, (groups + kCqtWarps - 1) / kCqtWarps);
+    cqt_kernel<R><<<grid, kCqtWarps * 32, 0, stream>>>(p, octave);
+}
+
+cudaError_t launch_cqt_chain(const CqtParams& p, cudaStream_t stream, long long* launches) {
+    if (p.n_clips <= 0) return cudaSuccess;
+    long long n = 0;
+    if (p.early_factor == 2) {
+        const int out_max = (p.max_len0 + 0);   // max_len0 already is the longest level-0 signal
+        decimate2_kernel<<<dim3(p.n_clips, (out_max + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, -1);
+        ++n;
+    } else if (p.early_factor > 2) {
+        const int tiles = min(4096, (p.max_len0 + 255) / 256);
+        decimate_any_kernel<<<dim3(p.n_clips, tiles), 256, 0, stream>>>(p);
+        ++n;
+    }
+    int len = p.max_len0;
+    for (int level = 0; level + 1 < kCqOctaves; ++level) {
+        len = (len + 1) >> 1;
+        decimate2_kernel<<<dim3(p.n_clips, (len + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, level);
+        ++n;
+    }
+    for (int octave = 0; octave < kCqOctaves; ++octave) {
+        switch (p.n_fft[octave]) {
+            case 256: launch_cqt_octave<4>(p, octave, stream); break;
+            case 512: launch_cqt_octave<8>(p, octave, stream); break;
+            case 1024: launch_cqt_octave<16>(p, octave, stream); break;
+            case 2048: launch_cqt_octave<32>(p, octave, stream); break;
+            default: return cudaErrorInvalidValue;
+        }
+        ++n;
+    }
+    tonnetz_kernel<<<p.n_clips, 128, 0, stream>>>(p);
+    ++n;
+    if (launches) *launches += n;
+    return cudaGetLastError();
+}
+
+}  // namespace serb

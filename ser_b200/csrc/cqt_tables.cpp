@@ -1,0 +1,288 @@
+// Host-side tables of the tonnetz chain (see cqt_tables.h).  float64 math with float32 /
+// complex64 rounding at the points where librosa 0.11.0 rounds.
+#include "cqt_tables.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+
+#include "filterbanks.h"
+
+namespace serb {
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kHannBandwidth = 1.50018310546875;   // librosa.filters.WINDOW_BANDWIDTHS["hann"]
+
+struct Wavelets {
+    double freqs[kCqtBins];
+    double alpha[kCqtBins];
+    double cutoff;
+};
+
+// freqs / alpha of the 252 bins for one tuning (librosa.vqt: fmin * 2^(tuning/bpo), equal
+// temperament; filters._relative_bandwidth) and the top wavelet's cutoff (wavelet_lengths)
+void wavelets_for_tuning(int tuning_idx, Wavelets& w) {
+    const double tuning = tuning_edge(tuning_idx);
+    const double c1 = 440.0 * std::pow(2.0, (24.0 - 69.0) / 12.0);
+    const double fmin = c1 * std::pow(2.0, tuning / static_cast<double>(kCqtBpo));
+    for (int o = 0; o < kCqtOctaves; ++o)
+        for (int j = 0; j < kCqtBpo; ++j) {
+            const double ratio = std::pow(2.0, static_cast<double>(j) / kCqtBpo);
+            w.freqs[o * kCqtBpo + j] = (std::pow(2.0, static_cast<double>(o)) * ratio) * fmin;
+        }
+    double logf[kCqtBins], bpo[kCqtBins];
+    for (int i = 0; i < kCqtBins; ++i) logf[i] = std::log2(w.freqs[i]);
+    bpo[0] = 1.0 / (logf[1] - logf[0]);
+    bpo[kCqtBins - 1] = 1.0 / (logf[kCqtBins - 1] - logf[kCqtBins - 2]);
+    for (int i = 1; i + 1 < kCqtBins; ++i) bpo[i] = 2.0 / (logf[i + 1] - logf[i - 1]);
+    double cutoff = 0.0;
+    for (int i = 0; i < kCqtBins; ++i) {
+        const double p = std::pow(2.0, 2.0 / bpo[i]);
+        w.alpha[i] = (p - 1.0) / (p + 1.0);
+        const double q = 1.0 / w.alpha[i];
+        cutoff = std::max(cutoff, w.freqs[i] * (1.0 + 0.5 * kHannBandwidth / q));
+    }
+    w.cutoff = cutoff;
+}
+
+int early_count(double nyquist, double cutoff) {
+    const int c1 = std::max(0, static_cast<int>(std::ceil(std::log2(nyquist / cutoff)) - 1) - 1);
+    const int c2 = std::max(0, 9 - kCqtOctaves + 1);   // hop 512 = 2^9
+    return std::min(c1, c2);
+}
+
+// per-octave FFT size: power of two >= the longest wavelet of the octave
+void octave_nfft(const Wavelets& w, double sr_eff, int* n_fft) {
+    for (int i = 0; i < kCqtOctaves; ++i) {
+        const double my_sr = sr_eff / std::pow(2.0, static_cast<double>(i));
+        double max_len = 0.0;
+        for (int j = 0; j < kCqtBpo; ++j) {
+            const int b = kCqtBins - kCqtBpo * (i + 1) + j;
+            max_len = std::max(max_len, (1.0 / w.alpha[b]) * my_sr / w.freqs[b]);
+        }
+        n_fft[i] = static_cast<int>(std::pow(2.0, std::ceil(std::log2(max_len))));
+    }
+}
+
+// iterative radix-2 FFT; tw[k] = exp(-2 pi i k / n), k < n / 2
+void fft_inplace(std::vector<std::complex<double>>& a, const std::vector<std::complex<double>>& tw) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t stride = n / len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * tw[k * stride];
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+// sparsified complex64 FFT-domain basis of one octave: dense[36][n_bins] (re, im) float32,
+// scaled by sqrt(sr_eff / my_sr); lengths[j] of the octave's wavelets at my_sr
+void octave_basis(const Wavelets& w, double sr_eff, int octave, int n_fft, std::vector<float>& dense) {
+    const int n_bins = 1 + n_fft / 2;
+    const double my_sr = sr_eff / std::pow(2.0, static_cast<double>(octave));
+    const double oct_scale = std::sqrt(sr_eff / my_sr);
+    dense.assign(static_cast<size_t>(kCqtBpo) * n_bins * 2, 0.0f);
+    std::vector<std::complex<double>> buf(n_fft), tw(n_fft / 2);
+    for (int k = 0; k < n_fft / 2; ++k) {
+        const double ang = -2.0 * kPi * static_cast<double>(k) / static_cast<double>(n_fft);
+        tw[k] = std::complex<double>(std::cos(ang), std::sin(ang));
+    }
+    std::vector<float> mags(n_bins), sorted(n_bins);
+    for (int j = 0; j < kCqtBpo; ++j) {
+        const int b = kCqtBins - kCqtBpo * (octave + 1) + j;
+        const double freq = w.freqs[b];
+        const double ilen = (1.0 / w.alpha[b]) * my_sr / freq;
+        const long n_lo = static_cast<long>(std::floor(-ilen / 2.0));
+        const long n_hi = static_cast<long>(std::floor(ilen / 2.0));
+        const int count = static_cast<int>(n_hi - n_lo);
+        std::vector<std::complex<double>> sig(count);
+        // periodic Hann of `count` points: scipy general_cosine over linspace(-pi, pi, count + 1)
+        const double step = (2.0 * kPi) / static_cast<double>(count);
+        double l1 = 0.0;
+        for (int t = 0; t < count; ++t) {
+            const double n = static_cast<double>(n_lo + t);
+            const double angle = (((n * 2.0) * kPi) * freq) / my_sr;
+            const double fac = static_cast<double>(t) * step + (-kPi);
+            const double win = 0.5 + 0.5 * std::cos(fac);
+            sig[t] = std::complex<double>(std::cos(angle), std::sin(angle)) * win;
+            l1 += std::abs(sig[t]);
+        }
+        if (l1 < 2.2250738585072014e-308) l1 = 1.0;
+        std::fill(buf.begin(), buf.end(), std::complex<double>(0.0, 0.0));
+        const int lpad = (n_fft - count) / 2;
+        const double len_scale = ilen / static_cast<double>(n_fft);
+        for (int t = 0; t < count; ++t) {
+            const std::complex<double> v = sig[t] / l1;
+            // asarray(..., complex64), then `basis *= lengths / n_fft` rounds to complex64 again
+            const float re32 = static_cast<float>(v.real()), im32 = static_cast<float>(v.imag());
+            const float re = static_cast<float>(static_cast<double>(re32) * len_scale);
+            const float im = static_cast<float>(static_cast<double>(im32) * len_scale);
+            buf[lpad + t] = std::complex<double>(re, im);
+        }
+        fft_inplace(buf, tw);
+        double l1m = 0.0;
+        for (int k = 0; k < n_bins; ++k) {
+            const float re = static_cast<float>(buf[k].real()), im = static_cast<float>(buf[k].imag());
+            buf[k] = std::complex<double>(re, im);   // complex64 result
+            mags[k] = static_cast<float>(std::hypot(static_cast<double>(re), static_cast<double>(im)));
+            l1m += mags[k];
+        }
+        // util.sparsify_rows(quantile=0.01): float32 magnitudes, float32 cumulative sum
+        sorted = mags;
+        std::sort(sorted.begin(), sorted.end());
+        const float norm = static_cast<float>(l1m);
+        float cum = 0.0f, thresh = sorted[n_bins - 1];
+        for (int k = 0; k < n_bins; ++k) {
+            cum += sorted[k] / norm;
+            if (!(cum < 0.01f)) { thresh = sorted[k]; break; }
+        }
+        float* row = dense.data() + static_cast<size_t>(j) * n_bins * 2;
+        for (int k = 0; k < n_bins; ++k) {
+            if (mags[k] >= thresh) {
+                row[2 * k] = static_cast<float>(buf[k].real() * oct_scale);
+                row[2 * k + 1] = static_cast<float>(buf[k].imag() * oct_scale);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void cqt_plan(int sample_rate, CqtPlan& plan) {
+    plan = CqtPlan();
+    plan.sample_rate = sample_rate;
+    const double sr = static_cast<double>(sample_rate);
+    const double nyquist = sr / 2.0;
+    int n_bad = 0;
+    bool first = true;
+    for (int t = 0; t < kNTunings; ++t) {
+        Wavelets w;
+        wavelets_for_tuning(t, w);
+        if (w.cutoff > nyquist) { ++n_bad; continue; }
+        const int count = early_count(nyquist, w.cutoff);
+        int n_fft[kCqtOctaves];
+        octave_nfft(w, sr / std::pow(2.0, static_cast<double>(count)), n_fft);
+        if (first) {
+            plan.early_factor = 1 << count;
+            plan.hop0 = 512 >> count;
+            for (int i = 0; i < kCqtOctaves; ++i) plan.n_fft[i] = n_fft[i];
+            first = false;
+        } else {
+            bool same = plan.early_factor == (1 << count);
+            for (int i = 0; i < kCqtOctaves; ++i) same = same && plan.n_fft[i] == n_fft[i];
+            if (!same) {
+                plan.status = 2;
+                plan.message = "tonnetz: the constant-Q plan at this sample rate depends on the tuning estimate (unsupported)";
+                return;
+            }
+        }
+    }
+    if (n_bad == kNTunings) {
+        plan.status = 1;
+        plan.message = "Wavelet basis would exceed the Nyquist frequency. Try reducing the number of frequency bins.";
+        return;
+    }
+    if (n_bad > 0) {
+        plan.status = 2;
+        plan.message = "tonnetz: the constant-Q Nyquist check at this sample rate depends on the tuning estimate (unsupported)";
+        return;
+    }
+    for (int i = 0; i < kCqtOctaves; ++i) {
+        if (plan.n_fft[i] < 128 || plan.n_fft[i] > 2048) {
+            plan.status = 2;
+            plan.message = "tonnetz: constant-Q FFT size outside 128..2048 at this sample rate (unsupported)";
+            return;
+        }
+    }
+}
+
+void cqt_basis_dense(const CqtPlan& plan, int tuning_idx, int octave, std::vector<float>& out) {
+    Wavelets w;
+    wavelets_for_tuning(tuning_idx, w);
+    const double sr_eff = static_cast<double>(plan.sample_rate) / static_cast<double>(plan.early_factor);
+    octave_basis(w, sr_eff, octave, plan.n_fft[octave], out);
+}
+
+bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank) {
+    Wavelets w;
+    wavelets_for_tuning(tuning_idx, w);
+    const double sr_eff = static_cast<double>(plan.sample_rate) / static_cast<double>(plan.early_factor);
+    bank.rows.assign(static_cast<size_t>(kCqtOctaves) * kCqtBpo, CqtRow{0, 0, 0.0f, 0});
+    bank.vals.assign(static_cast<size_t>(kCqtOctaves) * kCqtBpo * kCqtRowCap * 2, 0.0f);
+    std::vector<float> dense;
+    bool ok = true;
+    for (int i = 0; i < kCqtOctaves; ++i) {
+        const int n_bins = 1 + plan.n_fft[i] / 2;
+        octave_basis(w, sr_eff, i, plan.n_fft[i], dense);
+        for (int j = 0; j < kCqtBpo; ++j) {
+            const float* row = dense.data() + static_cast<size_t>(j) * n_bins * 2;
+            int first = -1, last = -1;
+            for (int k = 0; k < n_bins; ++k)
+                if (row[2 * k] != 0.0f || row[2 * k + 1] != 0.0f) { if (first < 0) first = k; last = k; }
+            const int b = kCqtBins - kCqtBpo * (i + 1) + j;
+            CqtRow& r = bank.rows[static_cast<size_t>(i) * kCqtBpo + j];
+            r.bin = b;
+            // V /= sqrt(lengths), lengths = Q * sr_eff / freqs over all 252 bins
+            r.scale = static_cast<float>(1.0 / std::sqrt((1.0 / w.alpha[b]) * sr_eff / w.freqs[b]));
+            if (first < 0) continue;
+            int count = last - first + 1;
+            if (count > kCqtRowCap) { ok = false; count = kCqtRowCap; }
+            r.start = first;
+            r.count = count;
+            float* dst = bank.vals.data() + (static_cast<size_t>(i) * kCqtBpo + j) * kCqtRowCap * 2;
+            for (int k = 0; k < count; ++k) { dst[2 * k] = row[2 * (first + k)]; dst[2 * k + 1] = row[2 * (first + k) + 1]; }
+        }
+    }
+    return ok;
+}
+
+void decimation_taps(int factor, std::vector<double>& taps) {
+    // scipy.signal.kaiserord(att, width) + firwin(numtaps, cutoff, window=("kaiser", beta), scale=True)
+    const double att = 21.0 * 6.0206;
+    const double f_pass = 0.913 / static_cast<double>(factor);
+    const double f_stop = 1.0 / static_cast<double>(factor);
+    const double width = f_stop - f_pass;
+    const double beta = 0.1102 * (att - 8.7);                       // att > 50
+    int numtaps = static_cast<int>(std::ceil((att - 7.95) / 2.285 / (kPi * width) + 1.0));
+    if (numtaps % 2 == 0) numtaps += 1;
+    const double cutoff = 0.5 * (f_pass + f_stop);
+    const double alpha = 0.5 * static_cast<double>(numtaps - 1);
+    taps.resize(numtaps);
+    const double i0_beta = std::cyl_bessel_i(0.0, beta);
+    double sum = 0.0;
+    for (int n = 0; n < numtaps; ++n) {
+        const double m = static_cast<double>(n) - alpha;
+        const double x = cutoff * m;
+        const double sinc = (x == 0.0) ? 1.0 : std::sin(kPi * x) / (kPi * x);
+        const double r = (static_cast<double>(n) - alpha) / alpha;
+        const double win = std::cyl_bessel_i(0.0, beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0_beta;
+        taps[n] = cutoff * sinc * win;
+        sum += taps[n];
+    }
+    for (double& t : taps) t /= sum;
+}
+
+void hann_squared_2048(std::vector<double>& w) {
+    // scipy get_window("hann", 2048, fftbins=True) squared (filters.window_sumsquare)
+    const int n = 2048;
+    w.resize(n);
+    const double step = (2.0 * kPi) / static_cast<double>(n);
+    for (int i = 0; i < n; ++i) {
+        const double fac = static_cast<double>(i) * step + (-kPi);
+        const double h = 0.5 + 0.5 * std::cos(fac);
+        w[i] = h * h;
+    }
+}
+
+}  // namespace serb

@@ -1,0 +1,270 @@
+// Tonnetz chain, first half: librosa.effects.harmonic(y) for a ragged batch of clips.
+//
+// Replaces ser/_internal/utils/dsp.py:139  `harmonic = librosa.effects.harmonic(prepared_audio)`
+//   = istft(hpss(stft(y, 2048, hop 512))[0], length=len(y))        (librosa 0.11.0 semantics,
+//   SURVEY.md Appendix A.7-A.8; oracle: oracle/shim/librosa/effects.py, core.py istft).
+//
+// hpss_harm_kernel  median of 31 along time  (scipy.ndimage.median_filter, mode="reflect")
+// hpss_perc_kernel  median of 31 along frequency
+// istft_kernel      soft mask (power 2, split_zeros) * X, inverse 2048-point real FFT per warp,
+//                   Hann window -> frames
+// ola_kernel        overlap-add in frame order / window sum-of-squares -> harmonic signal
+//
+// The medians keep a sorted window of 31 values in registers and slide it: one branch-free
+// remove pass (compare + select) and one insert pass (min + max) per step.  The work is
+// ALU-bound (FMNMX / FSEL), not memory-bound: every spectrogram value is read twice per
+// kernel from L2/L1 and written once.
+#include <cfloat>
+
+#include "fft.cuh"
+#include "kernels.h"
+
+namespace serb {
+
+namespace {
+
+constexpr int kMedW = 31;
+constexpr int kMedHalf = 15;
+
+// scipy "reflect" (numpy "symmetric"): d c b a | a b c d | d c b a, period 2n
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int period = 2 * n;
+    int m = i % period;
+    if (m < 0) m += period;
+    return m < n ? m : period - 1 - m;
+}
+
+struct SortedWindow {
+    float a[kMedW];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < kMedW; ++i) a[i] = FLT_MAX;
+    }
+    // insert into a window whose last slot holds FLT_MAX
+    __device__ __forceinline__ void insert(float x) {
+        float prev = a[0];
+        a[0] = fminf(prev, x);
+#pragma unroll
+        for (int i = 1; i < kMedW; ++i) {
+            const float cur = a[i];
+            a[i] = fmaxf(prev, fminf(cur, x));
+            prev = cur;
+        }
+    }
+    // remove one occurrence of `old` (which is in the window) and insert x
+    __device__ __forceinline__ void replace(float old, float x) {
+        float b[kMedW];
+#pragma unroll
+        for (int i = 0; i < kMedW - 1; ++i) b[i] = (a[i] >= old) ? a[i + 1] : a[i];
+        b[kMedW - 1] = FLT_MAX;
+        a[0] = fminf(b[0], x);
+#pragma unroll
+        for (int i = 1; i < kMedW; ++i) a[i] = fmaxf(b[i - 1], fminf(b[i], x));
+    }
+    __device__ __forceinline__ float median() const { return a[kMedHalf]; }
+};
+
+}  // namespace
+
+// ---- median along time -----------------------------------------------------------------
+// one thread per (segment of kHarmSeg columns, bin); bins are contiguous across the warp, so
+// every load / store is a coalesced 128-byte row piece
+__global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
+    const int2 seg = p.segs[blockIdx.x];
+    const TonClip clip = p.clips[seg.x];
+    const int f = blockIdx.y * blockDim.x + threadIdx.x;
+    if (f >= kNBins) return;
+    const int T = clip.n_cols;
+    const int t0 = seg.y;
+    const int t1 = min(t0 + kHarmSeg, T);
+    const float* src = p.mag + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    float* dst = p.harm + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    SortedWindow w;
+    w.clear();
+    for (int t = t0 - kMedHalf; t <= t0 + kMedHalf; ++t)
+        w.insert(src[static_cast<long long>(reflect_index(t, T)) * kSpillStride]);
+    for (int t = t0; t < t1; ++t) {
+        dst[static_cast<long long>(t) * kSpillStride] = w.median();
+        if (t + 1 < t1) {
+            const float old = src[static_cast<long long>(reflect_index(t - kMedHalf, T)) * kSpillStride];
+            const float nxt = src[static_cast<long long>(reflect_index(t + 1 + kMedHalf, T)) * kSpillStride];
+            w.replace(old, nxt);
+        }
+    }
+}
+
+// ---- median along frequency ------------------------------------------------------------
+// one warp per two columns: lane = (column, one of 16 runs of 65 bins)
+constexpr int kPercRun = 65;
+__global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int col = 2 * warp + (lane >> 4);
+    if (col >= n_cols) return;
+    const int f0 = (lane & 15) * kPercRun;
+    const int f1 = min(f0 + kPercRun, kNBins);
+    if (f0 >= kNBins) return;
+    const float* src = p.mag + static_cast<long long>(col) * kSpillStride;
+    float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
+    SortedWindow w;
+    w.clear();
+    for (int f = f0 - kMedHalf; f <= f0 + kMedHalf; ++f) w.insert(src[reflect_index(f, kNBins)]);
+    for (int f = f0; f < f1; ++f) {
+        dst[f] = w.median();
+        if (f + 1 < f1) w.replace(src[reflect_index(f - kMedHalf, kNBins)], src[reflect_index(f + 1 + kMedHalf, kNBins)]);
+    }
+}
+
+// ---- soft mask + inverse STFT frame ----------------------------------------------------
+struct IstftSmem {
+    float2 tw[32][32];                 // W_1024^(k1 n2)
+    float2 tw2[1024];                  // (cos, sin) 2 pi k / 2048
+    float2 buf[8][32 * 33];
+    float4 win[32];
+};
+
+__device__ __forceinline__ float harm_mask(float h, float q) {
+    // util.softmask(harm, perc, power=2, split_zeros=True)
+    const float z = fmaxf(h, q);
+    if (z < FLT_MIN) return 0.5f;
+    const float a = h / z, b = q / z;
+    const float ma = a * a, mb = b * b;
+    return ma / (ma + mb);
+}
+
+__global__ void __launch_bounds__(256, 2) istft_kernel(IstftParams p, int n_cols) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 2048; i += 256) reinterpret_cast<float2*>(&sm.tw[0][0])[i] = p.tables[i];
+    if (tid < 32) {
+        float ws0, wc0, ws1, wc1;
+        sincospif(static_cast<float>(2 * tid) * (2.0f / 2048.0f), &ws0, &wc0);
+        sincospif(static_cast<float>(2 * tid + 1) * (2.0f / 2048.0f), &ws1, &wc1);
+        sm.win[tid] = make_float4(wc0, ws0, wc1, ws1);
+    }
+    __syncthreads();
+    float2* buf = sm.buf[warp];
+    const int n_warps = gridDim.x * 8;
+    for (int col = blockIdx.x * 8 + warp; col < n_cols; col += n_warps) {
+        const float2* X = p.cspec + static_cast<long long>(col) * kSpillStride;
+        const float* H = p.harm + static_cast<long long>(col) * kSpillStride;
+        const float* Q = p.perc + static_cast<long long>(col) * kSpillStride;
+        // masked spectrum, k = 32 n1 + lane, kept in registers and mirrored in shared memory so
+        // that the partner X[1024 - k] is one conflict-free load away
+        float2 v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int k = 32 * n1 + lane;
+            const float2 x = X[k];
+            const float m = harm_mask(H[k], Q[k]);
+            v[n1] = make_float2(x.x * m, x.y * m);
+            buf[n1 * 33 + lane] = v[n1];
+        }
+        float nyq = 0.0f;   // X[1024] (real)
+        if (lane == 0) {
+            nyq = X[1024].x * harm_mask(H[1024], Q[1024]);
+            v[0].y = 0.0f;   // irfft ignores the imaginary part of the DC bin
+        }
+        __syncwarp();
+        // conj(Z[k]), Z[k] = E[k] + i O[k]:  2E = A + conj P, 2O = (A - conj P) e^{+i 2 pi k / 2048}
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int kp = 1024 - (32 * n1 + lane);
+            float2 pr = make_float2(nyq, 0.0f);
+            if (kp < 1024) pr = buf[(kp >> 5) * 33 + (kp & 31)];
+            const float ax = v[n1].x, ay = v[n1].y;
+            const float ex = ax + pr.x, ey = ay - pr.y;      // A + conj P
+            const float dx = ax - pr.x, dy = ay + pr.y;      // A - conj P
+            const float2 w = sm.tw2[32 * n1 + lane];
+            const float ox = dx * w.x - dy * w.y;            // (dx + i dy)(cos + i sin)
+            const float oy = dx * w.y + dy * w.x;
+            // 2Z = (ex - oy) + i (ey + ox); conjugate for the forward-FFT inverse
+            v[n1] = make_float2(ex - oy, -(ey + ox));
+        }
+        __syncwarp();
+        fft32(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            float2 y = v[k1];
+            if (k1 > 0) {
+                const float2 w = sm.tw[k1][lane];
+                y = make_float2(fmaf(y.x, w.x, -y.y * w.y), fmaf(y.x, w.y, y.y * w.x));
+            }
+            buf[k1 * 33 + lane] = y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[lane * 33 + n2];
+        __syncwarp();
+        fft32(v);
+        // z[n] = conj(F[n]) / (2 * 1024), n = lane + 32 k2; x[2n] = Re z, x[2n+1] = Im z; Hann
+        const float4 wa = sm.win[lane];
+        float2* out = reinterpret_cast<float2*>(p.frames + static_cast<long long>(col) * kNFft);
+        constexpr float scale = 1.0f / 2048.0f;
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) {
+            const float ca = cos32(k2), sa = sin32(k2);
+            const float w0 = fmaf(-0.5f * ca, wa.x, fmaf(0.5f * sa, wa.y, 0.5f));
+            const float w1 = fmaf(-0.5f * ca, wa.z, fmaf(0.5f * sa, wa.w, 0.5f));
+            out[lane + 32 * k2] = make_float2(v[k2].x * scale * w0, -v[k2].y * scale * w1);
+        }
+    }
+}
+
+// ---- overlap-add + window sum-of-squares ------------------------------------------------
+// one thread per output sample; the (at most four) frames are added in frame order in float32,
+// the squared windows in float64 rounded to float32 after each add, as librosa does
+__global__ void __launch_bounds__(256) ola_kernel(OlaParams p) {
+    const TonClip clip = p.clips[p.tile_clip[blockIdx.x]];
+    const int tile = blockIdx.x - clip.tile_base;
+    const int T = clip.n_cols;
+    const float* frames = p.frames + static_cast<long long>(clip.col_base) * kNFft;
+    float* y = p.yharm + clip.hoff;
+    const int n_lo = tile * kColsPerTile * kHop;
+    const int n_hi = min(n_lo + kColsPerTile * kHop, clip.length);
+    for (int n = n_lo + threadIdx.x; n < n_hi; n += blockDim.x) {
+        const int m = n + kNFft / 2;
+        const int t_hi = min(T - 1, m / kHop);
+        const int t_lo = max(0, (m - (kNFft - 1) + kHop - 1) / kHop);
+        float acc = 0.0f, wss = 0.0f;
+        for (int t = t_lo; t <= t_hi; ++t) {
+            const int j = m - t * kHop;
+            acc += frames[static_cast<long long>(t) * kNFft + j];
+            wss = static_cast<float>(static_cast<double>(wss) + p.hann_sq[j]);
+        }
+        y[n] = wss > FLT_MIN ? acc / wss : acc;
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------
+cudaError_t configure_hpss() {
+    return cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(IstftSmem)));
+}
+
+cudaError_t launch_hpss_medians(const HpssParams& p, int n_segs, int n_cols, cudaStream_t stream) {
+    if (n_segs <= 0 || n_cols <= 0) return cudaSuccess;
+    hpss_harm_kernel<<<dim3(n_segs, (kNBins + 255) / 256), 256, 0, stream>>>(p);
+    const int warps = (n_cols + 1) / 2;
+    hpss_perc_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream) {
+    if (n_cols <= 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = min((n_cols + 7) / 8, 2 * sms);
+    istft_kernel<<<grid, 256, sizeof(IstftSmem), stream>>>(p, n_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ola(const OlaParams& p, int n_tiles, cudaStream_t stream) {
+    if (n_tiles <= 0) return cudaSuccess;
+    ola_kernel<<<n_tiles, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace serb

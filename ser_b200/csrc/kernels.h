@@ -14,6 +14,7 @@ struct StftParams {
     const int* tile_clip;    // [tiles] clip index of every 16-column tile
     const float2* tables;    // W_1024^(k1 n2) [32][32] then W_2048^k [1024] as (cos, sin)
     float* spill;            // [cols][kSpillStride]  |X|
+    float2* cspill;          // [cols][kSpillStride]  X (complex), or NULL (tonnetz chain: HPSS needs the phase)
     int do_peaks;            // piptrack wanted (chroma enabled)
     int kmin, kmax;          // bins with 150 <= f < min(4000, sr/2):  kmin <= k < kmax
     int peak_cap;            // slots per column
@@ -94,6 +95,79 @@ struct ShortParams {
 };
 cudaError_t configure_short();
 cudaError_t launch_short(const ShortParams& p, int n_clips, cudaStream_t stream);
+
+// ---- tonnetz chain: hpss_kernels.cu, cqt_kernels.cu ----------------------------------------
+constexpr int kHarmSeg = 128;     // columns per time-median work item
+constexpr int kCqOctaves = 7;
+constexpr int kCqRows = 36;       // bins per octave
+constexpr int kCqBins = 252;
+constexpr int kCqRowCap = 32;     // complex values stored per basis row
+constexpr int kDecTaps2 = 381;    // soxr_hq stand-in, factor 2 (cqt_tables.cpp decimation_taps)
+
+struct TonClip {
+    long long hoff;      // harmonic signal of the clip: yharm[hoff .. hoff + length)
+    long long off0;      // level-0 constant-Q signal: yoct[off0 .. off0 + len0); level l at level_base[l] + (off0 >> l)
+    int length;          // samples
+    int n_cols;          // STFT columns, 1 + length / 512
+    int col_base;        // first STFT column inside the chunk scratch
+    int tile_base;       // first 16-column tile inside the chunk
+    int len0;            // ceil(length / early_factor)
+    int cq_cols;         // constant-Q columns kept (min over octaves, librosa __trim_stack)
+    int cq_base;         // first row of the clip in cqmag
+    int out_row;
+};
+
+struct HpssParams {
+    const TonClip* clips;
+    const int2* segs;        // (clip index, first column) per time-median work item
+    const float* mag;        // [cols][kSpillStride] |X|
+    float* harm;             // [cols][kSpillStride] median along time
+    float* perc;             // [cols][kSpillStride] median along frequency
+};
+struct IstftParams {
+    const float2* cspec;     // [cols][kSpillStride] X
+    const float* harm;
+    const float* perc;
+    const float2* tables;    // FFT twiddles (same layout as StftParams::tables)
+    float* frames;           // [cols][2048] windowed inverse-FFT frames
+};
+struct OlaParams {
+    const TonClip* clips;
+    const int* tile_clip;    // [tiles]
+    const float* frames;
+    const double* hann_sq;   // [2048] squared periodic Hann, float64
+    float* yharm;
+};
+cudaError_t configure_hpss();
+cudaError_t launch_hpss_medians(const HpssParams& p, int n_segs, int n_cols, cudaStream_t stream);
+cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream);
+cudaError_t launch_ola(const OlaParams& p, int n_tiles, cudaStream_t stream);
+
+struct CqRow { int start; int count; float scale; int bin; };
+struct CqtParams {
+    const TonClip* clips;
+    int n_clips;
+    const int* tuning_idx;       // [clips] 0..99 (36 bins per octave)
+    const float* yharm;          // full-rate harmonic signals
+    float* yoct;                 // decimated signals, all levels
+    long long level_base[kCqOctaves];
+    int early_factor;            // 1, 2, 4, 8
+    int hop0;                    // hop of level 0
+    int n_fft[kCqOctaves];
+    const float* early_taps;     // [n_early_taps] (scaled by sqrt(early_factor)); NULL if factor 1
+    int n_early_taps;
+    const CqRow* rows;           // [100][7][36]
+    const float2* vals;          // [100][7][36][kCqRowCap]
+    const float2* twiddles;      // W_N^j (cos, -sin), j < N, for N = 128, 256, 512, 1024 back to back, then
+                                 // (cos, sin) 2 pi k / (2N), k < N, for the same N
+    float* cqmag;                // [cq rows][252]
+    float* out;                  // [rows][dim]
+    int dim, off_tonnetz;
+    int max_len0;                // longest level-0 signal in the chunk
+    int max_cq_cols;             // most constant-Q columns of one clip
+};
+cudaError_t configure_cqt(const float* taps2_scaled);   // uploads the factor-2 taps (x sqrt 2) to constant memory
+cudaError_t launch_cqt_chain(const CqtParams& p, cudaStream_t stream, long long* launches);
 
 // ---- mlp_kernel.cu -----------------------------------------------------------------------
 struct MlpParams {

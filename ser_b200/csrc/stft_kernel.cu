@@ -102,7 +102,7 @@ __device__ __forceinline__ void issue_wave_copy(StftSmem& sm, const ItemDesc& d)
 // spill) and to the warp's staging buffer; returns the lane's running maximum of |X|.
 __device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[32],
                                             const float2* __restrict__ tw2, float2* __restrict__ buf,
-                                            int lane, float* __restrict__ row) {
+                                            int lane, float* __restrict__ row, float2* __restrict__ crow) {
     fft32(v);  // over n1 -> index k1
     // twiddle W_1024^(lane * k1), transpose through shared memory
 #pragma unroll
@@ -137,12 +137,14 @@ __device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[
         const float wy = fmaf(w.x, oy, -w.y * ox);
         const float xr = ex + wx, xi = ey + wy;
         const float mag = 0.5f * sqrt_approx(fmaf(xr, xr, xi * xi));
+        if (crow) crow[lane + 32 * k2] = make_float2(0.5f * xr, 0.5f * xi);
         row[lane + 32 * k2] = mag;
         sbuf[lane + 32 * k2] = mag;
         cmax = fmaxf(cmax, mag);
         if (k2 == 0 && lane == 0) {
             const float nr = ex - wx, ni = ey - wy;
             const float nyq = 0.5f * sqrt_approx(fmaf(nr, nr, ni * ni));
+            if (crow) crow[1024] = make_float2(0.5f * nr, 0.5f * ni);
             row[1024] = nyq;
             sbuf[1024] = nyq;
             cmax = fmaxf(cmax, nyq);
@@ -264,7 +266,8 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(StftParams p, int
         }
         if (active) {
             const long long col = d.col0 + warp;
-            float cmax = column_fft(v, sm.tw, sm.tw2, buf, lane, p.spill + col * kSpillStride);
+            float cmax = column_fft(v, sm.tw, sm.tw2, buf, lane, p.spill + col * kSpillStride,
+                                    p.cspill ? p.cspill + col * kSpillStride : nullptr);
             if (p.do_peaks) {
                 cmax = warp_max(cmax);
                 __syncwarp();
