@@ -36,6 +36,13 @@ UNIT = "audio-s/s"
 FRAME_SECONDS, STRIDE_SECONDS = 3, 1
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FFMA peak at max clock
 FLOP_PER_COLUMN = 97_000                                     # SURVEY.md section 8(d), 187-d slice
+FLOP_PER_COLUMN_193 = 1_140_000                              # itemised ops of the 193-d chain
+KERNEL_NAMES = {
+    "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
+    "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
+    "istft": "istft_kernel", "ola": "ola_kernel", "decimate": "decimate2_kernel", "cqt": "cqt_kernel",
+    "tonnetz": "tonnetz_kernel",
+}
 
 
 def parse_args():
@@ -335,36 +342,61 @@ def run_b200(args) -> None:
                "steps": e2e_steps, "ms_per_step": 1e3 * elapsed / e2e_steps}
         assert np.array_equal(l_host, labels.cpu().numpy()), "host-entry labels differ from the device path"
 
-    # ---- roofline of the dominant kernel: CUDA events around every stft launch, one extra pass ----
+    # ---- the 187-d slice (tonnetz off) timed the same way, for continuity with earlier rounds ----
+    slice187 = None
+    if flags.tonnetz:
+        from ser_b200.config import FeatureFlags
+
+        bits187 = flag_bits(FeatureFlags(tonnetz=False))
+        feats187 = torch.empty((n_rows, 187), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            ctx.features_device(wave.data_ptr(), wave.numel(), starts, lengths, sr, bits187, feats187.data_ptr(), stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ctx.features_device(wave.data_ptr(), wave.numel(), starts, lengths, sr, bits187, feats187.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms187 = max_over_ranks(float(e0.elapsed_time(e1))) / args.steps
+        slice187 = {"ms_per_step": ms187, "value": world * audio_seconds_step / (ms187 / 1e3), "unit": UNIT,
+                    "note": "features only, FeatureFlags(tonnetz=False): mfcc + chroma + mel + contrast"}
+        del feats187
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch, one extra pass ----
     ctx.set_profile(True)
     step()
     torch.cuda.synchronize()
     kms = ctx.kernel_ms()
     ctx.set_profile(False)
-    stft_ms, stft_n = kms["stft"]
+    dom = max(kms, key=lambda k: kms[k][0])
+    dom_ms, dom_n = kms[dom]
     total_cols = int(np.sum(1 + lengths // 512))
     # algorithmic bytes: every input sample once + every output row once
     alg_bytes_step = 4 * n_clips * n_samples + 4 * dim * n_rows
     peak, peak_src = peaks()
-    achieved = alg_bytes_step / (stft_ms / 1e3) / 1e9 if stft_ms > 0 else 0.0
+    achieved = alg_bytes_step / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
-    traffic_file = REPO / "profiles" / "stft_traffic.json"
+    traffic_file = REPO / "profiles" / "dominant_kernel_traffic.json"
     if traffic_file.exists():
         try:
-            traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+            entry = json.loads(traffic_file.read_text()).get(KERNEL_NAMES[dom])
+            traffic = entry.get("dram_bytes_per_launch") if entry else None
         except Exception:
             traffic = None
+    flop_per_column = FLOP_PER_COLUMN_193 if flags.tonnetz else FLOP_PER_COLUMN
     roofline = {
-        "kernel": "stft_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "kernel": KERNEL_NAMES[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes_step / max(stft_n, 1), "launches_per_step": stft_n,
-        "avg_launch_ms": stft_ms / max(stft_n, 1),
+        "algorithmic_bytes_per_launch": alg_bytes_step / max(dom_n, 1), "launches_per_step": dom_n,
+        "avg_launch_ms": dom_ms / max(dom_n, 1),
         "kernel_ms_per_step": {k: v[0] for k, v in kms.items()},
-        "share_of_step": stft_ms / max(sum(v[0] for v in kms.values()), 1e-9),
-        "fp32": {"achieved_tflops": total_cols * FLOP_PER_COLUMN / (ms_per_step / 1e3) / 1e12,
+        "share_of_step": dom_ms / max(sum(v[0] for v in kms.values()), 1e-9),
+        "fp32": {"achieved_tflops": total_cols * flop_per_column / (ms_per_step / 1e3) / 1e12,
                  "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
-                 "note": "whole step, 97 kflop/column (SURVEY.md 8d); the path is FP32/shared-memory bound, not HBM bound"},
-        "how": "CUDA events around each stft_kernel launch in one extra pass of the same step",
+                 "note": f"whole step, {flop_per_column // 1000} kop/column (DESIGN.md section 4); the path is "
+                         "ALU/FP32/shared-memory bound, not HBM bound"},
+        "how": "CUDA events around every launch of the dominant kernel in one extra pass of the same step",
     }
 
     cpu_baseline = None
@@ -392,7 +424,7 @@ def run_b200(args) -> None:
                 "parallelism": f"clips sharded over {world} GPU(s), no collective",
             },
             "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "slice_187d": slice187,
         }
         print(json.dumps(line), flush=True)
     if distributed:

@@ -164,7 +164,8 @@ int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octa
 int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity);
 /* kernels launched by this context since creation */
 int64_t serb_debug_launch_count(const serb_ctx* ctx);
-/* per-kernel CUDA-event timing: kinds 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp.
+/* per-kernel CUDA-event timing: kinds 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss_harm,
+ * 7 hpss_perc, 8 istft, 9 ola, 10 decimations, 11 constant-Q octaves, 12 tonnetz.
  * set_profile(1) brackets every launch with an event pair (and resets the totals);
  * kernel_ms returns the accumulated device time and launch count of one kind. */
 int serb_debug_set_profile(serb_ctx* ctx, int32_t enabled);

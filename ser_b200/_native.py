@@ -234,7 +234,8 @@ class Context:
     def kernel_ms(self) -> dict[str, tuple[float, int]]:
         """{kernel: (total device ms, launches)} since set_profile(True)."""
         out = {}
-        for kind, name in enumerate(("stft", "tuning", "proj", "pool", "short", "mlp", "hpss", "istft", "cqt")):
+        for kind, name in enumerate(("stft", "tuning", "proj", "pool", "short", "mlp", "hpss_harm", "hpss_perc", "istft", "ola",
+                                     "decimate", "cqt", "tonnetz")):
             ms = c_double(0.0)
             n = c_int64(0)
             self._check(self._lib.serb_debug_kernel_ms(self._handle, kind, ctypes.byref(ms), ctypes.byref(n)))

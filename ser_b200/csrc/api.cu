@@ -61,7 +61,7 @@ struct Mlp {
 
 }  // namespace
 
-constexpr int kProfKinds = 10;
+constexpr int kProfKinds = 13;
 
 struct serb_ctx {
     int device = 0;
@@ -120,8 +120,8 @@ int fail_cuda(serb_ctx* ctx, cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);    \
     } while (0)
 
-// kinds: 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss medians, 7 istft + overlap-add,
-// 8 decimation + constant-Q + tonnetz
+// kinds: 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss_harm, 7 hpss_perc, 8 istft, 9 ola,
+// 10 decimations, 11 constant-Q octaves, 12 tonnetz
 struct ProfScope {
     serb_ctx* ctx; int kind; cudaStream_t stream; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(serb_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), stream(s) {
@@ -431,7 +431,8 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
         hp.mag = ctx->spill.as<float>();
         hp.harm = ctx->harm.as<float>();
         hp.perc = ctx->perc.as<float>();
-        { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_medians(hp, c.n_segs, c.n_cols, stream)); }
+        { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_harm(hp, c.n_segs, stream)); }
+        { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, stream)); }
         ctx->launches += 2;
         // 3. soft mask + inverse STFT + overlap-add
         IstftParams ip{};
@@ -446,11 +447,8 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
         op.frames = ip.frames;
         op.hann_sq = ctx->hann_sq.as<double>();
         op.yharm = ctx->yharm.as<float>();
-        {
-            ProfScope ps(ctx, 7, stream);
-            SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream));
-            SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream));
-        }
+        { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream)); }
+        { ProfScope ps(ctx, 9, stream); SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream)); }
         ctx->launches += 2;
         // 4. tuning of the harmonic signal (36 bins per octave)
         sp.wave = ctx->yharm.as<float>();
@@ -491,7 +489,10 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
         qp.off_tonnetz = off.tonnetz;
         qp.max_len0 = c.max_len0;
         qp.max_cq_cols = c.max_cq_cols;
-        { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_cqt_chain(qp, stream, &ctx->launches)); }
+        { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
+        { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
+        { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
+        ctx->launches += 1;
     }
     return SERB_OK;
 }

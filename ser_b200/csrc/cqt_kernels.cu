@@ -309,12 +309,11 @@ static void launch_cqt_octave(const CqtParams& p, int octave, cudaStream_t strea
     cqt_kernel<R><<<grid, kCqtWarps * 32, 0, stream>>>(p, octave);
 }
 
-cudaError_t launch_cqt_chain(const CqtParams& p, cudaStream_t stream, long long* launches) {
+cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long long* launches) {
     if (p.n_clips <= 0) return cudaSuccess;
     long long n = 0;
     if (p.early_factor == 2) {
-        const int out_max = (p.max_len0 + 0);   // max_len0 already is the longest level-0 signal
-        decimate2_kernel<<<dim3(p.n_clips, (out_max + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, -1);
+        decimate2_kernel<<<dim3(p.n_clips, (p.max_len0 + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, -1);
         ++n;
     } else if (p.early_factor > 2) {
         const int tiles = min(4096, (p.max_len0 + 255) / 256);
@@ -327,6 +326,12 @@ cudaError_t launch_cqt_chain(const CqtParams& p, cudaStream_t stream, long long*
         decimate2_kernel<<<dim3(p.n_clips, (len + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, level);
         ++n;
     }
+    if (launches) *launches += n;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long long* launches) {
+    if (p.n_clips <= 0) return cudaSuccess;
     for (int octave = 0; octave < kCqOctaves; ++octave) {
         switch (p.n_fft[octave]) {
             case 256: launch_cqt_octave<4>(p, octave, stream); break;
@@ -335,11 +340,14 @@ cudaError_t launch_cqt_chain(const CqtParams& p, cudaStream_t stream, long long*
             case 2048: launch_cqt_octave<32>(p, octave, stream); break;
             default: return cudaErrorInvalidValue;
         }
-        ++n;
     }
+    if (launches) *launches += kCqOctaves;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tonnetz(const CqtParams& p, cudaStream_t stream) {
+    if (p.n_clips <= 0) return cudaSuccess;
     tonnetz_kernel<<<p.n_clips, 128, 0, stream>>>(p);
-    ++n;
-    if (launches) *launches += n;
     return cudaGetLastError();
 }
 

@@ -243,9 +243,14 @@ cudaError_t configure_hpss() {
                                 static_cast<int>(sizeof(IstftSmem)));
 }
 
-cudaError_t launch_hpss_medians(const HpssParams& p, int n_segs, int n_cols, cudaStream_t stream) {
-    if (n_segs <= 0 || n_cols <= 0) return cudaSuccess;
+cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t stream) {
+    if (n_segs <= 0) return cudaSuccess;
     hpss_harm_kernel<<<dim3(n_segs, (kNBins + 255) / 256), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream) {
+    if (n_cols <= 0) return cudaSuccess;
     const int warps = (n_cols + 1) / 2;
     hpss_perc_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
     return cudaGetLastError();

@@ -139,7 +139,8 @@ struct OlaParams {
     float* yharm;
 };
 cudaError_t configure_hpss();
-cudaError_t launch_hpss_medians(const HpssParams& p, int n_segs, int n_cols, cudaStream_t stream);
+cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t stream);
+cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_ola(const OlaParams& p, int n_tiles, cudaStream_t stream);
 
@@ -167,7 +168,9 @@ struct CqtParams {
     int max_cq_cols;             // most constant-Q columns of one clip
 };
 cudaError_t configure_cqt(const float* taps2_scaled);   // uploads the factor-2 taps (x sqrt 2) to constant memory
-cudaError_t launch_cqt_chain(const CqtParams& p, cudaStream_t stream, long long* launches);
+cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long long* launches);
+cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long long* launches);
+cudaError_t launch_tonnetz(const CqtParams& p, cudaStream_t stream);
 
 // ---- mlp_kernel.cu -----------------------------------------------------------------------
 struct MlpParams {

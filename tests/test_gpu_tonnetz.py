@@ -1,0 +1,134 @@
+"""GPU parity of the tonnetz chain and of the full 193-d fast-profile vector (default flags).
+
+Tolerances: pooled features scaled error <= 1e-4 per group (conftest.group_errors); harmonic
+signal and constant-Q magnitudes <= 5e-6 of their maxima; tuning bins identical.
+"""
+
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import group_errors
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+ALL_GROUPS = ("mfcc", "chroma", "mel", "contrast", "tonnetz")
+CASES = ["c16k_3s", "c48k_3p5s", "c22k_2s", "c44k_1s", "c16k_tail_5937", "c16k_2048", "sine16k_1p5s", "silence16k",
+         "c16k_short_1500", "c16k_short_1001", "c16k_short_300", "c48k_short_512"]
+
+
+def _audio(golden, name):
+    from ser_b200 import synth
+
+    return synth.decode_pcm16(golden[f"{name}/pcm"]), int(golden[f"{name}/sr"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_default_flags_give_the_193d_golden_vector(golden, name):
+    from ser_b200 import dsp
+
+    audio, sr = _audio(golden, name)
+    got = dsp.extract_feature_from_signal(audio, sr)          # FeatureFlags() default: all five groups
+    assert got.dtype == np.float64 and got.shape == (193,)
+    report = group_errors(got, golden[f"{name}/features"], groups=ALL_GROUPS)
+    print(name, {k: f"{v[0]:.2e}" for k, v in report.items()})
+    for group, (scaled, _raw) in report.items():
+        assert scaled <= TOL, f"{name}/{group}: scaled error {scaled:.3e}"
+
+
+@pytest.mark.parametrize("name", ["c16k_3s", "c48k_3p5s", "c44k_1s", "c16k_short_300"])
+def test_tonnetz_stages_match_oracle(golden, gpu_ctx, name):
+    from oracle.shim import librosa
+
+    audio, sr = _audio(golden, name)
+    padded = audio if audio.size >= 512 else np.pad(audio, (0, 512 - audio.size))
+    got = gpu_ctx.debug_tonnetz_stages(audio, sr)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yh = librosa.effects.harmonic(padded)
+        tuning = librosa.estimate_tuning(y=yh, sr=sr, bins_per_octave=36)
+        C = np.abs(librosa.cqt(yh, sr=sr, hop_length=512, n_bins=252, bins_per_octave=36, tuning=tuning)).T
+    assert np.max(np.abs(got["yharm"] - yh)) <= 5e-6 * np.max(np.abs(yh))
+    assert np.linspace(-0.5, 0.5, 101)[got["tuning_index"]] == pytest.approx(tuning, abs=1e-12)
+    assert got["cqmag"].shape == C.shape
+    assert np.max(np.abs(got["cqmag"] - C)) <= 5e-6 * np.max(C)
+
+
+def test_sliding_windows_match_golden_sequence_193(golden):
+    from ser_b200 import synth
+    from ser_b200.handcrafted import HandcraftedBackend
+
+    audio = synth.decode_pcm16(golden["seq/pcm"])
+    backend = HandcraftedBackend()
+    assert backend.feature_dim == 193
+    encoded = backend.encode_sequence(audio, int(golden["seq/sr"]))
+    np.testing.assert_array_equal(encoded.frame_start_seconds, golden["seq/starts"])
+    np.testing.assert_array_equal(encoded.frame_end_seconds, golden["seq/ends"])
+    assert encoded.embeddings.dtype == np.float32 and encoded.embeddings.shape == (5, 193)
+    for group, (scaled, _raw) in group_errors(encoded.embeddings, golden["seq/embeddings"], groups=ALL_GROUPS).items():
+        assert scaled <= TOL, group
+    vec = backend.extract_vector(audio, int(golden["seq/sr"]))
+    for group, (scaled, _raw) in group_errors(vec, golden["seq/vector"], groups=ALL_GROUPS).items():
+        assert scaled <= TOL, group
+
+
+def test_batch_equals_single_calls_bitwise_193(golden):
+    from ser_b200 import dsp
+
+    sr16 = [n for n in CASES if int(golden[f"{n}/sr"]) == 16000]
+    clips = [_audio(golden, n)[0] for n in sr16]
+    batch = dsp.extract_features_batch(clips, 16000)
+    assert batch.shape == (len(clips), 193)
+    for row, clip in zip(batch, clips):
+        np.testing.assert_array_equal(row, dsp.extract_feature_from_signal(clip, 16000))
+    np.testing.assert_array_equal(batch, dsp.extract_features_batch(clips, 16000))   # run-to-run deterministic
+
+
+def test_tonnetz_only_and_nyquist_error(golden):
+    from ser_b200 import dsp
+    from ser_b200.config import FeatureFlags
+
+    audio, sr = _audio(golden, "c22k_2s")
+    only = dsp.extract_feature_from_signal(audio, sr, feature_flags=FeatureFlags(False, False, False, False, True))
+    full = dsp.extract_feature_from_signal(audio, sr)
+    np.testing.assert_array_equal(only, full[187:])
+    # librosa.cqt: "Wavelet basis with max frequency=... would exceed the Nyquist frequency"
+    with pytest.raises(dsp.ParameterError, match="Nyquist"):
+        dsp.extract_feature_from_signal(np.zeros(4096, dtype=np.float32), 8000,
+                                        feature_flags=FeatureFlags(False, False, False, False, True))
+
+
+def test_full_size_properties_c2_batch_193(gpu_ctx):
+    """Config c2 at full size with tonnetz on: halving the input leaves tonnetz (a ratio of
+    magnitudes behind exact medians) bit-identical, and rows do not depend on batch position."""
+    import torch
+
+    from ser_b200 import synth
+    from ser_b200.config import FeatureFlags, flag_bits
+
+    n_clips, n_samples, sr = 1440, 168000, 48000
+    wave = synth.batch_audio_torch(n_clips, sr, n_samples, device="cuda")
+    starts = np.arange(n_clips, dtype=np.int64) * n_samples
+    lengths = np.full(n_clips, n_samples, dtype=np.int64)
+    bits = flag_bits(FeatureFlags())
+    out1 = torch.empty((n_clips, 193), dtype=torch.float32, device="cuda")
+    out2 = torch.empty_like(out1)
+    half = wave * 0.5
+    torch.cuda.synchronize()
+    gpu_ctx.features_device(wave.data_ptr(), wave.numel(), starts, lengths, sr, bits, out1.data_ptr(), 0)
+    gpu_ctx.features_device(half.data_ptr(), half.numel(), starts, lengths, sr, bits, out2.data_ptr(), 0)
+    torch.cuda.synchronize()
+    a, b = out1.cpu().numpy(), out2.cpu().numpy()
+    assert np.all(np.isfinite(a))
+    assert np.all(np.abs(a[:, 187:]) <= 1.0 + 1e-6)          # |phi| <= 1 on an L1-normalised chroma
+    np.testing.assert_array_equal(a[:, 187:], b[:, 187:])
+    for idx in (0, 719, 1439):
+        single = torch.empty((1, 193), dtype=torch.float32, device="cuda")
+        gpu_ctx.features_device(wave.data_ptr(), wave.numel(), starts[idx: idx + 1], lengths[idx: idx + 1], sr,
+                                bits, single.data_ptr(), 0)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(single.cpu().numpy()[0], a[idx])
