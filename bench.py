@@ -36,7 +36,7 @@ UNIT = "audio-s/s"
 FRAME_SECONDS, STRIDE_SECONDS = 3, 1
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FFMA peak at max clock
 FLOP_PER_COLUMN = 97_000                                     # SURVEY.md section 8(d), 187-d slice
-FLOP_PER_COLUMN_193 = 1_140_000                              # itemised ops of the 193-d chain
+FLOP_PER_COLUMN_193 = 1_155_000                              # itemised ops of the 193-d chain
 KERNEL_NAMES = {
     "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
     "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
@@ -244,28 +244,20 @@ def run_b200(args) -> None:
     from ser_b200 import _native, mlp, synth
     from ser_b200.config import feature_dim, flag_bits
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    distributed = world > 1
+    from ser_b200 import multi_gpu
+
+    info = multi_gpu.rank_info()
+    rank, local_rank, world, distributed = info.rank, info.local_rank, info.world, info.distributed
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: ser_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if distributed:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    multi_gpu.init_process_group(info, "nccl", device=torch.device("cuda", local_rank))
 
     def barrier():
-        if distributed:
-            dist.barrier()
+        multi_gpu.barrier(info)
 
     def max_over_ranks(x: float) -> float:
-        if not distributed:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return multi_gpu.max_over_ranks(info, x, device="cuda")
 
     flags = supported_flags()
     bits = flag_bits(flags)
@@ -427,8 +419,7 @@ def run_b200(args) -> None:
             "roofline": roofline, "cpu_baseline": cpu_baseline, "slice_187d": slice187,
         }
         print(json.dumps(line), flush=True)
-    if distributed:
-        dist.destroy_process_group()
+    multi_gpu.destroy_process_group(info)
 
 
 def main():
