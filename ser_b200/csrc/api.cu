@@ -87,9 +87,10 @@ struct serb_ctx {
     DevBuf wave, out, proba, labels, x64, pcm, pcm_max;
     // tonnetz chain
     DevBuf hann_sq, cq_twiddles;
-    DevBuf cspec, harm, perc, frames, yharm, yoct, cqmag;
+    DevBuf cspec, perc, frames, yharm, yoct, cqmag;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
-    int ton_chunk_cols = 65536;
+    int ton_chunk_cols = 262144;
+    int harm_seg = 128, perc_runs = 16;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
     std::vector<int> last_short_rows;
     long long last_n_clips = 0;
@@ -356,7 +357,7 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
         ClipDev& b = clips_b[i];
         b = a;
         b.start = c.hoff; b.length = c.length;
-        for (int t0 = 0; t0 < n_cols; t0 += kHarmSeg) segs.push_back(make_int2(static_cast<int>(i) - cur.clip_lo, t0));
+        for (int t0 = 0; t0 < n_cols; t0 += ctx->harm_seg) segs.push_back(make_int2(static_cast<int>(i) - cur.clip_lo, t0));
         cur.total0 += (len0 + 127) / 128 * 128;
         cur.n_cols += n_cols;
         cur.n_tiles += tiles;
@@ -380,7 +381,6 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
     const size_t col_f = static_cast<size_t>(max_cols) * kSpillStride;
     SERB_CUDA(ctx, ctx->spill.reserve(col_f * sizeof(float)));
     SERB_CUDA(ctx, ctx->cspec.reserve(col_f * sizeof(float2)));
-    SERB_CUDA(ctx, ctx->harm.reserve(col_f * sizeof(float)));
     SERB_CUDA(ctx, ctx->perc.reserve(col_f * sizeof(float)));
     SERB_CUDA(ctx, ctx->frames.reserve(static_cast<size_t>(max_cols) * kNFft * sizeof(float)));
     SERB_CUDA(ctx, ctx->yharm.reserve((static_cast<size_t>(max_total0) * fe + 64) * sizeof(float)));
@@ -429,16 +429,15 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
         hp.clips = d_clips;
         hp.segs = ctx->ton_segs.as<int2>() + seg_begin[ci];
         hp.mag = ctx->spill.as<float>();
-        hp.harm = ctx->harm.as<float>();
         hp.perc = ctx->perc.as<float>();
+        hp.seg_len = ctx->harm_seg;
+        hp.cspec = ctx->cspec.as<float2>();
+        { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, ctx->perc_runs, stream)); }
         { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_harm(hp, c.n_segs, stream)); }
-        { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, stream)); }
         ctx->launches += 2;
         // 3. soft mask + inverse STFT + overlap-add
         IstftParams ip{};
         ip.cspec = ctx->cspec.as<float2>();
-        ip.harm = hp.harm;
-        ip.perc = hp.perc;
         ip.tables = ctx->tables.as<float2>();
         ip.frames = ctx->frames.as<float>();
         OlaParams op{};
@@ -752,6 +751,9 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         const int v = std::atoi(env);
         if (v >= 64) ctx->chunk_cols = v;
     }
+    if (const char* env = std::getenv("SERB_TON_CHUNK_COLS")) { const int v = std::atoi(env); if (v >= 64) ctx->ton_chunk_cols = v; }
+    if (const char* env = std::getenv("SERB_HARM_SEG")) { const int v = std::atoi(env); if (v >= 16) ctx->harm_seg = v; }
+    if (const char* env = std::getenv("SERB_PERC_RUNS")) { const int v = std::atoi(env); if (v == 4 || v == 8 || v == 16) ctx->perc_runs = v; }
     ctx->timed = true;
 #define CREATE_CHECK(call)                                                                     \
     do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { int rc2 = fail_cuda(nullptr, e2, #call); delete ctx; return rc2; } } while (0)
@@ -833,7 +835,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->mlp.mean, &ctx->mlp.scale,
                       &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles,
-                      &ctx->cspec, &ctx->harm, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag,
+                      &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag,
                       &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
                       &ctx->ton_tile_clip})
         b->release();

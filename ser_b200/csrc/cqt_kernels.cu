@@ -141,99 +141,124 @@ __device__ __forceinline__ void fft_small(float2* v) {
     else fft16(v);
 }
 
-constexpr int kCqtWarps = 4;
+constexpr int kCqtWarps = 8;
+constexpr int kCqtValPitch = kCqRowCap + 1;   // float2 pitch of a staged basis row (bank spread)
 
-// R complex points per lane per column; N = 32 R complex = n_fft / 2; G = 32 / R columns per warp
+struct CqtSmemHead {
+    float2 buf[kCqtWarps][32 * 33];           // per-warp transpose buffer, then the column spectra
+    float2 vals[kCqRows][kCqtValPitch];       // sparse basis rows of this (tuning, octave)
+    CqRow rows[kCqRows];
+};
+
+// One CTA = one clip, one octave, `cols_per_block` consecutive columns.  The signal span those
+// columns touch is staged once in shared memory (zero padded at the clip ends), together with
+// the 36 sparse basis rows of the clip's tuning; after one barrier every warp works alone:
+// G = 32 / R columns per iteration, R complex points per lane per column (N = 32 R = n_fft / 2).
 template <int R>
-__global__ void __launch_bounds__(kCqtWarps * 32) cqt_kernel(CqtParams p, int octave) {
+__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int octave, int cols_per_block) {
     constexpr int G = 32 / R;
     constexpr int N = 32 * R;
-    __shared__ float2 sbuf[kCqtWarps][32 * 33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) unsigned char cqt_smem_raw[];
+    CqtSmemHead& sm = *reinterpret_cast<CqtSmemHead*>(cqt_smem_raw);
+    float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(CqtSmemHead));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TonClip clip = p.clips[blockIdx.x];
-    const int t_first = (blockIdx.y * kCqtWarps + warp) * G;
-    if (t_first >= clip.cq_cols) return;      // warps are independent: no CTA barrier below
+    const int t_block = blockIdx.y * cols_per_block;
+    if (t_block >= clip.cq_cols) return;
+    const int n_here = min(cols_per_block, clip.cq_cols - t_block);
     const int tuning = p.tuning_idx[blockIdx.x];
     const float* sig = level_ptr(p, clip, octave);
     const int len = level_length(clip.len0, octave);
     const int hop = p.hop0 >> octave;
+    // ---- stage the span and the basis ----
+    const int s0 = t_block * hop - N;                       // signal index of sig_s[0]
+    const int span = (n_here - 1) * hop + 2 * N;
+    for (int i = tid; i < span; i += kCqtWarps * 32) {
+        const int j = s0 + i;
+        sig_s[i] = (j >= 0 && j < len) ? sig[j] : 0.0f;
+    }
+    const size_t bank = (static_cast<size_t>(tuning) * kCqOctaves + octave) * kCqRows;
+    for (int i = tid; i < kCqRows * kCqRowCap; i += kCqtWarps * 32)
+        sm.vals[i / kCqRowCap][i % kCqRowCap] = p.vals[bank * kCqRowCap + i];
+    if (tid < kCqRows) sm.rows[tid] = p.rows[bank + tid];
+    __syncthreads();
+
     const float2* twa = p.twiddles + (N - 128);            // W_N^j = (cos, -sin)
     const float2* twb = p.twiddles + 1920 + (N - 128);     // (cos, sin) 2 pi k / (2N)
-    float2* buf = sbuf[warp];
-
-    // frames (rectangular window, centred, zero padded): z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane
-    float2 v[32];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int base = (t_first + g) * hop - N;
-#pragma unroll
-        for (int n1 = 0; n1 < R; ++n1) {
-            const int i = base + 2 * (32 * n1 + lane);
-            float a = 0.0f, b = 0.0f;
-            if (i >= 0 && i < len) a = sig[i];
-            if (i + 1 >= 0 && i + 1 < len) b = sig[i + 1];
-            v[g * R + n1] = make_float2(a, b);
-        }
-    }
-    // step A: R-point DFTs over n1 (per column), twiddle W_N^(lane k1), transpose
-    if constexpr (R == 32) {
-        fft32(v);
-    } else {
-#pragma unroll
-        for (int g = 0; g < G; ++g) fft_small<R>(v + g * R);
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int k1 = 0; k1 < R; ++k1) {
-            float2 y = v[g * R + k1];
-            if (k1 > 0) {
-                const float2 w = twa[lane * k1];
-                y = make_float2(fmaf(y.x, w.x, -y.y * w.y), fmaf(y.x, w.y, y.y * w.x));
-            }
-            buf[(g * R + k1) * 33 + lane] = y;
-        }
-    __syncwarp();
-#pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[lane * 33 + n2];
-    __syncwarp();
-    // step B: 32-point DFT over n2; lane = (column g2, k1): v[k2] = Z[k1 + R k2]
-    fft32(v);
+    float2* buf = sm.buf[warp];
     const int g2 = lane / R, k1 = lane % R;
     const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
-    float2* xs = buf + g2 * (N + 1);
+
+    for (int lc0 = warp * G; lc0 < n_here; lc0 += kCqtWarps * G) {
+        // frames (rectangular window): z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane
+        float2 v[32];
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-        float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
-        float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
-        if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
-        const float ax = v[k2].x, ay = v[k2].y;
-        const float ex = ax + px, ey = ay - py;
-        const float ox = ay + py, oy = px - ax;        // -i (A - conj P)
-        const int k = k1 + R * k2;
-        const float2 w = twb[k];
-        const float wx = fmaf(w.x, ox, w.y * oy);
-        const float wy = fmaf(w.x, oy, -w.y * ox);
-        xs[k] = make_float2(0.5f * (ex + wx), 0.5f * (ey + wy));
-        if (k2 == 0 && k1 == 0) xs[N] = make_float2(0.5f * (ex - wx), 0.5f * (ey - wy));
-    }
-    __syncwarp();
-    // sparse basis rows: C[r] = sum_c B[r][c] X[start + c]
-    const size_t bank = (static_cast<size_t>(tuning) * kCqOctaves + octave) * kCqRows;
-    for (int i = lane; i < kCqRows * G; i += 32) {
-        const int g = i / kCqRows, r = i % kCqRows;
-        const int t = t_first + g;
-        if (t >= clip.cq_cols) continue;
-        const CqRow row = p.rows[bank + r];
-        const float2* b = p.vals + (bank + r) * kCqRowCap;
-        const float2* x = buf + g * (N + 1) + row.start;
-        float cr = 0.0f, ci = 0.0f;
-        for (int c = 0; c < row.count; ++c) {
-            const float2 bv = b[c], xv = x[c];
-            cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
-            ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
+        for (int g = 0; g < G; ++g) {
+            const int lc = min(lc0 + g, n_here - 1);       // surplus columns repeat the last one (not stored)
+            const float* frame = sig_s + lc * hop;
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1)
+                v[g * R + n1] = *reinterpret_cast<const float2*>(frame + 2 * (32 * n1 + lane));
         }
-        p.cqmag[(static_cast<size_t>(clip.cq_base) + t) * kCqBins + row.bin] = sqrtf(fmaf(cr, cr, ci * ci)) * row.scale;
+        // step A: R-point DFTs over n1 (per column), twiddle W_N^(lane k1), transpose
+        if constexpr (R == 32) {
+            fft32(v);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) fft_small<R>(v + g * R);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                float2 y = v[g * R + q];
+                if (q > 0) {
+                    const float2 w = twa[lane * q];
+                    y = make_float2(fmaf(y.x, w.x, -y.y * w.y), fmaf(y.x, w.y, y.y * w.x));
+                }
+                buf[(g * R + q) * 33 + lane] = y;
+            }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[lane * 33 + n2];
+        __syncwarp();
+        // step B: 32-point DFT over n2; lane = (column g2, k1): v[k2] = Z[k1 + R k2]
+        fft32(v);
+        float2* xs = buf + g2 * (N + 1);
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) {
+            float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
+            float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
+            if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
+            const float ax = v[k2].x, ay = v[k2].y;
+            const float ex = ax + px, ey = ay - py;
+            const float ox = ay + py, oy = px - ax;        // -i (A - conj P)
+            const int k = k1 + R * k2;
+            const float2 w = twb[k];
+            const float wx = fmaf(w.x, ox, w.y * oy);
+            const float wy = fmaf(w.x, oy, -w.y * ox);
+            xs[k] = make_float2(0.5f * (ex + wx), 0.5f * (ey + wy));
+            if (k2 == 0 && k1 == 0) xs[N] = make_float2(0.5f * (ex - wx), 0.5f * (ey - wy));
+        }
+        __syncwarp();
+        // sparse basis rows: C[r] = sum_c B[r][c] X[start + c]
+        for (int i = lane; i < kCqRows * G; i += 32) {
+            const int g = i / kCqRows, r = i % kCqRows;
+            const int lc = lc0 + g;
+            if (lc >= n_here) continue;
+            const CqRow row = sm.rows[r];
+            const float2* b = sm.vals[r];
+            const float2* x = buf + g * (N + 1) + row.start;
+            float cr = 0.0f, ci = 0.0f;
+            for (int c = 0; c < row.count; ++c) {
+                const float2 bv = b[c], xv = x[c];
+                cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
+                ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
+            }
+            p.cqmag[(static_cast<size_t>(clip.cq_base) + t_block + lc) * kCqBins + row.bin] =
+                sqrtf(fmaf(cr, cr, ci * ci)) * row.scale;
+        }
+        __syncwarp();
     }
 }
 
@@ -301,12 +326,26 @@ cudaError_t configure_cqt(const float* taps2_scaled) {
     return cudaMemcpyToSymbol(c_taps2, taps2_scaled, kDecTaps2 * sizeof(float));
 }
 
+constexpr int kCqtSpanBudget = 8704;    // staged signal floats per CTA (two CTAs per SM)
+
 template <int R>
-static void launch_cqt_octave(const CqtParams& p, int octave, cudaStream_t stream) {
+static cudaError_t launch_cqt_octave(const CqtParams& p, int octave, cudaStream_t stream) {
     constexpr int G = 32 / R;
-    const int groups = (p.max_cq_cols + G - 1) / G;
-    dim3 grid(p.n_clips, (groups + kCqtWarps - 1) / kCqtWarps);
-    cqt_kernel<R><<<grid, kCqtWarps * 32, 0, stream>>>(p, octave);
+    constexpr int N = 32 * R;
+    const int hop = p.hop0 >> octave;
+    const int per_iter = kCqtWarps * G;
+    // as many whole iterations as fit the span budget, at least one, at most four
+    int iters = (kCqtSpanBudget - 2 * N + hop) / (per_iter * hop);
+    iters = max(1, min(4, iters));
+    const int cols_per_block = per_iter * iters;
+    const size_t span = static_cast<size_t>(cols_per_block - 1) * hop + 2 * N;
+    const size_t bytes = sizeof(CqtSmemHead) + span * sizeof(float);
+    // per-device attribute, so set on every launch (a host-side call, no synchronisation)
+    cudaError_t e = cudaFuncSetAttribute(cqt_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return e;
+    dim3 grid(p.n_clips, (p.max_cq_cols + cols_per_block - 1) / cols_per_block);
+    cqt_kernel<R><<<grid, kCqtWarps * 32, bytes, stream>>>(p, octave, cols_per_block);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long long* launches) {
@@ -332,14 +371,16 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
 
 cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long long* launches) {
     if (p.n_clips <= 0) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
     for (int octave = 0; octave < kCqOctaves; ++octave) {
         switch (p.n_fft[octave]) {
-            case 256: launch_cqt_octave<4>(p, octave, stream); break;
-            case 512: launch_cqt_octave<8>(p, octave, stream); break;
-            case 1024: launch_cqt_octave<16>(p, octave, stream); break;
-            case 2048: launch_cqt_octave<32>(p, octave, stream); break;
+            case 256: e = launch_cqt_octave<4>(p, octave, stream); break;
+            case 512: e = launch_cqt_octave<8>(p, octave, stream); break;
+            case 1024: e = launch_cqt_octave<16>(p, octave, stream); break;
+            case 2048: e = launch_cqt_octave<32>(p, octave, stream); break;
             default: return cudaErrorInvalidValue;
         }
+        if (e != cudaSuccess) return e;
     }
     if (launches) *launches += kCqOctaves;
     return cudaGetLastError();

@@ -4,10 +4,10 @@
 //   = istft(hpss(stft(y, 2048, hop 512))[0], length=len(y))        (librosa 0.11.0 semantics,
 //   SURVEY.md Appendix A.7-A.8; oracle: oracle/shim/librosa/effects.py, core.py istft).
 //
-// hpss_harm_kernel  median of 31 along time  (scipy.ndimage.median_filter, mode="reflect")
-// hpss_perc_kernel  median of 31 along frequency
-// istft_kernel      soft mask (power 2, split_zeros) * X, inverse 2048-point real FFT per warp,
-//                   Hann window -> frames
+// hpss_perc_kernel  median of 31 along frequency (scipy.ndimage.median_filter, mode="reflect")
+// hpss_harm_kernel  median of 31 along time, then the soft mask (power 2, split_zeros) applied
+//                   to the complex spectrum in place
+// istft_kernel      inverse 2048-point real FFT per warp, Hann window -> frames
 // ola_kernel        overlap-add in frame order / window sum-of-squares -> harmonic signal
 //
 // The medians keep a sorted window of 31 values in registers and slide it: one branch-free
@@ -66,9 +66,30 @@ struct SortedWindow {
 
 }  // namespace
 
+__device__ __forceinline__ float harm_mask(float h, float q) {
+    // util.softmask(harm, perc, power=2, split_zeros=True): (h/z)^2 / ((h/z)^2 + (q/z)^2) with
+    // z = max(h, q).  Dividing by z only guards the squares against under/overflow; scaling by
+    // the power of two nearest 1/z does the same exactly and leaves one division.
+    const float z = fmaxf(h, q);
+    if (z < FLT_MIN) return 0.5f;
+    const float s = __int_as_float(0x7e800000 - min(__float_as_int(z) & 0x7f800000, 0x7e000000));   // 2^(-exponent(z) - 1)
+    const float a = h * s, b = q * s;
+    const float ma = a * a, mb = b * b;
+    return __fdividef(ma, ma + mb);
+}
+
+// single reflection, valid for -n <= i < 2n
+__device__ __forceinline__ int reflect_once(int i, int n) {
+    if (i < 0) i = -1 - i;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+}
+
 // ---- median along time -----------------------------------------------------------------
-// one thread per (segment of kHarmSeg columns, bin); bins are contiguous across the warp, so
-// every load / store is a coalesced 128-byte row piece
+// one thread per (segment of seg_len columns, bin); bins are contiguous across the warp, so
+// every load / store is a coalesced 128-byte row piece.  Runs after hpss_perc_kernel: with both
+// medians in hand it applies the soft mask to the complex spectrum in place.  The loads of a
+// step are issued one step ahead of their use.
 __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
     const int2 seg = p.segs[blockIdx.x];
     const TonClip clip = p.clips[seg.x];
@@ -76,42 +97,58 @@ __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
     if (f >= kNBins) return;
     const int T = clip.n_cols;
     const int t0 = seg.y;
-    const int t1 = min(t0 + kHarmSeg, T);
+    const int t1 = min(t0 + p.seg_len, T);
     const float* src = p.mag + static_cast<long long>(clip.col_base) * kSpillStride + f;
-    float* dst = p.harm + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    const float* perc = p.perc + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    float2* spec = p.cspec + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    const bool wide = T > kMedHalf;     // one reflection reaches every index of the window
+    auto at = [&](int t) -> float {
+        const int i = wide ? reflect_once(t, T) : reflect_index(t, T);
+        return src[static_cast<long long>(i) * kSpillStride];
+    };
     SortedWindow w;
     w.clear();
-    for (int t = t0 - kMedHalf; t <= t0 + kMedHalf; ++t)
-        w.insert(src[static_cast<long long>(reflect_index(t, T)) * kSpillStride]);
+    for (int t = t0 - kMedHalf; t <= t0 + kMedHalf; ++t) w.insert(at(t));
+    float old = at(t0 - kMedHalf), nxt = at(t0 + 1 + kMedHalf);
+    float pq = perc[static_cast<long long>(t0) * kSpillStride];
+    float2 x = spec[static_cast<long long>(t0) * kSpillStride];
     for (int t = t0; t < t1; ++t) {
-        dst[static_cast<long long>(t) * kSpillStride] = w.median();
-        if (t + 1 < t1) {
-            const float old = src[static_cast<long long>(reflect_index(t - kMedHalf, T)) * kSpillStride];
-            const float nxt = src[static_cast<long long>(reflect_index(t + 1 + kMedHalf, T)) * kSpillStride];
-            w.replace(old, nxt);
-        }
+        const long long o = static_cast<long long>(t) * kSpillStride;
+        // next step's operands (clamped to the segment: the surplus loads are never used)
+        const int tn = min(t + 1, t1 - 1);
+        const float old_n = at(tn - kMedHalf), nxt_n = at(tn + 1 + kMedHalf);
+        const float pq_n = perc[static_cast<long long>(tn) * kSpillStride];
+        const float2 x_n = spec[static_cast<long long>(tn) * kSpillStride];
+        const float m = harm_mask(w.median(), pq);
+        spec[o] = make_float2(x.x * m, x.y * m);     // (S * mask) * phase
+        w.replace(old, nxt);
+        old = old_n; nxt = nxt_n; pq = pq_n; x = x_n;
     }
 }
 
 // ---- median along frequency ------------------------------------------------------------
-// one warp per two columns: lane = (column, one of 16 runs of 65 bins)
-constexpr int kPercRun = 65;
+// one lane per (column, run of RUN bins); RUNS runs per column, 32 / RUNS columns per warp.
+// Long runs amortise the 31-value window fill (large batches); short runs give small batches
+// enough threads.
+template <int RUNS>
 __global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols) {
+    constexpr int RUN = (kNBins + RUNS - 1) / RUNS;
+    constexpr int COLS = 32 / RUNS;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int col = 2 * warp + (lane >> 4);
+    const int col = COLS * warp + lane / RUNS;
     if (col >= n_cols) return;
-    const int f0 = (lane & 15) * kPercRun;
-    const int f1 = min(f0 + kPercRun, kNBins);
+    const int f0 = (lane % RUNS) * RUN;
+    const int f1 = min(f0 + RUN, kNBins);
     if (f0 >= kNBins) return;
     const float* src = p.mag + static_cast<long long>(col) * kSpillStride;
     float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
     SortedWindow w;
     w.clear();
-    for (int f = f0 - kMedHalf; f <= f0 + kMedHalf; ++f) w.insert(src[reflect_index(f, kNBins)]);
+    for (int f = f0 - kMedHalf; f <= f0 + kMedHalf; ++f) w.insert(src[reflect_once(f, kNBins)]);
     for (int f = f0; f < f1; ++f) {
         dst[f] = w.median();
-        if (f + 1 < f1) w.replace(src[reflect_index(f - kMedHalf, kNBins)], src[reflect_index(f + 1 + kMedHalf, kNBins)]);
+        if (f + 1 < f1) w.replace(src[reflect_once(f - kMedHalf, kNBins)], src[reflect_once(f + 1 + kMedHalf, kNBins)]);
     }
 }
 
@@ -122,15 +159,6 @@ struct IstftSmem {
     float2 buf[8][32 * 33];
     float4 win[32];
 };
-
-__device__ __forceinline__ float harm_mask(float h, float q) {
-    // util.softmask(harm, perc, power=2, split_zeros=True)
-    const float z = fmaxf(h, q);
-    if (z < FLT_MIN) return 0.5f;
-    const float a = h / z, b = q / z;
-    const float ma = a * a, mb = b * b;
-    return ma / (ma + mb);
-}
 
 __global__ void __launch_bounds__(256, 2) istft_kernel(IstftParams p, int n_cols) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -147,23 +175,19 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(IstftParams p, int n_cols
     float2* buf = sm.buf[warp];
     const int n_warps = gridDim.x * 8;
     for (int col = blockIdx.x * 8 + warp; col < n_cols; col += n_warps) {
-        const float2* X = p.cspec + static_cast<long long>(col) * kSpillStride;
-        const float* H = p.harm + static_cast<long long>(col) * kSpillStride;
-        const float* Q = p.perc + static_cast<long long>(col) * kSpillStride;
+        const float2* X = p.cspec + static_cast<long long>(col) * kSpillStride;   // already masked
         // masked spectrum, k = 32 n1 + lane, kept in registers and mirrored in shared memory so
         // that the partner X[1024 - k] is one conflict-free load away
         float2 v[32];
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
             const int k = 32 * n1 + lane;
-            const float2 x = X[k];
-            const float m = harm_mask(H[k], Q[k]);
-            v[n1] = make_float2(x.x * m, x.y * m);
+            v[n1] = X[k];
             buf[n1 * 33 + lane] = v[n1];
         }
         float nyq = 0.0f;   // X[1024] (real)
         if (lane == 0) {
-            nyq = X[1024].x * harm_mask(H[1024], Q[1024]);
+            nyq = X[1024].x;
             v[0].y = 0.0f;   // irfft ignores the imaginary part of the DC bin
         }
         __syncwarp();
@@ -249,10 +273,18 @@ cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t strea
     return cudaGetLastError();
 }
 
-cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream) {
+cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, int runs, cudaStream_t stream) {
     if (n_cols <= 0) return cudaSuccess;
-    const int warps = (n_cols + 1) / 2;
-    hpss_perc_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
+    if (runs == 4) {
+        const int warps = (n_cols + 7) / 8;                 // 4 runs of 257 bins, 8 columns per warp
+        hpss_perc_kernel<4><<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
+    } else if (runs == 8) {
+        const int warps = (n_cols + 3) / 4;                 // 8 runs of 129 bins, 4 columns per warp
+        hpss_perc_kernel<8><<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
+    } else {
+        const int warps = (n_cols + 1) / 2;                 // 16 runs of 65 bins, 2 columns per warp
+        hpss_perc_kernel<16><<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
+    }
     return cudaGetLastError();
 }
 

@@ -97,7 +97,6 @@ cudaError_t configure_short();
 cudaError_t launch_short(const ShortParams& p, int n_clips, cudaStream_t stream);
 
 // ---- tonnetz chain: hpss_kernels.cu, cqt_kernels.cu ----------------------------------------
-constexpr int kHarmSeg = 128;     // columns per time-median work item
 constexpr int kCqOctaves = 7;
 constexpr int kCqRows = 36;       // bins per octave
 constexpr int kCqBins = 252;
@@ -120,14 +119,13 @@ struct TonClip {
 struct HpssParams {
     const TonClip* clips;
     const int2* segs;        // (clip index, first column) per time-median work item
+    int seg_len;             // columns per time-median work item
     const float* mag;        // [cols][kSpillStride] |X|
-    float* harm;             // [cols][kSpillStride] median along time
     float* perc;             // [cols][kSpillStride] median along frequency
+    float2* cspec;           // [cols][kSpillStride] X, masked in place by hpss_harm_kernel
 };
 struct IstftParams {
-    const float2* cspec;     // [cols][kSpillStride] X
-    const float* harm;
-    const float* perc;
+    const float2* cspec;     // [cols][kSpillStride] masked X
     const float2* tables;    // FFT twiddles (same layout as StftParams::tables)
     float* frames;           // [cols][2048] windowed inverse-FFT frames
 };
@@ -140,7 +138,7 @@ struct OlaParams {
 };
 cudaError_t configure_hpss();
 cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t stream);
-cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream);
+cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, int runs, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_ola(const OlaParams& p, int n_tiles, cudaStream_t stream);
 
