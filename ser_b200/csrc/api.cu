@@ -72,7 +72,7 @@ struct serb_ctx {
     std::mutex mu;
     std::string err;
     long long launches = 0;
-    int chunk_cols = 131072;
+    int chunk_cols = 262144;
     float last_ms = 0.f;
     bool timed = false;
 
@@ -89,7 +89,6 @@ struct serb_ctx {
     DevBuf hann_sq, cq_twiddles;
     DevBuf cspec, perc, frames, yharm, yoct, cqmag;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
-    int ton_chunk_cols = 262144;
     int harm_seg = 128, perc_runs = 16;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
     std::vector<int> last_short_rows;
@@ -298,81 +297,71 @@ int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
 }
 
 struct TonChunk {
-    int clip_lo, clip_hi, n_cols, n_tiles, n_segs, cq_rows, max_len0, max_cq_cols;
-    long long max_end, total0;
+    int clip_lo, clip_hi;       // range in the request-wide TonClip array
+    int seg_lo, n_segs;
+    int n_cols, n_tiles, cq_rows, max_len0, max_cq_cols;
+    long long total0, max_end;
 };
 
-// librosa.effects.harmonic + librosa.feature.tonnetz for every clip of the request (any length),
-// written to out[row][off_tonnetz .. +6)
-template <typename BeforeChunk>
-int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const int64_t* lengths,
-                long long n_clips, int sr, SrTables* tab, const Offsets& off, float* d_out,
-                cudaStream_t stream, BeforeChunk before_chunk) {
-    const CqtPlan& plan = tab->plan;
-    if (plan.status == 1) return fail(ctx, SERB_ERR_NYQUIST, plan.message);
-    if (plan.status != 0) return fail(ctx, SERB_ERR_UNSUPPORTED, plan.message);
-    int rc = get_cqt_tables(ctx, tab);
-    if (rc) return rc;
-    const int fe = plan.early_factor;
-
-    std::vector<TonClip> clips(n_clips);
-    std::vector<ClipDev> clips_a(n_clips), clips_b(n_clips);
+struct TonPlan {
+    std::vector<TonClip> clips;
+    std::vector<ClipDev> clips_b;   // the harmonic signals as STFT clips (tuning pass)
     std::vector<int2> segs;
     std::vector<TonChunk> chunks;
-    std::vector<int> seg_begin;   // first segment of every chunk
-    TonChunk cur{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    seg_begin.push_back(0);
-    for (long long i = 0; i < n_clips; ++i) {
-        const long long len = lengths[i];
-        const long long plen = std::max<long long>(len, 512);          // dsp.py:38-45 _pad_audio_for_fft
-        const int n_cols = 1 + static_cast<int>(plen / kHop);
-        const int tiles = (n_cols + kColsPerTile - 1) / kColsPerTile;
-        if (cur.clip_hi > cur.clip_lo && cur.n_cols + n_cols > ctx->ton_chunk_cols) {
-            chunks.push_back(cur);
-            seg_begin.push_back(static_cast<int>(segs.size()));
-            cur = TonChunk{cur.clip_hi, cur.clip_hi, 0, 0, 0, 0, 0, 0, 0, 0};
-        }
-        const long long len0 = (plen + fe - 1) / fe;
-        if (len0 > (65535LL * 1024)) return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz: clip too long for one launch");
-        TonClip& c = clips[i];
-        c.off0 = cur.total0;
-        c.hoff = cur.total0 * fe;
-        c.length = static_cast<int>(plen);
-        c.n_cols = n_cols;
-        c.col_base = cur.n_cols;
-        c.tile_base = cur.n_tiles;
-        c.len0 = static_cast<int>(len0);
-        int cq = 0x7fffffff, ln = c.len0;
-        for (int l = 0; l < kCqOctaves; ++l) {
-            cq = std::min(cq, 1 + ln / (plan.hop0 >> l));
-            ln = (ln + 1) >> 1;
-        }
-        c.cq_cols = cq;
-        c.cq_base = cur.cq_rows;
-        c.out_row = static_cast<int>(i);
-        ClipDev& a = clips_a[i];
-        a = ClipDev{};
-        a.start = starts[i]; a.length = static_cast<int>(len); a.n_cols = n_cols;
-        a.col_base = c.col_base; a.tile_base = c.tile_base; a.out_row = c.out_row;
-        ClipDev& b = clips_b[i];
-        b = a;
-        b.start = c.hoff; b.length = c.length;
-        for (int t0 = 0; t0 < n_cols; t0 += ctx->harm_seg) segs.push_back(make_int2(static_cast<int>(i) - cur.clip_lo, t0));
-        cur.total0 += (len0 + 127) / 128 * 128;
-        cur.n_cols += n_cols;
-        cur.n_tiles += tiles;
-        cur.n_segs = static_cast<int>(segs.size()) - seg_begin.back();
-        cur.cq_rows += cq;
-        cur.max_len0 = std::max(cur.max_len0, c.len0);
-        cur.max_cq_cols = std::max(cur.max_cq_cols, cq);
-        cur.max_end = std::max(cur.max_end, starts[i] + len);
-        cur.clip_hi += 1;
-    }
-    if (cur.clip_hi > cur.clip_lo) chunks.push_back(cur);
+};
 
+TonChunk ton_open_chunk(const TonPlan& tp) {
+    TonChunk c{};
+    c.clip_lo = c.clip_hi = static_cast<int>(tp.clips.size());
+    c.seg_lo = static_cast<int>(tp.segs.size());
+    return c;
+}
+
+// appends one clip (padded length plen >= 512, dsp.py:38-45) to the open chunk
+int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur, const ClipDev& a, long long plen) {
+    const int fe = plan.early_factor;
+    const long long len0 = (plen + fe - 1) / fe;
+    if (len0 > (65535LL * 1024)) return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz: clip too long for one launch");
+    TonClip c{};
+    c.off0 = cur.total0;
+    c.hoff = cur.total0 * fe;
+    c.length = static_cast<int>(plen);
+    c.n_cols = a.n_cols;
+    c.col_base = a.col_base;
+    c.tile_base = a.tile_base;
+    c.len0 = static_cast<int>(len0);
+    int cq = 0x7fffffff, ln = c.len0;
+    for (int l = 0; l < kCqOctaves; ++l) {
+        cq = std::min(cq, 1 + ln / (plan.hop0 >> l));
+        ln = (ln + 1) >> 1;
+    }
+    c.cq_cols = cq;
+    c.cq_base = cur.cq_rows;
+    c.out_row = a.out_row;
+    ClipDev b = a;
+    b.start = c.hoff;
+    b.length = c.length;
+    const int local = static_cast<int>(tp.clips.size()) - cur.clip_lo;
+    for (int t0 = 0; t0 < a.n_cols; t0 += ctx->harm_seg) tp.segs.push_back(make_int2(local, t0));
+    tp.clips.push_back(c);
+    tp.clips_b.push_back(b);
+    cur.total0 += (len0 + 127) / 128 * 128;
+    cur.n_cols = std::max(cur.n_cols, a.col_base + a.n_cols);
+    cur.n_tiles = std::max(cur.n_tiles, a.tile_base + (a.n_cols + kColsPerTile - 1) / kColsPerTile);
+    cur.n_segs = static_cast<int>(tp.segs.size()) - cur.seg_lo;
+    cur.cq_rows += cq;
+    cur.max_len0 = std::max(cur.max_len0, c.len0);
+    cur.max_cq_cols = std::max(cur.max_cq_cols, cq);
+    cur.max_end = std::max(cur.max_end, a.start + a.length);
+    cur.clip_hi += 1;
+    return SERB_OK;
+}
+
+int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cudaStream_t stream) {
+    const int fe = tab->plan.early_factor;
     int max_cols = 0, max_tiles = 0, max_cq = 0;
     long long max_total0 = 0;
-    for (const TonChunk& c : chunks) {
+    for (const TonChunk& c : tp.chunks) {
         max_cols = std::max(max_cols, c.n_cols);
         max_tiles = std::max(max_tiles, c.n_tiles);
         max_cq = std::max(max_cq, c.cq_rows);
@@ -385,114 +374,117 @@ int run_tonnetz(serb_ctx* ctx, const float* d_wave, const int64_t* starts, const
     SERB_CUDA(ctx, ctx->frames.reserve(static_cast<size_t>(max_cols) * kNFft * sizeof(float)));
     SERB_CUDA(ctx, ctx->yharm.reserve((static_cast<size_t>(max_total0) * fe + 64) * sizeof(float)));
     SERB_CUDA(ctx, ctx->yoct.reserve((static_cast<size_t>(max_total0) * 2 + 64) * sizeof(float)));
-    SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(max_cq) * kCqBins * sizeof(float)));
-    SERB_CUDA(ctx, ctx->ton_tile_clip.reserve(static_cast<size_t>(max_tiles) * sizeof(int)));
+    SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(std::max(max_cq, 1)) * kCqBins * sizeof(float)));
+    SERB_CUDA(ctx, ctx->ton_tile_clip.reserve(static_cast<size_t>(std::max(max_tiles, 1)) * sizeof(int)));
     SERB_CUDA(ctx, ctx->peaks.reserve(static_cast<size_t>(max_cols) * tab->peak_cap * sizeof(float2)));
     SERB_CUDA(ctx, ctx->peak_count.reserve(static_cast<size_t>(max_cols) * sizeof(int)));
-    SERB_CUDA(ctx, ctx->ton_tuning.reserve(static_cast<size_t>(n_clips) * sizeof(int)));
-    if ((rc = upload(ctx, ctx->ton_clips, clips.data(), clips.size(), stream))) return rc;
-    if ((rc = upload(ctx, ctx->ton_clips_a, clips_a.data(), clips_a.size(), stream))) return rc;
-    if ((rc = upload(ctx, ctx->ton_clips_b, clips_b.data(), clips_b.size(), stream))) return rc;
-    if ((rc = upload(ctx, ctx->ton_segs, segs.data(), segs.size(), stream))) return rc;
-    // the pageable host vectors above must outlive their async copies
-    SERB_CUDA(ctx, cudaStreamSynchronize(stream));
+    SERB_CUDA(ctx, ctx->ton_tuning.reserve(std::max<size_t>(tp.clips.size(), 1) * sizeof(int)));
+    int rc;
+    if ((rc = upload(ctx, ctx->ton_clips, tp.clips.data(), tp.clips.size(), stream))) return rc;
+    if ((rc = upload(ctx, ctx->ton_clips_b, tp.clips_b.data(), tp.clips_b.size(), stream))) return rc;
+    if ((rc = upload(ctx, ctx->ton_segs, tp.segs.data(), tp.segs.size(), stream))) return rc;
+    return SERB_OK;
+}
 
-    for (size_t ci = 0; ci < chunks.size(); ++ci) {
-        const TonChunk& c = chunks[ci];
-        before_chunk(c.max_end);
-        const int nc = c.clip_hi - c.clip_lo;
-        const TonClip* d_clips = ctx->ton_clips.as<TonClip>() + c.clip_lo;
-        const ClipDev* d_a = ctx->ton_clips_a.as<ClipDev>() + c.clip_lo;
-        const ClipDev* d_b = ctx->ton_clips_b.as<ClipDev>() + c.clip_lo;
-        int* d_tuning = ctx->ton_tuning.as<int>() + c.clip_lo;
-        SERB_CUDA(ctx, launch_expand_tiles(d_a, nc, ctx->ton_tile_clip.as<int>(), stream));
-        ctx->launches += 1;
+// librosa.effects.harmonic + librosa.feature.tonnetz for the clips of one chunk, written to
+// out[row][off_tonnetz .. +6).  d_clips_a / d_tile_clip describe the chunk's clips inside the
+// waveform; when stft_done the chunk's |X| (ctx->spill) and X (ctx->cspec) are already there.
+int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, float* d_out, cudaStream_t stream,
+                  const TonChunk& c, const float* d_wave, const ClipDev* d_clips_a, const int* d_tile_clip,
+                  bool stft_done) {
+    const CqtPlan& plan = tab->plan;
+    const int nc = c.clip_hi - c.clip_lo;
+    if (nc <= 0) return SERB_OK;
+    const TonClip* d_clips = ctx->ton_clips.as<TonClip>() + c.clip_lo;
+    const ClipDev* d_b = ctx->ton_clips_b.as<ClipDev>() + c.clip_lo;
+    int* d_tuning = ctx->ton_tuning.as<int>() + c.clip_lo;
+    StftParams sp{};
+    sp.wave = d_wave;
+    sp.clips = d_clips_a;
+    sp.n_clips = nc;
+    sp.tile_clip = d_tile_clip;
+    sp.tables = ctx->tables.as<float2>();
+    sp.spill = ctx->spill.as<float>();
+    sp.cspill = ctx->cspec.as<float2>();
+    sp.do_peaks = 0;
+    sp.kmin = tab->kmin; sp.kmax = tab->kmax; sp.peak_cap = tab->peak_cap;
+    sp.peaks = ctx->peaks.as<float2>();
+    sp.peak_count = ctx->peak_count.as<int>();
+    sp.sr_over_nfft_num = static_cast<double>(sr);
+    sp.status = ctx->status.as<int>();
+    if (!stft_done) {
         // 1. complex STFT of the clip
-        StftParams sp{};
-        sp.wave = d_wave;
-        sp.clips = d_a;
-        sp.n_clips = nc;
-        sp.tile_clip = ctx->ton_tile_clip.as<int>();
-        sp.tables = ctx->tables.as<float2>();
-        sp.spill = ctx->spill.as<float>();
-        sp.cspill = ctx->cspec.as<float2>();
-        sp.do_peaks = 0;
-        sp.kmin = tab->kmin; sp.kmax = tab->kmax; sp.peak_cap = tab->peak_cap;
-        sp.peaks = ctx->peaks.as<float2>();
-        sp.peak_count = ctx->peak_count.as<int>();
-        sp.sr_over_nfft_num = static_cast<double>(sr);
-        sp.status = ctx->status.as<int>();
         { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
-        ctx->launches += 1;
-        // 2. HPSS medians
-        HpssParams hp{};
-        hp.clips = d_clips;
-        hp.segs = ctx->ton_segs.as<int2>() + seg_begin[ci];
-        hp.mag = ctx->spill.as<float>();
-        hp.perc = ctx->perc.as<float>();
-        hp.seg_len = ctx->harm_seg;
-        hp.cspec = ctx->cspec.as<float2>();
-        { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, ctx->perc_runs, stream)); }
-        { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_harm(hp, c.n_segs, stream)); }
-        ctx->launches += 2;
-        // 3. soft mask + inverse STFT + overlap-add
-        IstftParams ip{};
-        ip.cspec = ctx->cspec.as<float2>();
-        ip.tables = ctx->tables.as<float2>();
-        ip.frames = ctx->frames.as<float>();
-        OlaParams op{};
-        op.clips = d_clips;
-        op.tile_clip = ctx->ton_tile_clip.as<int>();
-        op.frames = ip.frames;
-        op.hann_sq = ctx->hann_sq.as<double>();
-        op.yharm = ctx->yharm.as<float>();
-        { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream)); }
-        { ProfScope ps(ctx, 9, stream); SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream)); }
-        ctx->launches += 2;
-        // 4. tuning of the harmonic signal (36 bins per octave)
-        sp.wave = ctx->yharm.as<float>();
-        sp.clips = d_b;
-        sp.cspill = nullptr;
-        sp.do_peaks = 1;
-        { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
-        TuneParams tp{};
-        tp.clips = d_b;
-        tp.peaks = sp.peaks;
-        tp.peak_count = sp.peak_count;
-        tp.peak_cap = tab->peak_cap;
-        tp.bins_per_octave = 36;
-        tp.edges = ctx->edges.as<double>();
-        tp.tuning_idx = d_tuning;
-        { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream)); }
-        ctx->launches += 2;
-        // 5. decimations, constant-Q, chroma, tonnetz
-        CqtParams qp{};
-        qp.clips = d_clips;
-        qp.n_clips = nc;
-        qp.tuning_idx = d_tuning;
-        qp.yharm = ctx->yharm.as<float>();
-        qp.yoct = ctx->yoct.as<float>();
-        long long base = 0;
-        for (int l = 0; l < kCqOctaves; ++l) { qp.level_base[l] = base; base += c.total0 >> l; }
-        qp.early_factor = fe;
-        qp.hop0 = plan.hop0;
-        for (int l = 0; l < kCqOctaves; ++l) qp.n_fft[l] = plan.n_fft[l];
-        qp.early_taps = tab->early_taps.as<float>();
-        qp.n_early_taps = tab->n_early_taps;
-        qp.rows = tab->cq_rows.as<CqRow>();
-        qp.vals = tab->cq_vals.as<float2>();
-        qp.twiddles = ctx->cq_twiddles.as<float2>();
-        qp.cqmag = ctx->cqmag.as<float>();
-        qp.out = d_out;
-        qp.dim = off.dim;
-        qp.off_tonnetz = off.tonnetz;
-        qp.max_len0 = c.max_len0;
-        qp.max_cq_cols = c.max_cq_cols;
-        { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
-        { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
-        { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
         ctx->launches += 1;
     }
+    // 2. HPSS medians; the time median applies the soft mask to X in place
+    HpssParams hp{};
+    hp.clips = d_clips;
+    hp.segs = ctx->ton_segs.as<int2>() + c.seg_lo;
+    hp.seg_len = ctx->harm_seg;
+    hp.mag = ctx->spill.as<float>();
+    hp.perc = ctx->perc.as<float>();
+    hp.cspec = ctx->cspec.as<float2>();
+    { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, ctx->perc_runs, stream)); }
+    { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_harm(hp, c.n_segs, stream)); }
+    ctx->launches += 2;
+    // 3. inverse STFT + overlap-add
+    IstftParams ip{};
+    ip.cspec = ctx->cspec.as<float2>();
+    ip.tables = ctx->tables.as<float2>();
+    ip.frames = ctx->frames.as<float>();
+    OlaParams op{};
+    op.clips = d_clips;
+    op.tile_clip = d_tile_clip;
+    op.frames = ip.frames;
+    op.hann_sq = ctx->hann_sq.as<double>();
+    op.yharm = ctx->yharm.as<float>();
+    { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream)); }
+    { ProfScope ps(ctx, 9, stream); SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream)); }
+    ctx->launches += 2;
+    // 4. tuning of the harmonic signal (36 bins per octave)
+    sp.wave = ctx->yharm.as<float>();
+    sp.clips = d_b;
+    sp.cspill = nullptr;
+    sp.do_peaks = 1;
+    { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
+    TuneParams tp{};
+    tp.clips = d_b;
+    tp.peaks = sp.peaks;
+    tp.peak_count = sp.peak_count;
+    tp.peak_cap = tab->peak_cap;
+    tp.bins_per_octave = 36;
+    tp.edges = ctx->edges.as<double>();
+    tp.tuning_idx = d_tuning;
+    { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream)); }
+    ctx->launches += 2;
+    // 5. decimations, constant-Q, chroma, tonnetz
+    CqtParams qp{};
+    qp.clips = d_clips;
+    qp.n_clips = nc;
+    qp.tuning_idx = d_tuning;
+    qp.yharm = ctx->yharm.as<float>();
+    qp.yoct = ctx->yoct.as<float>();
+    long long base = 0;
+    for (int l = 0; l < kCqOctaves; ++l) { qp.level_base[l] = base; base += c.total0 >> l; }
+    qp.early_factor = plan.early_factor;
+    qp.hop0 = plan.hop0;
+    for (int l = 0; l < kCqOctaves; ++l) qp.n_fft[l] = plan.n_fft[l];
+    qp.early_taps = tab->early_taps.as<float>();
+    qp.n_early_taps = tab->n_early_taps;
+    qp.rows = tab->cq_rows.as<CqRow>();
+    qp.vals = tab->cq_vals.as<float2>();
+    qp.twiddles = ctx->cq_twiddles.as<float2>();
+    qp.cqmag = ctx->cqmag.as<float>();
+    qp.out = d_out;
+    qp.dim = off.dim;
+    qp.off_tonnetz = off.tonnetz;
+    qp.max_len0 = c.max_len0;
+    qp.max_cq_cols = c.max_cq_cols;
+    { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
+    { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
+    { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
+    ctx->launches += 1;
     return SERB_OK;
 }
 
@@ -519,6 +511,47 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
     if ((rc = get_sr_tables(ctx, sr, &tab))) return rc;
     const bool want_chroma = off.chroma >= 0;
     const bool want_mel = off.mel >= 0 || off.mfcc >= 0;
+    const bool want_ton = off.tonnetz >= 0;
+
+    // ---- tonnetz plan: one chunk per main chunk (sharing its STFT), then the short clips ----
+    TonPlan tp;
+    std::vector<ClipDev> short_a;       // short clips as STFT-2048 clips (harmonic() always uses n_fft = 2048)
+    size_t n_main_ton_chunks = 0;
+    if (want_ton) {
+        const CqtPlan& cp = tab->plan;
+        if (cp.status == 1) return fail(ctx, SERB_ERR_NYQUIST, cp.message);
+        if (cp.status != 0) return fail(ctx, SERB_ERR_UNSUPPORTED, cp.message);
+        if ((rc = get_cqt_tables(ctx, tab))) return rc;
+        for (const Chunk& c : chunks) {
+            TonChunk cur = ton_open_chunk(tp);
+            for (int i = c.clip_lo; i < c.clip_hi; ++i)
+                if ((rc = ton_add_clip(ctx, cp, tp, cur, main_clips[i], main_clips[i].length))) return rc;
+            tp.chunks.push_back(cur);
+        }
+        n_main_ton_chunks = tp.chunks.size();
+        TonChunk cur = ton_open_chunk(tp);
+        int cols = 0, tiles = 0;
+        for (const ShortClip& sc : short_clips) {
+            const long long plen = std::max<long long>(sc.length, 512);
+            ClipDev a{};
+            a.start = sc.start;
+            a.length = sc.length;
+            a.n_cols = 1 + static_cast<int>(plen / kHop);
+            a.out_row = sc.out_row;
+            if (cur.clip_hi > cur.clip_lo && cols + a.n_cols > ctx->chunk_cols) {
+                tp.chunks.push_back(cur);
+                cur = ton_open_chunk(tp);
+                cols = 0; tiles = 0;
+            }
+            a.col_base = cols;
+            a.tile_base = tiles;
+            cols += a.n_cols;
+            tiles += (a.n_cols + kColsPerTile - 1) / kColsPerTile;
+            short_a.push_back(a);
+            if ((rc = ton_add_clip(ctx, cp, tp, cur, a, plen))) return rc;
+        }
+        if (cur.clip_hi > cur.clip_lo) tp.chunks.push_back(cur);
+    }
 
     int max_cols = 0, max_tiles = 0, max_clips = 0;
     for (const Chunk& c : chunks) {
@@ -533,7 +566,7 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         SERB_CUDA(ctx, ctx->tile_mel.reserve(static_cast<size_t>(max_tiles) * 128 * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_lmax.reserve(static_cast<size_t>(max_tiles) * sizeof(float)));
         SERB_CUDA(ctx, ctx->tile_chroma.reserve(static_cast<size_t>(max_tiles) * 12 * sizeof(float)));
-        if (want_chroma) {
+        if (want_chroma || want_ton) {
             SERB_CUDA(ctx, ctx->peaks.reserve(static_cast<size_t>(max_cols) * tab->peak_cap * sizeof(float2)));
             SERB_CUDA(ctx, ctx->peak_count.reserve(static_cast<size_t>(max_cols) * sizeof(int)));
         }
@@ -541,11 +574,16 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         if ((rc = upload(ctx, ctx->clips, main_clips.data(), main_clips.size(), stream))) return rc;
         for (const ClipDev& c : main_clips) ctx->last_tuning_rows.push_back(c.out_row);
     }
+    if (want_ton) {
+        if ((rc = ton_reserve_and_upload(ctx, tab, tp, stream))) return rc;
+        if ((rc = upload(ctx, ctx->ton_clips_a, short_a.data(), short_a.size(), stream))) return rc;
+    }
     SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
     SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), stream));
 
     if (ctx->timed) SERB_CUDA(ctx, cudaEventRecord(ctx->ev_start, stream));
-    for (const Chunk& c : chunks) {
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk& c = chunks[ci];
         before_chunk(c.max_end);
         const ClipDev* d_clips = ctx->clips.as<ClipDev>() + c.clip_lo;
         const int nc = c.clip_hi - c.clip_lo;
@@ -558,6 +596,7 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         sp.tile_clip = ctx->tile_clip.as<int>();
         sp.tables = ctx->tables.as<float2>();
         sp.spill = ctx->spill.as<float>();
+        sp.cspill = want_ton ? ctx->cspec.as<float2>() : nullptr;
         sp.do_peaks = want_chroma ? 1 : 0;
         sp.kmin = tab->kmin;
         sp.kmax = tab->kmax;
@@ -570,15 +609,15 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         ctx->launches += 1;
         int* d_tuning = ctx->tuning.as<int>() + c.clip_lo;
         if (want_chroma) {
-            TuneParams tp{};
-            tp.clips = d_clips;
-            tp.peaks = sp.peaks;
-            tp.peak_count = sp.peak_count;
-            tp.peak_cap = tab->peak_cap;
-            tp.bins_per_octave = 12;
-            tp.edges = ctx->edges.as<double>();
-            tp.tuning_idx = d_tuning;
-            { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream)); }
+            TuneParams tu{};
+            tu.clips = d_clips;
+            tu.peaks = sp.peaks;
+            tu.peak_count = sp.peak_count;
+            tu.peak_cap = tab->peak_cap;
+            tu.bins_per_octave = 12;
+            tu.edges = ctx->edges.as<double>();
+            tu.tuning_idx = d_tuning;
+            { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tu, nc, stream)); }
             ctx->launches += 1;
         }
         ProjParams pp{};
@@ -618,6 +657,11 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         qp.off_contrast = off.contrast;
         { ProfScope ps(ctx, 3, stream); SERB_CUDA(ctx, launch_pool(qp, nc, stream)); }
         ctx->launches += 1;
+        if (want_ton) {
+            // same clips, same columns: the chunk's |X| and X feed the harmonic separation directly
+            if ((rc = ton_run_chunk(ctx, tab, sr, off, d_out, stream, tp.chunks[ci], d_wave, d_clips,
+                                    ctx->tile_clip.as<int>(), true))) return rc;
+        }
     }
     if (!short_clips.empty()) {
         long long max_end = 0;
@@ -645,10 +689,16 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         hp.status = ctx->status.as<int>();
         { ProfScope ps(ctx, 4, stream); SERB_CUDA(ctx, launch_short(hp, static_cast<int>(short_clips.size()), stream)); }
         ctx->launches += 1;
-    }
-    if (off.tonnetz >= 0) {
-        rc = run_tonnetz(ctx, d_wave, starts, lengths, n_clips, sr, tab, off, d_out, stream, before_chunk);
-        if (rc) return rc;
+        // tonnetz of the short clips: their own STFT-2048 pass (the short kernel uses n_fft = len)
+        for (size_t ci = n_main_ton_chunks; ci < tp.chunks.size(); ++ci) {
+            const TonChunk& c = tp.chunks[ci];
+            const int first = c.clip_lo - static_cast<int>(main_clips.size());
+            const ClipDev* d_a = ctx->ton_clips_a.as<ClipDev>() + first;
+            SERB_CUDA(ctx, launch_expand_tiles(d_a, c.clip_hi - c.clip_lo, ctx->ton_tile_clip.as<int>(), stream));
+            ctx->launches += 1;
+            if ((rc = ton_run_chunk(ctx, tab, sr, off, d_out, stream, c, d_wave, d_a, ctx->ton_tile_clip.as<int>(), false)))
+                return rc;
+        }
     }
     if (ctx->timed) SERB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, stream));
     return SERB_OK;
@@ -751,7 +801,6 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         const int v = std::atoi(env);
         if (v >= 64) ctx->chunk_cols = v;
     }
-    if (const char* env = std::getenv("SERB_TON_CHUNK_COLS")) { const int v = std::atoi(env); if (v >= 64) ctx->ton_chunk_cols = v; }
     if (const char* env = std::getenv("SERB_HARM_SEG")) { const int v = std::atoi(env); if (v >= 16) ctx->harm_seg = v; }
     if (const char* env = std::getenv("SERB_PERC_RUNS")) { const int v = std::atoi(env); if (v == 4 || v == 8 || v == 16) ctx->perc_runs = v; }
     ctx->timed = true;
@@ -1121,9 +1170,8 @@ int serb_debug_tonnetz_stages(serb_ctx* ctx, const float* h_wave, int64_t n, int
     SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
     SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.ptr, h_wave, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t start = 0, length = n;
-    Offsets off{6, -1, -1, -1, -1, 0};
-    rc = run_tonnetz(ctx, ctx->wave.as<float>(), &start, &length, 1, sample_rate, tab, off, ctx->out.as<float>(),
-                     ctx->stream, [](long long) {});
+    rc = run_features(ctx, ctx->wave.as<float>(), n, &start, &length, 1, sample_rate, SERB_FLAG_TONNETZ,
+                      ctx->out.as<float>(), ctx->stream, [](long long) {});
     if (rc) return rc;
     const long long plen = std::max<long long>(n, 512);
     int cq = 0x7fffffff;
