@@ -130,6 +130,18 @@ int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave,
                     int32_t sample_rate, uint32_t flag_bits,
                     float* h_features, double* h_proba, int32_t* h_label_index);
 
+/*
+ * Segmented pooling of frame embeddings [n_frames x dim] float32 over frame ranges [lo[w], hi[w]):
+ * mode 0 float64 mean, mode 1 float64 mean then std (ddof 0), out [n_windows x 2 dim]
+ * (ser/_internal/pool/stats_pool.py:15-43 mean_std_pool), mode 2 float32 mean widened to float64
+ * (ser/_internal/repr/handcrafted.py:109-122 HandcraftedBackend.pool).  Row-order summation:
+ * bit-identical to numpy.  The host computes the ranges from the timestamps
+ * (ser/_internal/repr/backend.py:81-111 overlap_frame_mask selects a contiguous run).
+ */
+int serb_pool_frames_host(serb_ctx* ctx, const float* h_embeddings, int64_t n_frames, int32_t dim,
+                          const int32_t* h_lo, const int32_t* h_hi, int64_t n_windows, int32_t mode,
+                          double* h_out);
+
 /* mono PCM16 -> float32 (x / 32768) peak-normalised over the whole buffer, on the device */
 int serb_prepare_pcm16_host(serb_ctx* ctx, const int16_t* h_pcm, int64_t n, float* h_out);
 int serb_prepare_pcm16_device(serb_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out, void* stream);

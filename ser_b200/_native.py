@@ -37,6 +37,7 @@ SIGNATURES: dict[str, tuple] = {
     "serb_mlp_predict_host": (c_int, [_P, _P, c_int64, _P, _P]),
     "serb_mlp_predict_device": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "serb_infer_host": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P, _P, _P]),
+    "serb_pool_frames_host": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P]),
     "serb_prepare_pcm16_host": (c_int, [_P, _P, c_int64, _P]),
     "serb_prepare_pcm16_device": (c_int, [_P, _P, c_int64, _P, _P]),
     "serb_debug_filterbank": (c_int, [c_int32, c_int32, c_int32, c_int32, _P]),
@@ -186,6 +187,18 @@ class Context:
             self._handle, _ptr(wave), wave.size, _ptr(starts), _ptr(lengths), n, int(sample_rate),
             int(flag_bits), _ptr(feats), _ptr(proba), _ptr(labels)))
         return feats, proba, labels
+
+    # ---- pooling -------------------------------------------------------------------------
+    def pool_frames_host(self, embeddings: np.ndarray, lo: np.ndarray, hi: np.ndarray, mode: int) -> np.ndarray:
+        """Frame ranges [lo, hi) -> float64 rows: mode 0 mean, 1 mean+std, 2 float32 mean (widened)."""
+        emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+        lo = np.ascontiguousarray(lo, dtype=np.int32)
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        n_frames, dim = emb.shape
+        out = np.empty((lo.size, 2 * dim if mode == 1 else dim), dtype=np.float64)
+        self._check(self._lib.serb_pool_frames_host(self._handle, _ptr(emb), n_frames, dim, _ptr(lo), _ptr(hi),
+                                                    lo.size, int(mode), _ptr(out)))
+        return out
 
     # ---- audio prep ----------------------------------------------------------------------
     def prepare_pcm16_host(self, pcm: np.ndarray) -> np.ndarray:

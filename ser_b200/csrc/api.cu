@@ -1039,6 +1039,35 @@ int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const in
     return check_status(ctx, ctx->stream);
 }
 
+int serb_pool_frames_host(serb_ctx* ctx, const float* h_embeddings, int64_t n_frames, int32_t dim,
+                          const int32_t* h_lo, const int32_t* h_hi, int64_t n_windows, int32_t mode, double* h_out) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (mode < 0 || mode > 2 || dim <= 0 || n_frames < 0 || n_windows < 0)
+        return fail(ctx, SERB_ERR_INVALID_ARG, "bad pooling arguments");
+    if (n_windows == 0) return SERB_OK;
+    if (!h_embeddings || !h_lo || !h_hi || !h_out) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL buffer");
+    for (int64_t w = 0; w < n_windows; ++w)
+        if (h_lo[w] < 0 || h_hi[w] > n_frames || h_lo[w] >= h_hi[w])
+            return fail(ctx, SERB_ERR_INVALID_ARG, "Pooling window does not overlap any encoded frames");
+    const size_t width = static_cast<size_t>(mode == 1 ? 2 * dim : dim);
+    DevBuf& emb = ctx->wave;      // staging buffers are free between calls
+    DevBuf& idx = ctx->labels;
+    DevBuf& out = ctx->proba;
+    SERB_CUDA(ctx, emb.reserve(static_cast<size_t>(n_frames) * dim * sizeof(float) + 64));
+    SERB_CUDA(ctx, idx.reserve(static_cast<size_t>(n_windows) * 2 * sizeof(int)));
+    SERB_CUDA(ctx, out.reserve(static_cast<size_t>(n_windows) * width * sizeof(double)));
+    SERB_CUDA(ctx, cudaMemcpyAsync(emb.ptr, h_embeddings, static_cast<size_t>(n_frames) * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(idx.ptr, h_lo, static_cast<size_t>(n_windows) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    SERB_CUDA(ctx, cudaMemcpyAsync(idx.as<int>() + n_windows, h_hi, static_cast<size_t>(n_windows) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    SERB_CUDA(ctx, launch_pool_stats(emb.as<float>(), dim, idx.as<int>(), idx.as<int>() + n_windows, n_windows, mode, out.as<double>(), ctx->stream));
+    ctx->launches += 1;
+    SERB_CUDA(ctx, cudaMemcpyAsync(h_out, out.ptr, static_cast<size_t>(n_windows) * width * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SERB_OK;
+}
+
 int serb_prepare_pcm16_device(serb_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out, void* stream) {
     if (!ctx) return SERB_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);

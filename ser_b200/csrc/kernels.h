@@ -188,6 +188,9 @@ struct MlpParams {
 size_t mlp_smem_bytes(int n_in, int n_hidden, int n_out);
 cudaError_t configure_mlp(int n_in, int n_hidden, int n_out);
 cudaError_t launch_mlp(const MlpParams& p, cudaStream_t stream);
+// mode 0: float64 mean, 1: float64 mean + std (out [n][2 dim]), 2: float32 mean widened to float64
+cudaError_t launch_pool_stats(const float* d_emb, int dim, const int* d_lo, const int* d_hi, long long n_windows,
+                              int mode, double* d_out, cudaStream_t stream);
 cudaError_t launch_prepare_pcm16(const short* d_pcm, long long n, int* d_scratch_max, float* d_out,
                                  cudaStream_t stream);
 

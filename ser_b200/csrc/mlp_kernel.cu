@@ -132,6 +132,57 @@ __global__ void pcm_scale_kernel(const short* __restrict__ pcm, long long n, con
     }
 }
 
+// ---- segmented mean / std pooling over frame ranges -----------------------------------------
+// Replaces ser/_internal/pool/stats_pool.py:15-43 `mean_std_pool` (and the mean-only pool of
+// ser/_internal/repr/handcrafted.py:109-122): window w pools frames [lo[w], hi[w]).  One CTA per
+// window, threads over the feature dimension (coalesced rows); each (window, feature) is summed
+// in row order in float64, which is the order numpy reduces axis 0 of a C-contiguous matrix in,
+// so mean and std (ddof = 0) come out bit-identical to numpy's.
+__global__ void __launch_bounds__(128) pool_stats_kernel(const float* __restrict__ emb, int dim,
+                                                         const int* __restrict__ lo, const int* __restrict__ hi,
+                                                         int want_std, double* __restrict__ out) {
+    const int w = blockIdx.x;
+    const int a = lo[w], b = hi[w];
+    const int width = want_std ? 2 * dim : dim;
+    const double n = static_cast<double>(b - a);
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        double sum = 0.0;
+        for (int r = a; r < b; ++r) sum += static_cast<double>(emb[static_cast<size_t>(r) * dim + d]);
+        const double mean = sum / n;
+        out[static_cast<size_t>(w) * width + d] = mean;
+        if (want_std) {
+            double ss = 0.0;
+            for (int r = a; r < b; ++r) {
+                const double x = static_cast<double>(emb[static_cast<size_t>(r) * dim + d]) - mean;
+                ss = __dadd_rn(ss, __dmul_rn(x, x));     // numpy squares, then sums: no FMA contraction
+            }
+            out[static_cast<size_t>(w) * width + dim + d] = sqrt(ss / n);
+        }
+    }
+}
+
+// mean-only pooling in float32, as `embeddings[mask].mean(axis=0)` computes it on a float32 matrix
+__global__ void __launch_bounds__(128) pool_mean_f32_kernel(const float* __restrict__ emb, int dim,
+                                                            const int* __restrict__ lo, const int* __restrict__ hi,
+                                                            double* __restrict__ out) {
+    const int w = blockIdx.x;
+    const int a = lo[w], b = hi[w];
+    const float n = static_cast<float>(b - a);
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        float sum = 0.0f;
+        for (int r = a; r < b; ++r) sum = __fadd_rn(sum, emb[static_cast<size_t>(r) * dim + d]);
+        out[static_cast<size_t>(w) * dim + d] = static_cast<double>(__fdiv_rn(sum, n));
+    }
+}
+
+cudaError_t launch_pool_stats(const float* d_emb, int dim, const int* d_lo, const int* d_hi, long long n_windows,
+                              int mode, double* d_out, cudaStream_t stream) {
+    if (n_windows <= 0 || dim <= 0) return cudaSuccess;
+    if (mode == 2) pool_mean_f32_kernel<<<static_cast<unsigned>(n_windows), 128, 0, stream>>>(d_emb, dim, d_lo, d_hi, d_out);
+    else pool_stats_kernel<<<static_cast<unsigned>(n_windows), 128, 0, stream>>>(d_emb, dim, d_lo, d_hi, mode == 1 ? 1 : 0, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_prepare_pcm16(const short* d_pcm, long long n, int* d_scratch_max, float* d_out,
                                  cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(d_scratch_max, 0, sizeof(int), stream);

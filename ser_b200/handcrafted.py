@@ -91,13 +91,9 @@ class HandcraftedBackend:
 
     def pool(self, encoded: EncodedSequence, windows: Sequence[PoolingWindow]) -> NDArray[np.float64]:
         """Mean of the frames overlapping each window (handcrafted.py:109-122)."""
-        if not windows:
-            return np.empty((0, encoded.embeddings.shape[1]), dtype=np.float64)
-        rows = []
-        for window in windows:
-            mask = overlap_frame_mask(encoded, window)
-            rows.append(np.asarray(encoded.embeddings[mask].mean(axis=0), dtype=np.float64))
-        return np.vstack(rows)
+        from .pooling import mean_pool
+
+        return mean_pool(encoded, windows, device=self._device)
 
     def extract_vector(self, audio: NDArray[np.float32], sample_rate: int) -> NDArray[np.float64]:
         """One whole-clip vector (training path, handcrafted.py:124-137)."""

@@ -11,6 +11,7 @@ ser._internal.features.feature_extractor._extract_feature_from_signal  (same; it
 ser._internal.repr.handcrafted.HandcraftedBackend.encode_sequence      one ragged-batch GPU call per recording
 ser._internal.models.fast_path.predict_emotions_detailed_with_model    ser_b200.fast_path (fused CUDA MLP)
 ser._internal.models.emotion_model._fast_predict_emotions_detailed_with_model  (same; from-import alias)
+ser._internal.data.data_loader.load_checked_fast_data                  ser_b200.data_loader (ragged GPU batches)
 =====================================================================  =========================================
 
 ``ser.api.infer``, ``ser --file``, ``ser --train`` and ``run_fast_inference`` keep their
@@ -25,6 +26,7 @@ from __future__ import annotations
 import importlib
 from typing import Any
 
+from . import data_loader as _data_loader
 from . import dsp as _dsp
 from . import fast_path as _fast_path
 from .handcrafted import frame_bounds
@@ -87,6 +89,31 @@ def install(device: int = 0) -> list[str]:
             output_schema_version=output_schema_version,
             extract_feature_frames_fn=extract_feature_frames_fn, logger=logger, device=device)
 
+    ref_data_loader = importlib.import_module("ser._internal.data.data_loader")
+
+    def load_checked_fast_data(*, utterances, settings, handle_sample_failure=None):
+        # same signature as ser/_internal/data/data_loader.py:467-472; the reference's own splitter
+        # and progress recorder are used unchanged
+        from ser._internal.models.dataset_splitting import split_utterances
+        from ser._internal.models.training_orchestration import record_preparation_progress
+
+        def read_audio(path, *, start_seconds=None, duration_seconds=None):
+            return ref_data_loader.read_audio_file(path, start_seconds=start_seconds,
+                                                   duration_seconds=duration_seconds,
+                                                   audio_read_config=settings.audio_read)
+
+        if not utterances:
+            return None
+        train, test, _ = split_utterances(samples=list(utterances), settings=settings, logger=ref_data_loader.logger)
+        common = dict(feature_flags=settings.feature_flags, handle_sample_failure=handle_sample_failure,
+                      record_progress=record_preparation_progress, read_audio=read_audio, device=device)
+        x_train, y_train = _data_loader.extract_partition(train, **common)
+        x_test, y_test = _data_loader.extract_partition(test, **common)
+        if len(set(y_train)) < 2:
+            raise RuntimeError("Fast checked preparation left fewer than two training classes.")
+        return x_train, x_test, y_train, y_test
+
+    _swap(ref_data_loader, "load_checked_fast_data", load_checked_fast_data)
     _swap(ref_dsp, "extract_feature_from_signal", extract_feature_from_signal)
     _swap(ref_features, "_extract_feature_from_signal", extract_feature_from_signal)
     _swap(ref_handcrafted.HandcraftedBackend, "encode_sequence",
