@@ -325,13 +325,16 @@ def run_b200(args) -> None:
         ctx.infer_host(hw, starts, lengths, sr, bits, want_features=False)   # warm the staging buffers
         barrier()
         t0 = time.perf_counter()
+        chain_ms = []
         for _ in range(e2e_steps):
             _f, p_host, l_host = ctx.infer_host(hw, starts, lengths, sr, bits, want_features=False)
+            chain_ms.append(ctx.last_compute_ms())
         elapsed = max_over_ranks(time.perf_counter() - t0)
         barrier()
         e2e = {"value": world * audio_seconds_step * e2e_steps / elapsed, "unit": UNIT,
                "h2d_bytes_per_step": int(hw.nbytes), "d2h_bytes_per_step": int(p_host.nbytes + l_host.nbytes),
-               "steps": e2e_steps, "ms_per_step": 1e3 * elapsed / e2e_steps}
+               "steps": e2e_steps, "ms_per_step": 1e3 * elapsed / e2e_steps,
+               "device_chain_ms": float(np.median(chain_ms))}
         assert np.array_equal(l_host, labels.cpu().numpy()), "host-entry labels differ from the device path"
 
     # ---- the 187-d slice (tonnetz off) timed the same way, for continuity with earlier rounds ----

@@ -73,6 +73,7 @@ struct serb_ctx {
     std::string err;
     long long launches = 0;
     int chunk_cols = 262144;
+    bool ramp_chunks = false;   // set by the host-buffer entries for the duration of one call
     float last_ms = 0.f;
     bool timed = false;
 
@@ -216,6 +217,13 @@ struct Chunk { int clip_lo, clip_hi, n_cols, n_tiles; long long max_end; };
 int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* lengths, long long n_clips,
          int sr, uint32_t flags, std::vector<ClipDev>& main_clips, std::vector<ShortClip>& short_clips,
          std::vector<Chunk>& chunks) {
+    // host entries stream the waveform in while the chain runs: small first chunks let compute start
+    // after a few megabytes have landed, later chunks grow to the full size the kernels like
+    auto chunk_limit = [&](size_t index) -> int {
+        if (!ctx->ramp_chunks) return ctx->chunk_cols;
+        const long long ramp = 16384LL << std::min<size_t>(index, 8);
+        return static_cast<int>(std::min<long long>(ctx->chunk_cols, ramp));
+    };
     if (sr <= 0) return fail(ctx, SERB_ERR_SAMPLE_RATE, "Sample rate must be a positive integer.");
     if (n_clips < 0 || (n_clips > 0 && (!starts || !lengths))) return fail(ctx, SERB_ERR_INVALID_ARG, "bad clip arrays");
     if (flags & ~SERB_FLAG_ALL) return fail(ctx, SERB_ERR_INVALID_ARG, "unknown feature flag bits");
@@ -237,7 +245,7 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
         c.n_cols = 1 + static_cast<int>(len / kHop);
         c.out_row = static_cast<int>(i);
         const int tiles = (c.n_cols + kColsPerTile - 1) / kColsPerTile;
-        if (cur.clip_hi > cur.clip_lo && cur.n_cols + c.n_cols > ctx->chunk_cols) {
+        if (cur.clip_hi > cur.clip_lo && cur.n_cols + c.n_cols > chunk_limit(chunks.size())) {
             chunks.push_back(cur);
             cur = Chunk{cur.clip_hi, cur.clip_hi, 0, 0, 0};
         }
@@ -445,6 +453,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     // 4. tuning of the harmonic signal (36 bins per octave)
     sp.wave = ctx->yharm.as<float>();
     sp.clips = d_b;
+    sp.spill = nullptr;          // only the piptrack peaks of the harmonic signal are needed
     sp.cspill = nullptr;
     sp.do_peaks = 1;
     { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
@@ -493,7 +502,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
 template <typename BeforeChunk>
 int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int64_t* starts,
                  const int64_t* lengths, long long n_clips, int sr, uint32_t flags, float* d_out,
-                 cudaStream_t stream, BeforeChunk before_chunk) {
+                 cudaStream_t stream, BeforeChunk&& before_chunk) {
     std::vector<ClipDev> main_clips;
     std::vector<ShortClip> short_clips;
     std::vector<Chunk> chunks;
@@ -577,6 +586,10 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
     if (want_ton) {
         if ((rc = ton_reserve_and_upload(ctx, tab, tp, stream))) return rc;
         if ((rc = upload(ctx, ctx->ton_clips_a, short_a.data(), short_a.size(), stream))) return rc;
+    }
+    if (!short_clips.empty()) {
+        if ((rc = upload(ctx, ctx->short_clips, short_clips.data(), short_clips.size(), stream))) return rc;
+        SERB_CUDA(ctx, ctx->short_tuning.reserve(short_clips.size() * sizeof(int)));
     }
     SERB_CUDA(ctx, ctx->status.reserve(sizeof(int)));
     SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), stream));
@@ -670,8 +683,6 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
             ctx->last_short_rows.push_back(s.out_row);
         }
         before_chunk(max_end);
-        if ((rc = upload(ctx, ctx->short_clips, short_clips.data(), short_clips.size(), stream))) return rc;
-        SERB_CUDA(ctx, ctx->short_tuning.reserve(short_clips.size() * sizeof(int)));
         ShortParams hp{};
         hp.wave = d_wave;
         hp.clips = ctx->short_clips.as<ShortClip>();
@@ -714,14 +725,36 @@ int check_status(serb_ctx* ctx, cudaStream_t stream) {
 
 // host waveform -> ctx->wave in pieces on the copy stream; returns a functor making `stream`
 // wait for the piece holding sample (max_end - 1)
+// Host waveform -> ctx->wave in pieces on the copy stream.  The copies are enqueued lazily, at the
+// first chunk: every small table upload of the call has been issued by then, so none of them sits
+// behind a gigabyte of waveform in the H2D copy engine's queue.  operator()(max_end) makes the
+// compute stream wait for the piece holding sample (max_end - 1).
 struct PieceWaiter {
     serb_ctx* ctx;
     cudaStream_t stream;
-    long long piece;
-    int n_pieces;
+    const float* h_wave;
+    long long n_wave;
+    long long piece = 8LL << 20;   // samples per piece (32 MiB)
+    int n_pieces = 0;
     int waited = -1;
+    bool started = false;
+    cudaError_t error = cudaSuccess;
+    void start() {
+        started = true;
+        n_pieces = static_cast<int>((n_wave + piece - 1) / piece);
+        // the previous call's kernels may still read ctx->wave
+        if ((error = cudaEventRecord(ctx->ev_done, ctx->stream)) != cudaSuccess) return;
+        if ((error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0)) != cudaSuccess) return;
+        for (int i = 0; i < n_pieces; ++i) {
+            const long long lo = i * piece, hi = std::min(n_wave, lo + piece);
+            if ((error = cudaMemcpyAsync(ctx->wave.as<float>() + lo, h_wave + lo, (hi - lo) * sizeof(float),
+                                         cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess) return;
+            if ((error = cudaEventRecord(ctx->piece_events[i], ctx->copy_stream)) != cudaSuccess) return;
+        }
+    }
     void operator()(long long max_end) {
-        if (n_pieces == 0) return;
+        if (!started) start();
+        if (n_pieces == 0 || error != cudaSuccess) return;
         int idx = static_cast<int>(std::min<long long>((std::max<long long>(max_end, 1) - 1) / piece, n_pieces - 1));
         if (idx > waited) {
             cudaStreamWaitEvent(stream, ctx->piece_events[idx], 0);
@@ -732,23 +765,13 @@ struct PieceWaiter {
 
 int stage_wave(serb_ctx* ctx, const float* h_wave, long long n_wave, PieceWaiter& waiter) {
     SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
-    const long long piece = 8LL << 20;  // samples per piece (32 MiB)
-    const int n_pieces = static_cast<int>((n_wave + piece - 1) / piece);
+    waiter = PieceWaiter{ctx, ctx->stream, h_wave, n_wave};
+    const int n_pieces = static_cast<int>((n_wave + waiter.piece - 1) / waiter.piece);
     while (static_cast<int>(ctx->piece_events.size()) < n_pieces) {
         cudaEvent_t ev;
         SERB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->piece_events.push_back(ev);
     }
-    // the previous call's kernels may still read ctx->wave
-    SERB_CUDA(ctx, cudaEventRecord(ctx->ev_done, ctx->stream));
-    SERB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
-    for (int i = 0; i < n_pieces; ++i) {
-        const long long lo = i * piece, hi = std::min(n_wave, lo + piece);
-        SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.as<float>() + lo, h_wave + lo, (hi - lo) * sizeof(float),
-                                       cudaMemcpyHostToDevice, ctx->copy_stream));
-        SERB_CUDA(ctx, cudaEventRecord(ctx->piece_events[i], ctx->copy_stream));
-    }
-    waiter = PieceWaiter{ctx, ctx->stream, piece, n_pieces};
     return SERB_OK;
 }
 
@@ -923,12 +946,15 @@ int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const
     SERB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_clips > 0 && (!h_wave || !h_out)) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
     const int dim = serb_feature_dim(flag_bits);
-    PieceWaiter waiter{ctx, ctx->stream, 1, 0};
+    PieceWaiter waiter{ctx, ctx->stream, nullptr, 0};
     int rc = stage_wave(ctx, h_wave, n_wave, waiter);
     if (rc) return rc;
     SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
+    ctx->ramp_chunks = true;
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, waiter);
+    ctx->ramp_chunks = false;
+    if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips > 0 && dim > 0)
         SERB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.ptr, static_cast<size_t>(n_clips) * dim * sizeof(float),
@@ -1016,14 +1042,17 @@ int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const in
         return fail(ctx, SERB_ERR_INVALID_ARG,
                     "Feature vector size mismatch for loaded model. Expected " + std::to_string(m.n_in) +
                         ", got [" + std::to_string(dim) + "].");
-    PieceWaiter waiter{ctx, ctx->stream, 1, 0};
+    PieceWaiter waiter{ctx, ctx->stream, nullptr, 0};
     int rc = stage_wave(ctx, h_wave, n_wave, waiter);
     if (rc) return rc;
     SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
     SERB_CUDA(ctx, ctx->proba.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * m.n_classes, 1) * sizeof(double)));
     SERB_CUDA(ctx, ctx->labels.reserve(std::max<size_t>(static_cast<size_t>(n_clips), 1) * sizeof(int)));
+    ctx->ramp_chunks = true;
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, waiter);
+    ctx->ramp_chunks = false;
+    if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips == 0) return SERB_OK;
     rc = mlp_run(ctx, ctx->out.as<float>(), nullptr, n_clips, ctx->proba.as<double>(), ctx->labels.as<int>(), ctx->stream);

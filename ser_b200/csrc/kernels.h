@@ -13,7 +13,7 @@ struct StftParams {
     int n_clips;
     const int* tile_clip;    // [tiles] clip index of every 16-column tile
     const float2* tables;    // W_1024^(k1 n2) [32][32] then W_2048^k [1024] as (cos, sin)
-    float* spill;            // [cols][kSpillStride]  |X|
+    float* spill;            // [cols][kSpillStride]  |X|, or NULL when only the peaks are wanted
     float2* cspill;          // [cols][kSpillStride]  X (complex), or NULL (tonnetz chain: HPSS needs the phase)
     int do_peaks;            // piptrack wanted (chroma enabled)
     int kmin, kmax;          // bins with 150 <= f < min(4000, sr/2):  kmin <= k < kmax

@@ -138,14 +138,14 @@ __device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[
         const float xr = ex + wx, xi = ey + wy;
         const float mag = 0.5f * sqrt_approx(fmaf(xr, xr, xi * xi));
         if (crow) crow[lane + 32 * k2] = make_float2(0.5f * xr, 0.5f * xi);
-        row[lane + 32 * k2] = mag;
+        if (row) row[lane + 32 * k2] = mag;
         sbuf[lane + 32 * k2] = mag;
         cmax = fmaxf(cmax, mag);
         if (k2 == 0 && lane == 0) {
             const float nr = ex - wx, ni = ey - wy;
             const float nyq = 0.5f * sqrt_approx(fmaf(nr, nr, ni * ni));
             if (crow) crow[1024] = make_float2(0.5f * nr, 0.5f * ni);
-            row[1024] = nyq;
+            if (row) row[1024] = nyq;
             sbuf[1024] = nyq;
             cmax = fmaxf(cmax, nyq);
         }
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(StftParams p, int
         }
         if (active) {
             const long long col = d.col0 + warp;
-            float cmax = column_fft(v, sm.tw, sm.tw2, buf, lane, p.spill + col * kSpillStride,
+            float cmax = column_fft(v, sm.tw, sm.tw2, buf, lane, p.spill ? p.spill + col * kSpillStride : nullptr,
                                     p.cspill ? p.cspill + col * kSpillStride : nullptr);
             if (p.do_peaks) {
                 cmax = warp_max(cmax);
