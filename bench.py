@@ -246,6 +246,8 @@ def run_b200(args) -> None:
 
     from ser_b200 import multi_gpu
 
+    # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     info = multi_gpu.rank_info()
     rank, local_rank, world, distributed = info.rank, info.local_rank, info.world, info.distributed
     if not torch.cuda.is_available():

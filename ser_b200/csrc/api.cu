@@ -430,6 +430,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     hp.clips = d_clips;
     hp.segs = ctx->ton_segs.as<int2>() + c.seg_lo;
     hp.seg_len = ctx->harm_seg;
+    hp.one = 1.0f;
     hp.mag = ctx->spill.as<float>();
     hp.perc = ctx->perc.as<float>();
     hp.cspec = ctx->cspec.as<float2>();

@@ -173,14 +173,22 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     // ---- stage the span and the basis ----
     const int s0 = t_block * hop - N;                       // signal index of sig_s[0]
     const int span = (n_here - 1) * hop + 2 * N;
+    // asynchronous copies (LDGSTS): every request of the CTA is in flight at once; samples outside
+    // the clip are zero-filled by a zero source size
     for (int i = tid; i < span; i += kCqtWarps * 32) {
         const int j = s0 + i;
-        sig_s[i] = (j >= 0 && j < len) ? sig[j] : 0.0f;
+        const bool inside = j >= 0 && j < len;
+        const float* src = inside ? sig + j : sig;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sig_s + i))),
+                     "l"(src), "r"(inside ? 4 : 0) : "memory");
     }
     const size_t bank = (static_cast<size_t>(tuning) * kCqOctaves + octave) * kCqRows;
     for (int i = tid; i < kCqRows * kCqRowCap; i += kCqtWarps * 32)
-        sm.vals[i / kCqRowCap][i % kCqRowCap] = p.vals[bank * kCqRowCap + i];
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&sm.vals[i / kCqRowCap][i % kCqRowCap]))),
+                     "l"(p.vals + bank * kCqRowCap + i) : "memory");
     if (tid < kCqRows) sm.rows[tid] = p.rows[bank + tid];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const float2* twa = p.twiddles + (N - 128);            // W_N^j = (cos, -sin)

@@ -51,15 +51,24 @@ struct SortedWindow {
             prev = cur;
         }
     }
-    // remove one occurrence of `old` (which is in the window) and insert x
-    __device__ __forceinline__ void replace(float old, float x) {
-        float b[kMedW];
+    // remove one occurrence of `old` (which is in the window) and insert x.
+    // Remove pass: a[i] <- a[i+1] wherever a[i] >= old, in ascending order, as a compare plus a
+    // predicated multiply by an opaque 1.0f (exact) instead of a select: the compare issues on the
+    // ALU pipe next to the min/max of the insert pass, the multiply on the otherwise idle FMA pipe.
+    __device__ __forceinline__ void replace(float old, float x, float one) {
 #pragma unroll
-        for (int i = 0; i < kMedW - 1; ++i) b[i] = (a[i] >= old) ? a[i + 1] : a[i];
-        b[kMedW - 1] = FLT_MAX;
-        a[0] = fminf(b[0], x);
+        for (int i = 0; i < kMedW - 1; ++i)
+            asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p mul.f32 %0, %2, %3;\n\t}"
+                : "+f"(a[i]) : "f"(old), "f"(a[i + 1]), "f"(one));
+        a[kMedW - 1] = FLT_MAX;
+        float prev = a[0];
+        a[0] = fminf(prev, x);
 #pragma unroll
-        for (int i = 1; i < kMedW; ++i) a[i] = fmaxf(b[i - 1], fminf(b[i], x));
+        for (int i = 1; i < kMedW; ++i) {
+            const float cur = a[i];
+            a[i] = fmaxf(prev, fminf(cur, x));
+            prev = cur;
+        }
     }
     __device__ __forceinline__ float median() const { return a[kMedHalf]; }
 };
@@ -101,6 +110,7 @@ __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
     const float* src = p.mag + static_cast<long long>(clip.col_base) * kSpillStride + f;
     const float* perc = p.perc + static_cast<long long>(clip.col_base) * kSpillStride + f;
     float2* spec = p.cspec + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    const float one = p.one;            // 1.0f the compiler cannot fold (see SortedWindow::replace)
     const bool wide = T > kMedHalf;     // one reflection reaches every index of the window
     auto at = [&](int t) -> float {
         const int i = wide ? reflect_once(t, T) : reflect_index(t, T);
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
         const float2 x_n = spec[static_cast<long long>(tn) * kSpillStride];
         const float m = harm_mask(w.median(), pq);
         spec[o] = make_float2(x.x * m, x.y * m);     // (S * mask) * phase
-        w.replace(old, nxt);
+        w.replace(old, nxt, one);
         old = old_n; nxt = nxt_n; pq = pq_n; x = x_n;
     }
 }
@@ -141,6 +151,7 @@ __global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols
     const int f0 = (lane % RUNS) * RUN;
     const int f1 = min(f0 + RUN, kNBins);
     if (f0 >= kNBins) return;
+    const float one = p.one;            // 1.0f the compiler cannot fold (see SortedWindow::replace)
     const float* src = p.mag + static_cast<long long>(col) * kSpillStride;
     float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
     SortedWindow w;
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols
     for (int f = f0 - kMedHalf; f <= f0 + kMedHalf; ++f) w.insert(src[reflect_once(f, kNBins)]);
     for (int f = f0; f < f1; ++f) {
         dst[f] = w.median();
-        if (f + 1 < f1) w.replace(src[reflect_once(f - kMedHalf, kNBins)], src[reflect_once(f + 1 + kMedHalf, kNBins)]);
+        if (f + 1 < f1) w.replace(src[reflect_once(f - kMedHalf, kNBins)], src[reflect_once(f + 1 + kMedHalf, kNBins)], one);
     }
 }
 

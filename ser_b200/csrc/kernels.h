@@ -120,6 +120,7 @@ struct HpssParams {
     const TonClip* clips;
     const int2* segs;        // (clip index, first column) per time-median work item
     int seg_len;             // columns per time-median work item
+    float one;               // 1.0f, passed at run time so the predicated multiply-by-one of the median update stays a multiply
     const float* mag;        // [cols][kSpillStride] |X|
     float* perc;             // [cols][kSpillStride] median along frequency
     float2* cspec;           // [cols][kSpillStride] X, masked in place by hpss_harm_kernel
