@@ -102,6 +102,25 @@ def test_tonnetz_only_and_nyquist_error(golden):
                                         feature_flags=FeatureFlags(False, False, False, False, True))
 
 
+def test_long_form_c4_windows(gpu_ctx):
+    """BASELINE config c4: a one-hour 16 kHz recording, 3 s / 1 s sliding windows -> 3600 rows.
+    Timestamps follow handcrafted.py:78-97; a window's row equals the row of the same samples
+    extracted alone (windows are independent clips)."""
+    from ser_b200 import dsp, synth
+    from ser_b200.handcrafted import HandcraftedBackend
+
+    sr, n = 16000, 57_600_000
+    audio = synth.long_recording(sr, n)
+    encoded = HandcraftedBackend().encode_sequence(audio, sr)
+    assert encoded.embeddings.shape == (3600, 193) and np.all(np.isfinite(encoded.embeddings))
+    np.testing.assert_array_equal(encoded.frame_start_seconds, np.arange(3600, dtype=np.float64))
+    np.testing.assert_array_equal(encoded.frame_end_seconds, np.minimum(np.arange(3600) + 3.0, 3600.0))
+    for w in (0, 1234, 3598, 3599):
+        lo, hi = w * sr, min((w + 3) * sr, n)
+        single = dsp.extract_feature_from_signal(audio[lo:hi], sr)
+        np.testing.assert_array_equal(encoded.embeddings[w], single.astype(np.float32))
+
+
 def test_full_size_properties_c2_batch_193(gpu_ctx):
     """Config c2 at full size with tonnetz on: halving the input leaves tonnetz (a ratio of
     magnitudes behind exact medians) bit-identical, and rows do not depend on batch position."""
@@ -132,3 +151,31 @@ def test_full_size_properties_c2_batch_193(gpu_ctx):
                                 bits, single.data_ptr(), 0)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(single.cpu().numpy()[0], a[idx])
+
+
+def test_small_chunks_do_not_change_any_row(golden):
+    """SERB_CHUNK_COLS=96 forces a chunk boundary after nearly every clip (main path, tonnetz
+    chain and the ramped host entry alike); rows must equal the single-call rows bit for bit."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from ser_b200 import dsp
+
+    repo = Path(__file__).resolve().parents[1]
+    names = [n for n in CASES if int(golden[f"{n}/sr"]) == 16000]
+    script = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from ser_b200 import dsp, synth\n"
+        "g = np.load(%r)\n"
+        "clips = [synth.decode_pcm16(g[n + '/pcm']) for n in %r]\n"
+        "np.save(sys.argv[1], dsp.extract_features_batch(clips, 16000))\n"
+    ) % (str(repo), str(repo / "tests" / "golden" / "fast_profile_golden.npz"), names)
+    out = repo / "gpurun_out" / "small_chunks.npy"
+    out.parent.mkdir(exist_ok=True)
+    env = dict(os.environ, SERB_CHUNK_COLS="96")
+    subprocess.run([sys.executable, "-c", script, str(out)], check=True, env=env, timeout=300)
+    chunked = np.load(out)
+    whole = dsp.extract_features_batch([_audio(golden, n)[0] for n in names], 16000)
+    np.testing.assert_array_equal(chunked, whole)
