@@ -88,7 +88,8 @@ struct serb_ctx {
     DevBuf wave, out, proba, labels, x64, pcm, pcm_max;
     // tonnetz chain
     DevBuf hann_sq, cq_twiddles;
-    DevBuf cspec, perc, frames, yharm, yoct, cqmag;
+    DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
+    DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
     int harm_seg = 128, perc_runs = 16;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
@@ -304,10 +305,17 @@ int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
     return SERB_OK;
 }
 
+// clips of one chunk that take the multi-CTA tuning path (more than kTuneLongCols columns)
+struct LongList {
+    const int* d_idx = nullptr;
+    int n = 0;
+    int max_cols = 0;
+};
+
 struct TonChunk {
     int clip_lo, clip_hi;       // range in the request-wide TonClip array
     int seg_lo, n_segs;
-    int n_cols, n_tiles, cq_rows, max_len0, max_cq_cols;
+    int n_cols, n_tiles, cq_rows, max_len0, max_cq_cols, n_parts;
     long long total0, max_end;
 };
 
@@ -346,6 +354,7 @@ int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur,
     c.cq_cols = cq;
     c.cq_base = cur.cq_rows;
     c.out_row = a.out_row;
+    c.part_base = cur.n_parts;
     ClipDev b = a;
     b.start = c.hoff;
     b.length = c.length;
@@ -358,6 +367,7 @@ int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur,
     cur.n_tiles = std::max(cur.n_tiles, a.tile_base + (a.n_cols + kColsPerTile - 1) / kColsPerTile);
     cur.n_segs = static_cast<int>(tp.segs.size()) - cur.seg_lo;
     cur.cq_rows += cq;
+    cur.n_parts += (cq + kTonTile - 1) / kTonTile;
     cur.max_len0 = std::max(cur.max_len0, c.len0);
     cur.max_cq_cols = std::max(cur.max_cq_cols, cq);
     cur.max_end = std::max(cur.max_end, a.start + a.length);
@@ -367,9 +377,10 @@ int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur,
 
 int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cudaStream_t stream) {
     const int fe = tab->plan.early_factor;
-    int max_cols = 0, max_tiles = 0, max_cq = 0;
+    int max_cols = 0, max_tiles = 0, max_cq = 0, max_parts = 0;
     long long max_total0 = 0;
     for (const TonChunk& c : tp.chunks) {
+        max_parts = std::max(max_parts, c.n_parts);
         max_cols = std::max(max_cols, c.n_cols);
         max_tiles = std::max(max_tiles, c.n_tiles);
         max_cq = std::max(max_cq, c.cq_rows);
@@ -383,6 +394,7 @@ int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cuda
     SERB_CUDA(ctx, ctx->yharm.reserve((static_cast<size_t>(max_total0) * fe + 64) * sizeof(float)));
     SERB_CUDA(ctx, ctx->yoct.reserve((static_cast<size_t>(max_total0) * 2 + 64) * sizeof(float)));
     SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(std::max(max_cq, 1)) * kCqBins * sizeof(float)));
+    SERB_CUDA(ctx, ctx->ton_part.reserve(static_cast<size_t>(std::max(max_parts, 1)) * 6 * sizeof(double)));
     SERB_CUDA(ctx, ctx->ton_tile_clip.reserve(static_cast<size_t>(std::max(max_tiles, 1)) * sizeof(int)));
     SERB_CUDA(ctx, ctx->peaks.reserve(static_cast<size_t>(max_cols) * tab->peak_cap * sizeof(float2)));
     SERB_CUDA(ctx, ctx->peak_count.reserve(static_cast<size_t>(max_cols) * sizeof(int)));
@@ -399,7 +411,7 @@ int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cuda
 // waveform; when stft_done the chunk's |X| (ctx->spill) and X (ctx->cspec) are already there.
 int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, float* d_out, cudaStream_t stream,
                   const TonChunk& c, const float* d_wave, const ClipDev* d_clips_a, const int* d_tile_clip,
-                  bool stft_done) {
+                  bool stft_done, const LongList& longs) {
     const CqtPlan& plan = tab->plan;
     const int nc = c.clip_hi - c.clip_lo;
     if (nc <= 0) return SERB_OK;
@@ -466,8 +478,12 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     tp.bins_per_octave = 36;
     tp.edges = ctx->edges.as<double>();
     tp.tuning_idx = d_tuning;
-    { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream)); }
-    ctx->launches += 2;
+    tp.long_clips = longs.d_idx;
+    tp.n_long = longs.n;
+    tp.max_long_cols = longs.max_cols;
+    tp.long_state = ctx->long_state.as<TuneLongState>();
+    { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tp, nc, stream, &ctx->launches)); }
+    ctx->launches += 1;
     // 5. decimations, constant-Q, chroma, tonnetz
     CqtParams qp{};
     qp.clips = d_clips;
@@ -486,6 +502,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.vals = tab->cq_vals.as<float2>();
     qp.twiddles = ctx->cq_twiddles.as<float2>();
     qp.cqmag = ctx->cqmag.as<float>();
+    qp.ton_part = ctx->ton_part.as<double>();
     qp.out = d_out;
     qp.dim = off.dim;
     qp.off_tonnetz = off.tonnetz;
@@ -494,7 +511,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
-    ctx->launches += 1;
+    ctx->launches += 2;
     return SERB_OK;
 }
 
@@ -584,6 +601,32 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         if ((rc = upload(ctx, ctx->clips, main_clips.data(), main_clips.size(), stream))) return rc;
         for (const ClipDev& c : main_clips) ctx->last_tuning_rows.push_back(c.out_row);
     }
+    // clips long enough for the multi-CTA tuning path, per chunk
+    std::vector<LongList> longs(chunks.size());
+    {
+        std::vector<int> idx;
+        std::vector<size_t> first(chunks.size(), 0);
+        int max_n = 0;
+        for (size_t ci = 0; ci < chunks.size(); ++ci) {
+            first[ci] = idx.size();
+            for (int i = chunks[ci].clip_lo; i < chunks[ci].clip_hi; ++i)
+                if (main_clips[i].n_cols > kTuneLongCols) {
+                    idx.push_back(i - chunks[ci].clip_lo);
+                    longs[ci].n += 1;
+                    longs[ci].max_cols = std::max(longs[ci].max_cols, main_clips[i].n_cols);
+                }
+            max_n = std::max(max_n, longs[ci].n);
+        }
+        if (!idx.empty() && (want_chroma || want_ton)) {
+            if ((rc = upload(ctx, ctx->long_idx, idx.data(), idx.size(), stream))) return rc;
+            SERB_CUDA(ctx, ctx->long_state.reserve(static_cast<size_t>(max_n) * sizeof(TuneLongState)));
+            // prefixes and histograms start every call at zero (a few megabytes at most)
+            SERB_CUDA(ctx, cudaMemsetAsync(ctx->long_state.ptr, 0, static_cast<size_t>(max_n) * sizeof(TuneLongState), stream));
+            for (size_t ci = 0; ci < chunks.size(); ++ci) longs[ci].d_idx = ctx->long_idx.as<int>() + first[ci];
+        } else {
+            for (LongList& l : longs) l = LongList{};
+        }
+    }
     if (want_ton) {
         if ((rc = ton_reserve_and_upload(ctx, tab, tp, stream))) return rc;
         if ((rc = upload(ctx, ctx->ton_clips_a, short_a.data(), short_a.size(), stream))) return rc;
@@ -631,8 +674,11 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
             tu.bins_per_octave = 12;
             tu.edges = ctx->edges.as<double>();
             tu.tuning_idx = d_tuning;
-            { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tu, nc, stream)); }
-            ctx->launches += 1;
+            tu.long_clips = longs[ci].d_idx;
+            tu.n_long = longs[ci].n;
+            tu.max_long_cols = longs[ci].max_cols;
+            tu.long_state = ctx->long_state.as<TuneLongState>();
+            { ProfScope ps(ctx, 1, stream); SERB_CUDA(ctx, launch_tuning(tu, nc, stream, &ctx->launches)); }
         }
         ProjParams pp{};
         pp.clips = d_clips;
@@ -674,7 +720,7 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         if (want_ton) {
             // same clips, same columns: the chunk's |X| and X feed the harmonic separation directly
             if ((rc = ton_run_chunk(ctx, tab, sr, off, d_out, stream, tp.chunks[ci], d_wave, d_clips,
-                                    ctx->tile_clip.as<int>(), true))) return rc;
+                                    ctx->tile_clip.as<int>(), true, longs[ci]))) return rc;
         }
     }
     if (!short_clips.empty()) {
@@ -708,7 +754,8 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
             const ClipDev* d_a = ctx->ton_clips_a.as<ClipDev>() + first;
             SERB_CUDA(ctx, launch_expand_tiles(d_a, c.clip_hi - c.clip_lo, ctx->ton_tile_clip.as<int>(), stream));
             ctx->launches += 1;
-            if ((rc = ton_run_chunk(ctx, tab, sr, off, d_out, stream, c, d_wave, d_a, ctx->ton_tile_clip.as<int>(), false)))
+            if ((rc = ton_run_chunk(ctx, tab, sr, off, d_out, stream, c, d_wave, d_a, ctx->ton_tile_clip.as<int>(), false,
+                                    LongList{})))
                 return rc;
         }
     }
@@ -908,8 +955,8 @@ void serb_ctx_destroy(serb_ctx* ctx) {
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->mlp.mean, &ctx->mlp.scale,
                       &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles,
-                      &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag,
-                      &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
+                      &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag, &ctx->ton_part,
+                      &ctx->long_idx, &ctx->long_state, &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
                       &ctx->ton_tile_clip})
         b->release();
     for (auto& kv : ctx->sr_tables) {

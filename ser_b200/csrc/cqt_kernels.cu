@@ -271,12 +271,18 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
 }
 
 // ---- chroma fold + tonnetz ---------------------------------------------------------------
+// one CTA per (clip, kTonTile columns): partial sums of the six tonnetz rows in float64, then a
+// per-clip reduction in tile order (tonnetz_final_kernel), so long clips spread over many CTAs
+// and every clip's result is independent of the batch around it
 __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
     __shared__ float mags[4][256];
     __shared__ double phi[6][12];
     __shared__ double part[4][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const TonClip clip = p.clips[blockIdx.x];
+    const int t_lo = blockIdx.y * kTonTile;
+    if (t_lo >= clip.cq_cols) return;
+    const int t_hi = min(t_lo + kTonTile, clip.cq_cols);
     if (threadIdx.x < 72) {
         // librosa.feature.tonnetz: phi = R * cos(pi * V), V = outer(scale, 0..11), even rows - 0.5
         const int q = threadIdx.x / 12, c = threadIdx.x % 12;
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
     }
     __syncthreads();
     double acc = 0.0;   // lanes 0..5: running sum of tonnetz row `lane`
-    for (int t = warp; t < clip.cq_cols; t += 4) {
+    for (int t = t_lo + warp; t < t_hi; t += 4) {
         const float* row = p.cqmag + (static_cast<size_t>(clip.cq_base) + t) * kCqBins;
         for (int i = lane; i < kCqBins; i += 32) mags[warp][i] = row[i];
         __syncwarp();
@@ -322,11 +328,20 @@ __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
     }
     if (lane < 6) part[warp][lane] = acc;
     __syncthreads();
-    if (threadIdx.x < 6) {
-        const double total = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
-        p.out[static_cast<size_t>(clip.out_row) * p.dim + p.off_tonnetz + threadIdx.x] =
-            static_cast<float>(total / static_cast<double>(clip.cq_cols));
-    }
+    if (threadIdx.x < 6)
+        p.ton_part[(static_cast<size_t>(clip.part_base) + blockIdx.y) * 6 + threadIdx.x] =
+            part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+}
+
+__global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
+    const int c = blockIdx.x * 32 + threadIdx.x / 6, d = threadIdx.x % 6;
+    if (c >= p.n_clips) return;
+    const TonClip clip = p.clips[c];
+    const int tiles = (clip.cq_cols + kTonTile - 1) / kTonTile;
+    double total = 0.0;
+    for (int i = 0; i < tiles; ++i) total += p.ton_part[(static_cast<size_t>(clip.part_base) + i) * 6 + d];
+    p.out[static_cast<size_t>(clip.out_row) * p.dim + p.off_tonnetz + d] =
+        static_cast<float>(total / static_cast<double>(clip.cq_cols));
 }
 
 // ---- launchers ---------------------------------------------------------------------------
@@ -396,7 +411,8 @@ cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long lon
 
 cudaError_t launch_tonnetz(const CqtParams& p, cudaStream_t stream) {
     if (p.n_clips <= 0) return cudaSuccess;
-    tonnetz_kernel<<<p.n_clips, 128, 0, stream>>>(p);
+    tonnetz_kernel<<<dim3(p.n_clips, (p.max_cq_cols + kTonTile - 1) / kTonTile), 128, 0, stream>>>(p);
+    tonnetz_final_kernel<<<(p.n_clips + 31) / 32, 192, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

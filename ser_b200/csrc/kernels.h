@@ -28,6 +28,14 @@ cudaError_t launch_expand_tiles(const ClipDev* clips, int n_clips, int* tile_cli
 cudaError_t launch_stft(const StftParams& p, int n_tiles, cudaStream_t stream);
 
 // ---- K2/K3/K4 proj_kernels.cu ------------------------------------------------------------
+constexpr int kTuneLongCols = 1024;   // clips with more STFT columns take the multi-CTA tuning path
+struct TuneLongState {
+    unsigned hist[2][2048];   // pass histograms for the two middle ranks
+    unsigned prefix[2];       // selected key bits so far (zero between uses)
+    long long rank[2];
+    long long n;              // peaks of the clip
+    int counts[100];          // residual histogram
+};
 struct TuneParams {
     const ClipDev* clips;
     const float2* peaks;      // [cols][peak_cap] (mag, pitch)
@@ -36,8 +44,12 @@ struct TuneParams {
     int bins_per_octave;      // 12 (chroma_stft) or 36 (chroma_cqt)
     const double* edges;      // np.linspace(-0.5, 0.5, 101)
     int* tuning_idx;          // [clips] -> 0..99 ; 50 (tuning 0.0) when no pitch was found
+    const int* long_clips;    // [n_long] indices (into clips) of the clips longer than kTuneLongCols
+    int n_long;
+    int max_long_cols;
+    TuneLongState* long_state;   // [n_long], zero-initialised prefixes
 };
-cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream);
+cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream, long long* launches);
 
 struct ProjParams {
     const ClipDev* clips;
@@ -114,7 +126,10 @@ struct TonClip {
     int cq_cols;         // constant-Q columns kept (min over octaves, librosa __trim_stack)
     int cq_base;         // first row of the clip in cqmag
     int out_row;
+    int part_base;       // first kTonTile-column partial-sum slot of the clip (tonnetz reduction)
+    int pad_;
 };
+constexpr int kTonTile = 256;     // constant-Q columns per tonnetz partial sum
 
 struct HpssParams {
     const TonClip* clips;
@@ -161,6 +176,7 @@ struct CqtParams {
     const float2* twiddles;      // W_N^j (cos, -sin), j < N, for N = 128, 256, 512, 1024 back to back, then
                                  // (cos, sin) 2 pi k / (2N), k < N, for the same N
     float* cqmag;                // [cq rows][252]
+    double* ton_part;            // [partial slots][6] tonnetz sums per kTonTile columns
     float* out;                  // [rows][dim]
     int dim, off_tonnetz;
     int max_len0;                // longest level-0 signal in the chunk

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
     __shared__ int s_cursor;
     __shared__ int counts[100];
     const ClipDev clip = p.clips[blockIdx.x];
+    if (clip.n_cols > kTuneLongCols) return;      // handled by the multi-CTA path below
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kTuneThreads / 32;
 
     if (threadIdx.x == 0) { s_total = 0; s_cursor = 0; }
@@ -161,9 +162,157 @@ __global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
     }
 }
 
-cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream) {
+// ---- long clips: the same selection spread over many CTAs ---------------------------------
+// A clip with more than kTuneLongCols columns would keep one CTA busy for milliseconds, so its
+// order statistics come from a 3-pass (11 + 11 + 10 bit) radix select whose histograms are built
+// by one CTA per 64 columns, followed by a residual histogram built the same way.  Both middle
+// ranks are tracked at once.  Integer counting: the result is identical to the one-CTA kernel.
+constexpr int kTuneTileCols = 64;
+constexpr int kTuneBuckets = 2048;
+
+__device__ __forceinline__ void tune_pass_bits(int pass, int& shift, unsigned& mask, unsigned& hi_mask) {
+    shift = (pass == 0) ? 21 : (pass == 1) ? 10 : 0;
+    mask = (pass == 2) ? 1023u : 2047u;
+    hi_mask = (pass == 0) ? 0u : (0xffffffffu << (pass == 1 ? 21 : 10));
+}
+
+__global__ void __launch_bounds__(256) tune_long_hist_kernel(TuneParams p, int pass) {
+    __shared__ unsigned hist[2][kTuneBuckets];
+    const int li = blockIdx.x;
+    const ClipDev clip = p.clips[p.long_clips[li]];
+    const int t_lo = blockIdx.y * kTuneTileCols;
+    if (t_lo >= clip.n_cols) return;
+    const int t_hi = min(t_lo + kTuneTileCols, clip.n_cols);
+    TuneLongState* st = p.long_state + li;
+    int shift; unsigned mask, hi_mask;
+    tune_pass_bits(pass, shift, mask, hi_mask);
+    const unsigned pre0 = st->prefix[0], pre1 = st->prefix[1];
+    for (int i = threadIdx.x; i < 2 * kTuneBuckets; i += 256) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = t_lo + warp; t < t_hi; t += 8) {
+        const long long col = static_cast<long long>(clip.col_base) + t;
+        const int cnt = p.peak_count[col];
+        const float2* src = p.peaks + col * p.peak_cap;
+        for (int i = lane; i < cnt; i += 32) {
+            const unsigned key = key_of(src[i].x);
+            const unsigned b = (key >> shift) & mask;
+            if (((key ^ pre0) & hi_mask) == 0) atomicAdd(&hist[0][b], 1u);
+            if (((key ^ pre1) & hi_mask) == 0) atomicAdd(&hist[1][b], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kTuneBuckets; i += 256) {
+        const unsigned c = (&hist[0][0])[i];
+        if (c) atomicAdd(&st->hist[0][0] + i, c);
+    }
+}
+
+// one CTA per long clip: locate both ranks in the pass histograms, extend the prefixes, clear
+__global__ void __launch_bounds__(256) tune_long_pick_kernel(TuneParams p, int pass) {
+    TuneLongState* st = p.long_state + blockIdx.x;
+    int shift; unsigned mask, hi_mask;
+    tune_pass_bits(pass, shift, mask, hi_mask);
+    if (threadIdx.x < 2) {
+        const int j = threadIdx.x;
+        if (pass == 0) {
+            long long n = 0;
+            for (int b = 0; b < kTuneBuckets; ++b) n += st->hist[j][b];
+            st->n = n;
+            st->rank[j] = (j == 0) ? (n - 1) / 2 : n / 2;     // the two middle order statistics
+        }
+        long long r = st->rank[j];
+        unsigned b = 0;
+        if (st->n > 0) {
+            for (; b < mask; ++b) {
+                const long long c = st->hist[j][b];
+                if (r < c) break;
+                r -= c;
+            }
+        }
+        st->prefix[j] |= b << shift;
+        st->rank[j] = r;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kTuneBuckets; i += 256) (&st->hist[0][0])[i] = 0;
+    if (pass == 2 && threadIdx.x < 100) st->counts[threadIdx.x] = 0;
+}
+
+__device__ __forceinline__ int residual_bin(float pitch, float bpo, const double* __restrict__ edges) {
+    // residual = mod(bpo * log2(f / 27.5), 1.0) in float32, folded to [-0.5, 0.5)
+    const float q = __fdiv_rn(pitch, 27.5f);
+    const float l2 = static_cast<float>(log2(static_cast<double>(q)));
+    float r = fmodf(__fmul_rn(bpo, l2), 1.0f);
+    if (r < 0.f) r += 1.0f;
+    if (r >= 0.5f) r = __fsub_rn(r, 1.0f);
+    // np.histogram with explicit float64 edges: edges[i] <= r < edges[i+1]
+    const double rd = static_cast<double>(r);
+    int bin = static_cast<int>(floor((rd + 0.5) * 100.0));
+    bin = max(0, min(99, bin));
+    while (bin > 0 && rd < edges[bin]) --bin;
+    while (bin < 99 && rd >= edges[bin + 1]) ++bin;
+    return bin;
+}
+
+__global__ void __launch_bounds__(256) tune_long_resid_kernel(TuneParams p) {
+    __shared__ int counts[100];
+    const int li = blockIdx.x;
+    const ClipDev clip = p.clips[p.long_clips[li]];
+    const int t_lo = blockIdx.y * kTuneTileCols;
+    if (t_lo >= clip.n_cols) return;
+    const int t_hi = min(t_lo + kTuneTileCols, clip.n_cols);
+    TuneLongState* st = p.long_state + li;
+    if (st->n == 0) return;
+    // np.median: mean of the two middle order statistics in float32 (equal when n is odd)
+    const float thr = __fmul_rn(__fadd_rn(value_of(st->prefix[0]), value_of(st->prefix[1])), 0.5f);
+    if (threadIdx.x < 100) counts[threadIdx.x] = 0;
+    __syncthreads();
+    const float bpo = static_cast<float>(p.bins_per_octave);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = t_lo + warp; t < t_hi; t += 8) {
+        const long long col = static_cast<long long>(clip.col_base) + t;
+        const int cnt = p.peak_count[col];
+        const float2* src = p.peaks + col * p.peak_cap;
+        for (int i = lane; i < cnt; i += 32) {
+            const float2 pk = src[i];
+            if (!(pk.x >= thr) || !(pk.y > 0.f)) continue;
+            atomicAdd(&counts[residual_bin(pk.y, bpo, p.edges)], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 100 && counts[threadIdx.x]) atomicAdd(&st->counts[threadIdx.x], counts[threadIdx.x]);
+}
+
+__global__ void tune_long_argmax_kernel(TuneParams p) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= p.n_long) return;
+    TuneLongState* st = p.long_state + li;
+    int best = 50;      // pitch_tuning on an empty set returns 0.0 == np.linspace(-0.5, 0.5, 101)[50]
+    if (st->n > 0) {
+        best = 0;
+        int best_count = st->counts[0];
+        for (int i = 1; i < 100; ++i)
+            if (st->counts[i] > best_count) { best_count = st->counts[i]; best = i; }
+    }
+    p.tuning_idx[p.long_clips[li]] = best;
+    st->prefix[0] = st->prefix[1] = 0;     // ready for the next use of the slot
+}
+
+cudaError_t launch_tuning(const TuneParams& p, int n_clips, cudaStream_t stream, long long* launches) {
     if (n_clips <= 0) return cudaSuccess;
     tuning_kernel<<<n_clips, kTuneThreads, 0, stream>>>(p);
+    long long n = 1;
+    if (p.n_long > 0) {
+        const dim3 grid(p.n_long, (p.max_long_cols + kTuneTileCols - 1) / kTuneTileCols);
+        for (int pass = 0; pass < 3; ++pass) {
+            tune_long_hist_kernel<<<grid, 256, 0, stream>>>(p, pass);
+            tune_long_pick_kernel<<<p.n_long, 256, 0, stream>>>(p, pass);
+        }
+        tune_long_resid_kernel<<<grid, 256, 0, stream>>>(p);
+        tune_long_argmax_kernel<<<(p.n_long + 127) / 128, 128, 0, stream>>>(p);
+        n += 8;
+    }
+    if (launches) *launches += n;
     return cudaGetLastError();
 }
 

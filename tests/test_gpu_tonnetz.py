@@ -179,3 +179,31 @@ def test_small_chunks_do_not_change_any_row(golden):
     chunked = np.load(out)
     whole = dsp.extract_features_batch([_audio(golden, n)[0] for n in names], 16000)
     np.testing.assert_array_equal(chunked, whole)
+
+
+def test_long_clip_takes_the_multi_cta_tuning_path_and_matches_oracle(gpu_ctx):
+    """A 40 s clip at 16 kHz has 1251 STFT columns (> kTuneLongCols = 1024): its two tuning
+    estimates come from the multi-CTA radix select and its tonnetz means from per-tile partial
+    sums.  Everything must still match the oracle."""
+    from oracle import ser_oracle
+    from oracle.shim import librosa
+    from ser_b200 import dsp, synth
+
+    sr = 16000
+    audio = synth.long_recording(sr, 40 * sr, seed=5, section_seconds=7.0)
+    got = dsp.extract_feature_from_signal(audio, sr)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ser_oracle.extract_feature_from_signal(audio, sr)
+        S = np.abs(librosa.stft(audio, n_fft=2048))
+        tuning12 = librosa.estimate_tuning(S=S, sr=sr, bins_per_octave=12)
+    assert np.linspace(-0.5, 0.5, 101)[int(gpu_ctx.debug_last_tuning(1)[0])] == pytest.approx(tuning12, abs=1e-12)
+    report = group_errors(got, ref, groups=ALL_GROUPS)
+    print({k: f"{v[0]:.2e}" for k, v in report.items()})
+    for group, (scaled, _raw) in report.items():
+        assert scaled <= TOL, group
+    # the same clip inside a batch of short ones: identical row
+    short = synth.clip_audio(synth.ClipSpec(3, 4, 5), sr, 48000)
+    batch = dsp.extract_features_batch([short, audio, short], sr)
+    np.testing.assert_array_equal(batch[1], got)
+    np.testing.assert_array_equal(batch[0], batch[2])
