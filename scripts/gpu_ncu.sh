@@ -9,4 +9,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 8 -c 3 -o gpurun_out/prof_$KREGEX -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "exit $?"
 cat gpurun_out/ncu_plain.json
-tail -3 gpurun_out/ncu_list.log gpurun_out/ncu_full.log
+tail -n 3 gpurun_out/ncu_list.log; tail -n 3 gpurun_out/ncu_full.log
