@@ -345,8 +345,17 @@ __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------
+// per device (called from serb_ctx_create with the device current): opt every instantiation in
+// to the largest dynamic shared memory a launch can ask for, once, so that concurrent contexts
+// never race an attribute change against a launch
+constexpr size_t kCqtMaxSmem = 227 * 1024;
 cudaError_t configure_cqt(const float* taps2_scaled) {
-    return cudaMemcpyToSymbol(c_taps2, taps2_scaled, kDecTaps2 * sizeof(float));
+    cudaError_t e = cudaMemcpyToSymbol(c_taps2, taps2_scaled, kDecTaps2 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(cqt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem));
 }
 
 constexpr int kCqtSpanBudget = 8704;    // staged signal floats per CTA (two CTAs per SM)
@@ -363,9 +372,7 @@ static cudaError_t launch_cqt_octave(const CqtParams& p, int octave, cudaStream_
     const int cols_per_block = per_iter * iters;
     const size_t span = static_cast<size_t>(cols_per_block - 1) * hop + 2 * N;
     const size_t bytes = sizeof(CqtSmemHead) + span * sizeof(float);
-    // per-device attribute, so set on every launch (a host-side call, no synchronisation)
-    cudaError_t e = cudaFuncSetAttribute(cqt_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-    if (e != cudaSuccess) return e;
+    if (bytes > kCqtMaxSmem) return cudaErrorInvalidConfiguration;
     dim3 grid(p.n_clips, (p.max_cq_cols + cols_per_block - 1) / cols_per_block);
     cqt_kernel<R><<<grid, kCqtWarps * 32, bytes, stream>>>(p, octave, cols_per_block);
     return cudaGetLastError();
