@@ -207,3 +207,42 @@ def test_long_clip_takes_the_multi_cta_tuning_path_and_matches_oracle(gpu_ctx):
     batch = dsp.extract_features_batch([short, audio, short], sr)
     np.testing.assert_array_equal(batch[1], got)
     np.testing.assert_array_equal(batch[0], batch[2])
+
+
+def test_two_contexts_on_two_threads_agree(golden):
+    """Contexts are independent: concurrent calls from two threads (each its own context and
+    stream on the same device) give the rows a single context gives."""
+    import threading
+
+    from ser_b200 import _native, dsp
+    from ser_b200.config import FeatureFlags, flag_bits
+
+    names = [n for n in CASES if int(golden[f"{n}/sr"]) == 16000]
+    clips = [_audio(golden, n)[0] for n in names]
+    expected = dsp.extract_features_batch(clips, 16000).astype(np.float32)
+    lengths = np.asarray([c.size for c in clips], dtype=np.int64)
+    padded = (lengths + 3) // 4 * 4
+    starts = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
+    wave = np.zeros(int(padded.sum()), dtype=np.float32)
+    for s, c in zip(starts, clips):
+        wave[s:s + c.size] = c
+    bits = flag_bits(FeatureFlags())
+    results, errors = {}, []
+
+    def work(tag):
+        try:
+            ctx = _native.Context(0)
+            for _ in range(4):
+                results[tag] = ctx.features_host(wave, starts, lengths, 16000, bits)
+            ctx.close()
+        except Exception as error:  # noqa: BLE001
+            errors.append(error)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    np.testing.assert_array_equal(results[0], expected)
+    np.testing.assert_array_equal(results[1], expected)
