@@ -10,10 +10,8 @@ print("$tag", "ms/step %.2f" % d["ms_per_step"], {n: round(v,2) for n,v in k.ite
 PY
 }
 run base A=1
-run chunk131k SERB_TON_CHUNK_COLS=131072
-run chunk262k SERB_TON_CHUNK_COLS=262144
-run chunk262k_seg256 SERB_TON_CHUNK_COLS=262144 SERB_HARM_SEG=256
-run chunk262k_seg64 SERB_TON_CHUNK_COLS=262144 SERB_HARM_SEG=64
-run chunk262k_runs8 SERB_TON_CHUNK_COLS=262144 SERB_PERC_RUNS=8
-run chunk262k_runs4 SERB_TON_CHUNK_COLS=262144 SERB_PERC_RUNS=4
-run chunk32k SERB_TON_CHUNK_COLS=32768
+run seg256 SERB_HARM_SEG=256
+run seg512 SERB_HARM_SEG=512
+run runs8 SERB_PERC_RUNS=8
+run runs4 SERB_PERC_RUNS=4
+run chunk524k SERB_CHUNK_COLS=524288

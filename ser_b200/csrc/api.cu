@@ -91,7 +91,7 @@ struct serb_ctx {
     DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
-    int harm_seg = 128, perc_runs = 16;
+    int harm_seg = 512, perc_runs = 16;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
     std::vector<int> last_short_rows;
     long long last_n_clips = 0;
