@@ -204,9 +204,15 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         for (int g = 0; g < G; ++g) {
             const int lc = min(lc0 + g, n_here - 1);       // surplus columns repeat the last one (not stored)
             const float* frame = sig_s + lc * hop;
+            if (hop & 1) {     // bottom octave at 192 kHz and above: frames start on odd samples
 #pragma unroll
-            for (int n1 = 0; n1 < R; ++n1)
-                v[g * R + n1] = *reinterpret_cast<const float2*>(frame + 2 * (32 * n1 + lane));
+                for (int n1 = 0; n1 < R; ++n1)
+                    v[g * R + n1] = make_float2(frame[2 * (32 * n1 + lane)], frame[2 * (32 * n1 + lane) + 1]);
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < R; ++n1)
+                    v[g * R + n1] = *reinterpret_cast<const float2*>(frame + 2 * (32 * n1 + lane));
+            }
         }
         // step A: R-point DFTs over n1 (per column), twiddle W_N^(lane k1), transpose
         if constexpr (R == 32) {

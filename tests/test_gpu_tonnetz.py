@@ -246,3 +246,30 @@ def test_two_contexts_on_two_threads_agree(golden):
     assert not errors, errors
     np.testing.assert_array_equal(results[0], expected)
     np.testing.assert_array_equal(results[1], expected)
+
+
+@pytest.mark.parametrize("sr,contrast", [(10000, False), (11025, False), (24000, True), (32000, True), (96000, True),
+                                         (192000, True)])
+def test_other_sample_rates_match_oracle(sr, contrast):
+    """Constant-Q plans other than the golden ones: n_fft 256 (10 kHz), no early downsampling at
+    24 / 32 kHz, early factor 4 (96 kHz) and 8 (192 kHz, bottom-octave hop of one sample).
+    Spectral contrast needs sr > 12 800 Hz, as in the reference."""
+    from oracle import ser_oracle
+    from ser_b200 import dsp, synth
+    from ser_b200.config import FeatureFlags
+
+    audio = synth.clip_audio(synth.ClipSpec(31, 5, 3), sr, int(0.9 * sr))
+    flags = FeatureFlags(contrast=contrast)
+    got = dsp.extract_feature_from_signal(audio, sr, feature_flags=flags)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ser_oracle.extract_feature_from_signal(audio, sr, feature_flags=ser_oracle.FeatureFlags(contrast=contrast))
+    assert got.shape == ref.shape
+    ton = slice(got.size - 6, got.size)
+    groups = {"mfcc": slice(0, 40), "chroma": slice(40, 52), "mel": slice(52, 180), "tonnetz": ton}
+    for name, sl in groups.items():
+        a, b = got[sl], ref[sl]
+        floor = np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b)))
+        err = float(np.max(np.abs(a - b) / np.where(floor == 0, 1.0, floor)))
+        print(sr, name, f"{err:.2e}")
+        assert err <= TOL, f"{sr}/{name}: {err:.3e}"
