@@ -273,3 +273,38 @@ def test_other_sample_rates_match_oracle(sr, contrast):
         err = float(np.max(np.abs(a - b) / np.where(floor == 0, 1.0, floor)))
         print(sr, name, f"{err:.2e}")
         assert err <= TOL, f"{sr}/{name}: {err:.3e}"
+
+
+def test_labels_and_segments_agree_with_the_cpu_path_end_to_end(golden):
+    """North-star acceptance: labels, timestamps and merged segments of the GPU path (CUDA
+    features + CUDA MLP) equal those of the CPU path (oracle features + scikit-learn arithmetic)
+    on every window of a set of synthetic recordings."""
+    from oracle import ser_oracle
+    from ser_b200 import fast_path, mlp, synth
+    from ser_b200.handcrafted import HandcraftedBackend
+
+    weights = mlp.MlpWeights(golden["mlp/mean"], golden["mlp/scale"], golden["mlp/w1"], golden["mlp/b1"],
+                             golden["mlp/w2"], golden["mlp/b2"], tuple(golden["mlp/classes"].tolist()), 0)
+    oweights = ser_oracle.MlpWeights(weights.mean, weights.scale, (weights.w1, weights.w2), (weights.b1, weights.b2),
+                                     weights.classes, "softmax")
+    sr, total, same = 16000, 0, 0
+    backend = HandcraftedBackend()
+    for k in range(4):
+        audio = synth.clip_audio(synth.ClipSpec(40 + k, 3 + 5 * k, 1 + 2 * k), sr, int((3.2 + 0.9 * k) * sr))
+        encoded = backend.encode_sequence(audio, sr)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_emb, ref_starts, ref_ends = ser_oracle.encode_sequence(audio, sr)
+        np.testing.assert_array_equal(encoded.frame_start_seconds, ref_starts)
+        np.testing.assert_array_equal(encoded.frame_end_seconds, ref_ends)
+        frames = fast_path.predict_frames(weights, encoded.embeddings, encoded.frame_start_seconds,
+                                          encoded.frame_end_seconds)
+        oframes, osegments = ser_oracle.predict_frames(oweights, ref_emb, ref_starts, ref_ends)
+        total += len(frames)
+        same += sum(a.emotion == b.emotion for a, b in zip(frames, oframes))
+        if [f.emotion for f in frames] == [f.emotion for f in oframes]:
+            segments = fast_path.segment_predictions(frames)
+            assert [(s.emotion, s.start_seconds, s.end_seconds) for s in segments] == \
+                   [(s.emotion, s.start_seconds, s.end_seconds) for s in osegments]
+    print(f"label agreement {same}/{total}")
+    assert same == total
