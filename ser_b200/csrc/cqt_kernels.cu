@@ -22,7 +22,11 @@
 
 namespace serb {
 
-__constant__ float c_taps2[384];   // h[k] * sqrt(2), k < 381
+// Factor-2 decimator taps (x sqrt 2) split by polyphase and laid out for 16-byte uniform loads:
+// c_tap4[phase][j] holds tap(e = 4j - 3 .. 4j) with tap_even(e) = h[382 - 2e] (e = 1..191) and
+// tap_odd(e) = h[381 - 2e] (e = 1..190), zero outside.
+constexpr int kTapQuads = 50;
+__constant__ float4 c_tap4[2][kTapQuads];
 
 namespace {
 
@@ -44,19 +48,21 @@ constexpr int kDecTile = 1024;               // outputs per CTA
 constexpr int kDecHalo = 96;                 // polyphase samples staged before the tile
 constexpr int kDecSpan = kDecTile + 192;     // polyphase samples staged per phase
 
-template <int E_MAX, int TAP0>
+template <int E_MAX, int PHASE>
 __device__ __forceinline__ void fir_phase(const float* __restrict__ xs, int t, float (&acc)[4]) {
-    // acc[r] += h[TAP0 - 2 e] * xs[4 t + r + e], e = 1 .. E_MAX
+    // acc[r] += tap(e) * xs[4 t + r + e], e = 1 .. E_MAX
 #pragma unroll
     for (int g = 0; g <= (E_MAX + 3) / 4; ++g) {
         const float4 q = *reinterpret_cast<const float4*>(xs + 4 * t + 4 * g);
         const float v[4] = {q.x, q.y, q.z, q.w};
+        const float4 ta = c_tap4[PHASE][g], tb = c_tap4[PHASE][g + 1];
+        const float tap[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};   // tap[k] = tap(e = 4g - 3 + k)
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int e = 4 * g + c - r;
-                if (e >= 1 && e <= E_MAX) acc[r] = fmaf(c_taps2[TAP0 - 2 * e], v[c], acc[r]);
+                if (e >= 1 && e <= E_MAX) acc[r] = fmaf(tap[c - r + 3], v[c], acc[r]);
             }
     }
 }
@@ -88,8 +94,8 @@ __global__ void __launch_bounds__(256) decimate2_kernel(CqtParams p, int src_lev
     __syncthreads();
     // out[m] = sum_j h[2j] xe[m + 95 - j] + sum_j h[2j+1] xo[m + 94 - j]   (half = 190)
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    fir_phase<191, 382>(xe, threadIdx.x, acc);   // tap 2 (191 - e)
-    fir_phase<190, 381>(xo, threadIdx.x, acc);   // tap 2 (190 - e) + 1
+    fir_phase<191, 0>(xe, threadIdx.x, acc);   // even taps h[2 (191 - e)]
+    fir_phase<190, 1>(xo, threadIdx.x, acc);   // odd taps h[2 (190 - e) + 1]
     const int m = mb + 4 * threadIdx.x;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -356,7 +362,16 @@ __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
 // never race an attribute change against a launch
 constexpr size_t kCqtMaxSmem = 227 * 1024;
 cudaError_t configure_cqt(const float* taps2_scaled) {
-    cudaError_t e = cudaMemcpyToSymbol(c_taps2, taps2_scaled, kDecTaps2 * sizeof(float));
+    static float quads[2][kTapQuads][4];
+    for (int phase = 0; phase < 2; ++phase)
+        for (int j = 0; j < kTapQuads; ++j)
+            for (int k = 0; k < 4; ++k) {
+                const int e = 4 * j - 3 + k;
+                const int e_max = phase == 0 ? 191 : 190;
+                const int idx = (phase == 0 ? 382 : 381) - 2 * e;
+                quads[phase][j][k] = (e >= 1 && e <= e_max) ? taps2_scaled[idx] : 0.0f;
+            }
+    cudaError_t e = cudaMemcpyToSymbol(c_tap4, quads, sizeof(quads));
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
