@@ -379,7 +379,7 @@ cudaError_t configure_cqt(const float* taps2_scaled) {
     return cudaFuncSetAttribute(cqt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem));
 }
 
-constexpr int kCqtSpanBudget = 8704;    // staged signal floats per CTA (two CTAs per SM)
+constexpr int kCqtSpanBudget = 8960;    // staged signal floats per CTA (two CTAs per SM)
 
 template <int R>
 static cudaError_t launch_cqt_octave(const CqtParams& p, int octave, cudaStream_t stream) {
@@ -387,9 +387,9 @@ static cudaError_t launch_cqt_octave(const CqtParams& p, int octave, cudaStream_
     constexpr int N = 32 * R;
     const int hop = p.hop0 >> octave;
     const int per_iter = kCqtWarps * G;
-    // as many whole iterations as fit the span budget, at least one, at most four
+    // as many whole iterations as fit the span budget, at least one, at most eight
     int iters = (kCqtSpanBudget - 2 * N + hop) / (per_iter * hop);
-    iters = max(1, min(4, iters));
+    iters = max(1, min(8, iters));
     const int cols_per_block = per_iter * iters;
     const size_t span = static_cast<size_t>(cols_per_block - 1) * hop + 2 * N;
     const size_t bytes = sizeof(CqtSmemHead) + span * sizeof(float);
