@@ -32,7 +32,7 @@ SOURCES = [
     "mlp_kernel.cu",
     "api.cu",
 ]
-HEADERS = ["common.cuh", "fft.cuh", "kernels.h", "filterbanks.h", "cqt_tables.h", "../../include/ser_b200.h"]
+HEADERS = ["common.cuh", "fft.cuh", "kernels.h", "filterbanks.h", "cqt_tables.h", "median_net.cuh", "../../include/ser_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

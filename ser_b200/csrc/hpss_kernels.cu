@@ -10,21 +10,26 @@
 // istft_kernel      inverse 2048-point real FFT per warp, Hann window -> frames
 // ola_kernel        overlap-add in frame order / window sum-of-squares -> harmonic signal
 //
-// The medians keep a sorted window of 31 values in registers and slide it: one branch-free
-// remove pass (compare + select) and one insert pass (min + max) per step.  The work is
-// ALU-bound (FMNMX / FSEL), not memory-bound: every spectrogram value is read twice per
-// kernel from L2/L1 and written once.
+// The medians are computed eight positions at a time.  The eight windows of 31 share a core of
+// 24 values, sorted once by a network (132 compare-exchanges); the other seven values of each
+// window form a small sorted set that slides by one replace per position; the median is the
+// rank-15 element of the two sorted sets, eight max and seven min.  About 70 min/max/compare per
+// output and no window fill, against 124 (plus the fill) for a sliding sorted window of 31.
+// The work is ALU-bound (FMNMX), not memory-bound.
 #include <cfloat>
 
 #include "fft.cuh"
 #include "kernels.h"
+#include "median_net.cuh"
 
 namespace serb {
 
 namespace {
 
-constexpr int kMedW = 31;
 constexpr int kMedHalf = 15;
+constexpr int kMedBlock = 8;      // outputs per block
+constexpr int kMedCore = 24;      // values common to the block's eight windows: offsets -8 .. 15
+constexpr int kMedExt = 7;        // the rest of a window: offsets -15 .. -9 at first, 16 .. 22 at last
 
 // scipy "reflect" (numpy "symmetric"): d c b a | a b c d | d c b a, period 2n
 __device__ __forceinline__ int reflect_index(int i, int n) {
@@ -33,44 +38,62 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
     if (m < 0) m += period;
     return m < n ? m : period - 1 - m;
 }
+// single reflection, valid for -n <= i < 2n
+__device__ __forceinline__ int reflect_once(int i, int n) {
+    if (i < 0) i = -1 - i;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+}
 
-struct SortedWindow {
-    float a[kMedW];
-    __device__ __forceinline__ void clear() {
+// Rolling block median.  raw[k] holds the (boundary-extended) input at position f - 15 + k for the
+// current block of eight outputs f .. f+7 (k = 0 .. 37).  Consecutive blocks share 30 of the 38
+// values, so advancing costs eight loads and a register shift.  `one` is 1.0f passed at run time:
+// the remove pass of the small set is a compare plus a PREDICATED MULTIPLY by it (exact) instead of
+// a select, which keeps that work off the ALU pipe the min/max instructions saturate.
+struct BlockMedian {
+    float raw[38];
+
+    template <typename Load>   // x(i): input at position (f - 8) + i, f = the first block's start
+    __device__ __forceinline__ void prime(Load x) {
 #pragma unroll
-        for (int i = 0; i < kMedW; ++i) a[i] = FLT_MAX;
+        for (int k = 0; k < 30; ++k) raw[k + 8] = x(k - 7);      // f - 15 + k: raw[0..29] after the first advance
     }
-    // insert into a window whose last slot holds FLT_MAX
-    __device__ __forceinline__ void insert(float x) {
-        float prev = a[0];
-        a[0] = fminf(prev, x);
+    // move to the next block (first call: to the first block) and fetch its last eight values
+    template <typename Load>   // x(i): input at position f + i of the NEW block
+    __device__ __forceinline__ void advance(Load x) {
 #pragma unroll
-        for (int i = 1; i < kMedW; ++i) {
-            const float cur = a[i];
-            a[i] = fmaxf(prev, fminf(cur, x));
-            prev = cur;
+        for (int k = 0; k < 30; ++k) raw[k] = raw[k + 8];
+#pragma unroll
+        for (int k = 30; k < 38; ++k) raw[k] = x(k - 15);
+    }
+    __device__ __forceinline__ void medians(float one, float (&out)[kMedBlock]) const {
+        float core[kMedCore], ext[kMedExt];
+#pragma unroll
+        for (int i = 0; i < kMedCore; ++i) core[i] = raw[i + 7];      // offsets -8 .. 15
+#pragma unroll
+        for (int i = 0; i < kMedExt; ++i) ext[i] = raw[i];            // offsets -15 .. -9
+        sort_net24(core);
+        sort_net7(ext);
+#pragma unroll
+        for (int j = 0; j < kMedBlock; ++j) {
+            // rank 15 of core (24, sorted) U ext (7, sorted): min over m of max(core[15 - m], ext[m - 1])
+            float med = core[15];
+#pragma unroll
+            for (int m = 1; m <= kMedExt; ++m) med = fminf(med, fmaxf(core[15 - m], ext[m - 1]));
+            out[j] = med;
+            if (j + 1 < kMedBlock) {
+                // window j + 1 drops position f + j - 15 (raw[j]) and gains position f + j + 16 (raw[31 + j])
+#pragma unroll
+                for (int i = 0; i < kMedExt - 1; ++i)
+                    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p mul.f32 %0, %2, %3;\n\t}"
+                        : "+f"(ext[i]) : "f"(raw[j]), "f"(ext[i + 1]), "f"(one));
+                ext[kMedExt - 1] = FLT_MAX;
+#pragma unroll
+                for (int i = kMedExt - 1; i >= 1; --i) ext[i] = fmaxf(ext[i - 1], fminf(ext[i], raw[31 + j]));
+                ext[0] = fminf(ext[0], raw[31 + j]);
+            }
         }
     }
-    // remove one occurrence of `old` (which is in the window) and insert x.
-    // Remove pass: a[i] <- a[i+1] wherever a[i] >= old, in ascending order, as a compare plus a
-    // predicated multiply by an opaque 1.0f (exact) instead of a select: the compare issues on the
-    // ALU pipe next to the min/max of the insert pass, the multiply on the otherwise idle FMA pipe.
-    __device__ __forceinline__ void replace(float old, float x, float one) {
-#pragma unroll
-        for (int i = 0; i < kMedW - 1; ++i)
-            asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p mul.f32 %0, %2, %3;\n\t}"
-                : "+f"(a[i]) : "f"(old), "f"(a[i + 1]), "f"(one));
-        a[kMedW - 1] = FLT_MAX;
-        float prev = a[0];
-        a[0] = fminf(prev, x);
-#pragma unroll
-        for (int i = 1; i < kMedW; ++i) {
-            const float cur = a[i];
-            a[i] = fmaxf(prev, fminf(cur, x));
-            prev = cur;
-        }
-    }
-    __device__ __forceinline__ float median() const { return a[kMedHalf]; }
 };
 
 }  // namespace
@@ -87,18 +110,10 @@ __device__ __forceinline__ float harm_mask(float h, float q) {
     return __fdividef(ma, ma + mb);
 }
 
-// single reflection, valid for -n <= i < 2n
-__device__ __forceinline__ int reflect_once(int i, int n) {
-    if (i < 0) i = -1 - i;
-    if (i >= n) i = 2 * n - 1 - i;
-    return i;
-}
-
 // ---- median along time -----------------------------------------------------------------
 // one thread per (segment of seg_len columns, bin); bins are contiguous across the warp, so
 // every load / store is a coalesced 128-byte row piece.  Runs after hpss_perc_kernel: with both
-// medians in hand it applies the soft mask to the complex spectrum in place.  The loads of a
-// step are issued one step ahead of their use.
+// medians in hand it applies the soft mask to the complex spectrum in place.
 __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
     const int2 seg = p.segs[blockIdx.x];
     const TonClip clip = p.clips[seg.x];
@@ -110,36 +125,32 @@ __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
     const float* src = p.mag + static_cast<long long>(clip.col_base) * kSpillStride + f;
     const float* perc = p.perc + static_cast<long long>(clip.col_base) * kSpillStride + f;
     float2* spec = p.cspec + static_cast<long long>(clip.col_base) * kSpillStride + f;
-    const float one = p.one;            // 1.0f the compiler cannot fold (see SortedWindow::replace)
-    const bool wide = T > kMedHalf;     // one reflection reaches every index of the window
+    const float one = p.one;
+    const bool wide = T > 22;           // one reflection reaches every offset of a block
     auto at = [&](int t) -> float {
-        const int i = wide ? reflect_once(t, T) : reflect_index(t, T);
-        return src[static_cast<long long>(i) * kSpillStride];
+        const int k = wide ? reflect_once(t, T) : reflect_index(t, T);
+        return src[static_cast<long long>(k) * kSpillStride];
     };
-    SortedWindow w;
-    w.clear();
-    for (int t = t0 - kMedHalf; t <= t0 + kMedHalf; ++t) w.insert(at(t));
-    float old = at(t0 - kMedHalf), nxt = at(t0 + 1 + kMedHalf);
-    float pq = perc[static_cast<long long>(t0) * kSpillStride];
-    float2 x = spec[static_cast<long long>(t0) * kSpillStride];
-    for (int t = t0; t < t1; ++t) {
-        const long long o = static_cast<long long>(t) * kSpillStride;
-        // next step's operands (clamped to the segment: the surplus loads are never used)
-        const int tn = min(t + 1, t1 - 1);
-        const float old_n = at(tn - kMedHalf), nxt_n = at(tn + 1 + kMedHalf);
-        const float pq_n = perc[static_cast<long long>(tn) * kSpillStride];
-        const float2 x_n = spec[static_cast<long long>(tn) * kSpillStride];
-        const float m = harm_mask(w.median(), pq);
-        spec[o] = make_float2(x.x * m, x.y * m);     // (S * mask) * phase
-        w.replace(old, nxt, one);
-        old = old_n; nxt = nxt_n; pq = pq_n; x = x_n;
+    BlockMedian bm;
+    bm.prime([&](int i) -> float { return at(t0 - 8 + i); });
+    for (int t = t0; t < t1; t += kMedBlock) {
+        bm.advance([&](int i) -> float { return at(t + i); });
+        float med[kMedBlock];
+        bm.medians(one, med);
+#pragma unroll
+        for (int j = 0; j < kMedBlock; ++j) {
+            if (t + j < t1) {
+                const long long o = static_cast<long long>(t + j) * kSpillStride;
+                const float m = harm_mask(med[j], perc[o]);
+                const float2 x = spec[o];
+                spec[o] = make_float2(x.x * m, x.y * m);     // (S * mask) * phase
+            }
+        }
     }
 }
 
 // ---- median along frequency ------------------------------------------------------------
-// one lane per (column, run of RUN bins); RUNS runs per column, 32 / RUNS columns per warp.
-// Long runs amortise the 31-value window fill (large batches); short runs give small batches
-// enough threads.
+// one lane per (column, run of RUN bins); RUNS runs per column, 32 / RUNS columns per warp
 template <int RUNS>
 __global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols) {
     constexpr int RUN = (kNBins + RUNS - 1) / RUNS;
@@ -151,15 +162,18 @@ __global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols
     const int f0 = (lane % RUNS) * RUN;
     const int f1 = min(f0 + RUN, kNBins);
     if (f0 >= kNBins) return;
-    const float one = p.one;            // 1.0f the compiler cannot fold (see SortedWindow::replace)
+    const float one = p.one;
     const float* src = p.mag + static_cast<long long>(col) * kSpillStride;
     float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
-    SortedWindow w;
-    w.clear();
-    for (int f = f0 - kMedHalf; f <= f0 + kMedHalf; ++f) w.insert(src[reflect_once(f, kNBins)]);
-    for (int f = f0; f < f1; ++f) {
-        dst[f] = w.median();
-        if (f + 1 < f1) w.replace(src[reflect_once(f - kMedHalf, kNBins)], src[reflect_once(f + 1 + kMedHalf, kNBins)], one);
+    BlockMedian bm;
+    bm.prime([&](int i) -> float { return src[reflect_once(f0 - 8 + i, kNBins)]; });
+    for (int f = f0; f < f1; f += kMedBlock) {
+        bm.advance([&](int i) -> float { return src[reflect_once(f + i, kNBins)]; });
+        float med[kMedBlock];
+        bm.medians(one, med);
+#pragma unroll
+        for (int j = 0; j < kMedBlock; ++j)
+            if (f + j < f1) dst[f + j] = med[j];
     }
 }
 
