@@ -66,6 +66,13 @@ struct BlockMedian {
 #pragma unroll
         for (int k = 30; k < 38; ++k) raw[k] = x(k - 15);
     }
+    // the same with the eight new values already in registers (fetched one block ahead)
+    __device__ __forceinline__ void advance(const float (&fresh)[kMedBlock]) {
+#pragma unroll
+        for (int k = 0; k < 30; ++k) raw[k] = raw[k + 8];
+#pragma unroll
+        for (int k = 0; k < kMedBlock; ++k) raw[30 + k] = fresh[k];
+    }
     __device__ __forceinline__ void medians(float one, float (&out)[kMedBlock]) const {
         float core[kMedCore], ext[kMedExt];
 #pragma unroll
@@ -126,24 +133,37 @@ __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
     const float* perc = p.perc + static_cast<long long>(clip.col_base) * kSpillStride + f;
     float2* spec = p.cspec + static_cast<long long>(clip.col_base) * kSpillStride + f;
     const float one = p.one;
-    const bool wide = T > 22;           // one reflection reaches every offset of a block
+    const bool wide = T > 30;           // one reflection reaches every offset of a block and of the look-ahead
     auto at = [&](int t) -> float {
         const int k = wide ? reflect_once(t, T) : reflect_index(t, T);
         return src[static_cast<long long>(k) * kSpillStride];
     };
     BlockMedian bm;
     bm.prime([&](int i) -> float { return at(t0 - 8 + i); });
+    float fresh[kMedBlock];
+#pragma unroll
+    for (int k = 0; k < kMedBlock; ++k) fresh[k] = at(t0 + 15 + k);
     for (int t = t0; t < t1; t += kMedBlock) {
-        bm.advance([&](int i) -> float { return at(t + i); });
+        bm.advance(fresh);
+        // everything the block and its successor need from memory is requested before the sorting
+        // work, so it is in registers by the time the medians are
+#pragma unroll
+        for (int k = 0; k < kMedBlock; ++k) fresh[k] = at(t + kMedBlock + 15 + k);
+        float pq[kMedBlock];
+        float2 xs[kMedBlock];
+#pragma unroll
+        for (int j = 0; j < kMedBlock; ++j) {
+            const long long o = static_cast<long long>(min(t + j, t1 - 1)) * kSpillStride;
+            pq[j] = perc[o];
+            xs[j] = spec[o];
+        }
         float med[kMedBlock];
         bm.medians(one, med);
 #pragma unroll
         for (int j = 0; j < kMedBlock; ++j) {
             if (t + j < t1) {
-                const long long o = static_cast<long long>(t + j) * kSpillStride;
-                const float m = harm_mask(med[j], perc[o]);
-                const float2 x = spec[o];
-                spec[o] = make_float2(x.x * m, x.y * m);     // (S * mask) * phase
+                const float m = harm_mask(med[j], pq[j]);
+                spec[static_cast<long long>(t + j) * kSpillStride] = make_float2(xs[j].x * m, xs[j].y * m);   // (S * mask) * phase
             }
         }
     }
@@ -167,8 +187,13 @@ __global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols
     float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
     BlockMedian bm;
     bm.prime([&](int i) -> float { return src[reflect_once(f0 - 8 + i, kNBins)]; });
+    float fresh[kMedBlock];
+#pragma unroll
+    for (int k = 0; k < kMedBlock; ++k) fresh[k] = src[reflect_once(f0 + 15 + k, kNBins)];
     for (int f = f0; f < f1; f += kMedBlock) {
-        bm.advance([&](int i) -> float { return src[reflect_once(f + i, kNBins)]; });
+        bm.advance(fresh);
+#pragma unroll
+        for (int k = 0; k < kMedBlock; ++k) fresh[k] = src[reflect_once(f + kMedBlock + 15 + k, kNBins)];
         float med[kMedBlock];
         bm.medians(one, med);
 #pragma unroll
