@@ -121,7 +121,7 @@ __device__ __forceinline__ float harm_mask(float h, float q) {
 // one thread per (segment of seg_len columns, bin); bins are contiguous across the warp, so
 // every load / store is a coalesced 128-byte row piece.  Runs after hpss_perc_kernel: with both
 // medians in hand it applies the soft mask to the complex spectrum in place.
-__global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
+__global__ void __launch_bounds__(256, 3) hpss_harm_kernel(HpssParams p) {
     const int2 seg = p.segs[blockIdx.x];
     const TonClip clip = p.clips[seg.x];
     const int f = blockIdx.y * blockDim.x + threadIdx.x;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) hpss_harm_kernel(HpssParams p) {
 // ---- median along frequency ------------------------------------------------------------
 // one lane per (column, run of RUN bins); RUNS runs per column, 32 / RUNS columns per warp
 template <int RUNS>
-__global__ void __launch_bounds__(256) hpss_perc_kernel(HpssParams p, int n_cols) {
+__global__ void __launch_bounds__(256, 3) hpss_perc_kernel(HpssParams p, int n_cols) {
     constexpr int RUN = (kNBins + RUNS - 1) / RUNS;
     constexpr int COLS = 32 / RUNS;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
