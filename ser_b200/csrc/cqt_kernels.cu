@@ -154,6 +154,7 @@ struct CqtSmemHead {
     float2 buf[kCqtWarps][32 * 33];           // per-warp transpose buffer, then the column spectra
     float2 vals[kCqRows][kCqtValPitch];       // sparse basis rows of this (tuning, octave)
     CqRow rows[kCqRows];
+    int cmax;                                 // widest staged row, rounded up to a multiple of four
 };
 
 // One CTA = one clip, one octave, `cols_per_block` consecutive columns.  The signal span those
@@ -171,6 +172,8 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     const TonClip clip = p.clips[blockIdx.x];
     const int t_block = blockIdx.y * cols_per_block;
     if (t_block >= clip.cq_cols) return;
+    if (tid == 0) sm.cmax = 4;
+    __syncthreads();
     const int n_here = min(cols_per_block, clip.cq_cols - t_block);
     const int tuning = p.tuning_idx[blockIdx.x];
     const float* sig = level_ptr(p, clip, octave);
@@ -192,7 +195,11 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     for (int i = tid; i < kCqRows * kCqRowCap; i += kCqtWarps * 32)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&sm.vals[i / kCqRowCap][i % kCqRowCap]))),
                      "l"(p.vals + bank * kCqRowCap + i) : "memory");
-    if (tid < kCqRows) sm.rows[tid] = p.rows[bank + tid];
+    if (tid < kCqRows) {
+        const CqRow row = p.rows[bank + tid];
+        sm.rows[tid] = row;
+        atomicMax(&sm.cmax, (row.count + 3) & ~3);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     const float2* twa = p.twiddles + (N - 128);            // W_N^j = (cos, -sin)
     const float2* twb = p.twiddles + 1920 + (N - 128);     // (cos, sin) 2 pi k / (2N)
     float2* buf = sm.buf[warp];
+    const int cmax = min(sm.cmax, kCqRowCap);
     const int g2 = lane / R, k1 = lane % R;
     const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
 
@@ -261,22 +269,30 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
             if (k2 == 0 && k1 == 0) xs[N] = make_float2(0.5f * (ex - wx), 0.5f * (ey - wy));
         }
         __syncwarp();
-        // sparse basis rows: C[r] = sum_c B[r][c] X[start + c]
+        // sparse basis rows: C[r] = sum_c B[r][c] X[start + c].  The staged rows are zero padded, so
+        // every lane runs the same trip count (the widest row of this basis, a multiple of four).
+#pragma unroll 1
         for (int i = lane; i < kCqRows * G; i += 32) {
-            const int g = i / kCqRows, r = i % kCqRows;
+            const int g = i / kCqRows, r = i - g * kCqRows;
             const int lc = lc0 + g;
-            if (lc >= n_here) continue;
             const CqRow row = sm.rows[r];
             const float2* b = sm.vals[r];
             const float2* x = buf + g * (N + 1) + row.start;
             float cr = 0.0f, ci = 0.0f;
-            for (int c = 0; c < row.count; ++c) {
-                const float2 bv = b[c], xv = x[c];
-                cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
-                ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
+#pragma unroll 1
+            for (int c = 0; c < cmax; c += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 bv = b[c + u], xv = x[c + u];
+                    cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
+                    ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
+                }
             }
-            p.cqmag[(static_cast<size_t>(clip.cq_base) + t_block + lc) * kCqBins + row.bin] =
-                sqrtf(fmaf(cr, cr, ci * ci)) * row.scale;
+            if (lc < n_here) {
+                float mag;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr, cr, ci * ci)));
+                p.cqmag[(clip.cq_base + t_block + lc) * kCqBins + row.bin] = mag * row.scale;
+            }
         }
         __syncwarp();
     }
