@@ -271,10 +271,40 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         __syncwarp();
         // sparse basis rows: C[r] = sum_c B[r][c] X[start + c].  The staged rows are zero padded, so
         // every lane runs the same trip count (the widest row of this basis, a multiple of four).
+        // Rows 0..31: lane = row, all G columns of the warp at once (one basis load feeds G
+        // products: shared-memory bandwidth is what bounds this kernel).  Rows 32..35: lane =
+        // (row, column).
+        {
+            const CqRow row = sm.rows[lane];
+            const float2* b = sm.vals[lane];
+            const float2* x = buf + row.start;
+            float cr[G], ci[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) { cr[g] = 0.0f; ci[g] = 0.0f; }
 #pragma unroll 1
-        for (int i = lane; i < kCqRows * G; i += 32) {
-            const int g = i / kCqRows, r = i - g * kCqRows;
-            const int lc = lc0 + g;
+            for (int c = 0; c < cmax; c += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float2 bv = b[c + u];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float2 xv = x[g * (N + 1) + c + u];
+                        cr[g] = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr[g]));
+                        ci[g] = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci[g]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (lc0 + g < n_here) {
+                    float mag;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr[g], cr[g], ci[g] * ci[g])));
+                    p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mag * row.scale;
+                }
+            }
+        }
+        if (lane < 4 * G) {
+            const int r = 32 + (lane & 3), g = lane >> 2;
             const CqRow row = sm.rows[r];
             const float2* b = sm.vals[r];
             const float2* x = buf + g * (N + 1) + row.start;
@@ -288,10 +318,10 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
                     ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
                 }
             }
-            if (lc < n_here) {
+            if (lc0 + g < n_here) {
                 float mag;
                 asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr, cr, ci * ci)));
-                p.cqmag[(clip.cq_base + t_block + lc) * kCqBins + row.bin] = mag * row.scale;
+                p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mag * row.scale;
             }
         }
         __syncwarp();
