@@ -155,6 +155,7 @@ struct CqtSmemHead {
     float2 vals[kCqRows][kCqtValPitch];       // sparse basis rows of this (tuning, octave)
     CqRow rows[kCqRows];
     int cmax;                                 // widest staged row, rounded up to a multiple of four
+    int bin_lo, bin_hi;                       // smallest and largest first bin of the staged rows
 };
 
 // One CTA = one clip, one octave, `cols_per_block` consecutive columns.  The signal span those
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     const TonClip clip = p.clips[blockIdx.x];
     const int t_block = blockIdx.y * cols_per_block;
     if (t_block >= clip.cq_cols) return;
-    if (tid == 0) sm.cmax = 4;
+    if (tid == 0) { sm.cmax = 4; sm.bin_lo = N; sm.bin_hi = 0; }
     __syncthreads();
     const int n_here = min(cols_per_block, clip.cq_cols - t_block);
     const int tuning = p.tuning_idx[blockIdx.x];
@@ -199,6 +200,8 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         const CqRow row = p.rows[bank + tid];
         sm.rows[tid] = row;
         atomicMax(&sm.cmax, (row.count + 3) & ~3);
+        atomicMin(&sm.bin_lo, row.start);
+        atomicMax(&sm.bin_hi, row.start);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -208,6 +211,9 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     const float2* twb = p.twiddles + 1920 + (N - 128);     // (cos, sin) 2 pi k / (2N)
     float2* buf = sm.buf[warp];
     const int cmax = min(sm.cmax, kCqRowCap);
+    // the rows only read bins [bin_lo, bin_hi + cmax): the real-input split is done for the
+    // register indices k2 (bins k1 + R k2) that overlap that range and skipped for the rest
+    const int k2_lo = sm.bin_lo / R, k2_hi = min(31, (sm.bin_hi + cmax - 1) / R);
     const int g2 = lane / R, k1 = lane % R;
     const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
 
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         float2* xs = buf + g2 * (N + 1);
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2) {
+            if (k2 < k2_lo || k2 > k2_hi) continue;        // warp-uniform
             float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
             float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
             if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
@@ -266,8 +273,10 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
             const float wx = fmaf(w.x, ox, w.y * oy);
             const float wy = fmaf(w.x, oy, -w.y * ox);
             xs[k] = make_float2(0.5f * (ex + wx), 0.5f * (ey + wy));
-            if (k2 == 0 && k1 == 0) xs[N] = make_float2(0.5f * (ex - wx), 0.5f * (ey - wy));
         }
+        // Nyquist bin X[N] = Re Z[0] - Im Z[0], only if a row reaches it (sample rates whose top
+        // wavelet sits right under the Nyquist frequency)
+        if (sm.bin_hi + cmax > N && k1 == 0) xs[N] = make_float2(v[0].x - v[0].y, 0.0f);
         __syncwarp();
         // sparse basis rows: C[r] = sum_c B[r][c] X[start + c].  The staged rows are zero padded, so
         // every lane runs the same trip count (the widest row of this basis, a multiple of four).
