@@ -36,7 +36,7 @@ UNIT = "audio-s/s"
 FRAME_SECONDS, STRIDE_SECONDS = 3, 1
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FFMA peak at max clock
 FLOP_PER_COLUMN = 97_000                                     # SURVEY.md section 8(d), 187-d slice
-FLOP_PER_COLUMN_193 = 1_155_000                              # itemised ops of the 193-d chain
+FLOP_PER_COLUMN_193 = 1_045_000                              # itemised ops of the 193-d chain
 KERNEL_NAMES = {
     "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
     "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
@@ -373,12 +373,15 @@ def run_b200(args) -> None:
     alg_bytes_step = 4 * n_clips * n_samples + 4 * dim * n_rows
     peak, peak_src = peaks()
     achieved = alg_bytes_step / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture
+    # (bytes per STFT column per launch x the columns an average launch of this run covers)
     traffic = None
     traffic_file = REPO / "profiles" / "dominant_kernel_traffic.json"
     if traffic_file.exists():
         try:
             entry = json.loads(traffic_file.read_text()).get(KERNEL_NAMES[dom])
-            traffic = entry.get("dram_bytes_per_launch") if entry else None
+            if entry:
+                traffic = entry["dram_bytes_per_stft_column_per_launch"] * total_cols * (7 if dom == "cqt" else 1) / max(dom_n, 1)
         except Exception:
             traffic = None
     flop_per_column = FLOP_PER_COLUMN_193 if flags.tonnetz else FLOP_PER_COLUMN
