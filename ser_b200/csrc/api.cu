@@ -91,7 +91,7 @@ struct serb_ctx {
     DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
-    int harm_seg = 512, perc_runs = 16;
+    int harm_seg = 512;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
     std::vector<int> last_short_rows;
     long long last_n_clips = 0;
@@ -446,7 +446,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     hp.mag = ctx->spill.as<float>();
     hp.perc = ctx->perc.as<float>();
     hp.cspec = ctx->cspec.as<float2>();
-    { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, ctx->perc_runs, stream)); }
+    { ProfScope ps(ctx, 7, stream); SERB_CUDA(ctx, launch_hpss_perc(hp, c.n_cols, stream)); }
     { ProfScope ps(ctx, 6, stream); SERB_CUDA(ctx, launch_hpss_harm(hp, c.n_segs, stream)); }
     ctx->launches += 2;
     // 3. inverse STFT + overlap-add
@@ -873,7 +873,6 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         if (v >= 64) ctx->chunk_cols = v;
     }
     if (const char* env = std::getenv("SERB_HARM_SEG")) { const int v = std::atoi(env); if (v >= 16) ctx->harm_seg = v; }
-    if (const char* env = std::getenv("SERB_PERC_RUNS")) { const int v = std::atoi(env); if (v == 4 || v == 8 || v == 16) ctx->perc_runs = v; }
     ctx->timed = true;
 #define CREATE_CHECK(call)                                                                     \
     do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { int rc2 = fail_cuda(nullptr, e2, #call); delete ctx; return rc2; } } while (0)

@@ -170,35 +170,70 @@ __global__ void __launch_bounds__(256, 3) hpss_harm_kernel(HpssParams p) {
 }
 
 // ---- median along frequency ------------------------------------------------------------
-// one lane per (column, run of RUN bins); RUNS runs per column, 32 / RUNS columns per warp
-template <int RUNS>
+// One lane per (column, run of 64 bins): 16 runs per column (the last one also takes bin 1024), two
+// columns per warp.  A lane walks its run eight bins at a time; the eight new values of a step and
+// the eight medians are moved as two 16-byte accesses each (runs start on multiples of 8 bins),
+// which matters because the lanes of a warp walk 32 different cache lines.
+constexpr int kPercRun = 64;
+
+// values at bins pos .. pos + 7 (pos a multiple of 8) of one column, scipy "reflect" at the ends
+__device__ __forceinline__ void perc_load8(const float* __restrict__ src, int pos, float (&v)[8]) {
+    if (pos >= 0 && pos + 7 < kNBins) {
+        const float4 a = *reinterpret_cast<const float4*>(src + pos);
+        const float4 b = *reinterpret_cast<const float4*>(src + pos + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = src[reflect_once(pos + k, kNBins)];
+    }
+}
+
 __global__ void __launch_bounds__(256, 3) hpss_perc_kernel(HpssParams p, int n_cols) {
-    constexpr int RUN = (kNBins + RUNS - 1) / RUNS;
-    constexpr int COLS = 32 / RUNS;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int col = COLS * warp + lane / RUNS;
+    const int col = 2 * warp + (lane >> 4);
     if (col >= n_cols) return;
-    const int f0 = (lane % RUNS) * RUN;
-    const int f1 = min(f0 + RUN, kNBins);
-    if (f0 >= kNBins) return;
+    const int f0 = (lane & 15) * kPercRun;
+    const int f1 = ((lane & 15) == 15) ? kNBins : f0 + kPercRun;
     const float one = p.one;
     const float* src = p.mag + static_cast<long long>(col) * kSpillStride;
     float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
     BlockMedian bm;
-    bm.prime([&](int i) -> float { return src[reflect_once(f0 - 8 + i, kNBins)]; });
-    float fresh[kMedBlock];
+    float g[8], carry;
+    // bins f0 - 16 .. f0 + 15 in four aligned groups: f0 - 15 .. f0 + 14 prime the window, f0 + 15 is
+    // the first value of the first step
+    perc_load8(src, f0 - 16, g);
 #pragma unroll
-    for (int k = 0; k < kMedBlock; ++k) fresh[k] = src[reflect_once(f0 + 15 + k, kNBins)];
+    for (int k = 1; k < 8; ++k) bm.raw[8 + k - 1] = g[k];
+    perc_load8(src, f0 - 8, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bm.raw[15 + k] = g[k];
+    perc_load8(src, f0, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bm.raw[23 + k] = g[k];
+    perc_load8(src, f0 + 8, g);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) bm.raw[31 + k] = g[k];
+    carry = g[7];
+    float fresh[kMedBlock];
+    perc_load8(src, f0 + 16, g);
+    fresh[0] = carry;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) fresh[k + 1] = g[k];
+    carry = g[7];
     for (int f = f0; f < f1; f += kMedBlock) {
         bm.advance(fresh);
+        perc_load8(src, f + 24, g);          // bins f + 23 .. f + 30 feed the next step
+        fresh[0] = carry;
 #pragma unroll
-        for (int k = 0; k < kMedBlock; ++k) fresh[k] = src[reflect_once(f + kMedBlock + 15 + k, kNBins)];
+        for (int k = 0; k < 7; ++k) fresh[k + 1] = g[k];
+        carry = g[7];
         float med[kMedBlock];
         bm.medians(one, med);
-#pragma unroll
-        for (int j = 0; j < kMedBlock; ++j)
-            if (f + j < f1) dst[f + j] = med[j];
+        // the row pitch (1032) leaves room for a full 32-byte store at bin 1024
+        *reinterpret_cast<float4*>(dst + f) = make_float4(med[0], med[1], med[2], med[3]);
+        *reinterpret_cast<float4*>(dst + f + 4) = make_float4(med[4], med[5], med[6], med[7]);
     }
 }
 
@@ -323,18 +358,10 @@ cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t strea
     return cudaGetLastError();
 }
 
-cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, int runs, cudaStream_t stream) {
+cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream) {
     if (n_cols <= 0) return cudaSuccess;
-    if (runs == 4) {
-        const int warps = (n_cols + 7) / 8;                 // 4 runs of 257 bins, 8 columns per warp
-        hpss_perc_kernel<4><<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
-    } else if (runs == 8) {
-        const int warps = (n_cols + 3) / 4;                 // 8 runs of 129 bins, 4 columns per warp
-        hpss_perc_kernel<8><<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
-    } else {
-        const int warps = (n_cols + 1) / 2;                 // 16 runs of 65 bins, 2 columns per warp
-        hpss_perc_kernel<16><<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
-    }
+    const int warps = (n_cols + 1) / 2;                     // two columns per warp
+    hpss_perc_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
     return cudaGetLastError();
 }
 

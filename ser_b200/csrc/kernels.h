@@ -154,7 +154,7 @@ struct OlaParams {
 };
 cudaError_t configure_hpss();
 cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t stream);
-cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, int runs, cudaStream_t stream);
+cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_ola(const OlaParams& p, int n_tiles, cudaStream_t stream);
 
