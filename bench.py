@@ -368,9 +368,9 @@ def run_b200(args) -> None:
     ctx.set_profile(False)
     dom = max(kms, key=lambda k: kms[k][0])
     dom_ms, dom_n = kms[dom]
-    # the library brackets the seven per-octave launches of the constant-Q kernel (and the
-    # decimation launches) with one event pair per chunk: count kernel launches, not brackets
-    dom_n *= {"cqt": 7, "decimate": 7 if sr >= 33400 else 6, "tonnetz": 2}.get(dom, 1)
+    # the library brackets the decimation launches of a chunk (and the two tonnetz kernels) with one
+    # event pair: count kernel launches, not brackets (the constant-Q kernel is one launch per chunk)
+    dom_n *= {"decimate": 7 if sr >= 33400 else 6, "tonnetz": 2}.get(dom, 1)
     total_cols = int(np.sum(1 + lengths // 512))
     # algorithmic bytes: every input sample once + every output row once
     alg_bytes_step = 4 * n_clips * n_samples + 4 * dim * n_rows
@@ -384,8 +384,7 @@ def run_b200(args) -> None:
         try:
             entry = json.loads(traffic_file.read_text()).get(KERNEL_NAMES[dom])
             if entry:
-                launches_per_chunk = 7 if dom == "cqt" else 1
-                traffic = entry["dram_bytes_per_stft_column_per_launch"] * total_cols * launches_per_chunk / max(dom_n, 1)
+                traffic = entry["dram_bytes_per_stft_column_per_launch"] * total_cols / max(dom_n, 1)
         except Exception:
             traffic = None
     flop_per_column = FLOP_PER_COLUMN_193 if flags.tonnetz else FLOP_PER_COLUMN

@@ -147,6 +147,7 @@ __device__ __forceinline__ void fft_small(float2* v) {
     else fft16(v);
 }
 
+constexpr size_t kCqtMaxSmem = 227 * 1024;   // dynamic shared memory every instantiation is opted in to
 constexpr int kCqtWarps = 8;
 constexpr int kCqtValPitch = kCqRowCap + 1;   // float2 pitch of a staged basis row (bank spread)
 
@@ -163,13 +164,16 @@ struct CqtSmemHead {
 // the 36 sparse basis rows of the clip's tuning; after one barrier every warp works alone:
 // G = 32 / R columns per iteration, R complex points per lane per column (N = 32 R = n_fft / 2).
 template <int R>
-__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int octave, int cols_per_block) {
+__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int octave_arg) {
     constexpr int G = 32 / R;
     constexpr int N = 32 * R;
     extern __shared__ __align__(16) unsigned char cqt_smem_raw[];
     CqtSmemHead& sm = *reinterpret_cast<CqtSmemHead*>(cqt_smem_raw);
     float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(CqtSmemHead));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // one launch per octave, or all octaves of equal FFT size in one launch (blockIdx.z)
+    const int octave = octave_arg >= 0 ? octave_arg : static_cast<int>(blockIdx.z);
+    const int cols_per_block = p.cq_cols_per_block[octave];
     const TonClip clip = p.clips[blockIdx.x];
     const int t_block = blockIdx.y * cols_per_block;
     if (t_block >= clip.cq_cols) return;
@@ -415,7 +419,6 @@ __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
 // per device (called from serb_ctx_create with the device current): opt every instantiation in
 // to the largest dynamic shared memory a launch can ask for, once, so that concurrent contexts
 // never race an attribute change against a launch
-constexpr size_t kCqtMaxSmem = 227 * 1024;
 cudaError_t configure_cqt(const float* taps2_scaled) {
     static float quads[2][kTapQuads][4];
     for (int phase = 0; phase < 2; ++phase)
@@ -436,8 +439,9 @@ cudaError_t configure_cqt(const float* taps2_scaled) {
 
 constexpr int kCqtSpanBudget = 8960;    // staged signal floats per CTA (two CTAs per SM)
 
+// columns per CTA and dynamic shared memory of one octave's launch
 template <int R>
-static cudaError_t launch_cqt_octave(const CqtParams& p, int octave, cudaStream_t stream) {
+static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block, size_t& bytes) {
     constexpr int G = 32 / R;
     constexpr int N = 32 * R;
     const int hop = p.hop0 >> octave;
@@ -445,12 +449,36 @@ static cudaError_t launch_cqt_octave(const CqtParams& p, int octave, cudaStream_
     // as many whole iterations as fit the span budget, at least one, at most eight
     int iters = (kCqtSpanBudget - 2 * N + hop) / (per_iter * hop);
     iters = max(1, min(8, iters));
-    const int cols_per_block = per_iter * iters;
+    cols_per_block = per_iter * iters;
     const size_t span = static_cast<size_t>(cols_per_block - 1) * hop + 2 * N;
-    const size_t bytes = sizeof(CqtSmemHead) + span * sizeof(float);
-    if (bytes > kCqtMaxSmem) return cudaErrorInvalidConfiguration;
-    dim3 grid(p.n_clips, (p.max_cq_cols + cols_per_block - 1) / cols_per_block);
-    cqt_kernel<R><<<grid, kCqtWarps * 32, bytes, stream>>>(p, octave, cols_per_block);
+    bytes = sizeof(CqtSmemHead) + span * sizeof(float);
+}
+
+// octaves [first, first + count) share the FFT size 64 R: one launch, blockIdx.z = octave - first
+// is not needed because the kernel takes the octave from blockIdx.z only when count covers all
+template <int R>
+static cudaError_t launch_cqt_group(CqtParams p, int first, int count, cudaStream_t stream) {
+    size_t max_bytes = 0;
+    int min_cols = 1 << 30;
+    for (int o = first; o < first + count; ++o) {
+        size_t bytes;
+        cqt_octave_shape<R>(p, o, p.cq_cols_per_block[o], bytes);
+        max_bytes = max(max_bytes, bytes);
+        min_cols = min(min_cols, p.cq_cols_per_block[o]);
+    }
+    if (max_bytes > kCqtMaxSmem) return cudaErrorInvalidConfiguration;
+    if (first == 0 && count == kCqOctaves) {
+        dim3 grid(p.n_clips, (p.max_cq_cols + min_cols - 1) / min_cols, kCqOctaves);
+        cqt_kernel<R><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, -1);
+    } else {
+        for (int o = first; o < first + count; ++o) {
+            size_t bytes;
+            int cols;
+            cqt_octave_shape<R>(p, o, cols, bytes);
+            dim3 grid(p.n_clips, (p.max_cq_cols + cols - 1) / cols);
+            cqt_kernel<R><<<grid, kCqtWarps * 32, bytes, stream>>>(p, o);
+        }
+    }
     return cudaGetLastError();
 }
 
@@ -478,17 +506,23 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
 cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long long* launches) {
     if (p.n_clips <= 0) return cudaSuccess;
     cudaError_t e = cudaSuccess;
-    for (int octave = 0; octave < kCqOctaves; ++octave) {
-        switch (p.n_fft[octave]) {
-            case 256: e = launch_cqt_octave<4>(p, octave, stream); break;
-            case 512: e = launch_cqt_octave<8>(p, octave, stream); break;
-            case 1024: e = launch_cqt_octave<16>(p, octave, stream); break;
-            case 2048: e = launch_cqt_octave<32>(p, octave, stream); break;
+    long long n = 0;
+    // maximal runs of octaves with one FFT size (all seven at the common sample rates)
+    for (int first = 0; first < kCqOctaves;) {
+        int count = 1;
+        while (first + count < kCqOctaves && p.n_fft[first + count] == p.n_fft[first]) ++count;
+        switch (p.n_fft[first]) {
+            case 256: e = launch_cqt_group<4>(p, first, count, stream); break;
+            case 512: e = launch_cqt_group<8>(p, first, count, stream); break;
+            case 1024: e = launch_cqt_group<16>(p, first, count, stream); break;
+            case 2048: e = launch_cqt_group<32>(p, first, count, stream); break;
             default: return cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return e;
+        n += (first == 0 && count == kCqOctaves) ? 1 : count;
+        first += count;
     }
-    if (launches) *launches += kCqOctaves;
+    if (launches) *launches += n;
     return cudaGetLastError();
 }
 

@@ -169,6 +169,7 @@ struct CqtParams {
     int early_factor;            // 1, 2, 4, 8
     int hop0;                    // hop of level 0
     int n_fft[kCqOctaves];
+    int cq_cols_per_block[kCqOctaves];   // filled by the launcher
     const float* early_taps;     // [n_early_taps] (scaled by sqrt(early_factor)); NULL if factor 1
     int n_early_taps;
     const CqRow* rows;           // [100][7][36]
