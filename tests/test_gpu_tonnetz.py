@@ -308,3 +308,27 @@ def test_labels_and_segments_agree_with_the_cpu_path_end_to_end(golden):
                    [(s.emotion, s.start_seconds, s.end_seconds) for s in osegments]
     print(f"label agreement {same}/{total}")
     assert same == total
+
+
+@pytest.mark.parametrize("length", [1, 3, 17, 511, 513, 1023, 2047, 2049, 4095, 7777, 15999, 16385])
+def test_awkward_lengths_match_oracle(length):
+    """Lengths around every boundary of the path (padding to 512, n_fft = min(len, 2048), one
+    more STFT column, block-median and overlap-add edges, constant-Q levels of a few samples).
+    A 2-sample clip is left out on purpose: after the Hann window it is a single impulse, its
+    spectrum is flat to rounding noise, and the piptrack "peaks" that pick the tuning bin are that
+    noise (the discontinuity SURVEY.md section 7 warns about), on the CPU path as much as here."""
+    from oracle import ser_oracle
+    from ser_b200 import dsp, synth
+
+    sr = 16000
+    audio = synth.clip_audio(synth.ClipSpec(50 + length % 7, 2 + length % 20, 1 + length % 8), sr, max(length, 8))[:length]
+    if not np.any(audio):
+        audio = audio + np.float32(0.25)
+    got = dsp.extract_feature_from_signal(audio, sr)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ser_oracle.extract_feature_from_signal(audio, sr)
+    report = group_errors(got, ref, groups=ALL_GROUPS)
+    print(length, {k: f"{v[0]:.2e}" for k, v in report.items()})
+    for group, (scaled, _raw) in report.items():
+        assert scaled <= TOL, f"len {length} {group}: {scaled:.3e}"
