@@ -1323,7 +1323,7 @@ int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octa
     }
     if (out_scale36) {
         CqtBank bank;
-        if (!cqt_bank(plan, tuning_index, bank)) return SERB_ERR_UNSUPPORTED;
+        if (!cqt_bank(plan, tuning_index, bank, false)) return SERB_ERR_UNSUPPORTED;
         for (int j = 0; j < kCqtBpo; ++j) out_scale36[j] = bank.rows[static_cast<size_t>(octave) * kCqtBpo + j].scale;
     }
     return SERB_OK;

@@ -159,6 +159,71 @@ void octave_basis(const Wavelets& w, double sr_eff, int octave, int n_fft, std::
 
 }  // namespace
 
+
+namespace {
+
+// Kuhn's augmenting-path matching: lane -> row with adjacency `allowed`
+bool try_lane(int lane, const std::vector<std::vector<int>>& allowed, std::vector<int>& row_of_lane,
+              std::vector<int>& lane_of_row, std::vector<char>& seen) {
+    for (int r : allowed[lane]) {
+        if (seen[r]) continue;
+        seen[r] = 1;
+        if (lane_of_row[r] < 0 || try_lane(lane_of_row[r], allowed, row_of_lane, lane_of_row, seen)) {
+            row_of_lane[lane] = r;
+            lane_of_row[r] = lane;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Reorders the 36 rows of one octave for the kernel's lane = row mapping.  The kernel's lanes read
+// X[start + c] at the same c: a half-warp (16 lanes, 8-byte words) is conflict-free when the 16
+// first bins are distinct modulo 16.  Row r may start up to a few bins early (zero coefficients in
+// front); among all lane assignments with first bin = lane (mod 16) the one with the smallest
+// widest row is taken (bottleneck matching).  Entries 32..35 (handled four lanes at a time) keep
+// their bins.  Falls back to the natural order if no assignment fits the row capacity.
+void lane_order_octave(CqtBank& bank, int octave) {
+    CqtRow* rows = bank.rows.data() + static_cast<size_t>(octave) * kCqtBpo;
+    float* vals = bank.vals.data() + static_cast<size_t>(octave) * kCqtBpo * kCqtRowCap * 2;
+    int max_count = 0;
+    for (int r = 0; r < kCqtBpo; ++r) max_count = std::max(max_count, rows[r].count);
+    auto shift_of = [&](int lane, int r) { return ((rows[r].start - (lane & 15)) % 16 + 16) % 16; };
+    for (int tau = max_count; tau <= kCqtRowCap; ++tau) {
+        std::vector<std::vector<int>> allowed(32);
+        for (int lane = 0; lane < 32; ++lane)
+            for (int r = 0; r < kCqtBpo; ++r)
+                if (rows[r].count > 0 && rows[r].count + shift_of(lane, r) <= tau && rows[r].start - shift_of(lane, r) >= 0)
+                    allowed[lane].push_back(r);
+        std::vector<int> row_of_lane(32, -1), lane_of_row(kCqtBpo, -1);
+        int matched = 0;
+        for (int lane = 0; lane < 32; ++lane) {
+            std::vector<char> seen(kCqtBpo, 0);
+            if (try_lane(lane, allowed, row_of_lane, lane_of_row, seen)) ++matched;
+        }
+        if (matched < 32) continue;
+        std::vector<CqtRow> new_rows(kCqtBpo);
+        std::vector<float> new_vals(static_cast<size_t>(kCqtBpo) * kCqtRowCap * 2, 0.0f);
+        int spare = 32;
+        for (int r = 0; r < kCqtBpo; ++r) {
+            const int slot = lane_of_row[r] >= 0 ? lane_of_row[r] : spare++;
+            const int d = lane_of_row[r] >= 0 ? shift_of(slot, r) : 0;
+            new_rows[slot] = rows[r];
+            new_rows[slot].start = rows[r].start - d;
+            new_rows[slot].count = rows[r].count + d;
+            for (int k = 0; k < rows[r].count; ++k) {
+                new_vals[(static_cast<size_t>(slot) * kCqtRowCap + d + k) * 2] = vals[(static_cast<size_t>(r) * kCqtRowCap + k) * 2];
+                new_vals[(static_cast<size_t>(slot) * kCqtRowCap + d + k) * 2 + 1] = vals[(static_cast<size_t>(r) * kCqtRowCap + k) * 2 + 1];
+            }
+        }
+        std::copy(new_rows.begin(), new_rows.end(), rows);
+        std::copy(new_vals.begin(), new_vals.end(), vals);
+        return;
+    }
+}
+
+}  // namespace
+
 void cqt_plan(int sample_rate, CqtPlan& plan) {
     plan = CqtPlan();
     plan.sample_rate = sample_rate;
@@ -214,7 +279,7 @@ void cqt_basis_dense(const CqtPlan& plan, int tuning_idx, int octave, std::vecto
     octave_basis(w, sr_eff, octave, plan.n_fft[octave], out);
 }
 
-bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank) {
+bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank, bool lane_order) {
     Wavelets w;
     wavelets_for_tuning(tuning_idx, w);
     const double sr_eff = static_cast<double>(plan.sample_rate) / static_cast<double>(plan.early_factor);
@@ -243,6 +308,7 @@ bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank) {
             float* dst = bank.vals.data() + (static_cast<size_t>(i) * kCqtBpo + j) * kCqtRowCap * 2;
             for (int k = 0; k < count; ++k) { dst[2 * k] = row[2 * (first + k)]; dst[2 * k + 1] = row[2 * (first + k) + 1]; }
         }
+        if (lane_order) lane_order_octave(bank, i);
     }
     return ok;
 }

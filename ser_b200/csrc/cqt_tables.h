@@ -35,7 +35,8 @@ struct CqtRow {
 };
 
 struct CqtBank {
-    std::vector<CqtRow> rows;  // [7][36], octave-major (top octave first), rows low -> high inside
+    std::vector<CqtRow> rows;  // [7][36], octave-major (top octave first); inside an octave in the
+                               // kernel's lane order (see cqt_bank), each row naming its output bin
     std::vector<float> vals;   // [7][36][kCqtRowCap][2] complex64, zero padded
 };
 
@@ -43,7 +44,10 @@ struct CqtBank {
 // known); status 2 reports the sample rates where it would.
 void cqt_plan(int sample_rate, CqtPlan& plan);
 // basis for tuning = -0.5 + 0.01 * tuning_idx.  Returns false if a row is wider than kCqtRowCap.
-bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank);
+// lane_order: rows of an octave are permuted (and started a few bins early, zero filled) so that
+// the kernel's lane = row reads of the spectrum are shared-memory bank-conflict free; otherwise
+// rows stay in bin order.
+bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank, bool lane_order = true);
 // dense basis of one octave, [36][1 + n_fft/2] complex64 (tests)
 void cqt_basis_dense(const CqtPlan& plan, int tuning_idx, int octave, std::vector<float>& out);
 
