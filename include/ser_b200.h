@@ -99,6 +99,15 @@ int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave,
                        int32_t sample_rate, uint32_t flag_bits, float* h_out);
 
 /*
+ * The same for clips that live in separate host arrays (one per decoded file, as the training
+ * loader holds them): h_clips[i] points at lengths[i] float32 samples.  The library copies them
+ * piecewise while earlier chunks compute; the caller builds no packed buffer.
+ * (ser/_internal/data/data_loader.py:485-529, one extract_vector call per file there.)
+ */
+int serb_features_host_clips(serb_ctx* ctx, const float* const* h_clips, const int64_t* lengths,
+                             int64_t n_clips, int32_t sample_rate, uint32_t flag_bits, float* h_out);
+
+/*
  * Classifier weights (float64, row-major as sklearn stores them):
  * mean/scale [n_in], w1 [n_in x n_hidden], b1 [n_hidden], w2 [n_hidden x n_out], b2 [n_out].
  * n_out is the width of the output layer (1 for sklearn's binary logistic case).

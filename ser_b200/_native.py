@@ -32,6 +32,7 @@ SIGNATURES: dict[str, tuple] = {
     "serb_feature_dim": (c_int, [c_uint32]),
     "serb_features_device": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P, _P]),
     "serb_features_host": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P]),
+    "serb_features_host_clips": (c_int, [_P, _P, _P, c_int64, c_int32, c_uint32, _P]),
     "serb_mlp_load": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32]),
     "serb_mlp_n_classes": (c_int, [_P]),
     "serb_mlp_predict_host": (c_int, [_P, _P, c_int64, _P, _P]),
@@ -136,6 +137,18 @@ class Context:
         self._check(self._lib.serb_features_host(
             self._handle, _ptr(wave), wave.size, _ptr(starts), _ptr(lengths), starts.size,
             int(sample_rate), int(flag_bits), _ptr(out)))
+        return out
+
+    def features_host_clips(self, clips: list[np.ndarray], sample_rate: int, flag_bits: int) -> np.ndarray:
+        """One row per clip; every clip is its own contiguous float32 array (no packing copy)."""
+        arrays = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        n = len(arrays)
+        pointers = (c_void_p * max(n, 1))(*[a.ctypes.data for a in arrays])
+        lengths = np.asarray([a.size for a in arrays], dtype=np.int64)
+        dim = self._lib.serb_feature_dim(flag_bits)
+        out = np.empty((n, dim), dtype=np.float32)
+        self._check(self._lib.serb_features_host_clips(
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(lengths), n, int(sample_rate), int(flag_bits), _ptr(out)))
         return out
 
     def features_device(self, d_wave_ptr: int, n_wave: int, starts: np.ndarray, lengths: np.ndarray,

@@ -814,10 +814,7 @@ struct PieceWaiter {
     }
 };
 
-int stage_wave(serb_ctx* ctx, const float* h_wave, long long n_wave, PieceWaiter& waiter) {
-    SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
-    waiter = PieceWaiter{ctx, ctx->stream, h_wave, n_wave};
-    const int n_pieces = static_cast<int>((n_wave + waiter.piece - 1) / waiter.piece);
+int ensure_piece_events(serb_ctx* ctx, int n_pieces) {
     while (static_cast<int>(ctx->piece_events.size()) < n_pieces) {
         cudaEvent_t ev;
         SERB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -825,6 +822,61 @@ int stage_wave(serb_ctx* ctx, const float* h_wave, long long n_wave, PieceWaiter
     }
     return SERB_OK;
 }
+
+int stage_wave(serb_ctx* ctx, const float* h_wave, long long n_wave, PieceWaiter& waiter) {
+    SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
+    waiter = PieceWaiter{ctx, ctx->stream, h_wave, n_wave};
+    return ensure_piece_events(ctx, static_cast<int>((n_wave + waiter.piece - 1) / waiter.piece));
+}
+
+// The same for a list of separately allocated clips (the training loader's shape: one array per
+// file).  Clips are copied to 16-byte aligned offsets of ctx->wave in pieces of consecutive clips;
+// a piece is enqueued when the first chunk that needs it is about to launch, so the host's copy
+// work for chunk k + 1 (pageable memory: the driver stages it) overlaps the kernels of chunk k and
+// the caller never builds a packed copy of its own.
+struct ClipStager {
+    serb_ctx* ctx;
+    cudaStream_t stream;
+    const float* const* clips;
+    const int64_t* lengths;
+    const std::vector<int64_t>* starts;
+    long long n_clips;
+    long long next_clip = 0;      // first clip not yet enqueued
+    long long enqueued_end = 0;   // wave offset covered by the enqueued copies
+    int n_pieces = 0;
+    bool started = false;
+    cudaError_t error = cudaSuccess;
+    void operator()(long long max_end) {
+        if (error != cudaSuccess) return;
+        if (!started) {
+            started = true;
+            // the previous call's kernels may still read ctx->wave
+            if ((error = cudaEventRecord(ctx->ev_done, ctx->stream)) != cudaSuccess) return;
+            if ((error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0)) != cudaSuccess) return;
+        }
+        constexpr long long kPiece = 8LL << 20;   // samples per piece (32 MiB)
+        while (enqueued_end < max_end && next_clip < n_clips) {
+            long long in_piece = 0;
+            while (next_clip < n_clips && in_piece < kPiece) {
+                const long long len = lengths[next_clip];
+                if ((error = cudaMemcpyAsync(ctx->wave.as<float>() + (*starts)[next_clip], clips[next_clip],
+                                             static_cast<size_t>(len) * sizeof(float), cudaMemcpyHostToDevice,
+                                             ctx->copy_stream)) != cudaSuccess) return;
+                enqueued_end = (*starts)[next_clip] + len;
+                in_piece += len;
+                ++next_clip;
+            }
+            if (n_pieces >= static_cast<int>(ctx->piece_events.size())) {
+                cudaEvent_t ev;
+                if ((error = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return;
+                ctx->piece_events.push_back(ev);
+            }
+            if ((error = cudaEventRecord(ctx->piece_events[n_pieces], ctx->copy_stream)) != cudaSuccess) return;
+            ++n_pieces;
+        }
+        if (n_pieces > 0) cudaStreamWaitEvent(stream, ctx->piece_events[n_pieces - 1], 0);
+    }
+};
 
 int mlp_run(serb_ctx* ctx, const float* d_x32, const double* d_x64, long long n, double* d_proba,
             int* d_label, cudaStream_t stream) {
@@ -1005,6 +1057,38 @@ int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const
                       ctx->out.as<float>(), ctx->stream, waiter);
     ctx->ramp_chunks = false;
     if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+    if (n_clips > 0 && dim > 0)
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.ptr, static_cast<size_t>(n_clips) * dim * sizeof(float),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_clips > 0 && dim > 0) return check_status(ctx, ctx->stream);
+    return SERB_OK;
+}
+
+int serb_features_host_clips(serb_ctx* ctx, const float* const* h_clips, const int64_t* lengths, int64_t n_clips,
+                             int32_t sample_rate, uint32_t flag_bits, float* h_out) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_clips < 0 || (n_clips > 0 && (!h_clips || !lengths || !h_out))) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+    std::vector<int64_t> starts(static_cast<size_t>(n_clips));
+    long long n_wave = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        if (lengths[i] <= 0) return fail(ctx, SERB_ERR_EMPTY, "Audio contains no samples.");
+        if (!h_clips[i]) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL clip pointer");
+        starts[i] = n_wave;
+        n_wave += (lengths[i] + 3) / 4 * 4;       // 16-byte aligned clip starts: every tile takes the TMA path
+    }
+    const int dim = serb_feature_dim(flag_bits);
+    SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
+    SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
+    ClipStager stager{ctx, ctx->stream, h_clips, lengths, &starts, n_clips};
+    ctx->ramp_chunks = true;
+    int rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts.data(), lengths, n_clips, sample_rate, flag_bits,
+                          ctx->out.as<float>(), ctx->stream, stager);
+    ctx->ramp_chunks = false;
+    if (!rc && stager.error != cudaSuccess) rc = fail_cuda(ctx, stager.error, "clip staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips > 0 && dim > 0)
         SERB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.ptr, static_cast<size_t>(n_clips) * dim * sizeof(float),

@@ -108,12 +108,6 @@ def extract_features_batch(
     flags = feature_flags if feature_flags is not None else FeatureFlags()
     if not arrays:
         return np.empty((0, feature_dim(flags)), dtype=np.float64)
-    # pack with 16-byte aligned clip starts so every tile takes the TMA bulk-copy path
-    lengths = np.asarray([a.size for a in arrays], dtype=np.int64)
-    padded = (lengths + 3) // 4 * 4
-    starts = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
-    wave = np.zeros(int(padded.sum()), dtype=np.float32)
-    for a, s in zip(arrays, starts):
-        wave[s : s + a.size] = a
-    rows = extract_features_ragged(wave, starts, lengths, sample_rate, feature_flags=flags, device=device)
+    # every clip stays in its own array: the library copies them to aligned offsets piecewise
+    rows = _native.get_context(device).features_host_clips(arrays, sample_rate, flag_bits(flags))
     return rows.astype(np.float64)
