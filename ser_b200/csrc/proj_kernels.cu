@@ -31,58 +31,65 @@ __device__ __forceinline__ float value_of(unsigned k) {
 
 constexpr int kTuneCache = 10240;   // peak magnitudes cached in shared memory (40 KB)
 
-// k-th smallest (0-based) key; every thread returns the same value.  Keys come from the
-// shared-memory cache when the clip's peaks fit, else from the global peak lists.
-__device__ float select_rank(const TuneParams& p, const ClipDev& clip, long long rank, unsigned* hist,
-                             unsigned* shared_prefix, long long* shared_rank, const float* cache, int n_cached) {
+// The two middle order statistics (0-based ranks rank_lo <= rank_hi <= rank_lo + 1) in one 4-pass
+// radix select; every thread returns the same pair.  While both ranks still fall in the same
+// bucket one histogram serves both.  Keys come from the shared-memory cache when the clip's peaks
+// fit, else from the global peak lists.
+__device__ float2 select_middle(const TuneParams& p, const ClipDev& clip, long long rank_lo, long long rank_hi,
+                                unsigned (*hist)[256], unsigned* shared_prefix, long long* shared_rank,
+                                const float* cache, int n_cached) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kTuneThreads / 32;
-    unsigned prefix = 0;
+    unsigned prefix0 = 0, prefix1 = 0;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         const unsigned hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = threadIdx.x; i < 256; i += kTuneThreads) hist[i] = 0;
+        const bool same = prefix0 == prefix1;
+        for (int i = threadIdx.x; i < 512; i += kTuneThreads) (&hist[0][0])[i] = 0;
         __syncthreads();
+        auto count = [&](unsigned key) {
+            const unsigned b = (key >> shift) & 255u;
+            if ((key & hi_mask) == (prefix0 & hi_mask)) atomicAdd(&hist[0][b], 1u);
+            if (!same && (key & hi_mask) == (prefix1 & hi_mask)) atomicAdd(&hist[1][b], 1u);
+        };
         if (cache) {
-            for (int i = threadIdx.x; i < n_cached; i += kTuneThreads) {
-                const unsigned key = key_of(cache[i]);
-                if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-            }
+            for (int i = threadIdx.x; i < n_cached; i += kTuneThreads) count(key_of(cache[i]));
         } else {
             for (int t = warp; t < clip.n_cols; t += n_warps) {
                 const long long col = static_cast<long long>(clip.col_base) + t;
                 const int cnt = p.peak_count[col];
                 const float2* src = p.peaks + col * p.peak_cap;
-                for (int i = lane; i < cnt; i += 32) {
-                    const unsigned key = key_of(src[i].x);
-                    if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-                }
+                for (int i = lane; i < cnt; i += 32) count(key_of(src[i].x));
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            long long r = rank;
+        if (threadIdx.x < 2) {
+            const int j = threadIdx.x;
+            const unsigned* h = hist[(j == 1 && !same) ? 1 : 0];
+            long long r = (j == 0) ? rank_lo : rank_hi;
             unsigned b = 0;
             for (; b < 255; ++b) {
-                const unsigned c = hist[b];
+                const unsigned c = h[b];
                 if (r < static_cast<long long>(c)) break;
                 r -= c;
             }
-            *shared_prefix = prefix | (b << shift);
-            *shared_rank = r;
+            shared_prefix[j] = ((j == 0) ? prefix0 : prefix1) | (b << shift);
+            shared_rank[j] = r;
         }
         __syncthreads();
-        prefix = *shared_prefix;
-        rank = *shared_rank;
+        prefix0 = shared_prefix[0];
+        prefix1 = shared_prefix[1];
+        rank_lo = shared_rank[0];
+        rank_hi = shared_rank[1];
         __syncthreads();
     }
-    return value_of(prefix);
+    return make_float2(value_of(prefix0), value_of(prefix1));
 }
 
 __global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
     __shared__ float cache[kTuneCache];
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix;
-    __shared__ long long s_rank;
+    __shared__ unsigned hist[2][256];
+    __shared__ unsigned s_prefix[2];
+    __shared__ long long s_rank[2];
     __shared__ long long s_total;
     __shared__ int s_cursor;
     __shared__ int counts[100];
@@ -122,14 +129,8 @@ __global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
     const float* keys = cached ? cache : nullptr;
     const int n_cached = static_cast<int>(cached ? n : 0);
     // np.median: mean of the two middle order statistics (float32 arithmetic) when n is even
-    float thr;
-    if (n & 1) {
-        thr = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank, keys, n_cached);
-    } else {
-        const float a = select_rank(p, clip, n / 2 - 1, hist, &s_prefix, &s_rank, keys, n_cached);
-        const float b = select_rank(p, clip, n / 2, hist, &s_prefix, &s_rank, keys, n_cached);
-        thr = __fmul_rn(__fadd_rn(a, b), 0.5f);
-    }
+    const float2 mid = select_middle(p, clip, (n - 1) / 2, n / 2, hist, s_prefix, s_rank, keys, n_cached);
+    const float thr = (n & 1) ? mid.x : __fmul_rn(__fadd_rn(mid.x, mid.y), 0.5f);
     const float bpo = static_cast<float>(p.bins_per_octave);
     for (int t = warp; t < clip.n_cols; t += n_warps) {
         const long long col = static_cast<long long>(clip.col_base) + t;
