@@ -35,6 +35,7 @@ METRIC = "audio_seconds_per_second_fast_profile_features_predict"
 UNIT = "audio-s/s"
 FRAME_SECONDS, STRIDE_SECONDS = 3, 1
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FFMA peak at max clock
+FP32_PEAK_TFLOPS_MEASURED = 72.2                             # profiles/r01_fp32_microbench.txt (dependent-free FFMA)
 FLOP_PER_COLUMN = 97_000                                     # SURVEY.md section 8(d), 187-d slice
 FLOP_PER_COLUMN_193 = 1_045_000                              # itemised ops of the 193-d chain
 KERNEL_NAMES = {
@@ -396,7 +397,7 @@ def run_b200(args) -> None:
         "kernel_ms_per_step": {k: v[0] for k, v in kms.items()},
         "share_of_step": dom_ms / max(sum(v[0] for v in kms.values()), 1e-9),
         "fp32": {"achieved_tflops": total_cols * flop_per_column / (ms_per_step / 1e3) / 1e12,
-                 "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
+                 "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL, "peak_tflops_measured": FP32_PEAK_TFLOPS_MEASURED,
                  "note": f"whole step, {flop_per_column // 1000} kop/column (DESIGN.md section 4); the path is "
                          "ALU/FP32/shared-memory bound, not HBM bound"},
         "how": "CUDA events around every launch of the dominant kernel in one extra pass of the same step",
