@@ -340,7 +340,6 @@ TonChunk ton_open_chunk(const TonPlan& tp) {
 int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur, const ClipDev& a, long long plen) {
     const int fe = plan.early_factor;
     const long long len0 = (plen + fe - 1) / fe;
-    if (len0 > (65535LL * 1024)) return fail(ctx, SERB_ERR_UNSUPPORTED, "tonnetz: clip too long for one launch");
     TonClip c{};
     c.off0 = cur.total0;
     c.hoff = cur.total0 * fe;

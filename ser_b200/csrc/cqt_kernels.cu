@@ -74,32 +74,34 @@ __global__ void __launch_bounds__(256) decimate2_kernel(CqtParams p, int src_lev
     const TonClip clip = p.clips[blockIdx.x];
     const int len_in = src_level < 0 ? clip.length : level_length(clip.len0, src_level);
     const int len_out = (len_in + 1) >> 1;
-    const int mb = blockIdx.y * kDecTile;
-    if (mb >= len_out) return;
     const float* src = level_ptr(p, clip, src_level);
     float* dst = p.yoct + p.level_base[src_level + 1] + (clip.off0 >> (src_level + 1));
-    for (int q = threadIdx.x; q < kDecSpan; q += 256) {
-        const int i = 2 * (mb - kDecHalo + q);
-        float a = 0.0f, b = 0.0f;
-        if (i >= 0 && i + 1 < len_in) {
-            const float2 v = *reinterpret_cast<const float2*>(src + i);
-            a = v.x; b = v.y;
-        } else {
-            if (i >= 0 && i < len_in) a = src[i];
-            if (i + 1 >= 0 && i + 1 < len_in) b = src[i + 1];
+    // grid.y is capped at 65535 tiles: longer signals walk the tiles with a grid stride
+    for (int mb = blockIdx.y * kDecTile; mb < len_out; mb += gridDim.y * kDecTile) {
+        for (int q = threadIdx.x; q < kDecSpan; q += 256) {
+            const int i = 2 * (mb - kDecHalo + q);
+            float a = 0.0f, b = 0.0f;
+            if (i >= 0 && i + 1 < len_in) {
+                const float2 v = *reinterpret_cast<const float2*>(src + i);
+                a = v.x; b = v.y;
+            } else {
+                if (i >= 0 && i < len_in) a = src[i];
+                if (i + 1 >= 0 && i + 1 < len_in) b = src[i + 1];
+            }
+            xe[q] = a;
+            xo[q] = b;
         }
-        xe[q] = a;
-        xo[q] = b;
-    }
-    __syncthreads();
-    // out[m] = sum_j h[2j] xe[m + 95 - j] + sum_j h[2j+1] xo[m + 94 - j]   (half = 190)
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    fir_phase<191, 0>(xe, threadIdx.x, acc);   // even taps h[2 (191 - e)]
-    fir_phase<190, 1>(xo, threadIdx.x, acc);   // odd taps h[2 (190 - e) + 1]
-    const int m = mb + 4 * threadIdx.x;
+        __syncthreads();
+        // out[m] = sum_j h[2j] xe[m + 95 - j] + sum_j h[2j+1] xo[m + 94 - j]   (half = 190)
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        fir_phase<191, 0>(xe, threadIdx.x, acc);   // even taps h[2 (191 - e)]
+        fir_phase<190, 1>(xo, threadIdx.x, acc);   // odd taps h[2 (190 - e) + 1]
+        const int m = mb + 4 * threadIdx.x;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        if (m + r < len_out) dst[m + r] = acc[r];
+        for (int r = 0; r < 4; ++r)
+            if (m + r < len_out) dst[m + r] = acc[r];
+        __syncthreads();
+    }
 }
 
 // yharm -> level 0 for early factors 4 and 8 (taps pre-scaled by sqrt(factor))
@@ -486,7 +488,7 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
     if (p.n_clips <= 0) return cudaSuccess;
     long long n = 0;
     if (p.early_factor == 2) {
-        decimate2_kernel<<<dim3(p.n_clips, (p.max_len0 + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, -1);
+        decimate2_kernel<<<dim3(p.n_clips, min(65535, (p.max_len0 + kDecTile - 1) / kDecTile)), 256, 0, stream>>>(p, -1);
         ++n;
     } else if (p.early_factor > 2) {
         const int tiles = min(4096, (p.max_len0 + 255) / 256);
@@ -496,7 +498,7 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
     int len = p.max_len0;
     for (int level = 0; level + 1 < kCqOctaves; ++level) {
         len = (len + 1) >> 1;
-        decimate2_kernel<<<dim3(p.n_clips, (len + kDecTile - 1) / kDecTile), 256, 0, stream>>>(p, level);
+        decimate2_kernel<<<dim3(p.n_clips, min(65535, (len + kDecTile - 1) / kDecTile)), 256, 0, stream>>>(p, level);
         ++n;
     }
     if (launches) *launches += n;
