@@ -373,3 +373,23 @@ def test_signal_families_match_oracle(sr):
             if group == "tonnetz" and float(np.max(np.abs(got[187:] - ref[187:]))) <= 1e-6:
                 continue
             assert scaled <= TOL, f"{sr}/{name}/{group}: {scaled:.3e}"
+
+
+def test_sharded_extraction_matches_single_device(golden):
+    """``extract_features_sharded`` (one host thread per visible device, no collective) returns the
+    rows of a single-device call in the original order; with one device it is the degenerate case."""
+    from ser_b200 import _native, dsp
+    from ser_b200.sharding import extract_features_sharded
+
+    names = [n for n in CASES if int(golden[f"{n}/sr"]) == 16000]
+    clips = [_audio(golden, n)[0] for n in names] * 3
+    lengths = np.asarray([c.size for c in clips], dtype=np.int64)
+    padded = (lengths + 3) // 4 * 4
+    starts = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
+    wave = np.zeros(int(padded.sum()), dtype=np.float32)
+    for s, c in zip(starts, clips):
+        wave[s:s + c.size] = c
+    expected = dsp.extract_features_ragged(wave, starts, lengths, 16000)
+    devices = list(range(_native.device_count()))
+    got = extract_features_sharded(wave, starts, lengths, 16000, devices=devices)
+    np.testing.assert_array_equal(got, expected)
