@@ -260,3 +260,20 @@ def test_full_size_properties_c2_batch(gpu_ctx):
         torch.cuda.synchronize()
         np.testing.assert_array_equal(single.cpu().numpy()[0], a[idx])
     assert _native.device_count() >= 1
+
+
+def test_clip_list_entry_errors_and_empty_batch(gpu_ctx):
+    """serb_features_host_clips: empty batch, an empty clip (reference text), zero feature groups."""
+    from ser_b200 import _native, dsp
+    from ser_b200.config import FeatureFlags, flag_bits
+
+    bits = flag_bits(FeatureFlags())
+    assert gpu_ctx.features_host_clips([], 16000, bits).shape == (0, 193)
+    good = np.ones(3000, dtype=np.float32)
+    with pytest.raises(ValueError, match="Audio contains no samples."):
+        gpu_ctx.features_host_clips([good, np.zeros(0, dtype=np.float32)], 16000, bits)
+    assert gpu_ctx.features_host_clips([good], 16000, 0).shape == (1, 0)
+    rows = dsp.extract_features_batch([good, good[:700]], 16000)
+    np.testing.assert_array_equal(rows[0], dsp.extract_feature_from_signal(good, 16000))
+    np.testing.assert_array_equal(rows[1], dsp.extract_feature_from_signal(good[:700], 16000))
+    assert _native.device_count() >= 1
