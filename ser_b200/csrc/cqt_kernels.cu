@@ -8,8 +8,8 @@
 // sparsified FFT-domain wavelet basis.
 //
 // decimate2_kernel   factor-2 FIR decimation (381-tap Kaiser stand-in for soxr_hq, x sqrt 2):
-//                    polyphase split in shared memory, 4 outputs per thread, taps as
-//                    constant-bank FFMA operands (fully unrolled)
+//                    the two polyphase branches in the halves of packed f32x2 FMAs (FFMA2),
+//                    8 outputs per thread, bank-group padded window, fully unrolled
 // decimate_any_kernel  early downsampling by 4 / 8 (sample rates >= 64 kHz), plain
 // cqt_kernel<R>      n_fft = 64 R real FFT per column (32 / R columns per warp, register DFTs
 //                    around one shared-memory transpose), sparse complex rows, |.| / sqrt(len)
@@ -22,11 +22,11 @@
 
 namespace serb {
 
-// Factor-2 decimator taps (x sqrt 2) split by polyphase and laid out for 16-byte uniform loads:
-// c_tap4[phase][j] holds tap(e = 4j - 3 .. 4j) with tap_even(e) = h[382 - 2e] (e = 1..191) and
-// tap_odd(e) = h[381 - 2e] (e = 1..190), zero outside.
-constexpr int kTapQuads = 50;
-__constant__ float4 c_tap4[2][kTapQuads];
+// Factor-2 decimator taps (x sqrt 2) paired for packed FP32 FMAs: c_tap2[e] = (h[382 - 2e],
+// h[381 - 2e]) multiplies the sample pair (x[2q], x[2q + 1]) at pair distance e = 1..191 from the
+// output (zero outside the 381 taps).
+constexpr int kTapPairs = 192;
+__constant__ __align__(16) float2 c_tap2[kTapPairs];
 
 namespace {
 
@@ -48,58 +48,73 @@ constexpr int kDecTile = 1024;               // outputs per CTA
 constexpr int kDecHalo = 96;                 // polyphase samples staged before the tile
 constexpr int kDecSpan = kDecTile + 192;     // polyphase samples staged per phase
 
-template <int E_MAX, int PHASE>
-__device__ __forceinline__ void fir_phase(const float* __restrict__ xs, int t, float (&acc)[4]) {
-    // acc[r] += tap(e) * xs[4 t + r + e], e = 1 .. E_MAX
-#pragma unroll
-    for (int g = 0; g <= (E_MAX + 3) / 4; ++g) {
-        const float4 q = *reinterpret_cast<const float4*>(xs + 4 * t + 4 * g);
-        const float v[4] = {q.x, q.y, q.z, q.w};
-        const float4 ta = c_tap4[PHASE][g], tb = c_tap4[PHASE][g + 1];
-        const float tap[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};   // tap[k] = tap(e = 4g - 3 + k)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int e = 4 * g + c - r;
-                if (e >= 1 && e <= E_MAX) acc[r] = fmaf(tap[c - r + 3], v[c], acc[r]);
-            }
-    }
+// d = a * b + c on both halves of a register pair (FFMA2: one issue slot for two FMAs)
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
 // src_level -1: yharm -> level 0 (early downsampling by 2); otherwise level l -> l + 1
-__global__ void __launch_bounds__(256) decimate2_kernel(CqtParams p, int src_level) {
-    __shared__ __align__(16) float xe[kDecSpan];
-    __shared__ __align__(16) float xo[kDecSpan];
+//   out[m] = sum_k h[k] x[2 m + 190 - k]
+//          = sum_{e = 1..191} h[382 - 2e] x[2 (m + e - 96)] + h[381 - 2e] x[2 (m + e - 96) + 1]:
+// the two polyphase branches ride in the two halves of one packed accumulator (the signal is
+// read as natural (even, odd) sample pairs) and are added once at the end.  Thread t owns
+// kDecOuts consecutive outputs; its window starts at pair kDecOuts t, and kDecPad pairs of
+// padding after every kDecOuts pairs put the 16-byte reads of eight neighbouring threads into
+// distinct bank groups (80-byte thread stride): without it the shared-memory wavefronts, not
+// the FMA pipe, bound this kernel (scripts/microbench/decimate_variants.cu).
+constexpr int kDecOuts = 8;
+constexpr int kDecThreads = kDecTile / kDecOuts;
+constexpr int kDecPad = 2;
+constexpr int kDecPhys = kDecSpan + kDecPad * (kDecSpan / kDecOuts);
+
+__global__ void __launch_bounds__(kDecThreads) decimate2_kernel(CqtParams p, int src_level) {
+    __shared__ __align__(16) float2 xs[kDecPhys];
     const TonClip clip = p.clips[blockIdx.x];
     const int len_in = src_level < 0 ? clip.length : level_length(clip.len0, src_level);
     const int len_out = (len_in + 1) >> 1;
     const float* src = level_ptr(p, clip, src_level);
     float* dst = p.yoct + p.level_base[src_level + 1] + (clip.off0 >> (src_level + 1));
+    const unsigned long long* tap2 = reinterpret_cast<const unsigned long long*>(c_tap2);
     // grid.y is capped at 65535 tiles: longer signals walk the tiles with a grid stride
     for (int mb = blockIdx.y * kDecTile; mb < len_out; mb += gridDim.y * kDecTile) {
-        for (int q = threadIdx.x; q < kDecSpan; q += 256) {
+        for (int q = threadIdx.x; q < kDecSpan; q += kDecThreads) {
             const int i = 2 * (mb - kDecHalo + q);
-            float a = 0.0f, b = 0.0f;
+            float2 v = make_float2(0.0f, 0.0f);
             if (i >= 0 && i + 1 < len_in) {
-                const float2 v = *reinterpret_cast<const float2*>(src + i);
-                a = v.x; b = v.y;
+                v = *reinterpret_cast<const float2*>(src + i);
             } else {
-                if (i >= 0 && i < len_in) a = src[i];
-                if (i + 1 >= 0 && i + 1 < len_in) b = src[i + 1];
+                if (i >= 0 && i < len_in) v.x = src[i];
+                if (i + 1 >= 0 && i + 1 < len_in) v.y = src[i + 1];
             }
-            xe[q] = a;
-            xo[q] = b;
+            xs[q + kDecPad * (q / kDecOuts)] = v;
         }
         __syncthreads();
-        // out[m] = sum_j h[2j] xe[m + 95 - j] + sum_j h[2j+1] xo[m + 94 - j]   (half = 190)
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        fir_phase<191, 0>(xe, threadIdx.x, acc);   // even taps h[2 (191 - e)]
-        fir_phase<190, 1>(xo, threadIdx.x, acc);   // odd taps h[2 (190 - e) + 1]
-        const int m = mb + 4 * threadIdx.x;
+        // acc[r] += tap2[e] * xs[kDecOuts t + r + e], e = 1 .. 191
+        unsigned long long acc[kDecOuts];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (m + r < len_out) dst[m + r] = acc[r];
+        for (int r = 0; r < kDecOuts; ++r) acc[r] = 0ull;
+        const float2* row = xs + (kDecOuts + kDecPad) * threadIdx.x;
+#pragma unroll
+        for (int g = 0; g < (kDecOuts + kTapPairs) / 2; ++g) {     // window positions 2g, 2g + 1
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + 2 * g + kDecPad * ((2 * g) / kDecOuts));
+            const unsigned long long vv[2] = {v.x, v.y};
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int r = 0; r < kDecOuts; ++r) {
+                    const int e = 2 * g + k - r;
+                    if (e >= 1 && e < kTapPairs) acc[r] = fma2(tap2[e], vv[k], acc[r]);
+                }
+        }
+        const int m = mb + kDecOuts * threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < kDecOuts; ++r)
+            if (m + r < len_out) {
+                const float2 a = *reinterpret_cast<const float2*>(&acc[r]);
+                dst[m + r] = a.x + a.y;
+            }
         __syncthreads();
     }
 }
@@ -422,16 +437,12 @@ __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
 // to the largest dynamic shared memory a launch can ask for, once, so that concurrent contexts
 // never race an attribute change against a launch
 cudaError_t configure_cqt(const float* taps2_scaled) {
-    static float quads[2][kTapQuads][4];
-    for (int phase = 0; phase < 2; ++phase)
-        for (int j = 0; j < kTapQuads; ++j)
-            for (int k = 0; k < 4; ++k) {
-                const int e = 4 * j - 3 + k;
-                const int e_max = phase == 0 ? 191 : 190;
-                const int idx = (phase == 0 ? 382 : 381) - 2 * e;
-                quads[phase][j][k] = (e >= 1 && e <= e_max) ? taps2_scaled[idx] : 0.0f;
-            }
-    cudaError_t e = cudaMemcpyToSymbol(c_tap4, quads, sizeof(quads));
+    static float pairs[kTapPairs][2];
+    for (int e = 0; e < kTapPairs; ++e) {
+        pairs[e][0] = e >= 1 ? taps2_scaled[382 - 2 * e] : 0.0f;              // h[380] .. h[0]
+        pairs[e][1] = (e >= 1 && e <= 190) ? taps2_scaled[381 - 2 * e] : 0.0f;   // h[379] .. h[1]
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs));
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
@@ -488,7 +499,7 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
     if (p.n_clips <= 0) return cudaSuccess;
     long long n = 0;
     if (p.early_factor == 2) {
-        decimate2_kernel<<<dim3(p.n_clips, min(65535, (p.max_len0 + kDecTile - 1) / kDecTile)), 256, 0, stream>>>(p, -1);
+        decimate2_kernel<<<dim3(p.n_clips, min(65535, (p.max_len0 + kDecTile - 1) / kDecTile)), kDecThreads, 0, stream>>>(p, -1);
         ++n;
     } else if (p.early_factor > 2) {
         const int tiles = min(4096, (p.max_len0 + 255) / 256);
@@ -498,7 +509,7 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
     int len = p.max_len0;
     for (int level = 0; level + 1 < kCqOctaves; ++level) {
         len = (len + 1) >> 1;
-        decimate2_kernel<<<dim3(p.n_clips, min(65535, (len + kDecTile - 1) / kDecTile)), 256, 0, stream>>>(p, level);
+        decimate2_kernel<<<dim3(p.n_clips, min(65535, (len + kDecTile - 1) / kDecTile)), kDecThreads, 0, stream>>>(p, level);
         ++n;
     }
     if (launches) *launches += n;
