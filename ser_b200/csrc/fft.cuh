@@ -60,8 +60,26 @@ __host__ __device__ constexpr float sin64(int j) {
     return t[j & 31];
 }
 
-__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract: one packed FADD2 on the device (IEEE per half, so bit-identical to the
+// two scalar adds), which halves the issue slots of the butterflies
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && !defined(SERB_SCALAR_BUTTERFLIES)
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && !defined(SERB_SCALAR_BUTTERFLIES)
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 // a * (c - i s)   (forward twiddle e^(-i theta), c = cos theta, s = sin theta)
 __host__ __device__ __forceinline__ float2 cmul_conj_tw(float2 a, float c, float s) {
     return make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
