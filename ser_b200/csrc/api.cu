@@ -461,6 +461,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     op.tile_clip = d_tile_clip;
     op.frames = ip.frames;
     op.hann_sq = ctx->hann_sq.as<double>();
+    op.wss4 = reinterpret_cast<const float*>(ctx->hann_sq.as<double>() + 2048);
     op.yharm = ctx->yharm.as<float>();
     { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream)); }
     { ProfScope ps(ctx, 9, stream); SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream)); }
@@ -950,8 +951,18 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         for (size_t i = 0; i < taps.size(); ++i) taps32[i] = static_cast<float>(taps[i] * std::sqrt(2.0));
         CREATE_CHECK(configure_cqt(taps32.data()));
         hann_squared_2048(hsq);
-        CREATE_CHECK(ctx->hann_sq.reserve(hsq.size() * sizeof(double)));
+        // behind the 2048 doubles: the overlap-add's window sum of squares where four frames
+        // overlap, accumulated in frame order exactly as ola_sample does (float64 add, float32 store)
+        std::vector<float> wss4(kHop);
+        for (int r = 0; r < kHop; ++r) {
+            float wss = 0.0f;
+            for (int j = r + 3 * kHop; j >= r; j -= kHop) wss = static_cast<float>(static_cast<double>(wss) + hsq[j]);
+            wss4[r] = wss;
+        }
+        CREATE_CHECK(ctx->hann_sq.reserve(hsq.size() * sizeof(double) + wss4.size() * sizeof(float)));
         CREATE_CHECK(cudaMemcpy(ctx->hann_sq.ptr, hsq.data(), hsq.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CREATE_CHECK(cudaMemcpy(static_cast<char*>(ctx->hann_sq.ptr) + hsq.size() * sizeof(double), wss4.data(),
+                                wss4.size() * sizeof(float), cudaMemcpyHostToDevice));
         // constant-Q FFT twiddles: W_N^j = (cos, -sin) for N = 128..1024, then (cos, sin) 2 pi k / (2N)
         std::vector<float> tw;
         const double pi = 3.14159265358979323846;

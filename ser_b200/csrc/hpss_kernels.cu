@@ -322,8 +322,22 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(IstftParams p, int n_cols
 }
 
 // ---- overlap-add + window sum-of-squares ------------------------------------------------
-// one thread per output sample; the (at most four) frames are added in frame order in float32,
-// the squared windows in float64 rounded to float32 after each add, as librosa does
+// one thread per four consecutive output samples; the (at most four) frames are added in frame
+// order in float32, the squared windows in float64 rounded to float32 after each add, as librosa
+// does.  Where all four frames exist the window sum depends only on n mod 512 and comes from a
+// table built with the same arithmetic (wss4); the clip's first and last hops take the general
+// path sample by sample.
+__device__ __forceinline__ float ola_sample(const float* __restrict__ frames, const double* __restrict__ hann_sq,
+                                            int m, int t_lo, int t_hi) {
+    float acc = 0.0f, wss = 0.0f;
+    for (int t = t_lo; t <= t_hi; ++t) {
+        const int j = m - t * kHop;
+        acc += frames[static_cast<long long>(t) * kNFft + j];
+        wss = static_cast<float>(static_cast<double>(wss) + hann_sq[j]);
+    }
+    return wss > FLT_MIN ? acc / wss : acc;
+}
+
 __global__ void __launch_bounds__(256) ola_kernel(OlaParams p) {
     const TonClip clip = p.clips[p.tile_clip[blockIdx.x]];
     const int tile = blockIdx.x - clip.tile_base;
@@ -332,17 +346,29 @@ __global__ void __launch_bounds__(256) ola_kernel(OlaParams p) {
     float* y = p.yharm + clip.hoff;
     const int n_lo = tile * kColsPerTile * kHop;
     const int n_hi = min(n_lo + kColsPerTile * kHop, clip.length);
-    for (int n = n_lo + threadIdx.x; n < n_hi; n += blockDim.x) {
+    for (int n = n_lo + 4 * threadIdx.x; n < n_hi; n += 4 * blockDim.x) {
+        // the four samples n .. n + 3 see the same frames (n and the hop are multiples of four)
         const int m = n + kNFft / 2;
         const int t_hi = min(T - 1, m / kHop);
         const int t_lo = max(0, (m - (kNFft - 1) + kHop - 1) / kHop);
-        float acc = 0.0f, wss = 0.0f;
-        for (int t = t_lo; t <= t_hi; ++t) {
-            const int j = m - t * kHop;
-            acc += frames[static_cast<long long>(t) * kNFft + j];
-            wss = static_cast<float>(static_cast<double>(wss) + p.hann_sq[j]);
+        if (t_hi - t_lo == 3 && n + 3 < n_hi) {
+            const float* f = frames + static_cast<long long>(t_lo) * kNFft + (m - t_lo * kHop);
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float4 v = *reinterpret_cast<const float4*>(f + t * (kNFft - kHop));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const float4 w = *reinterpret_cast<const float4*>(p.wss4 + (m & (kHop - 1)));
+            float4 out;
+            out.x = w.x > FLT_MIN ? acc.x / w.x : acc.x;
+            out.y = w.y > FLT_MIN ? acc.y / w.y : acc.y;
+            out.z = w.z > FLT_MIN ? acc.z / w.z : acc.z;
+            out.w = w.w > FLT_MIN ? acc.w / w.w : acc.w;
+            *reinterpret_cast<float4*>(y + n) = out;
+        } else {
+            for (int i = 0; i < 4 && n + i < n_hi; ++i) y[n + i] = ola_sample(frames, p.hann_sq, m + i, t_lo, t_hi);
         }
-        y[n] = wss > FLT_MIN ? acc / wss : acc;
     }
 }
 

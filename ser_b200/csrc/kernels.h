@@ -150,6 +150,7 @@ struct OlaParams {
     const int* tile_clip;    // [tiles]
     const float* frames;
     const double* hann_sq;   // [2048] squared periodic Hann, float64
+    const float* wss4;       // [512] window sum of squares where four frames overlap (n mod 512)
     float* yharm;
 };
 cudaError_t configure_hpss();

@@ -62,18 +62,33 @@ __device__ float2 select_middle(const TuneParams& p, const ClipDev& clip, long l
             }
         }
         __syncthreads();
-        if (threadIdx.x < 2) {
-            const int j = threadIdx.x;
+        if (warp < 2) {
+            // warp j finds the bucket of rank j: eight buckets per lane, a warp scan of the lane
+            // sums, then the owning lane walks its eight (the smallest b with r < h[0] + .. + h[b])
+            const int j = warp;
             const unsigned* h = hist[(j == 1 && !same) ? 1 : 0];
-            long long r = (j == 0) ? rank_lo : rank_hi;
-            unsigned b = 0;
-            for (; b < 255; ++b) {
-                const unsigned c = h[b];
-                if (r < static_cast<long long>(c)) break;
-                r -= c;
+            const long long r = (j == 0) ? rank_lo : rank_hi;
+            unsigned c[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { c[k] = h[8 * lane + k]; sum += c[k]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
             }
-            shared_prefix[j] = ((j == 0) ? prefix0 : prefix1) | (b << shift);
-            shared_rank[j] = r;
+            const unsigned ballot = __ballot_sync(0xffffffffu, r < static_cast<long long>(incl));
+            const int owner = ballot ? __ffs(ballot) - 1 : 31;
+            if (lane == owner) {
+                long long rr = r - static_cast<long long>(incl - sum);
+                unsigned b = 0;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    if (b == static_cast<unsigned>(k) && rr >= static_cast<long long>(c[k])) { rr -= c[k]; ++b; }
+                }
+                shared_prefix[j] = ((j == 0) ? prefix0 : prefix1) | ((8u * lane + b) << shift);
+                shared_rank[j] = rr;
+            }
         }
         __syncthreads();
         prefix0 = shared_prefix[0];
