@@ -280,9 +280,12 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         // step B: 32-point DFT over n2; lane = (column g2, k1): v[k2] = Z[k1 + R k2]
         fft32(v);
         float2* xs = buf + g2 * (N + 1);
+        // in groups of four register indices (one warp-uniform branch per group, so that the
+        // twiddle loads and shuffles of a group are in flight together); the up to three surplus
+        // bins at either end are written and never read
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2) {
-            if (k2 < k2_lo || k2 > k2_hi) continue;        // warp-uniform
+            if ((k2 | 3) < k2_lo || (k2 & ~3) > k2_hi) continue;        // warp-uniform, same for a group of four
             float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
             float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
             if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
@@ -333,22 +336,28 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
                 }
             }
         }
-        if (lane < 4 * G) {
-            const int r = 32 + (lane & 3), g = lane >> 2;
+        {
+            // rows 32..35 for all G columns: every (row, column) is shared by P = 8 / G lanes that
+            // take every P-th basis value and add up with shuffles, so the whole warp stays busy
+            constexpr int P = 8 / G;
+            const int part = lane % P, rg = lane / P;
+            const int r = 32 + (rg & 3), g = rg >> 2;
             const CqRow row = sm.rows[r];
             const float2* b = sm.vals[r];
             const float2* x = buf + g * (N + 1) + row.start;
             float cr = 0.0f, ci = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < cmax; c += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float2 bv = b[c + u], xv = x[c + u];
-                    cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
-                    ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
-                }
+#pragma unroll 4
+            for (int c = part; c < cmax; c += P) {
+                const float2 bv = b[c], xv = x[c];
+                cr = fmaf(bv.x, xv.x, fmaf(-bv.y, xv.y, cr));
+                ci = fmaf(bv.x, xv.y, fmaf(bv.y, xv.x, ci));
             }
-            if (lc0 + g < n_here) {
+#pragma unroll
+            for (int o = P / 2; o > 0; o >>= 1) {
+                cr += __shfl_xor_sync(0xffffffffu, cr, o);
+                ci += __shfl_xor_sync(0xffffffffu, ci, o);
+            }
+            if (part == 0 && lc0 + g < n_here) {
                 float mag;
                 asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr, cr, ci * ci)));
                 p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mag * row.scale;
@@ -363,10 +372,12 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
 // per-clip reduction in tile order (tonnetz_final_kernel), so long clips spread over many CTAs
 // and every clip's result is independent of the batch around it
 __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
-    __shared__ float mags[4][256];
+    __shared__ __align__(16) float mags[8][256];
     __shared__ double phi[6][12];
-    __shared__ double part[4][6];
+    __shared__ double part[8][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, hl = lane & 15;      // one column per half warp
+    const int slot = 2 * warp + half;
     const TonClip clip = p.clips[blockIdx.x];
     const int t_lo = blockIdx.y * kTonTile;
     if (t_lo >= clip.cq_cols) return;
@@ -380,24 +391,33 @@ __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
         phi[q][c] = ((q < 4) ? 1.0 : 0.5) * cospi(vv);
     }
     __syncthreads();
-    double acc = 0.0;   // lanes 0..5: running sum of tonnetz row `lane`
-    for (int t = t_lo + warp; t < t_hi; t += 4) {
-        const float* row = p.cqmag + (static_cast<size_t>(clip.cq_base) + t) * kCqBins;
-        for (int i = lane; i < kCqBins; i += 32) mags[warp][i] = row[i];
+    // chroma c <- constant-Q bins 36 o + fold[j], j = 0..2 (filters.cq_to_chroma, bins_per_octave 36)
+    int fold[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) fold[j] = (3 * min(hl, 11) - 1 + j + 36) % 36;
+    double acc = 0.0;   // lanes 0..5 of each half: running sum of tonnetz row `hl` over the half's columns
+    for (int tb = t_lo + 2 * warp; tb < t_hi; tb += 8) {
+        const int t = tb + half;
+        const bool valid = t < t_hi;
+        // one row of 252 magnitudes = 63 16-byte pieces
+        const float4* row = reinterpret_cast<const float4*>(p.cqmag + (static_cast<size_t>(clip.cq_base) + (valid ? t : tb)) * kCqBins);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (hl + 16 * i < kCqBins / 4) reinterpret_cast<float4*>(mags[slot])[hl + 16 * i] = row[hl + 16 * i];
         __syncwarp();
-        // filters.cq_to_chroma(252, bins_per_octave=36): chroma c <- bins 36 o + ((3c - 1 + j) mod 36)
         float ch = 0.0f;
-        if (lane < 12) {
+        if (hl < 12) {
+#pragma unroll
             for (int o = 0; o < kCqOctaves; ++o)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) ch += mags[warp][36 * o + (3 * lane - 1 + j + 36) % 36];
+                for (int j = 0; j < 3; ++j) ch += mags[slot][36 * o + fold[j]];
         }
         __syncwarp();
         // util.normalize(norm=inf) then util.normalize(norm=1): float32 values, float64 lengths
         float mx = ch;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        // lanes 12..15 hold 0, which never wins a max of non-negative values
+        // lanes 12..15 of a half hold 0, which never wins a max of non-negative values
         double len_inf = static_cast<double>(mx);
         if (len_inf < static_cast<double>(FLT_MIN)) len_inf = 1.0;
         const float cn = static_cast<float>(static_cast<double>(ch) / len_inf);
@@ -409,16 +429,19 @@ __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
         double proj = 0.0;
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
-            const double cv = static_cast<double>(__shfl_sync(0xffffffffu, c1, c));
-            if (lane < 6) proj = fma(phi[lane][c], cv, proj);
+            const double cv = static_cast<double>(__shfl_sync(0xffffffffu, c1, 16 * half + c));
+            if (hl < 6) proj = fma(phi[hl][c], cv, proj);
         }
-        acc += proj;
+        if (valid) acc += proj;
     }
-    if (lane < 6) part[warp][lane] = acc;
+    if (hl < 6) part[slot][hl] = acc;
     __syncthreads();
-    if (threadIdx.x < 6)
-        p.ton_part[(static_cast<size_t>(clip.part_base) + blockIdx.y) * 6 + threadIdx.x] =
-            part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+    if (threadIdx.x < 6) {
+        double total = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) total += part[i][threadIdx.x];
+        p.ton_part[(static_cast<size_t>(clip.part_base) + blockIdx.y) * 6 + threadIdx.x] = total;
+    }
 }
 
 __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
