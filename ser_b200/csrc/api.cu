@@ -454,6 +454,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     // 3. inverse STFT + overlap-add
     IstftParams ip{};
     ip.cspec = ctx->cspec.as<float2>();
+    ip.mask = ctx->perc.as<float>();
     ip.tables = ctx->tables.as<float2>();
     ip.frames = ctx->frames.as<float>();
     OlaParams op{};

@@ -5,9 +5,9 @@
 //   SURVEY.md Appendix A.7-A.8; oracle: oracle/shim/librosa/effects.py, core.py istft).
 //
 // hpss_perc_kernel  median of 31 along frequency (scipy.ndimage.median_filter, mode="reflect")
-// hpss_harm_kernel  median of 31 along time, then the soft mask (power 2, split_zeros) applied
-//                   to the complex spectrum in place
-// istft_kernel      inverse 2048-point real FFT per warp, Hann window -> frames
+// hpss_harm_kernel  median of 31 along time, then the soft mask (power 2, split_zeros), written
+//                   over the frequency median
+// istft_kernel      (S * mask) * phase, inverse 2048-point real FFT per warp, Hann window -> frames
 // ola_kernel        overlap-add in frame order / window sum-of-squares -> harmonic signal
 //
 // The medians are computed eight positions at a time.  The eight windows of 31 share a core of
@@ -120,7 +120,8 @@ __device__ __forceinline__ float harm_mask(float h, float q) {
 // ---- median along time -----------------------------------------------------------------
 // one thread per (segment of seg_len columns, bin); bins are contiguous across the warp, so
 // every load / store is a coalesced 128-byte row piece.  Runs after hpss_perc_kernel: with both
-// medians in hand it applies the soft mask to the complex spectrum in place.
+// medians in hand it overwrites the frequency median with the soft mask (12 bytes of traffic per
+// bin; istft_kernel applies the mask to the complex spectrum as it loads it).
 __global__ void __launch_bounds__(256, 3) hpss_harm_kernel(HpssParams p) {
     const int2 seg = p.segs[blockIdx.x];
     const TonClip clip = p.clips[seg.x];
@@ -130,8 +131,7 @@ __global__ void __launch_bounds__(256, 3) hpss_harm_kernel(HpssParams p) {
     const int t0 = seg.y;
     const int t1 = min(t0 + p.seg_len, T);
     const float* src = p.mag + static_cast<long long>(clip.col_base) * kSpillStride + f;
-    const float* perc = p.perc + static_cast<long long>(clip.col_base) * kSpillStride + f;
-    float2* spec = p.cspec + static_cast<long long>(clip.col_base) * kSpillStride + f;
+    float* perc = p.perc + static_cast<long long>(clip.col_base) * kSpillStride + f;   // in: median along frequency; out: the mask
     const float one = p.one;
     const bool wide = T > 30;           // one reflection reaches every offset of a block and of the look-ahead
     auto at = [&](int t) -> float {
@@ -150,22 +150,13 @@ __global__ void __launch_bounds__(256, 3) hpss_harm_kernel(HpssParams p) {
 #pragma unroll
         for (int k = 0; k < kMedBlock; ++k) fresh[k] = at(t + kMedBlock + 15 + k);
         float pq[kMedBlock];
-        float2 xs[kMedBlock];
 #pragma unroll
-        for (int j = 0; j < kMedBlock; ++j) {
-            const long long o = static_cast<long long>(min(t + j, t1 - 1)) * kSpillStride;
-            pq[j] = perc[o];
-            xs[j] = spec[o];
-        }
+        for (int j = 0; j < kMedBlock; ++j) pq[j] = perc[static_cast<long long>(min(t + j, t1 - 1)) * kSpillStride];
         float med[kMedBlock];
         bm.medians(one, med);
 #pragma unroll
-        for (int j = 0; j < kMedBlock; ++j) {
-            if (t + j < t1) {
-                const float m = harm_mask(med[j], pq[j]);
-                spec[static_cast<long long>(t + j) * kSpillStride] = make_float2(xs[j].x * m, xs[j].y * m);   // (S * mask) * phase
-            }
-        }
+        for (int j = 0; j < kMedBlock; ++j)
+            if (t + j < t1) perc[static_cast<long long>(t + j) * kSpillStride] = harm_mask(med[j], pq[j]);
     }
 }
 
@@ -260,19 +251,22 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(IstftParams p, int n_cols
     float2* buf = sm.buf[warp];
     const int n_warps = gridDim.x * 8;
     for (int col = blockIdx.x * 8 + warp; col < n_cols; col += n_warps) {
-        const float2* X = p.cspec + static_cast<long long>(col) * kSpillStride;   // already masked
-        // masked spectrum, k = 32 n1 + lane, kept in registers and mirrored in shared memory so
-        // that the partner X[1024 - k] is one conflict-free load away
+        const float2* X = p.cspec + static_cast<long long>(col) * kSpillStride;
+        const float* M = p.mask + static_cast<long long>(col) * kSpillStride;
+        // masked spectrum (S * mask) * phase, k = 32 n1 + lane, kept in registers and mirrored in
+        // shared memory so that the partner X[1024 - k] is one conflict-free load away
         float2 v[32];
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
             const int k = 32 * n1 + lane;
-            v[n1] = X[k];
+            const float2 x = X[k];
+            const float m = M[k];
+            v[n1] = make_float2(x.x * m, x.y * m);
             buf[n1 * 33 + lane] = v[n1];
         }
         float nyq = 0.0f;   // X[1024] (real)
         if (lane == 0) {
-            nyq = X[1024].x;
+            nyq = X[1024].x * M[1024];
             v[0].y = 0.0f;   // irfft ignores the imaginary part of the DC bin
         }
         __syncwarp();

@@ -141,7 +141,8 @@ struct HpssParams {
     float2* cspec;           // [cols][kSpillStride] X, masked in place by hpss_harm_kernel
 };
 struct IstftParams {
-    const float2* cspec;     // [cols][kSpillStride] masked X
+    const float2* cspec;     // [cols][kSpillStride] X
+    const float* mask;       // [cols][kSpillStride] soft mask (hpss_harm_kernel's output)
     const float2* tables;    // FFT twiddles (same layout as StftParams::tables)
     float* frames;           // [cols][2048] windowed inverse-FFT frames
 };
