@@ -29,7 +29,7 @@ __device__ __forceinline__ float value_of(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-constexpr int kTuneCache = 10240;   // peak magnitudes cached in shared memory (40 KB)
+constexpr int kTuneCache = 6144;    // peak magnitudes cached in shared memory (24 KB: eight CTAs per SM)
 
 // The two middle order statistics (0-based ranks rank_lo <= rank_hi <= rank_lo + 1) in one 4-pass
 // radix select; every thread returns the same pair.  While both ranks still fall in the same
@@ -100,7 +100,7 @@ __device__ float2 select_middle(const TuneParams& p, const ClipDev& clip, long l
     return make_float2(value_of(prefix0), value_of(prefix1));
 }
 
-__global__ void __launch_bounds__(kTuneThreads) tuning_kernel(TuneParams p) {
+__global__ void __launch_bounds__(kTuneThreads, 8) tuning_kernel(TuneParams p) {
     __shared__ float cache[kTuneCache];
     __shared__ unsigned hist[2][256];
     __shared__ unsigned s_prefix[2];
