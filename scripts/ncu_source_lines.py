@@ -6,12 +6,12 @@ rows = list(csv.reader(out.splitlines()))
 # find header
 hi = next(i for i,r in enumerate(rows) if r and r[0]=="Line No")
 hdr = rows[hi]
-si = hdr.index("# Samples"); ii = hdr.index("Instructions Executed"); wi = hdr.index("L1 Wavefronts Shared")
+si = hdr.index("# Samples"); ii = hdr.index("Instructions Executed"); wi = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
 lines=[]
 for r in rows[hi+1:]:
     if len(r) <= si: continue
     if r[0] != "":   # source line aggregate row
-        try: lines.append((int(r[si]), int(r[ii]), int(r[wi] or 0), r[0], r[1][:110]))
+        try: lines.append((int(r[si]), int(r[ii]), (int(r[wi] or 0) if wi is not None else 0), r[0], r[1][:110]))
         except ValueError: pass
 tot = sum(l[0] for l in lines); toti = sum(l[1] for l in lines); totw = sum(l[2] for l in lines)
 print("total samples", tot, "instr", toti, "smem wavefronts", totw)
