@@ -233,7 +233,7 @@ def run_reference(args) -> None:
         "note": "librosa 0.11.0 is not installable here (SURVEY.md F2): this is the CPU restatement "
                 "(oracle/) of the reference's librosa+sklearn path, one process per host core",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -430,12 +430,37 @@ def run_b200(args) -> None:
             "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "slice_187d": slice187,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     multi_gpu.destroy_process_group(info)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    """stdout must carry exactly one JSON line.  Libraries write banners straight to file
+    descriptor 1 (NCCL's version line; NCCL_DEBUG_FILE=/dev/stderr does not hold when stderr is a
+    redirected file or a socket), so the real stdout is set aside for the result and descriptor 1
+    is pointed at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -220,13 +220,27 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
          std::vector<Chunk>& chunks) {
     // host entries stream the waveform in while the chain runs: small first chunks let compute start
     // after a few megabytes have landed, later chunks grow to the full size the kernels like
+    long long total_cols = 0, consumed_cols = 0;     // STFT columns of the main path: all, and in finished chunks
+    if (starts && lengths)
+        for (long long i = 0; i < n_clips; ++i)
+            if (lengths[i] >= kNFft) total_cols += 1 + lengths[i] / kHop;
     auto chunk_limit = [&](size_t index) -> int {
-        if (!ctx->ramp_chunks) return ctx->chunk_cols;
-        // H2D from pinned memory runs about three times faster than the chain consumes columns, so
-        // each chunk may be three times the previous one without starving
-        long long ramp = 16384;
-        for (size_t i = 0; i < std::min<size_t>(index, 6); ++i) ramp *= 3;
-        return static_cast<int>(std::min<long long>(ctx->chunk_cols, ramp));
+        long long limit = ctx->chunk_cols;
+        if (ctx->ramp_chunks) {
+            // H2D from pinned memory runs about three times faster than the chain consumes columns, so
+            // each chunk may be three times the previous one without starving
+            long long ramp = 16384;
+            for (size_t i = 0; i < std::min<size_t>(index, 6); ++i) ramp *= 3;
+            limit = std::min(limit, ramp);
+        }
+        if (limit >= ctx->chunk_cols) {
+            // full-size chunks share what is left evenly, so the last one is not a sliver whose twenty
+            // launches run mostly empty
+            const long long left = std::max<long long>(1, total_cols - consumed_cols);
+            const long long n = (left + ctx->chunk_cols - 1) / ctx->chunk_cols;
+            limit = std::min<long long>(limit, (left + n - 1) / n);
+        }
+        return static_cast<int>(limit);
     };
     if (sr <= 0) return fail(ctx, SERB_ERR_SAMPLE_RATE, "Sample rate must be a positive integer.");
     if (n_clips < 0 || (n_clips > 0 && (!starts || !lengths))) return fail(ctx, SERB_ERR_INVALID_ARG, "bad clip arrays");
@@ -250,6 +264,7 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
         c.out_row = static_cast<int>(i);
         const int tiles = (c.n_cols + kColsPerTile - 1) / kColsPerTile;
         if (cur.clip_hi > cur.clip_lo && cur.n_cols + c.n_cols > chunk_limit(chunks.size())) {
+            consumed_cols += cur.n_cols;
             chunks.push_back(cur);
             cur = Chunk{cur.clip_hi, cur.clip_hi, 0, 0, 0};
         }
