@@ -146,17 +146,36 @@ __global__ void __launch_bounds__(256, 3) hpss_harm_kernel(HpssParams p) {
     for (int t = t0; t < t1; t += kMedBlock) {
         bm.advance(fresh);
         // everything the block and its successor need from memory is requested before the sorting
-        // work, so it is in registers by the time the medians are
-#pragma unroll
-        for (int k = 0; k < kMedBlock; ++k) fresh[k] = at(t + kMedBlock + 15 + k);
+        // work, so it is in registers by the time the medians are.  Away from the clip's end the
+        // rows are addressed straight off one base pointer (immediate offsets): the reflection and
+        // clamp arithmetic of the general path is integer work on the same ALU pipe the min/max
+        // instructions saturate.
+        const bool interior = (t + 2 * kMedBlock + 15 <= T) && (t + kMedBlock <= t1);    // warp-uniform
         float pq[kMedBlock];
+        if (interior) {
+            const float* s_row = src + static_cast<long long>(t + kMedBlock + 15) * kSpillStride;
+            const float* p_row = perc + static_cast<long long>(t) * kSpillStride;
 #pragma unroll
-        for (int j = 0; j < kMedBlock; ++j) pq[j] = perc[static_cast<long long>(min(t + j, t1 - 1)) * kSpillStride];
+            for (int k = 0; k < kMedBlock; ++k) fresh[k] = s_row[k * kSpillStride];
+#pragma unroll
+            for (int j = 0; j < kMedBlock; ++j) pq[j] = p_row[j * kSpillStride];
+        } else {
+#pragma unroll
+            for (int k = 0; k < kMedBlock; ++k) fresh[k] = at(t + kMedBlock + 15 + k);
+#pragma unroll
+            for (int j = 0; j < kMedBlock; ++j) pq[j] = perc[static_cast<long long>(min(t + j, t1 - 1)) * kSpillStride];
+        }
         float med[kMedBlock];
         bm.medians(one, med);
+        if (interior) {
+            float* p_row = perc + static_cast<long long>(t) * kSpillStride;
 #pragma unroll
-        for (int j = 0; j < kMedBlock; ++j)
-            if (t + j < t1) perc[static_cast<long long>(t + j) * kSpillStride] = harm_mask(med[j], pq[j]);
+            for (int j = 0; j < kMedBlock; ++j) p_row[j * kSpillStride] = harm_mask(med[j], pq[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kMedBlock; ++j)
+                if (t + j < t1) perc[static_cast<long long>(t + j) * kSpillStride] = harm_mask(med[j], pq[j]);
+        }
     }
 }
 
