@@ -166,10 +166,11 @@ __device__ __forceinline__ void fft_small(float2* v) {
 
 constexpr size_t kCqtMaxSmem = 227 * 1024;   // dynamic shared memory every instantiation is opted in to
 constexpr int kCqtWarps = 8;
+constexpr int kCqtBufPitch = 34;              // float2 pitch of the transpose buffer: 16-byte aligned rows 272 bytes apart
 constexpr int kCqtValPitch = kCqRowCap + 1;   // float2 pitch of a staged basis row (bank spread)
 
 struct CqtSmemHead {
-    float2 buf[kCqtWarps][32 * 33];           // per-warp transpose buffer, then the column spectra
+    float2 buf[kCqtWarps][32 * kCqtBufPitch]; // per-warp transpose buffer, then the column spectra
     float2 vals[kCqRows][kCqtValPitch];       // sparse basis rows of this (tuning, octave)
     CqRow rows[kCqRows];
     int cmax;                                 // widest staged row, rounded up to a multiple of four
@@ -271,11 +272,15 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
                     const float2 w = twa[lane * q];
                     y = make_float2(fmaf(y.x, w.x, -y.y * w.y), fmaf(y.x, w.y, y.y * w.x));
                 }
-                buf[(g * R + q) * 33 + lane] = y;
+                buf[(g * R + q) * kCqtBufPitch + lane] = y;
             }
         __syncwarp();
 #pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[lane * 33 + n2];
+        for (int n2 = 0; n2 < 32; n2 += 2) {     // conflict-free 16-byte loads
+            const float4 q2 = *reinterpret_cast<const float4*>(&buf[lane * kCqtBufPitch + n2]);
+            v[n2] = make_float2(q2.x, q2.y);
+            v[n2 + 1] = make_float2(q2.z, q2.w);
+        }
         __syncwarp();
         // step B: 32-point DFT over n2; lane = (column g2, k1): v[k2] = Z[k1 + R k2]
         fft32(v);
