@@ -454,7 +454,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
         { ProfScope ps(ctx, 0, stream); SERB_CUDA(ctx, launch_stft(sp, c.n_tiles, stream)); }
         ctx->launches += 1;
     }
-    // 2. HPSS medians; the time median applies the soft mask to X in place
+    // 2. HPSS medians; the time median leaves the soft mask in ctx->perc
     HpssParams hp{};
     hp.clips = d_clips;
     hp.segs = ctx->ton_segs.as<int2>() + c.seg_lo;

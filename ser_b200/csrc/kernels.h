@@ -138,7 +138,7 @@ struct HpssParams {
     float one;               // 1.0f, passed at run time so the predicated multiply-by-one of the median update stays a multiply
     const float* mag;        // [cols][kSpillStride] |X|
     float* perc;             // [cols][kSpillStride] median along frequency
-    float2* cspec;           // [cols][kSpillStride] X, masked in place by hpss_harm_kernel
+    float2* cspec;           // [cols][kSpillStride] X (not touched by the median kernels)
 };
 struct IstftParams {
     const float2* cspec;     // [cols][kSpillStride] X
