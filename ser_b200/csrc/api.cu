@@ -73,6 +73,8 @@ struct serb_ctx {
     std::string err;
     long long launches = 0;
     int chunk_cols = 262144;
+    int ramp_start = 32768;     // first chunk of a host-buffer call (SERB_RAMP_START), then x ramp_factor_x10 / 10 per chunk
+    int ramp_factor_x10 = 30;   // SERB_RAMP_FACTOR_X10
     bool ramp_chunks = false;   // set by the host-buffer entries for the duration of one call
     float last_ms = 0.f;
     bool timed = false;
@@ -229,8 +231,8 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
         if (ctx->ramp_chunks) {
             // H2D from pinned memory runs about three times faster than the chain consumes columns, so
             // each chunk may be three times the previous one without starving
-            long long ramp = 16384;
-            for (size_t i = 0; i < std::min<size_t>(index, 6); ++i) ramp *= 3;
+            long long ramp = ctx->ramp_start;
+            for (size_t i = 0; i < std::min<size_t>(index, 12) && ramp < ctx->chunk_cols; ++i) ramp = ramp * ctx->ramp_factor_x10 / 10;
             limit = std::min(limit, ramp);
         }
         if (limit >= ctx->chunk_cols) {
@@ -944,6 +946,8 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         if (v >= 64) ctx->chunk_cols = v;
     }
     if (const char* env = std::getenv("SERB_HARM_SEG")) { const int v = std::atoi(env); if (v >= 16) ctx->harm_seg = v; }
+    if (const char* env = std::getenv("SERB_RAMP_START")) { const int v = std::atoi(env); if (v >= 1024) ctx->ramp_start = v; }
+    if (const char* env = std::getenv("SERB_RAMP_FACTOR_X10")) { const int v = std::atoi(env); if (v >= 11 && v <= 100) ctx->ramp_factor_x10 = v; }
     ctx->timed = true;
 #define CREATE_CHECK(call)                                                                     \
     do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { int rc2 = fail_cuda(nullptr, e2, #call); delete ctx; return rc2; } } while (0)
