@@ -294,14 +294,14 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
             float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
             float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
             if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
-            const float ax = v[k2].x, ay = v[k2].y;
-            const float ex = ax + px, ey = ay - py;
-            const float ox = ay + py, oy = px - ax;        // -i (A - conj P)
+            // E = A + conj P, D = A - conj P as two packed adds; O = -i D = (D.y, -D.x)
+            const float2 pc = make_float2(px, -py);
+            const float2 e = cadd(v[k2], pc), d = csub(v[k2], pc);
             const int k = k1 + R * k2;
             const float2 w = twb[k];
-            const float wx = fmaf(w.x, ox, w.y * oy);
-            const float wy = fmaf(w.x, oy, -w.y * ox);
-            xs[k] = make_float2(0.5f * (ex + wx), 0.5f * (ey + wy));
+            const float wx = fmaf(w.x, d.y, -(w.y * d.x));     // w.x O.x + w.y O.y
+            const float wy = fmaf(w.x, -d.x, -(w.y * d.y));    // w.x O.y - w.y O.x
+            xs[k] = cscale(cadd(e, make_float2(wx, wy)), 0.5f);
         }
         // Nyquist bin X[N] = Re Z[0] - Im Z[0], only if a row reaches it (sample rates whose top
         // wavelet sits right under the Nyquist frequency)

@@ -80,6 +80,17 @@ __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
     return make_float2(a.x - b.x, a.y - b.y);
 #endif
 }
+// a * s on both halves: one packed FMUL2 on the device
+__host__ __device__ __forceinline__ float2 cscale(float2 a, float s) {
+#if defined(__CUDA_ARCH__) && !defined(SERB_SCALAR_BUTTERFLIES)
+    unsigned long long d;
+    const float2 ss = make_float2(s, s);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&ss)));
+    return *reinterpret_cast<float2*>(&d);
+#else
+    return make_float2(a.x * s, a.y * s);
+#endif
+}
 // a * (c - i s)   (forward twiddle e^(-i theta), c = cos theta, s = sin theta)
 __host__ __device__ __forceinline__ float2 cmul_conj_tw(float2 a, float c, float s) {
     return make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
