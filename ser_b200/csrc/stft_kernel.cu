@@ -129,20 +129,21 @@ __device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[
         float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
         float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
         if (lane == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
-        const float ax = v[k2].x, ay = v[k2].y;
-        const float ex = ax + px, ey = ay - py;
-        const float ox = ay + py, oy = px - ax;       // -i (A - conj P)
+        // E = A + conj P, D = A - conj P as two packed adds; O = -i D = (D.y, -D.x)
+        const float2 pc = make_float2(px, -py);
+        const float2 e = cadd(v[k2], pc), d = csub(v[k2], pc);
         const float2 w = tw2[lane + 32 * k2];          // (cos, sin) of 2 pi k / 2048
-        const float wx = fmaf(w.x, ox, w.y * oy);
-        const float wy = fmaf(w.x, oy, -w.y * ox);
-        const float xr = ex + wx, xi = ey + wy;
+        const float wx = fmaf(w.x, d.y, -(w.y * d.x));     // w.x O.x + w.y O.y
+        const float wy = fmaf(w.x, -d.x, -(w.y * d.y));    // w.x O.y - w.y O.x
+        const float2 x2 = cadd(e, make_float2(wx, wy));
+        const float xr = x2.x, xi = x2.y;
         const float mag = 0.5f * sqrt_approx(fmaf(xr, xr, xi * xi));
-        if (crow) crow[lane + 32 * k2] = make_float2(0.5f * xr, 0.5f * xi);
+        if (crow) crow[lane + 32 * k2] = cscale(x2, 0.5f);
         if (row) row[lane + 32 * k2] = mag;
         sbuf[lane + 32 * k2] = mag;
         cmax = fmaxf(cmax, mag);
         if (k2 == 0 && lane == 0) {
-            const float nr = ex - wx, ni = ey - wy;
+            const float nr = e.x - wx, ni = e.y - wy;
             const float nyq = 0.5f * sqrt_approx(fmaf(nr, nr, ni * ni));
             if (crow) crow[1024] = make_float2(0.5f * nr, 0.5f * ni);
             if (row) row[1024] = nyq;
