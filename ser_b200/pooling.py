@@ -17,37 +17,44 @@ from . import _native
 from .backend import EncodedSequence, PoolingWindow, overlap_frame_mask
 
 
+def _positive_finite(value: float, name: str) -> float:
+    value = float(value)
+    if not (value > 0.0 and np.isfinite(value)):
+        raise ValueError(f"{name} must be a positive finite float.")
+    return value
+
+
 def temporal_pooling_windows(encoded: EncodedSequence, *, window_size_seconds: float,
                              window_stride_seconds: float) -> list[PoolingWindow]:
-    """Ordered pooling windows covering the encoded timeline (windowing.py:10-71)."""
-    if window_size_seconds <= 0.0 or not np.isfinite(window_size_seconds):
-        raise ValueError("window_size_seconds must be a positive finite float.")
-    if window_stride_seconds <= 0.0 or not np.isfinite(window_stride_seconds):
-        raise ValueError("window_stride_seconds must be a positive finite float.")
-    clip_start = float(encoded.frame_start_seconds[0])
-    clip_end = float(encoded.frame_end_seconds[-1])
-    clip_duration = clip_end - clip_start
-    if clip_duration <= 0.0:
+    """Pooling windows over the encoded timeline, same values as the reference's generator
+    (ser/_internal/pool/windowing.py:10-71) computed in closed form.
+
+    The reference walks a cursor (``cursor += stride``) while a whole window still fits; here the
+    window starts are one sequential ``np.add.accumulate`` over ``[t0, stride, stride, ...]`` (the
+    same left-to-right float64 sums, hence bit-identical starts), cut where ``start + size`` leaves
+    the timeline by more than 1e-9, plus the reference's single tail rule: if the last regular
+    window ends short of the timeline, one window of the same size is anchored at its end."""
+    size = _positive_finite(window_size_seconds, "window_size_seconds")
+    stride = _positive_finite(window_stride_seconds, "window_stride_seconds")
+    t0 = float(encoded.frame_start_seconds[0])
+    t1 = float(encoded.frame_end_seconds[-1])
+    if not t1 - t0 > 0.0:
         raise ValueError("Encoded sequence duration must be positive.")
-    effective_window = min(window_size_seconds, clip_duration)
-    if np.isclose(effective_window, clip_duration):
-        return [PoolingWindow(start_seconds=clip_start, end_seconds=clip_end)]
-    windows: list[PoolingWindow] = []
-    epsilon = 1e-9
-    cursor = clip_start
-    while cursor + effective_window <= clip_end + epsilon:
-        end = min(clip_end, cursor + effective_window)
-        windows.append(PoolingWindow(start_seconds=cursor, end_seconds=end))
-        cursor += window_stride_seconds
-    if not windows:
-        return [PoolingWindow(start_seconds=max(clip_start, clip_end - effective_window), end_seconds=clip_end)]
-    if windows[-1].end_seconds < clip_end - epsilon:
-        tail = PoolingWindow(start_seconds=max(clip_start, clip_end - effective_window), end_seconds=clip_end)
-        previous = windows[-1]
-        if not (np.isclose(previous.start_seconds, tail.start_seconds)
-                and np.isclose(previous.end_seconds, tail.end_seconds)):
-            windows.append(tail)
-    return windows
+    span = min(size, t1 - t0)
+    if np.isclose(span, t1 - t0):                      # one window spans the whole recording
+        return [PoolingWindow(start_seconds=t0, end_seconds=t1)]
+    slack = 1e-9
+    upper = int(max(0.0, (t1 - t0 - span + slack) / stride)) + 2      # no more starts than this fit
+    starts = np.add.accumulate(np.concatenate(([t0], np.full(upper, stride, dtype=np.float64))))
+    starts = starts[: int(np.count_nonzero(np.logical_and.accumulate(starts + span <= t1 + slack)))]
+    ends = np.minimum(t1, starts + span)
+    anchored = (max(t0, t1 - span), t1)
+    pairs = list(zip(starts.tolist(), ends.tolist()))
+    if not pairs:
+        pairs = [anchored]
+    elif pairs[-1][1] < t1 - slack and not (np.isclose(pairs[-1][0], anchored[0]) and np.isclose(pairs[-1][1], anchored[1])):
+        pairs.append(anchored)
+    return [PoolingWindow(start_seconds=a, end_seconds=b) for a, b in pairs]
 
 
 def frame_ranges(encoded: EncodedSequence, windows: Sequence[PoolingWindow]) -> tuple[NDArray[np.int32], NDArray[np.int32]]:

@@ -60,6 +60,25 @@ def main() -> None:
         names.append(name)
         print(name, emb.shape, len(windows), payload[f"{name}/mean_std"].shape)
     payload["names"] = np.asarray(names)
+    # window generation only: 400 random (timeline, size, stride) configurations -> flattened windows
+    cfg, flat, counts = [], [], []
+    for _ in range(400):
+        n = int(rng.integers(1, 40))
+        t0 = float(rng.choice([0.0, rng.random() * 5]))
+        step = float(rng.choice([1.0, 0.02, rng.random() + 0.01]))
+        flen = float(rng.choice([step, 3 * step, 0.025]))
+        size = float(rng.choice([0.1, 0.5, 1.0, 3.0, rng.random() * 4 + 1e-3, (n - 1) * step + flen]))
+        stride = float(rng.choice([0.1, 0.25, 1.0, rng.random() * 2 + 1e-3]))
+        starts = t0 + np.arange(n) * step
+        encoded = EncodedSequence(embeddings=np.zeros((n, 1), np.float32), frame_start_seconds=starts,
+                                  frame_end_seconds=starts + flen, backend_id="handcrafted")
+        windows = temporal_pooling_windows(encoded, window_size_seconds=size, window_stride_seconds=stride)
+        cfg.append([n, t0, step, flen, size, stride])
+        counts.append(len(windows))
+        flat.extend((w.start_seconds, w.end_seconds) for w in windows)
+    payload["random_windows/config"] = np.asarray(cfg, dtype=np.float64)
+    payload["random_windows/counts"] = np.asarray(counts, dtype=np.int64)
+    payload["random_windows/bounds"] = np.asarray(flat, dtype=np.float64)
     np.savez_compressed(OUT / "pooling_golden.npz", **payload)
 
 
