@@ -15,12 +15,14 @@ from .util import ParameterError
 def _median_filter_reflect(S, width, *, axis):
     """scipy.ndimage.median_filter(S, size=<width along axis>, mode="reflect").
 
-    librosa calls scipy directly.  When the axis is shorter than the kernel (clips under
-    ~31 STFT columns) scipy 1.18.1's 1-D rank filter reads uninitialised memory and returns
-    run-to-run different values, NaN included (observed here on a 1025x3 Fortran-ordered
-    input), so that case is restated explicitly with scipy's documented "reflect" extension
-    (d c b a | a b c d | d c b a, periodic with period 2n).  For axes at least as long as the
-    kernel the two are bit-identical (tests/test_oracle_crosscheck.py) and scipy is used.
+    librosa calls scipy directly.  When the axis is much shorter than the kernel scipy 1.18.1's
+    1-D rank filter is unreliable in this image: for 2-column (sometimes 3-column) spectrograms it
+    returns run-to-run different values, NaN included (about 1 trial in 17 in
+    tests/test_oracle_crosscheck.py::test_scipy_short_axis_median_instability_...; stable and
+    equal to this restatement otherwise), so axes shorter than the kernel are restated explicitly
+    with scipy's documented "reflect" extension (d c b a | a b c d | d c b a, period 2n).  For
+    axes at least as long as the kernel the two are bit-identical (same test file) and scipy
+    itself is used.
     """
     n = S.shape[axis]
     if n >= width:
