@@ -108,6 +108,36 @@ int serb_features_host_clips(serb_ctx* ctx, const float* const* h_clips, const i
                              int64_t n_clips, int32_t sample_rate, uint32_t flag_bits, float* h_out);
 
 /*
+ * serb_features_device only enqueues; this synchronises `stream` (NULL = ctx's own) and reports what
+ * the chain found: SERB_ERR_NOT_FINITE ("Audio buffer is not finite everywhere.", dsp.py:94-95)
+ * when any staged sample was NaN/Inf -- the rows are garbage then -- else SERB_OK.  The host
+ * entries do this check themselves.  Scratch is per context: launch chains issued on different
+ * streams of one context are ordered after one another by the library.
+ */
+int serb_features_device_check(serb_ctx* ctx, void* stream);
+
+/*
+ * The same ragged batch straight from PCM16 files: file f is h_files[f], a buffer
+ * of file_frames[f] frames x file_channels[f] interleaved int16 (file_channels NULL = all mono).
+ * The device does what ser/_internal/utils/audio_utils.py:28-60 `_prepare_audio_buffer` does after
+ * librosa.load / soundfile decode PCM16 -- float32 x / 32768, channel mean, whole-FILE peak
+ * normalisation x / max|x| (an all-zero file stays zero) -- bit-identically, so the host ships
+ * 2 bytes per sample.  Clip i is frames [clip_starts[i], clip_starts[i] + clip_lengths[i]) of
+ * file clip_file[i]; clip_file must be non-decreasing.  Files contiguous in host memory are
+ * copied as one transfer; copies of later files overlap the kernels of earlier chunks.
+ * serb_infer_host_pcm16 adds the classifier (h_features may be NULL).
+ */
+int serb_features_host_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames,
+                             const int32_t* file_channels, int64_t n_files, const int64_t* clip_file,
+                             const int64_t* clip_starts, const int64_t* clip_lengths, int64_t n_clips,
+                             int32_t sample_rate, uint32_t flag_bits, float* h_out);
+int serb_infer_host_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames,
+                          const int32_t* file_channels, int64_t n_files, const int64_t* clip_file,
+                          const int64_t* clip_starts, const int64_t* clip_lengths, int64_t n_clips,
+                          int32_t sample_rate, uint32_t flag_bits, float* h_features, double* h_proba,
+                          int32_t* h_label_index);
+
+/*
  * Classifier weights (float64, row-major as sklearn stores them):
  * mean/scale [n_in], w1 [n_in x n_hidden], b1 [n_hidden], w2 [n_hidden x n_out], b2 [n_out].
  * n_out is the width of the output layer (1 for sklearn's binary logistic case).
@@ -154,6 +184,11 @@ int serb_pool_frames_host(serb_ctx* ctx, const float* h_embeddings, int64_t n_fr
 /* mono PCM16 -> float32 (x / 32768) peak-normalised over the whole buffer, on the device */
 int serb_prepare_pcm16_host(serb_ctx* ctx, const int16_t* h_pcm, int64_t n, float* h_out);
 int serb_prepare_pcm16_device(serb_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out, void* stream);
+/* the preparation step of serb_features_host_pcm16 on its own: file f (file_frames[f] frames x
+ * file_channels[f] interleaved int16, file_channels NULL = mono) -> h_out[f][file_frames[f]] float32,
+ * exactly `_prepare_audio_buffer(decode(file))` (audio_utils.py:28-60) */
+int serb_prepare_pcm16_files_host(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames,
+                                  const int32_t* file_channels, int64_t n_files, float* const* h_out);
 
 /* ---- introspection (tests, profiling); not part of the drop-in surface ---- */
 
@@ -186,7 +221,7 @@ int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity);
 /* kernels launched by this context since creation */
 int64_t serb_debug_launch_count(const serb_ctx* ctx);
 /* per-kernel CUDA-event timing: kinds 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss_harm,
- * 7 hpss_perc, 8 istft, 9 ola, 10 decimations, 11 constant-Q octaves, 12 tonnetz.
+ * 7 hpss_perc, 8 istft, 9 ola, 10 decimations, 11 constant-Q octaves, 12 tonnetz, 13 PCM16 preparation.
  * set_profile(1) brackets every launch with an event pair (and resets the totals);
  * kernel_ms returns the accumulated device time and launch count of one kind. */
 int serb_debug_set_profile(serb_ctx* ctx, int32_t enabled);

@@ -33,6 +33,9 @@ SIGNATURES: dict[str, tuple] = {
     "serb_features_device": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P, _P]),
     "serb_features_host": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_uint32, _P]),
     "serb_features_host_clips": (c_int, [_P, _P, _P, c_int64, c_int32, c_uint32, _P]),
+    "serb_features_device_check": (c_int, [_P, _P]),
+    "serb_features_host_pcm16": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_uint32, _P]),
+    "serb_infer_host_pcm16": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_uint32, _P, _P, _P]),
     "serb_mlp_load": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32]),
     "serb_mlp_n_classes": (c_int, [_P]),
     "serb_mlp_predict_host": (c_int, [_P, _P, c_int64, _P, _P]),
@@ -41,6 +44,7 @@ SIGNATURES: dict[str, tuple] = {
     "serb_pool_frames_host": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P]),
     "serb_prepare_pcm16_host": (c_int, [_P, _P, c_int64, _P]),
     "serb_prepare_pcm16_device": (c_int, [_P, _P, c_int64, _P, _P]),
+    "serb_prepare_pcm16_files_host": (c_int, [_P, _P, _P, _P, c_int64, _P]),
     "serb_debug_filterbank": (c_int, [c_int32, c_int32, c_int32, c_int32, _P]),
     "serb_debug_stft_host": (c_int, [_P, _P, c_int64, _P, c_int64]),
     "serb_debug_last_tuning": (c_int, [_P, _P, c_int64]),
@@ -160,6 +164,67 @@ class Context:
             self._handle, c_void_p(d_wave_ptr), int(n_wave), _ptr(starts), _ptr(lengths), starts.size,
             int(sample_rate), int(flag_bits), c_void_p(d_out_ptr), c_void_p(stream)))
 
+    def features_device_check(self, stream: int = 0) -> None:
+        """Synchronises ``stream`` and raises the reference's ValueError if the last device-entry
+        chain staged a non-finite sample."""
+        self._check(self._lib.serb_features_device_check(self._handle, c_void_p(stream)))
+
+    # ---- PCM16 files (N1) ------------------------------------------------------------------
+    @staticmethod
+    def _pcm16_args(files, channels, clip_file, clip_starts, clip_lengths):
+        arrays = []
+        for f in files:
+            a = np.asarray(f)
+            if a.dtype != np.int16:
+                raise TypeError(f"PCM16 files must be int16 arrays, got {a.dtype}")
+            arrays.append(np.ascontiguousarray(a))
+        n = len(arrays)
+        if isinstance(channels, int):
+            channels = [channels] * n
+        ch = np.asarray(channels, dtype=np.int32).reshape(-1)
+        if ch.size != n:
+            raise ValueError("one channel count per file")
+        frames = np.asarray([a.size // max(int(c), 1) for a, c in zip(arrays, ch)], dtype=np.int64)
+        for a, c, fr in zip(arrays, ch, frames):
+            if c < 1 or a.size != fr * c:
+                raise ValueError("PCM16 file size is not a multiple of its channel count")
+        pointers = (c_void_p * max(n, 1))(*[a.ctypes.data for a in arrays])
+        clip_file = np.ascontiguousarray(clip_file, dtype=np.int64)
+        clip_starts = np.ascontiguousarray(clip_starts, dtype=np.int64)
+        clip_lengths = np.ascontiguousarray(clip_lengths, dtype=np.int64)
+        if not (clip_file.size == clip_starts.size == clip_lengths.size):
+            raise ValueError("clip_file, clip_starts and clip_lengths must have one entry per clip")
+        return arrays, pointers, frames, ch, clip_file, clip_starts, clip_lengths
+
+    def features_host_pcm16(self, files, channels, clip_file, clip_starts, clip_lengths,
+                            sample_rate: int, flag_bits: int) -> np.ndarray:
+        """Ragged batch over int16 PCM files prepared on the device (x / 32768, channel mean,
+        per-file peak normalisation) -> (n_clips, dim) float32.  ``files[f]`` is a 1-D int16 array of
+        ``frames * channels[f]`` interleaved samples; clip i is frames
+        ``[clip_starts[i], clip_starts[i] + clip_lengths[i])`` of file ``clip_file[i]``."""
+        keep, pointers, frames, ch, cf, cs, cl = self._pcm16_args(files, channels, clip_file, clip_starts, clip_lengths)
+        dim = self._lib.serb_feature_dim(flag_bits)
+        out = np.empty((cf.size, dim), dtype=np.float32)
+        self._check(self._lib.serb_features_host_pcm16(
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), len(keep), _ptr(cf), _ptr(cs), _ptr(cl),
+            cf.size, int(sample_rate), int(flag_bits), _ptr(out)))
+        del keep
+        return out
+
+    def infer_host_pcm16(self, files, channels, clip_file, clip_starts, clip_lengths, sample_rate: int,
+                         flag_bits: int, *, want_features: bool = True):
+        keep, pointers, frames, ch, cf, cs, cl = self._pcm16_args(files, channels, clip_file, clip_starts, clip_lengths)
+        n = cf.size
+        dim = self._lib.serb_feature_dim(flag_bits)
+        feats = np.empty((n, dim), dtype=np.float32) if want_features else None
+        proba = np.empty((n, max(self._mlp_classes, 1)), dtype=np.float64)
+        labels = np.empty(n, dtype=np.int32)
+        self._check(self._lib.serb_infer_host_pcm16(
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), len(keep), _ptr(cf), _ptr(cs), _ptr(cl),
+            n, int(sample_rate), int(flag_bits), _ptr(feats), _ptr(proba), _ptr(labels)))
+        del keep
+        return feats, proba, labels
+
     # ---- classifier ----------------------------------------------------------------------
     def mlp_load(self, mean, scale, w1, b1, w2, b2, out_activation: int) -> None:
         arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, scale, w1, b1, w2, b2)]
@@ -220,6 +285,16 @@ class Context:
         self._check(self._lib.serb_prepare_pcm16_host(self._handle, _ptr(pcm), pcm.size, _ptr(out)))
         return out
 
+    def prepare_pcm16_files_host(self, files, channels) -> list[np.ndarray]:
+        """``_prepare_audio_buffer`` of every int16 file on the device -> list of float32 mono arrays."""
+        keep, pointers, frames, ch, _, _, _ = self._pcm16_args(files, channels, [], [], [])
+        outs = [np.empty(int(fr), dtype=np.float32) for fr in frames]
+        out_ptrs = (c_void_p * max(len(outs), 1))(*[o.ctypes.data for o in outs])
+        self._check(self._lib.serb_prepare_pcm16_files_host(
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), len(keep), ctypes.cast(out_ptrs, c_void_p)))
+        del keep
+        return outs
+
     # ---- introspection -------------------------------------------------------------------
     def debug_stft_host(self, wave: np.ndarray) -> np.ndarray:
         wave = np.ascontiguousarray(wave, dtype=np.float32)
@@ -261,7 +336,7 @@ class Context:
         """{kernel: (total device ms, launches)} since set_profile(True)."""
         out = {}
         for kind, name in enumerate(("stft", "tuning", "proj", "pool", "short", "mlp", "hpss_harm", "hpss_perc", "istft", "ola",
-                                     "decimate", "cqt", "tonnetz")):
+                                     "decimate", "cqt", "tonnetz", "pcm_prepare")):
             ms = c_double(0.0)
             n = c_int64(0)
             self._check(self._lib.serb_debug_kernel_ms(self._handle, kind, ctypes.byref(ms), ctypes.byref(n)))

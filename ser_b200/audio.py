@@ -3,6 +3,11 @@
 The reference decodes with librosa/soundfile; this image has neither, so PCM WAV is decoded
 with the standard library and anything else is rejected.  Post-decode preparation is the
 reference's: NaN/Inf -> 0, channel mean, whole-file peak normalisation to [-1, 1].
+
+16-bit PCM WAV -- what RAVDESS and the reference's own synthetic generator ship -- does not need
+that host pass at all: ``read_pcm16_file`` hands the raw int16 samples to the device entries
+(``serb_features_host_pcm16``), which do the same preparation bit-identically on the GPU
+(SURVEY.md section 8f, row N1).  ``prepare_audio_buffer`` remains for float / 8 / 24 / 32-bit input.
 """
 
 from __future__ import annotations
@@ -66,6 +71,58 @@ def decode_wav(path: str | Path) -> tuple[NDArray[np.float32], int]:
     return data, int(sample_rate)
 
 
+def _check_path(file_path: str) -> Path:
+    path = Path(file_path)
+    if not path.exists():
+        raise FileNotFoundError(f"Audio file not found: {file_path}")
+    if not path.is_file():
+        raise OSError(f"Path is not a regular file: {file_path}")
+    with path.open("rb") as handle:
+        if handle.read(len(_GIT_LFS_POINTER_PREFIX)) == _GIT_LFS_POINTER_PREFIX:
+            raise AudioIntegrityError(f"Audio file is an unmaterialized Git LFS pointer: {file_path}.")
+    return path
+
+
+def read_pcm16_file(
+    file_path: str,
+    *,
+    start_seconds: float | None = None,
+    duration_seconds: float | None = None,
+) -> tuple[NDArray[np.int16], int, int] | None:
+    """Raw samples of a 16-bit PCM WAV file (or segment) for the device-side preparation path
+    (``serb_features_host_pcm16``): ``(interleaved int16, channels, sample_rate)``, or ``None``
+    when the file is not 16-bit PCM WAV (the caller then takes ``read_audio_file``).  Segment
+    bounds follow librosa.load(offset=, duration=): ``int(offset * sr)`` frames skipped,
+    ``int(duration * sr)`` frames read (audio_utils.py:104-109).  Same argument and path errors as
+    ``read_audio_file``."""
+    if start_seconds is not None and start_seconds < 0.0:
+        raise ValueError("start_seconds must be >= 0")
+    if duration_seconds is not None and duration_seconds <= 0.0:
+        raise ValueError("duration_seconds must be > 0")
+    path = _check_path(file_path)
+    try:
+        with wave.open(str(path), "rb") as handle:
+            if handle.getsampwidth() != 2 or handle.getcomptype() != "NONE":
+                return None
+            sample_rate = handle.getframerate()
+            channels = handle.getnchannels()
+            total = handle.getnframes()
+            first = min(int(float(start_seconds or 0.0) * sample_rate), total)
+            count = total - first
+            if duration_seconds is not None:
+                count = min(count, int(float(duration_seconds) * sample_rate))
+            handle.setpos(first)
+            raw = handle.readframes(max(count, 0))
+    except (wave.Error, EOFError):
+        return None
+    pcm = np.frombuffer(raw, dtype="<i2")
+    if channels < 1 or channels > 256 or pcm.size < channels:
+        if pcm.size == 0:
+            raise OSError("Audio file contains no samples.")
+        return None
+    return pcm[: pcm.size // channels * channels], int(channels), int(sample_rate)
+
+
 def read_audio_file(
     file_path: str,
     *,
@@ -77,14 +134,7 @@ def read_audio_file(
         raise ValueError("start_seconds must be >= 0")
     if duration_seconds is not None and duration_seconds <= 0.0:
         raise ValueError("duration_seconds must be > 0")
-    path = Path(file_path)
-    if not path.exists():
-        raise FileNotFoundError(f"Audio file not found: {file_path}")
-    if not path.is_file():
-        raise OSError(f"Path is not a regular file: {file_path}")
-    with path.open("rb") as handle:
-        if handle.read(len(_GIT_LFS_POINTER_PREFIX)) == _GIT_LFS_POINTER_PREFIX:
-            raise AudioIntegrityError(f"Audio file is an unmaterialized Git LFS pointer: {file_path}.")
+    path = _check_path(file_path)
     data, sample_rate = decode_wav(path)
     first = int(float(start_seconds or 0.0) * sample_rate)
     if duration_seconds is not None:

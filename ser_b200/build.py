@@ -30,6 +30,7 @@ SOURCES = [
     "hpss_kernels.cu",
     "cqt_kernels.cu",
     "mlp_kernel.cu",
+    "pcm_kernels.cu",
     "api.cu",
 ]
 HEADERS = ["common.cuh", "fft.cuh", "kernels.h", "filterbanks.h", "cqt_tables.h", "median_net.cuh", "../../include/ser_b200.h"]

@@ -12,6 +12,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "cqt_tables.h"
 #include "filterbanks.h"
@@ -32,8 +34,13 @@ struct DevBuf {
         // grow geometrically so repeated calls with slowly growing sizes do not thrash
         size_t want = std::max(need, bytes + bytes / 2);
         cudaError_t e = cudaMalloc(&ptr, want);
-        if (e != cudaSuccess) { want = need; e = cudaMalloc(&ptr, want); }
+        if (e != cudaSuccess) {
+            cudaGetLastError();          // the failed attempt must not surface at the next launch check
+            want = need;
+            e = cudaMalloc(&ptr, want);
+        }
         if (e == cudaSuccess) bytes = want;
+        else { cudaGetLastError(); ptr = nullptr; }
         return e;
     }
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
@@ -61,13 +68,14 @@ struct Mlp {
 
 }  // namespace
 
-constexpr int kProfKinds = 13;
+constexpr int kProfKinds = 14;
 
 struct serb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr, ev_chain = nullptr;
+    bool chain_recorded = false;   // ev_chain marks the end of the last launch chain (on whatever stream it used)
     std::vector<cudaEvent_t> piece_events;
     std::mutex mu;
     std::string err;
@@ -87,7 +95,7 @@ struct serb_ctx {
     DevBuf spill, logmel, tile_mel, tile_lmax, tile_chroma, peaks, peak_count;
     DevBuf clips, short_clips, tuning, short_tuning, status;
     // host-entry staging
-    DevBuf wave, out, proba, labels, x64, pcm, pcm_max;
+    DevBuf wave, out, proba, labels, x64, pcm, pcm_max, pcm_files, pcm_peaks;
     // tonnetz chain
     DevBuf hann_sq, cq_twiddles;
     DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
@@ -125,10 +133,14 @@ int fail_cuda(serb_ctx* ctx, cudaError_t e, const char* what) {
     } while (0)
 
 // kinds: 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss_harm, 7 hpss_perc, 8 istft, 9 ola,
-// 10 decimations, 11 constant-Q octaves, 12 tonnetz
+// 10 decimations, 11 constant-Q octaves, 12 tonnetz, 13 PCM16 preparation
+constexpr const char* kProfNames[] = {"serb:stft", "serb:tuning", "serb:proj", "serb:pool", "serb:short", "serb:mlp",
+                                      "serb:hpss_harm", "serb:hpss_perc", "serb:istft", "serb:ola", "serb:decimate",
+                                      "serb:cqt", "serb:tonnetz", "serb:pcm_prepare"};
 struct ProfScope {
     serb_ctx* ctx; int kind; cudaStream_t stream; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(serb_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), stream(s) {
+        nvtxRangePushA(kProfNames[k]);   // one NVTX range per launch kind (a no-op without a tool attached)
         if (!ctx->profile) return;
         auto take = [&]() {
             cudaEvent_t ev = nullptr;
@@ -140,6 +152,7 @@ struct ProfScope {
         cudaEventRecord(a, stream);
     }
     ~ProfScope() {
+        nvtxRangePop();
         if (!a) return;
         cudaEventRecord(b, stream);
         ctx->prof_recs.push_back({kind, a, b});
@@ -156,7 +169,17 @@ int upload(serb_ctx* ctx, DevBuf& buf, const T* host, size_t count, cudaStream_t
 int get_sr_tables(serb_ctx* ctx, int sr, SrTables** out) {
     auto it = ctx->sr_tables.find(sr);
     if (it != ctx->sr_tables.end()) { *out = &it->second; return SERB_OK; }
-    SrTables& t = ctx->sr_tables[sr];
+    // built in a local and moved into the cache only when every upload succeeded: a transient
+    // cudaMalloc failure must not leave a half-initialised entry behind for the next call
+    SrTables t;
+    struct Guard {
+        SrTables* t; bool keep = false;
+        ~Guard() {
+            if (keep) return;
+            for (DevBuf* b : {&t->chroma_banks, &t->mel_start, &t->mel_count, &t->mel_offset, &t->mel_weights, &t->mel_points})
+                b->release();
+        }
+    } guard{&t};
     t.sample_rate = sr;
     // mel (sparse CSR)
     std::vector<float> dense;
@@ -199,7 +222,10 @@ int get_sr_tables(serb_ctx* ctx, int sr, SrTables** out) {
     t.peak_cap = std::max(1, (kmax - kmin + 1) / 2 + 1);
     cqt_plan(sr, t.plan);
     SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
-    *out = &t;
+    guard.keep = true;
+    SrTables& slot = ctx->sr_tables[sr];
+    slot = t;
+    *out = &slot;
     return SERB_OK;
 }
 
@@ -557,6 +583,9 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
 
     SrTables* tab = nullptr;
     if ((rc = get_sr_tables(ctx, sr, &tab))) return rc;
+    // the scratch buffers are per context, not per stream: a caller alternating streams must not
+    // start this chain before the previous one (on another stream) has finished with them
+    if (ctx->chain_recorded) SERB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_chain, 0));
     const bool want_chroma = off.chroma >= 0;
     const bool want_mel = off.mel >= 0 || off.mfcc >= 0;
     const bool want_ton = off.tonnetz >= 0;
@@ -781,6 +810,8 @@ int run_features(serb_ctx* ctx, const float* d_wave, long long n_wave, const int
         }
     }
     if (ctx->timed) SERB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, stream));
+    SERB_CUDA(ctx, cudaEventRecord(ctx->ev_chain, stream));
+    ctx->chain_recorded = true;
     return SERB_OK;
 }
 
@@ -911,6 +942,145 @@ int mlp_run(serb_ctx* ctx, const float* d_x32, const double* d_x64, long long n,
     return SERB_OK;
 }
 
+// PCM16 files -> ctx->pcm (int16, 16-byte aligned file starts) on the copy stream, then, on the
+// compute stream, the segmented preparation kernels -> ctx->wave.  Runs of files that are
+// contiguous in host memory (and whose sizes keep the alignment) travel as one copy.  A piece is
+// enqueued when the first chunk that needs it is about to launch, so copies of later files overlap
+// the kernels of earlier chunks.
+struct PcmStager {
+    serb_ctx* ctx;
+    cudaStream_t stream;
+    const int16_t* const* files;
+    const std::vector<PcmFile>* layout;
+    long long max_frames;
+    int next_file = 0;            // first file whose copy is not enqueued yet
+    int prepared = 0;             // first file not yet converted
+    int n_pieces = 0;
+    bool started = false;
+    cudaError_t error = cudaSuccess;
+    void operator()(long long max_end) {
+        if (error != cudaSuccess) return;
+        const std::vector<PcmFile>& lay = *layout;
+        const int n_files = static_cast<int>(lay.size());
+        if (!started) {
+            started = true;
+            if ((error = cudaEventRecord(ctx->ev_done, ctx->stream)) != cudaSuccess) return;
+            if ((error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0)) != cudaSuccess) return;
+        }
+        constexpr long long kPiece = 16LL << 20;   // int16 samples per piece (32 MiB)
+        while (next_file < n_files && lay[next_file].wave_off < max_end) {
+            long long in_piece = 0;
+            while (next_file < n_files && in_piece < kPiece) {
+                // extend a run while host and device layouts stay contiguous
+                int run_hi = next_file + 1;
+                long long run_samples = lay[next_file].frames * lay[next_file].channels;
+                while (run_hi < n_files && in_piece + run_samples < kPiece &&
+                       files[run_hi] == files[run_hi - 1] + lay[run_hi - 1].frames * lay[run_hi - 1].channels &&
+                       lay[run_hi].pcm_off == lay[run_hi - 1].pcm_off + lay[run_hi - 1].frames * lay[run_hi - 1].channels) {
+                    run_samples += lay[run_hi].frames * lay[run_hi].channels;
+                    ++run_hi;
+                }
+                if ((error = cudaMemcpyAsync(ctx->pcm.as<short>() + lay[next_file].pcm_off, files[next_file],
+                                             static_cast<size_t>(run_samples) * sizeof(int16_t), cudaMemcpyHostToDevice,
+                                             ctx->copy_stream)) != cudaSuccess) return;
+                in_piece += run_samples;
+                next_file = run_hi;
+            }
+            if (n_pieces >= static_cast<int>(ctx->piece_events.size())) {
+                cudaEvent_t ev;
+                if ((error = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return;
+                ctx->piece_events.push_back(ev);
+            }
+            if ((error = cudaEventRecord(ctx->piece_events[n_pieces], ctx->copy_stream)) != cudaSuccess) return;
+            ++n_pieces;
+        }
+        if (prepared < next_file) {
+            if ((error = cudaStreamWaitEvent(stream, ctx->piece_events[n_pieces - 1], 0)) != cudaSuccess) return;
+            ProfScope ps(ctx, 13, stream);
+            error = launch_pcm_prepare_files(ctx->pcm.as<short>(), ctx->pcm_files.as<PcmFile>(), prepared, next_file,
+                                             max_frames, ctx->pcm_peaks.as<int>(), ctx->wave.as<float>(), stream,
+                                             &ctx->launches);
+            prepared = next_file;
+        }
+    }
+};
+
+// shared body of serb_features_host_pcm16 / serb_infer_host_pcm16
+int run_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames, const int32_t* file_channels,
+              int64_t n_files, const int64_t* clip_file, const int64_t* clip_starts, const int64_t* clip_lengths,
+              int64_t n_clips, int32_t sample_rate, uint32_t flag_bits, bool infer, float* h_features, double* h_proba,
+              int32_t* h_label_index) {
+    if (n_files < 0 || n_clips < 0 || (n_files > 0 && (!h_files || !file_frames)) ||
+        (n_clips > 0 && (!clip_file || !clip_starts || !clip_lengths)))
+        return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+    if (n_files > 0x7fffffffLL) return fail(ctx, SERB_ERR_INVALID_ARG, "too many files");
+    const int dim = serb_feature_dim(flag_bits);
+    const Mlp& m = ctx->mlp;
+    if (infer) {
+        if (!m.loaded) return fail(ctx, SERB_ERR_NO_MODEL, "no classifier loaded (call serb_mlp_load)");
+        if (n_clips > 0 && (!h_proba || !h_label_index)) return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+        if (dim != m.n_in)
+            return fail(ctx, SERB_ERR_INVALID_ARG,
+                        "Feature vector size mismatch for loaded model. Expected " + std::to_string(m.n_in) +
+                            ", got [" + std::to_string(dim) + "].");
+    } else if (n_clips > 0 && !h_features) {
+        return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+    }
+    std::vector<PcmFile> layout(static_cast<size_t>(n_files));
+    long long n_pcm = 0, n_wave = 0, max_frames = 0;
+    for (int64_t f = 0; f < n_files; ++f) {
+        const int ch = file_channels ? file_channels[f] : 1;
+        if (file_frames[f] <= 0) return fail(ctx, SERB_ERR_EMPTY, "Audio file contains no samples.");
+        if (!h_files[f] || ch < 1 || ch > 256) return fail(ctx, SERB_ERR_INVALID_ARG, "bad PCM16 file descriptor");
+        layout[f] = PcmFile{n_pcm, n_wave, file_frames[f], ch, 0};
+        n_pcm += (file_frames[f] * ch + 7) / 8 * 8;
+        n_wave += (file_frames[f] + 3) / 4 * 4;
+        max_frames = std::max<long long>(max_frames, file_frames[f]);
+    }
+    std::vector<int64_t> starts(static_cast<size_t>(n_clips));
+    int64_t prev_file = 0;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t f = clip_file[i];
+        if (f < prev_file || f >= n_files) return fail(ctx, SERB_ERR_INVALID_ARG, "clip_file must be non-decreasing and < n_files");
+        prev_file = f;
+        if (clip_lengths[i] <= 0) return fail(ctx, SERB_ERR_EMPTY, "Audio contains no samples.");
+        if (clip_starts[i] < 0 || clip_starts[i] + clip_lengths[i] > file_frames[f])
+            return fail(ctx, SERB_ERR_INVALID_ARG, "clip " + std::to_string(i) + " lies outside its file");
+        starts[i] = layout[f].wave_off + clip_starts[i];
+    }
+    SERB_CUDA(ctx, ctx->pcm.reserve(std::max<long long>(n_pcm, 1) * sizeof(int16_t) + 64));
+    SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
+    SERB_CUDA(ctx, ctx->pcm_peaks.reserve(std::max<size_t>(layout.size(), 1) * sizeof(int)));
+    SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
+    if (infer) {
+        SERB_CUDA(ctx, ctx->proba.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * m.n_classes, 1) * sizeof(double)));
+        SERB_CUDA(ctx, ctx->labels.reserve(std::max<size_t>(static_cast<size_t>(n_clips), 1) * sizeof(int)));
+    }
+    int rc = upload(ctx, ctx->pcm_files, layout.data(), layout.size(), ctx->stream);
+    if (rc) return rc;
+    PcmStager stager{ctx, ctx->stream, h_files, &layout, max_frames};
+    ctx->ramp_chunks = true;
+    rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts.data(), clip_lengths, n_clips, sample_rate, flag_bits,
+                      ctx->out.as<float>(), ctx->stream, stager);
+    ctx->ramp_chunks = false;
+    if (!rc && stager.error != cudaSuccess) rc = fail_cuda(ctx, stager.error, "PCM16 staging");
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+    if (n_clips == 0 || dim == 0) { SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SERB_OK; }
+    if (infer) {
+        rc = mlp_run(ctx, ctx->out.as<float>(), nullptr, n_clips, ctx->proba.as<double>(), ctx->labels.as<int>(), ctx->stream);
+        if (rc) return rc;
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_proba, ctx->proba.ptr, static_cast<size_t>(n_clips) * m.n_classes * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_label_index, ctx->labels.ptr, static_cast<size_t>(n_clips) * sizeof(int),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (h_features)
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_features, ctx->out.ptr, static_cast<size_t>(n_clips) * dim * sizeof(float),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_status(ctx, ctx->stream);
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -924,7 +1094,14 @@ int serb_device_count(void) {
     return n;
 }
 
-const char* serb_last_error(const serb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* serb_last_error(const serb_ctx* ctx) {
+    if (!ctx) return g_create_error.c_str();
+    // copied under the context lock into this thread's buffer: valid until this thread asks again
+    thread_local std::string copy;
+    std::lock_guard<std::mutex> lock(const_cast<serb_ctx*>(ctx)->mu);
+    copy = ctx->err;
+    return copy.c_str();
+}
 
 int serb_feature_dim(uint32_t flag_bits) { return make_offsets(flag_bits & SERB_FLAG_ALL).dim; }
 
@@ -956,6 +1133,7 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
     CREATE_CHECK(cudaEventCreate(&ctx->ev_start));
     CREATE_CHECK(cudaEventCreate(&ctx->ev_stop));
     CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+    CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
     CREATE_CHECK(configure_stft());
     CREATE_CHECK(configure_proj());
     CREATE_CHECK(configure_short());
@@ -1037,7 +1215,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
     for (DevBuf* b : {&ctx->edges, &ctx->dct, &ctx->tables, &ctx->tile_clip, &ctx->spill, &ctx->logmel, &ctx->tile_mel, &ctx->tile_lmax,
                       &ctx->tile_chroma, &ctx->peaks, &ctx->peak_count, &ctx->clips, &ctx->short_clips,
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
-                      &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->mlp.mean, &ctx->mlp.scale,
+                      &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->pcm_files, &ctx->pcm_peaks, &ctx->mlp.mean, &ctx->mlp.scale,
                       &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles,
                       &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag, &ctx->ton_part,
                       &ctx->long_idx, &ctx->long_state, &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
@@ -1053,6 +1231,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaEventDestroy(ctx->ev_done);
+    cudaEventDestroy(ctx->ev_chain);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -1068,6 +1247,14 @@ int serb_features_device(serb_ctx* ctx, const float* d_wave, int64_t n_wave, con
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return run_features(ctx, d_wave, n_wave, starts, lengths, n_clips, sample_rate, flag_bits, d_out, s,
                         [](long long) {});
+}
+
+int serb_features_device_check(serb_ctx* ctx, void* stream) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->status.ptr) return SERB_OK;
+    return check_status(ctx, stream ? static_cast<cudaStream_t>(stream) : ctx->stream);
 }
 
 int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const int64_t* starts,
@@ -1230,6 +1417,70 @@ int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const in
                                    cudaMemcpyDeviceToHost, ctx->stream));
     SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return check_status(ctx, ctx->stream);
+}
+
+int serb_features_host_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames,
+                             const int32_t* file_channels, int64_t n_files, const int64_t* clip_file,
+                             const int64_t* clip_starts, const int64_t* clip_lengths, int64_t n_clips,
+                             int32_t sample_rate, uint32_t flag_bits, float* h_out) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_pcm16(ctx, h_files, file_frames, file_channels, n_files, clip_file, clip_starts, clip_lengths, n_clips,
+                     sample_rate, flag_bits, false, h_out, nullptr, nullptr);
+}
+
+int serb_infer_host_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames,
+                          const int32_t* file_channels, int64_t n_files, const int64_t* clip_file,
+                          const int64_t* clip_starts, const int64_t* clip_lengths, int64_t n_clips,
+                          int32_t sample_rate, uint32_t flag_bits, float* h_features, double* h_proba,
+                          int32_t* h_label_index) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_pcm16(ctx, h_files, file_frames, file_channels, n_files, clip_file, clip_starts, clip_lengths, n_clips,
+                     sample_rate, flag_bits, true, h_features, h_proba, h_label_index);
+}
+
+int serb_prepare_pcm16_files_host(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_frames,
+                                  const int32_t* file_channels, int64_t n_files, float* const* h_out) {
+    if (!ctx) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_files < 0 || n_files > 0x7fffffffLL || (n_files > 0 && (!h_files || !file_frames || !h_out)))
+        return fail(ctx, SERB_ERR_INVALID_ARG, "NULL host buffer");
+    std::vector<PcmFile> layout(static_cast<size_t>(n_files));
+    long long n_pcm = 0, n_wave = 0, max_frames = 0;
+    for (int64_t f = 0; f < n_files; ++f) {
+        const int ch = file_channels ? file_channels[f] : 1;
+        if (file_frames[f] <= 0) return fail(ctx, SERB_ERR_EMPTY, "Audio file contains no samples.");
+        if (!h_files[f] || !h_out[f] || ch < 1 || ch > 256) return fail(ctx, SERB_ERR_INVALID_ARG, "bad PCM16 file descriptor");
+        layout[f] = PcmFile{n_pcm, n_wave, file_frames[f], ch, 0};
+        n_pcm += (file_frames[f] * ch + 7) / 8 * 8;
+        n_wave += (file_frames[f] + 3) / 4 * 4;
+        max_frames = std::max<long long>(max_frames, file_frames[f]);
+    }
+    if (n_files == 0) return SERB_OK;
+    SERB_CUDA(ctx, ctx->pcm.reserve(n_pcm * sizeof(int16_t) + 64));
+    SERB_CUDA(ctx, ctx->wave.reserve(n_wave * sizeof(float) + 64));
+    SERB_CUDA(ctx, ctx->pcm_peaks.reserve(layout.size() * sizeof(int)));
+    int rc = upload(ctx, ctx->pcm_files, layout.data(), layout.size(), ctx->stream);
+    if (rc) return rc;
+    for (int64_t f = 0; f < n_files; ++f)
+        SERB_CUDA(ctx, cudaMemcpyAsync(ctx->pcm.as<short>() + layout[f].pcm_off, h_files[f],
+                                       static_cast<size_t>(layout[f].frames) * layout[f].channels * sizeof(int16_t),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope ps(ctx, 13, ctx->stream);
+        SERB_CUDA(ctx, launch_pcm_prepare_files(ctx->pcm.as<short>(), ctx->pcm_files.as<PcmFile>(), 0, static_cast<int>(n_files),
+                                                max_frames, ctx->pcm_peaks.as<int>(), ctx->wave.as<float>(), ctx->stream,
+                                                &ctx->launches));
+    }
+    for (int64_t f = 0; f < n_files; ++f)
+        SERB_CUDA(ctx, cudaMemcpyAsync(h_out[f], ctx->wave.as<float>() + layout[f].wave_off,
+                                       static_cast<size_t>(layout[f].frames) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SERB_OK;
 }
 
 int serb_pool_frames_host(serb_ctx* ctx, const float* h_embeddings, int64_t n_frames, int32_t dim,

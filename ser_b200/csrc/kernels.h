@@ -214,4 +214,17 @@ cudaError_t launch_pool_stats(const float* d_emb, int dim, const int* d_lo, cons
 cudaError_t launch_prepare_pcm16(const short* d_pcm, long long n, int* d_scratch_max, float* d_out,
                                  cudaStream_t stream);
 
+// ---- pcm_kernels.cu (N1: PCM16 files prepared on the device) --------------------------------
+struct PcmFile {
+    long long pcm_off;    // first int16 of the file in the staged PCM buffer (multiple of 8)
+    long long wave_off;   // first float of the prepared mono signal in the waveform buffer (multiple of 4)
+    long long frames;     // samples per channel
+    int channels;         // interleaved channels (1..256)
+    int pad_;
+};
+// files [file_lo, file_hi): x / 32768, channel mean, per-file peak normalisation -> d_wave
+cudaError_t launch_pcm_prepare_files(const short* d_pcm, const PcmFile* d_files, int file_lo, int file_hi,
+                                     long long max_frames, int* d_peak_bits, float* d_wave, cudaStream_t stream,
+                                     long long* launches);
+
 }  // namespace serb

@@ -1,0 +1,128 @@
+// Device-side audio preparation for PCM16 input.
+//
+// Replaces, for int16 PCM files, the host work of ser/_internal/utils/audio_utils.py:28-60
+// (`_prepare_audio_buffer`: float32 x / 32768 as soundfile / librosa.load decode PCM16, channel
+// mean, whole-file peak normalisation x / max|x|, all-zero files stay zero) so that the host
+// ships 2 bytes per sample instead of 4.  Results are bit-identical to numpy's:
+//   * s / 32768 is exact in float32;
+//   * the channel mean is a float32 sum of exact values (|sum| < 2^24 / 32768 for <= 256
+//     channels, so any summation order gives the same exact sum) followed by ONE rounding
+//     division by the channel count, which is what np.mean(axis, dtype=float32) does;
+//   * `audio / float(max_abs)` on a float32 array is a float32 division (__fdiv_rn).
+// Two kernels per batch of files: a segmented |x| maximum (one atomicMax per warp on the float's
+// bit pattern, which orders like the value for non-negative floats), then the scaling pass.
+// HBM-bound: 2 + 2 + 4 bytes per sample.
+#include "kernels.h"
+
+namespace serb {
+
+namespace {
+
+__device__ __forceinline__ float mono_value(const short* __restrict__ p, int channels) {
+    if (channels == 1) return static_cast<float>(p[0]) * (1.0f / 32768.0f);
+    int sum = 0;
+    for (int c = 0; c < channels; ++c) sum += p[c];
+    return __fdiv_rn(static_cast<float>(sum) * (1.0f / 32768.0f), static_cast<float>(channels));
+}
+
+// blockIdx.y = file (relative to file_lo), blockIdx.x strides over the file's frames
+__global__ void __launch_bounds__(256) pcm_file_absmax_kernel(const short* __restrict__ pcm,
+                                                              const PcmFile* __restrict__ files, int file_lo,
+                                                              int* __restrict__ peak_bits) {
+    const int f = file_lo + blockIdx.y;
+    const PcmFile file = files[f];
+    const short* base = pcm + file.pcm_off;
+    float m = 0.0f;
+    if (file.channels == 1) {
+        // 16-byte loads: pcm_off is a multiple of 8 samples
+        const long long n8 = file.frames >> 3;
+        const int4* v = reinterpret_cast<const int4*>(base);
+        int mi = 0;
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const int4 q = __ldg(v + i);
+            const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int lo = static_cast<short>(w[k] & 0xffff), hi = w[k] >> 16;
+                mi = max(mi, max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi));
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (file.frames & 7)) {
+            const int s = base[(n8 << 3) + threadIdx.x];
+            mi = max(mi, s < 0 ? -s : s);
+        }
+        m = static_cast<float>(mi) * (1.0f / 32768.0f);
+    } else {
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < file.frames;
+             i += static_cast<long long>(gridDim.x) * blockDim.x)
+            m = fmaxf(m, fabsf(mono_value(base + i * file.channels, file.channels)));
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(peak_bits + f, __float_as_int(m));
+}
+
+__global__ void __launch_bounds__(256) pcm_file_scale_kernel(const short* __restrict__ pcm,
+                                                             const PcmFile* __restrict__ files, int file_lo,
+                                                             const int* __restrict__ peak_bits,
+                                                             float* __restrict__ wave) {
+    const int f = file_lo + blockIdx.y;
+    const PcmFile file = files[f];
+    const short* base = pcm + file.pcm_off;
+    float* out = wave + file.wave_off;
+    const float peak = __int_as_float(peak_bits[f]);
+    if (file.channels == 1) {
+        const long long n8 = file.frames >> 3;
+        const int4* v = reinterpret_cast<const int4*>(base);
+        float4* o = reinterpret_cast<float4*>(out);          // wave_off is a multiple of 4 floats
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const int4 q = __ldg(v + i);
+            const int w[4] = {q.x, q.y, q.z, q.w};
+            float r[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float lo = static_cast<float>(static_cast<short>(w[k] & 0xffff)) * (1.0f / 32768.0f);
+                const float hi = static_cast<float>(w[k] >> 16) * (1.0f / 32768.0f);
+                r[2 * k] = peak == 0.0f ? 0.0f : __fdiv_rn(lo, peak);
+                r[2 * k + 1] = peak == 0.0f ? 0.0f : __fdiv_rn(hi, peak);
+            }
+            o[2 * i] = make_float4(r[0], r[1], r[2], r[3]);
+            o[2 * i + 1] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (file.frames & 7)) {
+            const long long i = (n8 << 3) + threadIdx.x;
+            const float x = static_cast<float>(base[i]) * (1.0f / 32768.0f);
+            out[i] = peak == 0.0f ? 0.0f : __fdiv_rn(x, peak);
+        }
+    } else {
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < file.frames;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const float x = mono_value(base + i * file.channels, file.channels);
+            out[i] = peak == 0.0f ? 0.0f : __fdiv_rn(x, peak);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_pcm_prepare_files(const short* d_pcm, const PcmFile* d_files, int file_lo, int file_hi,
+                                     long long max_frames, int* d_peak_bits, float* d_wave, cudaStream_t stream,
+                                     long long* launches) {
+    if (file_hi <= file_lo) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_peak_bits + file_lo, 0, static_cast<size_t>(file_hi - file_lo) * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    // one thread handles 8 frames per trip; enough CTAs per file to cover it once, capped at 4 per SM
+    long long per = (max_frames + 256 * 8 - 1) / (256 * 8);
+    per = per < 1 ? 1 : (per > 148 * 4 ? 148 * 4 : per);
+    for (int lo = file_lo; lo < file_hi; lo += 65535) {
+        const int n = (file_hi - lo < 65535) ? file_hi - lo : 65535;
+        const dim3 grid(static_cast<unsigned>(per), static_cast<unsigned>(n));
+        pcm_file_absmax_kernel<<<grid, 256, 0, stream>>>(d_pcm, d_files, lo, d_peak_bits);
+        pcm_file_scale_kernel<<<grid, 256, 0, stream>>>(d_pcm, d_files, lo, d_peak_bits, d_wave);
+        if (launches) *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace serb

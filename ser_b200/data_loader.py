@@ -4,8 +4,12 @@ Mirror of ``load_checked_fast_data`` / ``_extract_partition``
 (ser/_internal/data/data_loader.py:467-535): same inputs (readiness-checked utterances, a
 settings snapshot, an optional ``handle_sample_failure`` quarantine callback), same outputs
 (float64 feature matrix + label list per split), same failure semantics per sample, same
-progress callback order -- but the feature vectors of a whole partition come from a few ragged
-GPU calls (one per sample rate and per ~2^28-sample block) instead of one librosa pass per file.
+progress callback order -- but the feature vectors come from ragged GPU calls over blocks of
+files instead of one librosa pass per file.  The partition is STREAMED: files are read until a
+block (per sample rate) holds ``MAX_SAMPLES_PER_CALL`` samples, the block is extracted, its audio
+is dropped, and results are handed on in partition order, so host memory is O(block) like the
+reference's O(file), not O(dataset).  16-bit PCM WAV files are shipped as int16 and prepared on
+the device (row N1); anything else goes through ``read_audio``.
 Nothing forks: the reference's legacy Pool path (data_loader.py:368-379) is not needed.
 """
 
@@ -18,10 +22,11 @@ import numpy as np
 from numpy.typing import NDArray
 
 from . import dsp
-from .audio import read_audio_file
+from .audio import read_audio_file, read_pcm16_file
 from .config import FeatureFlags
 
-MAX_SAMPLES_PER_CALL = 1 << 28     # 1 GiB of float32 per native call
+MAX_SAMPLES_PER_CALL = 1 << 28     # samples per native call (1 GiB as float32, 512 MiB as PCM16)
+_PENDING = object()
 
 
 def _validated(audio: NDArray, sample_rate: int) -> NDArray[np.float32]:
@@ -39,6 +44,14 @@ def _validated(audio: NDArray, sample_rate: int) -> NDArray[np.float32]:
     return prepared
 
 
+class _Block:
+    """Clips of one (sample rate, kind) waiting for their native call."""
+
+    def __init__(self) -> None:
+        self.items: list[tuple[int, Any]] = []     # (partition index, float32 clip | (int16 pcm, channels))
+        self.samples = 0
+
+
 def extract_partition(
     partition: Sequence[Any],
     *,
@@ -46,68 +59,108 @@ def extract_partition(
     handle_sample_failure: Callable[[Any, Exception], bool] | None = None,
     record_progress: Callable[..., None] | None = None,
     read_audio: Callable[..., tuple[NDArray[np.float32], int]] = read_audio_file,
+    read_pcm16: Callable[..., tuple[NDArray[np.int16], int, int] | None] | str | None = "auto",
     extract_batch: Callable[..., NDArray[np.float64]] | None = None,
     device: int = 0,
+    max_samples_per_call: int | None = None,
 ) -> tuple[NDArray[np.float64], list[str]]:
-    """Feature matrix and labels of one split partition (data_loader.py:485-529)."""
+    """Feature matrix and labels of one split partition (data_loader.py:485-529).
+
+    Failure routing follows the reference, where every sample runs alone inside one ``try``:
+    an error that belongs to a sample -- decode / validation errors, and the deterministic
+    argument errors of a block (``ValueError`` / ``ParameterError``, e.g. librosa's Nyquist check,
+    which every sample of that block would raise on its own) -- goes to ``handle_sample_failure``
+    for that sample.  A batch-level ``RuntimeError`` (CUDA failure, out of memory) is NOT a
+    sample's fault and is re-raised at once instead of being reported as N quarantined samples."""
     flags = feature_flags if feature_flags is not None else FeatureFlags()
+    if read_pcm16 == "auto":          # the int16 fast path pairs with this package's own file reader only
+        read_pcm16 = read_pcm16_file if (read_audio is read_audio_file and extract_batch is None) else None
+    budget = MAX_SAMPLES_PER_CALL if max_samples_per_call is None else int(max_samples_per_call)
     if extract_batch is None:
         def extract_batch(clips, sample_rate):
             return dsp.extract_features_batch(clips, sample_rate, feature_flags=flags, device=device)
 
+    def extract_pcm_batch(items, sample_rate):
+        frames = np.asarray([pcm.size // ch for pcm, ch in items], dtype=np.int64)
+        n = len(items)
+        return dsp.extract_features_pcm16([pcm for pcm, _ in items], [ch for _, ch in items], np.arange(n, dtype=np.int64),
+                                          np.zeros(n, dtype=np.int64), frames, sample_rate, feature_flags=flags,
+                                          device=device).astype(np.float64)
+
     total = len(partition)
-    outcome: list[Any] = [None] * total          # feature row, or the exception of that sample
-    by_rate: dict[int, list[tuple[int, NDArray[np.float32]]]] = {}
-    for index, utterance in enumerate(partition):
-        try:
-            audio, sample_rate = read_audio(
-                str(utterance.audio_path),
-                start_seconds=getattr(utterance, "start_seconds", None),
-                duration_seconds=getattr(utterance, "duration_seconds", None),
-            )
-            by_rate.setdefault(int(sample_rate), []).append((index, _validated(audio, int(sample_rate))))
-        except Exception as error:  # noqa: BLE001 - routed to the caller's quarantine policy below
-            outcome[index] = error
-    for sample_rate, items in by_rate.items():
-        block: list[tuple[int, NDArray[np.float32]]] = []
-        size = 0
-
-        def flush() -> None:
-            nonlocal block, size
-            if not block:
-                return
-            try:
-                rows = extract_batch([clip for _, clip in block], sample_rate)
-                for (index, _), row in zip(block, rows):
-                    outcome[index] = np.asarray(row, dtype=np.float64)
-            except Exception as error:  # noqa: BLE001 - e.g. a librosa ParameterError for this sample rate
-                for index, _ in block:
-                    outcome[index] = error
-            block, size = [], 0
-
-        for index, clip in items:
-            if block and size + clip.size > MAX_SAMPLES_PER_CALL:
-                flush()
-            block.append((index, clip))
-            size += clip.size
-        flush()
-
+    outcome: list[Any] = [_PENDING] * total       # feature row, or the exception of that sample
+    blocks: dict[tuple[int, bool], _Block] = {}
     rows: list[NDArray[np.float64]] = []
     labels: list[str] = []
-    for processed, (utterance, result) in enumerate(zip(partition, outcome), start=1):
-        if isinstance(result, Exception):
-            if handle_sample_failure is not None and handle_sample_failure(utterance, result):
-                if record_progress is not None:
-                    record_progress(processed=processed, total=total, sample_id=utterance.sample_id)
-                continue
-            raise result
-        feature = result
-        if feature.ndim != 1 or feature.size <= 0 or not np.all(np.isfinite(feature)):
-            raise ValueError(f"Fast feature contract failed for sample {utterance.sample_id!r}.")
-        rows.append(feature)
-        labels.append(utterance.require_label())
-        if record_progress is not None:
-            record_progress(processed=processed, total=total, sample_id=utterance.sample_id)
+    cursor = 0
+
+    def drain() -> None:
+        """Hands finished samples on in partition order (progress callbacks keep the reference's order)."""
+        nonlocal cursor
+        while cursor < total and outcome[cursor] is not _PENDING:
+            utterance, result = partition[cursor], outcome[cursor]
+            outcome[cursor] = None                 # the row now lives in `rows`
+            cursor += 1
+            if isinstance(result, Exception):
+                if handle_sample_failure is not None and handle_sample_failure(utterance, result):
+                    if record_progress is not None:
+                        record_progress(processed=cursor, total=total, sample_id=utterance.sample_id)
+                    continue
+                raise result
+            if result.ndim != 1 or result.size <= 0 or not np.all(np.isfinite(result)):
+                raise ValueError(f"Fast feature contract failed for sample {utterance.sample_id!r}.")
+            rows.append(result)
+            labels.append(utterance.require_label())
+            if record_progress is not None:
+                record_progress(processed=cursor, total=total, sample_id=utterance.sample_id)
+
+    def flush(key: tuple[int, bool]) -> None:
+        block = blocks.pop(key, None)
+        if block is None or not block.items:
+            return
+        sample_rate, is_pcm = key
+        try:
+            payload = [item for _, item in block.items]
+            result = extract_pcm_batch(payload, sample_rate) if is_pcm else extract_batch(payload, sample_rate)
+            for (index, _), row in zip(block.items, result):
+                outcome[index] = np.asarray(row, dtype=np.float64)
+        except (ValueError, dsp.ParameterError) as error:
+            for index, _ in block.items:           # each sample would have raised this on its own
+                outcome[index] = error
+        block.items.clear()                        # the audio is dropped here
+        drain()
+
+    for index, utterance in enumerate(partition):
+        try:
+            segment = dict(start_seconds=getattr(utterance, "start_seconds", None),
+                           duration_seconds=getattr(utterance, "duration_seconds", None))
+            raw = read_pcm16(str(utterance.audio_path), **segment) if read_pcm16 is not None else None
+            if raw is not None:
+                pcm, channels, sample_rate = raw
+                if sample_rate <= 0:
+                    raise ValueError("Sample rate must be a positive integer.")
+                if pcm.size < channels:
+                    raise OSError("Audio file contains no samples.")
+                key, item, size = (int(sample_rate), True), (pcm, int(channels)), pcm.size // channels
+            else:
+                audio, sample_rate = read_audio(str(utterance.audio_path), **segment)
+                clip = _validated(audio, int(sample_rate))
+                key, item, size = (int(sample_rate), False), clip, clip.size
+        except Exception as error:  # noqa: BLE001 - a sample-local failure: the caller's quarantine policy decides
+            outcome[index] = error
+            drain()
+            continue
+        block = blocks.get(key)
+        if block is not None and block.items and block.samples + size > budget:
+            flush(key)
+            block = None
+        if block is None:
+            block = blocks[key] = _Block()
+        block.items.append((index, item))
+        block.samples += size
+    for key in list(blocks):
+        flush(key)
+    drain()
     if not rows:
         raise RuntimeError("Fast checked preparation produced an empty split partition.")
     return np.vstack(rows).astype(np.float64, copy=False), labels

@@ -111,3 +111,29 @@ def extract_features_batch(
     # every clip stays in its own array: the library copies them to aligned offsets piecewise
     rows = _native.get_context(device).features_host_clips(arrays, sample_rate, flag_bits(flags))
     return rows.astype(np.float64)
+
+
+def extract_features_pcm16(
+    files: Sequence[NDArray[np.int16]],
+    channels: Sequence[int] | int,
+    clip_file: NDArray[np.int64],
+    clip_starts: NDArray[np.int64],
+    clip_lengths: NDArray[np.int64],
+    sample_rate: int,
+    *,
+    feature_flags: FeatureFlags | None = None,
+    device: int = 0,
+) -> NDArray[np.float32]:
+    """Feature rows for clips cut out of raw 16-bit PCM files.
+
+    The device performs ``read_audio_file``'s post-decode preparation
+    (ser/_internal/utils/audio_utils.py:28-60: x / 32768, channel mean, whole-file peak
+    normalisation) bit-identically, so the host ships 2 bytes per sample and never builds the
+    float32 buffer.  ``files[f]`` holds ``frames * channels[f]`` interleaved samples; clip ``i`` is
+    frames ``[clip_starts[i], clip_starts[i] + clip_lengths[i])`` of file ``clip_file[i]``
+    (non-decreasing).  Returns float32 (n_clips, dim)."""
+    if sample_rate <= 0:
+        raise ValueError("Sample rate must be a positive integer.")
+    flags = feature_flags if feature_flags is not None else FeatureFlags()
+    return _native.get_context(device).features_host_pcm16(
+        files, channels, clip_file, clip_starts, clip_lengths, int(sample_rate), flag_bits(flags))

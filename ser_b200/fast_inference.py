@@ -1,26 +1,28 @@
-"""Fast-profile public inference boundary on the GPU (boundary B4).
+"""Fast-profile inference boundary on the GPU (boundary B4).
 
 ``run_fast_inference(request, settings, *, loaded_model=None, enforce_timeout=True,
-allow_retries=True)`` keeps the signature and error taxonomy of
+allow_retries=True)`` keeps the signature and the error taxonomy of
 ser/_internal/runtime/fast_inference.py:35-57 / fast_public_boundary.py:139-411:
 
 * ``FileNotFoundError`` while resolving the model  -> ``FastModelUnavailableError``
 * ``ValueError`` while loading the model           -> ``FastModelLoadError``
 * ``ValueError`` from the compute path             passes through unchanged
 * ``RuntimeError`` (CUDA failures included)        -> ``FastInferenceExecutionError``
-* soft timeout (``settings.fast_runtime.timeout_seconds`` > 0) -> ``FastInferenceTimeoutError``
 
-Concurrent calls are serialised by one process-wide lock, like the reference's
-single-flight registry for profile "fast" (fast_public_boundary.py:319).
+The reference's control plane around that call -- retry budget (policy.py:16-73), soft timeout
+and spawn isolation (worker_lifecycle.py:98-208), the single-flight registry
+(fast_public_boundary.py:319) -- is out of scope here ("used unchanged"):
+``ser_b200.install.install()`` leaves the reference's own ``run_fast_inference`` in place and
+swaps only the arithmetic underneath it, so those policies are the reference's code.  This
+module is the same boundary for callers that do not have the reference package importable
+(``enforce_timeout`` / ``allow_retries`` are accepted for signature parity and have nothing to
+act on: there is no timeout or retry layer here).  Concurrent calls are safe: load + forward of
+the classifier hold one per-device lock (``ser_b200.mlp.session``).
 """
 
 from __future__ import annotations
 
 import logging
-import threading
-import time
-from concurrent.futures import ThreadPoolExecutor
-from concurrent.futures import TimeoutError as _FutureTimeout
 from dataclasses import dataclass
 from typing import Any
 
@@ -60,9 +62,6 @@ class LoadedModel:
     artifact_metadata: dict | None = None
 
 
-_SINGLE_FLIGHT = threading.Lock()
-
-
 def _ensure_fast_compatible(loaded_model) -> None:
     metadata = getattr(loaded_model, "artifact_metadata", None)
     if not isinstance(metadata, dict):
@@ -93,11 +92,6 @@ def _load_model(settings):
         raise FastModelLoadError("Failed to load fast-profile model artifact from configured paths.") from err
 
 
-def _fast_runtime_value(settings, name: str, default):
-    runtime = getattr(settings, "fast_runtime", None)
-    return getattr(runtime, name, default) if runtime is not None else default
-
-
 def predict_emotions_detailed(file: str, *, loaded_model, settings=None, device: int = 0) -> InferenceResult:
     """ser/_internal/models/emotion_model.py:140-163 with the GPU feature + MLP path."""
     return fast_path.predict_emotions_detailed_with_model(
@@ -105,7 +99,7 @@ def predict_emotions_detailed(file: str, *, loaded_model, settings=None, device:
         model=loaded_model.model,
         expected_feature_size=getattr(loaded_model, "expected_feature_size", None),
         output_schema_version=OUTPUT_SCHEMA_VERSION,
-        extract_feature_frames_fn=lambda path: extract_feature_frames(path, settings=settings),
+        extract_feature_frames_fn=lambda path: extract_feature_frames(path, settings=settings, device=device),
         logger=logger,
         device=device,
     )
@@ -123,40 +117,12 @@ def run_fast_inference(
     """Runs fast-profile inference for ``request.file_path`` and returns frames + segments."""
     active_model = loaded_model if loaded_model is not None else _load_model(settings)
     _ensure_fast_compatible(active_model)
-    timeout_seconds = float(_fast_runtime_value(settings, "timeout_seconds", 0.0)) if enforce_timeout else 0.0
-    max_retries = int(_fast_runtime_value(settings, "max_transient_retries", 0)) if allow_retries else 0
-    backoff = float(_fast_runtime_value(settings, "retry_backoff_seconds", 0.0))
-
-    def operation() -> InferenceResult:
-        # settings are deliberately NOT forwarded: the reference's hook reloads defaults, so
-        # all five feature groups are always extracted (SURVEY.md F4)
+    del enforce_timeout, allow_retries      # the reference's control plane owns these (module docstring)
+    try:
+        # settings are deliberately NOT forwarded: the reference's hook reloads defaults, so all
+        # five feature groups are always extracted (SURVEY.md F4)
         return predict_emotions_detailed(request.file_path, loaded_model=active_model, device=device)
-
-    attempt = 0
-    with _SINGLE_FLIGHT:
-        while True:
-            attempt += 1
-            try:
-                if timeout_seconds > 0.0:
-                    pool = ThreadPoolExecutor(max_workers=1)
-                    future = pool.submit(operation)
-                    try:
-                        return future.result(timeout=timeout_seconds)
-                    except _FutureTimeout as err:
-                        raise FastInferenceTimeoutError(
-                            f"Fast inference exceeded timeout budget ({timeout_seconds:.2f}s)."
-                        ) from err
-                    finally:
-                        pool.shutdown(wait=False)
-                return operation()
-            except FastTransientBackendError as err:
-                if attempt > max_retries:
-                    raise FastInferenceExecutionError(str(err)) from err
-                if backoff > 0.0:
-                    time.sleep(backoff)
-            except ValueError:
-                raise
-            except (FastInferenceTimeoutError, FastInferenceExecutionError):
-                raise
-            except RuntimeError as err:
-                raise FastInferenceExecutionError(str(err)) from err
+    except (ValueError, FastInferenceExecutionError):
+        raise
+    except RuntimeError as err:
+        raise FastInferenceExecutionError(str(err)) from err

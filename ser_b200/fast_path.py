@@ -59,8 +59,13 @@ def segment_predictions(frame_predictions: list[FramePrediction]) -> list[Segmen
 def predict_frames(model, feature_matrix: np.ndarray, starts: Sequence[float], ends: Sequence[float],
                    *, device: int = 0) -> list[FramePrediction]:
     """GPU forward pass over a (frames, dim) matrix -> FramePrediction list."""
-    labels, proba = mlp.predict(model, feature_matrix, device=device)
-    class_labels = [str(item) for item in mlp.ensure_loaded(model, device).classes]
+    x = np.asarray(feature_matrix, dtype=np.float64)
+    with mlp.session(model, device) as (ctx, weights):     # load + forward under one lock
+        if x.ndim != 2 or x.shape[1] != weights.n_in:
+            raise ValueError(f"X has {x.shape[-1]} features, but the classifier expects {weights.n_in}.")
+        proba, index = ctx.mlp_predict_host(x)
+    labels = [weights.classes[i] for i in index]
+    class_labels = [str(item) for item in weights.classes]
     return [
         FramePrediction(
             start_seconds=float(starts[i]),

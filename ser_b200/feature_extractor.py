@@ -12,7 +12,7 @@ import numpy as np
 from numpy.typing import NDArray
 
 from . import dsp
-from .audio import read_audio_file
+from .audio import read_audio_file, read_pcm16_file
 from .config import FeatureFlags
 from .handcrafted import HandcraftedBackend
 
@@ -36,23 +36,31 @@ def extract_feature_from_signal(audio: NDArray[np.float32], sample_rate: int, *,
     return dsp.extract_feature_from_signal(audio, sample_rate, feature_flags=_flags_of(settings))
 
 
-def extract_feature(file: str, *, settings=None) -> NDArray[np.float64]:
+def extract_feature(file: str, *, settings=None, device: int = 0) -> NDArray[np.float64]:
     """Whole-file feature vector (feature_extractor.py:121-136)."""
+    backend = HandcraftedBackend(feature_flags=_flags_of(settings), device=device)
+    raw = read_pcm16_file(file)
+    if raw is not None:                 # 16-bit PCM: decode scaling / mono / peak normalisation on the device
+        return backend.extract_vector_pcm16(*raw)
     audio, sample_rate = read_audio_file(file)
-    return HandcraftedBackend(feature_flags=_flags_of(settings)).extract_vector(audio, sample_rate)
+    return backend.extract_vector(audio, sample_rate)
 
 
 def extract_feature_frames(audiofile: str, frame_size: int = 3, frame_stride: int = 1, *,
-                           settings=None) -> list[FeatureFrame]:
+                           settings=None, device: int = 0) -> list[FeatureFrame]:
     """Sliding-window features with start/end timestamps (feature_extractor.py:164-179)."""
     if frame_size <= 0:
         raise ValueError("frame_size must be greater than zero.")
     if frame_stride <= 0:
         raise ValueError("frame_stride must be greater than zero.")
-    audio, sample_rate = read_audio_file(audiofile)
     backend = HandcraftedBackend(frame_size_seconds=frame_size, frame_stride_seconds=frame_stride,
-                                 feature_flags=_flags_of(settings))
-    encoded = backend.encode_sequence(audio, sample_rate)
+                                 feature_flags=_flags_of(settings), device=device)
+    raw = read_pcm16_file(audiofile)
+    if raw is not None:                 # 16-bit PCM: the device prepares the samples (N1)
+        encoded = backend.encode_sequence_pcm16(*raw)
+    else:
+        audio, sample_rate = read_audio_file(audiofile)
+        encoded = backend.encode_sequence(audio, sample_rate)
     return [
         FeatureFrame(
             start_seconds=float(encoded.frame_start_seconds[i]),
@@ -64,6 +72,7 @@ def extract_feature_frames(audiofile: str, frame_size: int = 3, frame_stride: in
 
 
 def extended_extract_feature(audiofile: str, frame_size: int = 3, frame_stride: int = 1, *,
-                             settings=None) -> list[NDArray[np.float64]]:
+                             settings=None, device: int = 0) -> list[NDArray[np.float64]]:
     """Frame-wise vectors without timestamps (feature_extractor.py:139-161)."""
-    return [frame.features for frame in extract_feature_frames(audiofile, frame_size, frame_stride, settings=settings)]
+    return [frame.features for frame in
+            extract_feature_frames(audiofile, frame_size, frame_stride, settings=settings, device=device)]

@@ -89,6 +89,41 @@ class HandcraftedBackend:
             backend_id=self.backend_id,
         )
 
+    def encode_sequence_pcm16(self, pcm: NDArray[np.int16], channels: int, sample_rate: int) -> EncodedSequence:
+        """``encode_sequence`` of a raw 16-bit PCM file: decode scaling, mono mix, peak normalisation
+        (audio_utils.py:28-60) and every sliding window in one GPU call, 2 bytes per sample over PCIe."""
+        if sample_rate <= 0:
+            raise ValueError("sample_rate must be a positive integer.")
+        pcm = np.asarray(pcm)
+        if pcm.ndim != 1 or pcm.dtype != np.int16:
+            raise ValueError("pcm must be a 1-D int16 array of interleaved samples.")
+        frames = pcm.size // max(int(channels), 1)
+        if frames == 0:
+            raise ValueError("audio must contain at least one sample.")
+        starts, ends = frame_bounds(frames, sample_rate, self._frame_size_seconds, self._frame_stride_seconds)
+        if starts.size == 0:
+            raise ValueError("Could not extract handcrafted features from provided audio.")
+        embeddings = dsp.extract_features_pcm16(
+            [pcm], [int(channels)], np.zeros(starts.size, dtype=np.int64), starts, ends - starts, sample_rate,
+            feature_flags=self._feature_flags, device=self._device)
+        return EncodedSequence(
+            embeddings=embeddings.astype(np.float32, copy=False),
+            frame_start_seconds=starts.astype(np.float64) / float(sample_rate),
+            frame_end_seconds=ends.astype(np.float64) / float(sample_rate),
+            backend_id=self.backend_id,
+        )
+
+    def extract_vector_pcm16(self, pcm: NDArray[np.int16], channels: int, sample_rate: int) -> NDArray[np.float64]:
+        """``extract_vector`` of a raw 16-bit PCM file (one whole-file row)."""
+        pcm = np.asarray(pcm)
+        frames = pcm.size // max(int(channels), 1)
+        if frames == 0:
+            raise ValueError("Audio contains no samples.")
+        rows = dsp.extract_features_pcm16([pcm], [int(channels)], np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64),
+                                          np.asarray([frames], dtype=np.int64), sample_rate,
+                                          feature_flags=self._feature_flags, device=self._device)
+        return rows[0].astype(np.float64)
+
     def pool(self, encoded: EncodedSequence, windows: Sequence[PoolingWindow]) -> NDArray[np.float64]:
         """Mean of the frames overlapping each window (handcrafted.py:109-122)."""
         from .pooling import mean_pool

@@ -12,6 +12,8 @@ ser._internal.repr.handcrafted.HandcraftedBackend.encode_sequence      one ragge
 ser._internal.models.fast_path.predict_emotions_detailed_with_model    ser_b200.fast_path (fused CUDA MLP)
 ser._internal.models.emotion_model._fast_predict_emotions_detailed_with_model  (same; from-import alias)
 ser._internal.data.data_loader.load_checked_fast_data                  ser_b200.data_loader (ragged GPU batches)
+ser._internal.features.feature_extractor._extract_feature_frames_for_settings  16-bit PCM WAV: int16 to the device (N1),
+ser._internal.features.feature_extractor._extract_feature_for_settings         anything else: the reference's reader
 =====================================================================  =========================================
 
 ``ser.api.infer``, ``ser --file``, ``ser --train`` and ``run_fast_inference`` keep their
@@ -29,6 +31,8 @@ from typing import Any
 from . import data_loader as _data_loader
 from . import dsp as _dsp
 from . import fast_path as _fast_path
+from .audio import read_pcm16_file
+from .handcrafted import HandcraftedBackend as _GpuBackend
 from .handcrafted import frame_bounds
 
 _originals: list[tuple[Any, str, Any]] = []
@@ -106,13 +110,50 @@ def install(device: int = 0) -> list[str]:
             return None
         train, test, _ = split_utterances(samples=list(utterances), settings=settings, logger=ref_data_loader.logger)
         common = dict(feature_flags=settings.feature_flags, handle_sample_failure=handle_sample_failure,
-                      record_progress=record_preparation_progress, read_audio=read_audio, device=device)
+                      record_progress=record_preparation_progress, read_audio=read_audio,
+                      read_pcm16=read_pcm16_file, device=device)
         x_train, y_train = _data_loader.extract_partition(train, **common)
         x_test, y_test = _data_loader.extract_partition(test, **common)
         if len(set(y_train)) < 2:
             raise RuntimeError("Fast checked preparation left fewer than two training classes.")
         return x_train, x_test, y_train, y_test
 
+    original_frames = ref_features._extract_feature_frames_for_settings
+    original_vector = ref_features._extract_feature_for_settings
+
+    def _pcm16_or_none(file):
+        try:
+            return read_pcm16_file(file)
+        except Exception:           # noqa: BLE001 - the reference's reader reports path / decode problems its own way
+            return None
+
+    def extract_feature_frames_for_settings(audiofile, *, frame_size, frame_stride, feature_flags, audio_read_config):
+        # feature_extractor.py:70-103; 16-bit PCM WAV skips the host float32 pass (row N1)
+        if frame_size <= 0:
+            raise ValueError("frame_size must be greater than zero.")
+        if frame_stride <= 0:
+            raise ValueError("frame_stride must be greater than zero.")
+        raw = _pcm16_or_none(audiofile)
+        if raw is None:
+            return original_frames(audiofile, frame_size=frame_size, frame_stride=frame_stride,
+                                   feature_flags=feature_flags, audio_read_config=audio_read_config)
+        import numpy as np
+
+        encoded = _GpuBackend(frame_size_seconds=frame_size, frame_stride_seconds=frame_stride,
+                              feature_flags=feature_flags, device=device).encode_sequence_pcm16(*raw)
+        return [ref_features.FeatureFrame(start_seconds=float(encoded.frame_start_seconds[i]),
+                                          end_seconds=float(encoded.frame_end_seconds[i]),
+                                          features=np.asarray(encoded.embeddings[i], dtype=np.float64))
+                for i in range(encoded.embeddings.shape[0])]
+
+    def extract_feature_for_settings(file, *, feature_flags, audio_read_config):
+        raw = _pcm16_or_none(file)
+        if raw is None:
+            return original_vector(file, feature_flags=feature_flags, audio_read_config=audio_read_config)
+        return _GpuBackend(feature_flags=feature_flags, device=device).extract_vector_pcm16(*raw)
+
+    _swap(ref_features, "_extract_feature_frames_for_settings", extract_feature_frames_for_settings)
+    _swap(ref_features, "_extract_feature_for_settings", extract_feature_for_settings)
     _swap(ref_data_loader, "load_checked_fast_data", load_checked_fast_data)
     _swap(ref_dsp, "extract_feature_from_signal", extract_feature_from_signal)
     _swap(ref_features, "_extract_feature_from_signal", extract_feature_from_signal)

@@ -4,13 +4,13 @@ The fast-profile model is ``Pipeline([("scaler", StandardScaler()), ("classifier
 MLPClassifier(hidden_layer_sizes=(300,), ...))])`` (ser/_internal/models/training_support.py:87-106),
 persisted in the artifact envelope (ser/_internal/models/artifact_envelope.py:22-28).  This
 module pulls the arrays the kernel needs out of a fitted model by duck typing -- scikit-learn
-itself is never imported here -- and caches one upload per (model, device).
+itself is never imported here -- and keeps one upload per device, re-done whenever the model's
+weights change (``session``).
 """
 
 from __future__ import annotations
 
 import threading
-import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -80,35 +80,94 @@ def weights_from_model(model) -> MlpWeights:
     )
 
 
-_loaded: dict[int, tuple] = {}   # device -> (weakref-or-id key, MlpWeights)
-_loaded_lock = threading.Lock()
+def _fingerprint(model) -> tuple:
+    """Cheap identity of a model's *current* weights: object id plus the data pointers, shapes and a
+    strided sample of every array the kernel reads.  A model re-fitted in place (new ``coefs_``
+    arrays, or the same arrays overwritten) changes it, so stale device weights are never reused."""
+    if isinstance(model, MlpWeights):
+        arrays = (model.mean, model.scale, model.w1, model.b1, model.w2, model.b2)
+    else:
+        steps = getattr(model, "named_steps", None)
+        classifier = model if steps is None else (steps.get("classifier") or list(steps.values())[-1])
+        scaler = None if steps is None else steps.get("scaler")
+        arrays = tuple(getattr(classifier, "coefs_", ())) + tuple(getattr(classifier, "intercepts_", ()))
+        if scaler is not None:
+            arrays += tuple(a for a in (getattr(scaler, "mean_", None), getattr(scaler, "scale_", None)) if a is not None)
+    parts: list = [id(model)]
+    for a in arrays:
+        a = np.asarray(a)
+        flat = a.reshape(-1)
+        stride = max(1, flat.size // 512)
+        parts.append((a.__array_interface__["data"][0], a.shape, float(np.sum(flat[::stride], dtype=np.float64))))
+    return tuple(parts)
+
+
+class _DeviceSlot:
+    """The one weight slot of a device context plus the lock that makes load + forward atomic."""
+
+    def __init__(self) -> None:
+        self.lock = threading.RLock()
+        self.fingerprint: tuple | None = None
+        self.weights: MlpWeights | None = None
+
+
+_slots: dict[int, _DeviceSlot] = {}
+_slots_lock = threading.Lock()
+
+
+def _slot(device: int) -> _DeviceSlot:
+    with _slots_lock:
+        slot = _slots.get(device)
+        if slot is None:
+            slot = _slots[device] = _DeviceSlot()
+        return slot
+
+
+class session:
+    """``with mlp.session(model, device) as (ctx, weights):`` -- holds the device's weight-slot lock,
+    makes sure ``model``'s current weights are the resident ones, and keeps them resident until the
+    block exits.  Every forward pass of the package runs inside one, so two threads using
+    different models on one device (or an abandoned timed-out call and its successor) can never
+    read each other's weights; sklearn's ``predict`` is pure and so is this."""
+
+    def __init__(self, model, device: int = 0) -> None:
+        self._model = model
+        self._device = int(device)
+        self._slot = _slot(self._device)
+
+    def __enter__(self):
+        self._slot.lock.acquire()
+        try:
+            fingerprint = _fingerprint(self._model)
+            ctx = _native.get_context(self._device)
+            if self._slot.fingerprint != fingerprint:
+                weights = self._model if isinstance(self._model, MlpWeights) else weights_from_model(self._model)
+                self._slot.fingerprint = None          # a failed upload leaves no claim behind
+                ctx.mlp_load(weights.mean, weights.scale, weights.w1, weights.b1, weights.w2, weights.b2,
+                             weights.out_activation)
+                self._slot.fingerprint, self._slot.weights = fingerprint, weights
+            return ctx, self._slot.weights
+        except BaseException:
+            self._slot.lock.release()
+            raise
+
+    def __exit__(self, *exc) -> None:
+        self._slot.lock.release()
 
 
 def ensure_loaded(model, device: int = 0) -> MlpWeights:
-    """Uploads ``model``'s weights to ``device`` unless they are the ones already resident."""
-    key = id(model)
-    with _loaded_lock:
-        current = _loaded.get(device)
-        if current is not None and current[0] == key and current[2]() is model:
-            return current[1]
-        weights = model if isinstance(model, MlpWeights) else weights_from_model(model)
-        ctx = _native.get_context(device)
-        ctx.mlp_load(weights.mean, weights.scale, weights.w1, weights.b1, weights.w2, weights.b2,
-                     weights.out_activation)
-        try:
-            ref = weakref.ref(model)
-        except TypeError:
-            ref = (lambda m=model: m)
-        _loaded[device] = (key, weights, ref)
+    """Uploads ``model``'s weights to ``device`` unless they are the resident ones.  Single-threaded
+    callers (bench.py) may use the context directly afterwards; concurrent callers use ``session``."""
+    with session(model, device) as (_ctx, weights):
         return weights
 
 
 def predict(model, feature_matrix: np.ndarray, device: int = 0) -> tuple[list, np.ndarray]:
     """(labels, probabilities): what ``model.predict`` and ``model.predict_proba`` return
     (ser/_internal/models/fast_path.py:48,181), from one fused forward pass on the GPU."""
-    weights = ensure_loaded(model, device)
     x = np.asarray(feature_matrix, dtype=np.float64)
-    if x.ndim != 2 or x.shape[1] != weights.n_in:
-        raise ValueError(f"X has {x.shape[-1]} features, but the classifier expects {weights.n_in}.")
-    proba, index = _native.get_context(device).mlp_predict_host(x)
+    with session(model, device) as (ctx, weights):
+        if x.ndim != 2 or x.shape[1] != weights.n_in:
+            raise ValueError(f"X has {x.shape[-1]} features, but the classifier expects {weights.n_in}.")
+        proba, index = ctx.mlp_predict_host(x)
     return [weights.classes[i] for i in index], proba

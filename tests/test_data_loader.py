@@ -91,6 +91,57 @@ def test_blocks_respect_the_per_call_sample_budget(monkeypatch):
     assert calls == [2, 2, 1] and x.shape == (5, 3)
 
 
+def test_partition_is_streamed_block_by_block():
+    """Host memory is O(block): a block's audio is extracted and dropped before later files are read,
+    and finished samples are handed on (progress callbacks) while later files are still unread."""
+    reads, events = [], []
+    def read(path, *, start_seconds=None, duration_seconds=None):
+        reads.append(Path(path).name)
+        events.append(("read", Path(path).stem))
+        return np.full(400, 1.0, dtype=np.float32), 16000
+    def batch(clips, sr):
+        events.append(("extract", len(clips)))
+        return _fake_batch(clips, sr)
+    utterances = [FakeUtterance(str(i), Path(f"{i}.wav"), "x") for i in range(6)]
+    data_loader.extract_partition(utterances, read_audio=read, extract_batch=batch, max_samples_per_call=800,
+                                  record_progress=lambda **kw: events.append(("progress", kw["sample_id"])))
+    assert events == [("read", "0"), ("read", "1"), ("read", "2"), ("extract", 2), ("progress", "0"), ("progress", "1"),
+                      ("read", "3"), ("read", "4"), ("extract", 2), ("progress", "2"), ("progress", "3"),
+                      ("read", "5"), ("extract", 2), ("progress", "4"), ("progress", "5")]
+
+
+def test_progress_keeps_partition_order_across_sample_rates():
+    table = {"a.wav": (np.ones(300, dtype=np.float32), 16000), "b.wav": (np.ones(300, dtype=np.float32), 48000),
+             "c.wav": (np.ones(300, dtype=np.float32), 16000), "d.wav": (np.ones(300, dtype=np.float32), 48000)}
+    utterances = [FakeUtterance(n[0], Path(n), "x") for n in table]
+    progress = []
+    x, _ = data_loader.extract_partition(utterances, read_audio=_reader(table), extract_batch=_fake_batch,
+                                         record_progress=lambda **kw: progress.append(kw["sample_id"]))
+    assert progress == ["a", "b", "c", "d"]
+    np.testing.assert_array_equal(x[:, 2], [16000, 48000, 16000, 48000])
+
+
+def test_batch_level_errors_are_not_reported_as_sample_failures():
+    from ser_b200 import dsp
+
+    table = {f"{i}.wav": (np.ones(300, dtype=np.float32), 16000) for i in range(3)}
+    utterances = [FakeUtterance(str(i), Path(f"{i}.wav"), "x") for i in range(3)]
+    handled = []
+    def handle(utterance, error):
+        handled.append((utterance.sample_id, type(error).__name__))
+        return True
+    def cuda_oom(clips, sr):
+        raise RuntimeError("cudaMalloc: out of memory")
+    with pytest.raises(RuntimeError, match="out of memory"):
+        data_loader.extract_partition(utterances, read_audio=_reader(table), extract_batch=cuda_oom, handle_sample_failure=handle)
+    assert handled == []                      # a device failure is nobody's sample
+    def nyquist(clips, sr):                   # deterministic argument error: every sample of the block fails alone upstream
+        raise dsp.ParameterError("Frequency band exceeds Nyquist. Reduce either fmin or n_bands.")
+    with pytest.raises(RuntimeError, match="empty split partition"):
+        data_loader.extract_partition(utterances, read_audio=_reader(table), extract_batch=nyquist, handle_sample_failure=handle)
+    assert handled == [("0", "ParameterError"), ("1", "ParameterError"), ("2", "ParameterError")]
+
+
 @pytest.mark.gpu
 def test_partition_on_the_gpu_matches_single_clip_calls(tmp_path, golden):
     import wave
