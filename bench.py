@@ -1,17 +1,26 @@
 """Headline benchmark: audio-seconds/sec of fast-profile features + predict (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU path on the host cores
+    python bench.py --gpus N --steps K --warmup W                 # config c2, this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...       # the CPU path on the host cores
+    python bench.py --config c3 --gpus N ...                      # config c3: 20 000 clips, strong scaling
 
-A step is one pass of the hot path over one batch of synthetic RAVDESS-shape audio
-(config c2: 1 440 mono clips x 168 000 samples @ 48 kHz per GPU), run the way
-``ser.api.infer`` runs it: every clip is cut into 3 s / 1 s sliding windows
-(ser/_internal/repr/handcrafted.py:78-97), each window yields one feature row, and the
-scaler+MLP classifier labels every row.  Clips are independent, so with N GPUs every rank
-processes its own 1 440 clips (weak scaling) and no data-path collective exists; NCCL is
-used only for the timing barrier and the max-over-ranks reduction.
+Config c2 (default): a step is one pass of the hot path over one batch of synthetic RAVDESS-shape
+audio (1 440 mono clips x 168 000 samples @ 48 kHz per GPU), run the way ``ser.api.infer`` runs
+it: every clip is cut into 3 s / 1 s sliding windows (ser/_internal/repr/handcrafted.py:78-97),
+each window yields one 193-d feature row, and the scaler + MLP classifier labels every row.
+Clips are independent, so with N GPUs every rank processes its own 1 440 clips (weak scaling)
+and no data-path collective exists; NCCL carries only the timing barrier, the max-over-ranks
+reduction and the gather of the small result rows to rank 0.
 
-One JSON line is printed by rank 0 (keys: see the task contract).
+Config c3: 20 000 whole clips (the ``ser --train`` extraction, one row per file,
+ser/_internal/data/data_loader.py:485-529) split over the ranks by ``sharding.shard_bounds``;
+total work is fixed, rows are gathered to rank 0 (``"scaling": "strong"``).
+
+The classifier is a Pipeline(StandardScaler, MLPClassifier(300)) FITTED by scikit-learn on oracle
+rows of the same synthetic family (tests/golden/c2_oracle_rows.npz, made by
+tests/golden/make_c2_oracle_rows.py); both arms load the same weights.
+
+One JSON line is printed by rank 0 (keys: the task contract; DESIGN.md sections 4 and 8).
 """
 
 from __future__ import annotations
@@ -34,16 +43,18 @@ if str(REPO) not in sys.path:
 METRIC = "audio_seconds_per_second_fast_profile_features_predict"
 UNIT = "audio-s/s"
 FRAME_SECONDS, STRIDE_SECONDS = 3, 1
-FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FFMA peak at max clock
-FP32_PEAK_TFLOPS_MEASURED = 72.2                             # profiles/r01_fp32_microbench.txt (dependent-free FFMA)
-FLOP_PER_COLUMN = 97_000                                     # SURVEY.md section 8(d), 187-d slice
-FLOP_PER_COLUMN_193 = 1_045_000                              # itemised ops of the 193-d chain
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FFMA peak at the maximum SM clock
+OPS_PER_COLUMN_SURVEY = {187: 97_000, 193: 750_000}
+OPS_PER_COLUMN_ITEMISED = {187: 97_000, 193: 1_045_000}      # DESIGN.md section 4 (counts min/max/compare as ops)
+PARITY_TOLERANCE = 1e-4                                      # north_star: pooled features within 1e-4 (scaled, conftest.group_errors)
+GROUPS = {"mfcc": (0, 40), "chroma": (40, 52), "mel": (52, 180), "contrast": (180, 187), "tonnetz": (187, 193)}
 KERNEL_NAMES = {
     "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
     "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
     "istft": "istft_kernel", "ola": "ola_kernel", "decimate": "decimate2_kernel", "cqt": "cqt_kernel",
-    "tonnetz": "tonnetz_kernel",
+    "tonnetz": "tonnetz_kernel", "pcm_prepare": "pcm_file_scale_kernel",
 }
+TONNETZ = os.environ.get("SERB_BENCH_TONNETZ", "1") == "1"   # the build implements all five groups (193-d)
 
 
 def parse_args():
@@ -52,7 +63,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips", type=int, default=1440, help="clips per GPU per step")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--clips", type=int, default=0, help="clips per step (c2: per GPU, default 1440; c3: total, default 20000)")
     ap.add_argument("--clip-samples", type=int, default=168000)
     ap.add_argument("--sample-rate", type=int, default=48000)
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the bounded CPU sample (0 = auto)")
@@ -61,39 +73,44 @@ def parse_args():
     return ap.parse_args()
 
 
-def supported_flags():
-    """Feature groups this build computes: everything the library implements."""
-    from ser_b200 import _native
-    from ser_b200.config import FeatureFlags
-
-    lib = _native.load_library()
-    del lib
-    tonnetz = os.environ.get("SERB_BENCH_TONNETZ", "auto")
-    if tonnetz == "auto":
-        tonnetz = "1" if getattr(_native, "HAS_TONNETZ", False) else "0"
-    return FeatureFlags(tonnetz=(tonnetz == "1"))
-
-
 def window_plan(n_clips: int, clip_samples: int, sr: int):
-    """(starts, lengths) of every sliding window of every clip inside one packed buffer."""
+    """(clip index, start inside the clip, length) of every sliding window of every clip."""
     from ser_b200.handcrafted import frame_bounds
 
     w_starts, w_ends = frame_bounds(clip_samples, sr, FRAME_SECONDS, STRIDE_SECONDS)
-    base = (np.arange(n_clips, dtype=np.int64) * clip_samples)[:, None]
-    starts = (base + w_starts[None, :]).reshape(-1)
+    clip_of = np.repeat(np.arange(n_clips, dtype=np.int64), w_starts.size)
+    starts = np.tile(w_starts, n_clips).astype(np.int64)
     lengths = np.tile(w_ends - w_starts, n_clips).astype(np.int64)
-    return starts, lengths, int(w_starts.size)
+    return clip_of, starts, lengths, int(w_starts.size)
 
 
-def peaks():
+def hbm_peak():
     path = REPO / "MEASURED_PEAKS.json"
     if path.exists():
         try:
-            data = json.loads(path.read_text())
-            return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_fitted_model():
+    """The fitted classifier both arms use: arrays of a scikit-learn Pipeline(StandardScaler,
+    MLPClassifier(300)) trained by tests/golden/make_c2_oracle_rows.py."""
+    with np.load(REPO / "tests" / "golden" / "c2_oracle_rows.npz", allow_pickle=False) as data:
+        return {k.split("/", 1)[1]: data[k] for k in data.files if k.startswith("model/")}
+
+
+def scaled_group_errors(actual: np.ndarray, expected: np.ndarray) -> dict[str, float]:
+    """|a - b| / max(|b|, 1e-3 * max|b| over the group): the parity metric of tests/conftest.py."""
+    out = {}
+    for name, (lo, hi) in GROUPS.items():
+        if hi > expected.shape[1]:
+            continue
+        a, b = actual[:, lo:hi].astype(np.float64), expected[:, lo:hi].astype(np.float64)
+        floor = np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b), axis=1, keepdims=True))
+        out[name] = float(np.max(np.abs(a - b) / np.where(floor == 0.0, 1.0, floor))) if a.size else 0.0
+    return out
 
 
 class ClockSampler:
@@ -148,10 +165,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-# CPU arm: the oracle (numpy/scipy restatement of the reference's librosa + sklearn path)
+# CPU arm: the oracle (numpy/scipy restatement of the reference's librosa + sklearn path).
+# Nothing in this section imports ser_b200._native or loads libser_b200.so.
 # ----------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    clip, sr, flag_tuple, weights = args
+    index, clip, sr, flag_tuple, weights, whole_clip = args
     import warnings
 
     from oracle import ser_oracle
@@ -164,38 +182,46 @@ def _cpu_worker(args):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         flags = ser_oracle.FeatureFlags(*flag_tuple)
-        emb, starts, ends = ser_oracle.encode_sequence(clip, sr, feature_flags=flags)
-        frames, segments = ser_oracle.predict_frames(weights, emb, starts, ends)
+        if whole_clip:
+            rows = ser_oracle.extract_feature_from_signal(clip, sr, feature_flags=flags)[None, :].astype(np.float32)
+            labels = []
+        else:
+            rows, starts, ends = ser_oracle.encode_sequence(clip, sr, feature_flags=flags)
+            frames, _segments = ser_oracle.predict_frames(weights, rows, starts, ends)
+            labels = [f.emotion for f in frames]
     del limiter
-    return len(frames)
+    return index, rows, labels
 
 
-def cpu_pass(clips: np.ndarray, sr: int, flags, weights, workers: int) -> float:
-    """Seconds to run the CPU path over ``clips`` (rows) with ``workers`` processes."""
-    flag_tuple = (flags.mfcc, flags.chroma, flags.mel, flags.contrast, flags.tonnetz)
-    jobs = [(clips[i], sr, flag_tuple, weights) for i in range(clips.shape[0])]
+def cpu_pass(clips: np.ndarray, sr: int, flag_tuple, weights, workers: int, whole_clip: bool = False):
+    """(seconds, rows, labels) of the CPU path over ``clips`` (one clip per row) with ``workers`` processes."""
+    jobs = [(i, clips[i], sr, flag_tuple, weights, whole_clip) for i in range(clips.shape[0])]
     t0 = time.perf_counter()
     if workers <= 1:
-        for job in jobs:
-            _cpu_worker(job)
+        results = [_cpu_worker(job) for job in jobs]
     else:
         import multiprocessing as mp
 
         with mp.get_context("fork").Pool(workers) as pool:
-            list(pool.imap_unordered(_cpu_worker, jobs, chunksize=max(1, len(jobs) // (4 * workers))))
-    return time.perf_counter() - t0
+            results = list(pool.imap_unordered(_cpu_worker, jobs, chunksize=1))
+    seconds = time.perf_counter() - t0
+    results.sort(key=lambda r: r[0])
+    rows = np.concatenate([r[1] for r in results], axis=0)
+    labels = [label for r in results for label in r[2]]
+    return seconds, rows, labels
 
 
-def oracle_weights(dim: int, seed: int = 0):
+def oracle_weights(model: dict):
     from oracle import ser_oracle
-    from ser_b200 import synth
 
-    rng = np.random.default_rng(seed)
-    return ser_oracle.MlpWeights(
-        mean=rng.standard_normal(dim), scale=1.0 + rng.random(dim),
-        coefs=(rng.standard_normal((dim, 300)) * 0.1, rng.standard_normal((300, 8)) * 0.1),
-        intercepts=(rng.standard_normal(300) * 0.1, rng.standard_normal(8) * 0.1),
-        classes=tuple(sorted(synth.RAVDESS_EMOTIONS.values())), out_activation="softmax")
+    return ser_oracle.MlpWeights(mean=model["mean"], scale=model["scale"], coefs=(model["w1"], model["w2"]),
+                                 intercepts=(model["b1"], model["b2"]), classes=tuple(model["classes"].tolist()),
+                                 out_activation=str(model["out_activation"]))
+
+
+def flag_tuple_and_dim():
+    flags = (True, True, True, True, TONNETZ)
+    return flags, 193 if TONNETZ else 187
 
 
 def run_reference(args) -> None:
@@ -203,35 +229,42 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from ser_b200 import synth
-    from ser_b200.config import feature_dim
+    from ser_b200 import synth        # pure numpy; the native library is never loaded by this arm
 
-    flags = supported_flags()
-    dim = feature_dim(flags)
+    flag_tuple, dim = flag_tuple_and_dim()
     sr, n = args.sample_rate, args.clip_samples
     cores = os.cpu_count() or 1
     per_step = args.cpu_clips or max(cores, 8)
+    whole_clip = args.config == "c3"
     specs = synth.ravdess_specs(per_step)
     clips = np.stack([synth.clip_audio(s, sr, n) for s in specs])
-    weights = oracle_weights(dim)
-    for _ in range(args.warmup):
-        cpu_pass(clips, sr, flags, weights, cores)
+    model = load_fitted_model()
+    if dim != model["w1"].shape[0]:
+        raise RuntimeError("the committed classifier expects 193-d rows; run without SERB_BENCH_TONNETZ=0")
+    weights = oracle_weights(model)
+    warm = max(args.warmup, 1)
+    for _ in range(warm):
+        cpu_pass(clips, sr, flag_tuple, weights, cores, whole_clip)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_pass(clips, sr, flags, weights, cores)
+        cpu_pass(clips, sr, flag_tuple, weights, cores, whole_clip)
     elapsed = time.perf_counter() - t0
     audio_seconds = per_step * n / sr * args.steps
     value = audio_seconds / elapsed
-    sample = f"{per_step} clips x {n} samples @ {sr} Hz per step ({dim}-d features + MLP), numpy/scipy oracle"
+    what = "whole-clip rows" if whole_clip else f"{FRAME_SECONDS}s/{STRIDE_SECONDS}s windows + MLP"
+    sample = (f"{per_step} clips x {n} samples @ {sr} Hz per step ({dim}-d features, {what}), "
+              f"numpy/scipy oracle, one process per host core")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"c2 sample: {sample}", "feature_dim": dim},
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * elapsed / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong" if whole_clip else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.config} sample: {sample}", "feature_dim": dim,
+                   "weights": "fitted scikit-learn Pipeline(StandardScaler, MLPClassifier(300)) (tests/golden/c2_oracle_rows.npz)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "librosa 0.11.0 is not installable here (SURVEY.md F2): this is the CPU restatement "
-                "(oracle/) of the reference's librosa+sklearn path, one process per host core",
+                "(oracle/) of the reference's librosa+sklearn path",
     }
     emit(line)
 
@@ -239,18 +272,24 @@ def run_reference(args) -> None:
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
+def kernel_bounds():
+    """Binding unit of each kernel as ncu reports it (profiles/kernel_bounds.json, with sources)."""
+    path = REPO / "profiles" / "kernel_bounds.json"
+    try:
+        return json.loads(path.read_text())
+    except Exception:
+        return {}
+
+
 def run_b200(args) -> None:
     import torch
 
-    from ser_b200 import _native, mlp, synth
-    from ser_b200.config import feature_dim, flag_bits
-
-    from ser_b200 import multi_gpu
+    from ser_b200 import _native, mlp, multi_gpu, sharding, synth
 
     # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     info = multi_gpu.rank_info()
-    rank, local_rank, world, distributed = info.rank, info.local_rank, info.world, info.distributed
+    rank, local_rank, world = info.rank, info.local_rank, info.world
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: ser_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -262,28 +301,51 @@ def run_b200(args) -> None:
     def max_over_ranks(x: float) -> float:
         return multi_gpu.max_over_ranks(info, x, device="cuda")
 
-    flags = supported_flags()
-    bits = flag_bits(flags)
-    dim = feature_dim(flags)
-    sr, n_samples, n_clips = args.sample_rate, args.clip_samples, args.clips
+    flag_tuple, dim = flag_tuple_and_dim()
+    bits = sum(bit for bit, on in zip((1, 2, 4, 8, 16), flag_tuple) if on)
+    sr, n_samples = args.sample_rate, args.clip_samples
+    c3 = args.config == "c3"
+    if c3:
+        total_clips = args.clips or 20000
+        lo, hi = sharding.shard_bounds(np.full(total_clips, n_samples, dtype=np.int64), world)[rank]
+        n_clips, first_index = hi - lo, lo
+        audio_seconds_step = total_clips * n_samples / sr          # total work is fixed
+    else:
+        n_clips, first_index = args.clips or 1440, rank * (args.clips or 1440)
+        total_clips = n_clips * world
+        audio_seconds_step = total_clips * n_samples / sr
     ctx = _native.get_context(local_rank)
 
-    wave = synth.batch_audio_torch(n_clips, sr, n_samples, device="cuda", first_index=rank * n_clips)
+    # synthetic audio on the device: float32 as read_audio_file returns it, and the int16 PCM it was decoded from
+    wave = torch.empty((n_clips, n_samples), dtype=torch.float32, device="cuda")
+    pcm = torch.empty((n_clips, n_samples), dtype=torch.int16, device="cuda")
+    for a in range(0, n_clips, 1440):
+        b = min(a + 1440, n_clips)
+        wave[a:b], pcm[a:b] = synth.batch_audio_torch(b - a, sr, n_samples, device="cuda", first_index=first_index + a,
+                                                      return_pcm=True)
     wave = wave.reshape(-1).contiguous()
-    starts, lengths, windows_per_clip = window_plan(n_clips, n_samples, sr)
+    if c3:
+        clip_of = np.arange(n_clips, dtype=np.int64)
+        w_starts = np.zeros(n_clips, dtype=np.int64)
+        lengths = np.full(n_clips, n_samples, dtype=np.int64)
+        windows_per_clip = 1
+    else:
+        clip_of, w_starts, lengths, windows_per_clip = window_plan(n_clips, n_samples, sr)
+    starts = clip_of * n_samples + w_starts
     n_rows = int(starts.size)
-    audio_seconds_step = n_clips * n_samples / sr
+    total_rows = total_clips * windows_per_clip        # rows of all ranks: what rank 0 holds after the gather
 
-    rng = np.random.default_rng(0)
-    weights = mlp.MlpWeights(
-        mean=rng.standard_normal(dim), scale=1.0 + rng.random(dim),
-        w1=rng.standard_normal((dim, 300)) * 0.1, b1=rng.standard_normal(300) * 0.1,
-        w2=rng.standard_normal((300, 8)) * 0.1, b2=rng.standard_normal(8) * 0.1,
-        classes=tuple(sorted(synth.RAVDESS_EMOTIONS.values())), out_activation=_native.OUT_SOFTMAX)
+    model = load_fitted_model()
+    if dim != model["w1"].shape[0]:
+        raise RuntimeError("the committed classifier expects 193-d rows; run without SERB_BENCH_TONNETZ=0")
+    weights = mlp.MlpWeights(mean=model["mean"], scale=model["scale"], w1=model["w1"], b1=model["b1"], w2=model["w2"],
+                             b2=model["b2"], classes=tuple(model["classes"].tolist()),
+                             out_activation=_native.OUT_SOFTMAX if str(model["out_activation"]) == "softmax" else _native.OUT_LOGISTIC)
     mlp.ensure_loaded(weights, local_rank)
+    n_classes = len(weights.classes)
 
     feats = torch.empty((n_rows, dim), dtype=torch.float32, device="cuda")
-    proba = torch.empty((n_rows, 8), dtype=torch.float64, device="cuda")
+    proba = torch.empty((n_rows, n_classes), dtype=torch.float64, device="cuda")
     labels = torch.empty((n_rows,), dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     side = torch.cuda.Stream()          # an explicit stream: torch events and the library share it
@@ -292,11 +354,13 @@ def run_b200(args) -> None:
 
     def step():
         ctx.features_device(wave.data_ptr(), wave.numel(), starts, lengths, sr, bits, feats.data_ptr(), stream)
-        ctx.mlp_predict_device(feats.data_ptr(), n_rows, proba.data_ptr(), labels.data_ptr(), stream)
+        if not c3:
+            ctx.mlp_predict_device(feats.data_ptr(), n_rows, proba.data_ptr(), labels.data_ptr(), stream)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)          # the timing rules ask for at least three warm-up steps
+    for _ in range(warm):
         step()
-    torch.cuda.synchronize()
+    ctx.features_device_check(stream)   # synchronises; raises if any staged sample was not finite
 
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count
@@ -315,37 +379,83 @@ def run_b200(args) -> None:
     ms_total = max_over_ranks(float(ev0.elapsed_time(ev1)))
     launches = ctx.launch_count - launches0
     ms_per_step = ms_total / args.steps
-    value = world * audio_seconds_step * args.steps / (ms_total / 1e3)
+    value = audio_seconds_step * args.steps / (ms_total / 1e3)
+    dev_labels = labels.cpu().numpy()
+    dev_feats = feats.cpu().numpy()
 
-    # ---- end to end: pinned host buffers in, labels + probabilities back, every step ----
+    # ---- end to end: host PCM16 in (what the files hold), labels + probabilities back, every step ----
     e2e = None
     if not args.no_e2e:
-        host_wave = torch.empty(wave.numel(), dtype=torch.float32, pin_memory=True)
-        host_wave.copy_(wave)
+        files_pinned = torch.empty((n_clips, n_samples), dtype=torch.int16, pin_memory=True)
+        files_pinned.copy_(pcm)
         torch.cuda.synchronize()
-        hw = host_wave.numpy()
+        pinned_np = files_pinned.numpy()
+        file_list = [pinned_np[i] for i in range(n_clips)]          # views: one contiguous pinned buffer
+
+        def e2e_call(files):
+            if c3:
+                rows = ctx.features_host_pcm16(files, 1, clip_of, w_starts, lengths, sr, bits)
+                return rows, None, None
+            return ctx.infer_host_pcm16(files, 1, clip_of, w_starts, lengths, sr, bits, want_features=False)
+
+        def e2e_timed(files, steps):
+            e2e_call(files)                                          # warm the staging buffers
+            barrier()
+            t0 = time.perf_counter()
+            chain = []
+            gathered = None
+            for _ in range(steps):
+                f_host, p_host, l_host = e2e_call(files)
+                chain.append(ctx.last_compute_ms())
+                # the small per-row results go to rank 0 inside the timed region (north_star)
+                local = f_host if c3 else np.concatenate([p_host, l_host[:, None].astype(np.float64)], axis=1)
+                gathered = multi_gpu.gather_rows(info, local, total_rows)
+            elapsed = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            return elapsed, float(np.median(chain)), (f_host, p_host, l_host), gathered
+
         e2e_steps = max(2, min(args.steps, 5))
-        ctx.infer_host(hw, starts, lengths, sr, bits, want_features=False)   # warm the staging buffers
-        barrier()
-        t0 = time.perf_counter()
-        chain_ms = []
-        for _ in range(e2e_steps):
-            _f, p_host, l_host = ctx.infer_host(hw, starts, lengths, sr, bits, want_features=False)
-            chain_ms.append(ctx.last_compute_ms())
-        elapsed = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        e2e = {"value": world * audio_seconds_step * e2e_steps / elapsed, "unit": UNIT,
-               "h2d_bytes_per_step": int(hw.nbytes), "d2h_bytes_per_step": int(p_host.nbytes + l_host.nbytes),
-               "steps": e2e_steps, "ms_per_step": 1e3 * elapsed / e2e_steps,
-               "device_chain_ms": float(np.median(chain_ms))}
-        assert np.array_equal(l_host, labels.cpu().numpy()), "host-entry labels differ from the device path"
+        elapsed, chain_ms, last, gathered = e2e_timed(file_list, e2e_steps)
+        f_host, p_host, l_host = last
+        d2h = int(f_host.nbytes) if c3 else int(p_host.nbytes + l_host.nbytes)
+        e2e = {"value": audio_seconds_step * e2e_steps / elapsed, "unit": UNIT,
+               "h2d_bytes_per_step": int(pinned_np.nbytes), "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "ms_per_step": 1e3 * elapsed / e2e_steps, "device_chain_ms": chain_ms,
+               "input": "int16 PCM in pinned host memory (serb_infer_host_pcm16: decode scaling, peak normalisation, "
+                        "features and classifier on the device)" if not c3 else
+                        "int16 PCM in pinned host memory (serb_features_host_pcm16)",
+               "gathered_rows_on_rank0": None if gathered is None else int(gathered.shape[0])}
+        if c3:
+            assert np.array_equal(f_host, dev_feats), "PCM16 host-entry rows differ from the device path"
+        else:
+            assert np.array_equal(l_host, dev_labels), "PCM16 host-entry labels differ from the device path"
+        # the same call from pageable memory (what a numpy caller of the Python API passes)
+        pageable = [np.array(pinned_np[i]) for i in range(n_clips)]
+        elapsed_p, chain_p, _, _ = e2e_timed(pageable, 2)
+        e2e["pageable"] = {"value": audio_seconds_step * 2 / elapsed_p, "unit": UNIT, "ms_per_step": 1e3 * elapsed_p / 2,
+                           "device_chain_ms": chain_p, "input": "one pageable int16 numpy array per file"}
+        del pageable
+        if not c3:
+            # round 1's float32 entry, for continuity: 4 bytes per sample over PCIe
+            host_wave = torch.empty(wave.numel(), dtype=torch.float32, pin_memory=True)
+            host_wave.copy_(wave)
+            torch.cuda.synchronize()
+            hw = host_wave.numpy()
+            ctx.infer_host(hw, starts, lengths, sr, bits, want_features=False)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ctx.infer_host(hw, starts, lengths, sr, bits, want_features=False)
+            elapsed_f = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            e2e["float32_pinned"] = {"value": audio_seconds_step * 2 / elapsed_f, "unit": UNIT,
+                                     "ms_per_step": 1e3 * elapsed_f / 2, "h2d_bytes_per_step": int(hw.nbytes)}
+            del host_wave, hw
 
     # ---- the 187-d slice (tonnetz off) timed the same way, for continuity with earlier rounds ----
     slice187 = None
-    if flags.tonnetz:
-        from ser_b200.config import FeatureFlags
-
-        bits187 = flag_bits(FeatureFlags(tonnetz=False))
+    if TONNETZ and not c3:
+        bits187 = 15
         feats187 = torch.empty((n_rows, 187), dtype=torch.float32, device="cuda")
         for _ in range(3):
             ctx.features_device(wave.data_ptr(), wave.numel(), starts, lengths, sr, bits187, feats187.data_ptr(), stream)
@@ -357,7 +467,7 @@ def run_b200(args) -> None:
         e1.record()
         torch.cuda.synchronize()
         ms187 = max_over_ranks(float(e0.elapsed_time(e1))) / args.steps
-        slice187 = {"ms_per_step": ms187, "value": world * audio_seconds_step / (ms187 / 1e3), "unit": UNIT,
+        slice187 = {"ms_per_step": ms187, "value": audio_seconds_step / (ms187 / 1e3), "unit": UNIT,
                     "note": "features only, FeatureFlags(tonnetz=False): mfcc + chroma + mel + contrast"}
         del feats187
 
@@ -373,65 +483,86 @@ def run_b200(args) -> None:
     # event pair: count kernel launches, not brackets (the constant-Q kernel is one launch per chunk)
     dom_n *= {"decimate": 7 if sr >= 33400 else 6, "tonnetz": 2}.get(dom, 1)
     total_cols = int(np.sum(1 + lengths // 512))
-    # algorithmic bytes: every input sample once + every output row once
+    # algorithmic bytes: every input sample once (float32 at boundary B1/B2) + every output row once
     alg_bytes_step = 4 * n_clips * n_samples + 4 * dim * n_rows
-    peak, peak_src = peaks()
+    peak, peak_src = hbm_peak()
     achieved = alg_bytes_step / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture
-    # (bytes per STFT column per launch x the columns an average launch of this run covers)
+    bounds = kernel_bounds().get(KERNEL_NAMES[dom], {})
     traffic = None
-    traffic_file = REPO / "profiles" / "dominant_kernel_traffic.json"
-    if traffic_file.exists():
-        try:
-            entry = json.loads(traffic_file.read_text()).get(KERNEL_NAMES[dom])
-            if entry:
-                traffic = entry["dram_bytes_per_stft_column_per_launch"] * total_cols / max(dom_n, 1)
-        except Exception:
-            traffic = None
-    flop_per_column = FLOP_PER_COLUMN_193 if flags.tonnetz else FLOP_PER_COLUMN
+    if bounds.get("dram_bytes_per_stft_column_per_launch") is not None:
+        traffic = bounds["dram_bytes_per_stft_column_per_launch"] * total_cols / max(dom_n, 1)
+    fp32_measured = ctx.fp32_peak_tflops()
+    step_ops_survey = total_cols * OPS_PER_COLUMN_SURVEY[dim]
+    step_ops_itemised = total_cols * OPS_PER_COLUMN_ITEMISED[dim]
+    sum_kernel_ms = max(sum(v[0] for v in kms.values()), 1e-9)
     roofline = {
-        "kernel": KERNEL_NAMES[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "kernel": KERNEL_NAMES[dom], "bound": bounds.get("bound", "unprofiled"),
+        "binding_pipe": bounds.get("binding_pipe"), "binding_pipe_frac": bounds.get("binding_pipe_frac"),
+        "bound_source": bounds.get("source"),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": bounds.get("traffic_source"), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes_step / max(dom_n, 1), "launches_per_step": dom_n,
         "avg_launch_ms": dom_ms / max(dom_n, 1),
         "kernel_ms_per_step": {k: v[0] for k, v in kms.items()},
-        "share_of_step": dom_ms / max(sum(v[0] for v in kms.values()), 1e-9),
-        "fp32": {"achieved_tflops": total_cols * flop_per_column / (ms_per_step / 1e3) / 1e12,
-                 "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL, "peak_tflops_measured": FP32_PEAK_TFLOPS_MEASURED,
-                 "note": f"whole step, {flop_per_column // 1000} kop/column (DESIGN.md section 4); the path is "
-                         "ALU/FP32/shared-memory bound, not HBM bound"},
+        "share_of_step": dom_ms / sum_kernel_ms,
+        "whole_step_hbm_frac": alg_bytes_step / (ms_per_step / 1e3) / 1e9 / peak,
+        "fp32": {"peak_tflops_measured": fp32_measured, "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
+                 "peak_how": "serb_debug_fp32_peak: dependent-free FFMA chains on every SM, this run",
+                 "achieved_tflops_survey": step_ops_survey / (ms_per_step / 1e3) / 1e12,
+                 "achieved_tflops_itemised": step_ops_itemised / (ms_per_step / 1e3) / 1e12,
+                 "frac_survey": step_ops_survey / (ms_per_step / 1e3) / 1e12 / max(fp32_measured, 1e-9),
+                 "frac_itemised": step_ops_itemised / (ms_per_step / 1e3) / 1e12 / max(fp32_measured, 1e-9),
+                 "note": f"whole step; SURVEY 8(d) {OPS_PER_COLUMN_SURVEY[dim] // 1000} kop/column next to this repo's "
+                         f"itemised {OPS_PER_COLUMN_ITEMISED[dim] // 1000} kop/column (DESIGN.md section 4, counts "
+                         "min/max/compare as ops)"},
         "how": "CUDA events around every launch of the dominant kernel in one extra pass of the same step",
     }
 
-    cpu_baseline = None
+    # ---- CPU baseline on the box's host cores + parity of the GPU rows against it, rank 0 at N=1 ----
+    cpu_baseline = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        per = args.cpu_clips or (8 if flags.tonnetz else 24)
+        cores = min(os.cpu_count() or 1, 32)
+        per = args.cpu_clips or min(n_clips, max(2 * cores, 8) if TONNETZ else 4 * cores)
         sample_clips = wave[: per * n_samples].reshape(per, n_samples).cpu().numpy()
-        secs = cpu_pass(sample_clips, sr, flags, oracle_weights(dim), workers=1)
-        cpu_baseline = {"value": per * n_samples / sr / secs, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"first {per} clips of the step ({per * windows_per_clip} windows), one process, "
-                                  f"BLAS threads limited to 1, {secs:.1f} s",
+        secs, cpu_rows, cpu_labels = cpu_pass(sample_clips, sr, flag_tuple, oracle_weights(model), workers=cores,
+                                              whole_clip=c3)
+        cpu_baseline = {"value": per * n_samples / sr / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"first {per} clips of the step ({per * windows_per_clip} rows), one process per core, "
+                                  f"BLAS threads limited to 1, {secs:.1f} s wall",
                         "host_cores_available": os.cpu_count()}
+        gpu_rows = dev_feats[: per * windows_per_clip]
+        errors = scaled_group_errors(gpu_rows, cpu_rows)
+        parity = {"rows": int(gpu_rows.shape[0]), "max_scaled_err": errors, "tolerance": PARITY_TOLERANCE,
+                  "against": "oracle rows of the same clips (the cpu_baseline pass)"}
+        if not c3:
+            gpu_labels = [weights.classes[i] for i in dev_labels[: per * windows_per_clip]]
+            parity["labels_equal"] = gpu_labels == cpu_labels
+            parity["labels_compared"] = len(cpu_labels)
+        parity["ok"] = bool(max(errors.values()) <= PARITY_TOLERANCE and parity.get("labels_equal", True))
 
     if rank == 0:
+        what = "whole-clip rows (training extraction)" if c3 else \
+            f"{FRAME_SECONDS}s/{STRIDE_SECONDS}s sliding windows ({n_rows} rows/GPU), {dim}-d features + MLP(300) predict"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": warm, "warmup_requested": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if c3 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"c2: {n_clips} clips x {n_samples} samples @ {sr} Hz per GPU, "
-                            f"{FRAME_SECONDS}s/{STRIDE_SECONDS}s sliding windows ({n_rows} rows/GPU), "
-                            f"{dim}-d features + MLP(300) predict",
+                "workload": (f"c3: {total_clips} clips x {n_samples} samples @ {sr} Hz split over {world} GPU(s), {what}" if c3 else
+                             f"c2: {n_clips} clips x {n_samples} samples @ {sr} Hz per GPU, {what}"),
                 "feature_dim": dim, "rows_per_gpu": n_rows, "stft_columns_per_gpu": total_cols,
-                "weights": "random-init Pipeline(StandardScaler, MLPClassifier(300)) shape",
+                "weights": "fitted scikit-learn Pipeline(StandardScaler, MLPClassifier(300)) (tests/golden/c2_oracle_rows.npz)",
                 "l2": f"inputs {wave.numel() * 4 / 1e6:.0f} MB per GPU exceed the 126 MB L2; no explicit flush",
-                "parallelism": f"clips sharded over {world} GPU(s), no collective",
+                "parallelism": f"clips sharded over {world} GPU(s), no data-path collective; result rows gathered to rank 0 in e2e",
             },
             "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "slice_187d": slice187,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "slice_187d": slice187,
         }
         emit(line)
     multi_gpu.destroy_process_group(info)
+    if parity is not None and not parity["ok"]:
+        print(f"bench.py: parity check failed: {parity}", file=sys.stderr)
+        sys.exit(3)
 
 
 _RESULT_FD = None

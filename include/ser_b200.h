@@ -218,6 +218,9 @@ int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octa
 /* decimation filter (soxr_hq stand-in) for an integer factor 2..8; returns the tap count
  * (> 0) and, when out is non-NULL and capacity suffices, the taps.  Host only. */
 int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity);
+/* FP32 ceiling of this GPU right now: dependent-free FFMA chains on every SM, best of four timed
+ * launches, in TFLOP/s (the denominator of bench.py's whole-step FP32 fraction) */
+int serb_debug_fp32_peak(serb_ctx* ctx, double* tflops);
 /* kernels launched by this context since creation */
 int64_t serb_debug_launch_count(const serb_ctx* ctx);
 /* per-kernel CUDA-event timing: kinds 0 stft, 1 tuning, 2 proj, 3 pool, 4 short, 5 mlp, 6 hpss_harm,

@@ -17,6 +17,7 @@ import warnings
 import numpy as np
 import scipy.fft
 import scipy.signal
+import scipy.special
 
 from . import filters, util
 from .util import ParameterError
@@ -72,27 +73,70 @@ def load(path, *, sr=22050, mono=True, offset=0.0, duration=None, dtype=np.float
 
 _SOXR_FILTER_CACHE: dict[int, np.ndarray] = {}
 
+# libsoxr's cubic fits of the Kaiser beta against attenuation (>= 60 dB), one row per octave of
+# relative transition width 0.0005 * 2^row, interpolated linearly in log2(width).  Restated from
+# memory of libsoxr's filter.c (the library is an un-vendored, un-installable dependency here:
+# soxr 1.0.0, uv.lock:2175-2176); the digits cannot be verified offline and
+# scripts/soxr_sensitivity_study.py bounds what an error in them would do (profiles/r02_soxr_sensitivity.txt).
+_LSX_BETA_ROWS = (
+    (-6.784957e-10, 1.02856e-05, 0.1087556, -0.8988365 + 0.001),
+    (-6.897885e-10, 1.027433e-05, 0.10876, -0.8994658 + 0.002),
+    (-1.000683e-09, 1.030092e-05, 0.1087677, -0.9007898 + 0.003),
+    (-3.654474e-10, 1.040631e-05, 0.1087085, -0.8977766 + 0.006),
+    (8.106988e-09, 6.983091e-06, 0.1091387, -0.9172048 + 0.015),
+    (9.519571e-09, 7.272678e-06, 0.1090068, -0.9140768 + 0.025),
+    (-5.626821e-09, 1.342186e-05, 0.1083999, -0.9065452 + 0.05),
+    (-9.965946e-08, 5.073548e-05, 0.1040967, -0.7672778 + 0.085),
+    (1.604808e-07, -5.856462e-05, 0.1185998, -1.34824 + 0.1),
+    (-1.511964e-07, 6.363034e-05, 0.1064627, -0.9876665 + 0.18),
+)
+
+
+def _lsx_kaiser_beta(att, tr_bw):
+    realm = np.log(tr_bw / 0.0005) / np.log(2.0)
+    i0 = min(max(int(realm), 0), len(_LSX_BETA_ROWS) - 1)
+    i1 = min(max(1 + int(realm), 0), len(_LSX_BETA_ROWS) - 1)
+    b0, b1 = (((c[0] * att + c[1]) * att + c[2]) * att + c[3] for c in (_LSX_BETA_ROWS[i0], _LSX_BETA_ROWS[i1]))
+    return float(b0 + (b1 - b0) * (realm - int(realm)))
+
 
 def _soxr_hq_decimation_filter(factor):
-    """Linear-phase low-pass standing in for libsoxr's HQ decimator (soxr 1.0.0, un-vendored).
+    """Linear-phase low-pass restating libsoxr's "HQ" decimation filter (soxr 1.0.0, un-vendored).
 
-    libsoxr "HQ" = 20-bit precision: pass-band ends at 0.913 of the output Nyquist, the
-    stop-band starts at the output Nyquist, rejection >= (20+1)*6.02 dB, linear phase,
-    latency compensated.  libsoxr is not available here, so this designs a Kaiser-windowed
-    sinc to the same published spec.  For the CQT path every band the reference reads lies
-    below 0.66 of the output Nyquist, i.e. inside the flat
-    pass-band, so the two filters agree there to their pass-band ripple (< 1e-6).
+    Quality recipe (soxr_quality_spec(SOXR_HQ)): 20-bit precision, i.e. rejection
+    (20 + 1) * 20 log10(2) = 126.43 dB; pass-band end 1 - 0.05 / TO_3dB(120.41) = 0.913628 of the
+    output Nyquist with TO_3dB(a) = (1.6e-6 a - 7.5e-4) a + 0.646; stop-band at the output Nyquist;
+    linear phase.  Design procedure (lsx_design_lpf / lsx_kaiser_params / lsx_make_lpf): with
+    frequencies normalised to the input Nyquist, tr_bw = (Fs - Fp) / 2, Fc = Fs - tr_bw, Kaiser beta
+    from the library's cubic fit at relative width tr_bw / 2 / Fc, tap count
+    ceil(A(beta) / tr_bw + 1) rounded up to 1 mod 4, h[i] = sin(Fc pi z) / (pi z) *
+    I0(beta sqrt(1 - (z / (m/2 + 1/2))^2)) / I0(beta), z = i - m/2, no DC renormalisation.
+    For the 2:1 stage of librosa.cqt that is 389 taps, beta = 13.04, Fc = 0.478407.
+    The library applies it by FFT overlap-save in float32; here it is a float64 convolution.
+
+    This is a restatement, not libsoxr: see scripts/soxr_sensitivity_study.py for what the
+    uncertain digits (beta, hence the tap count) can move -- tonnetz <= 1e-4 scaled inside the
+    family, no label change -- and for how far out-of-spec filters land (>= 1e-3).
     """
     if factor in _SOXR_FILTER_CACHE:
         return _SOXR_FILTER_CACHE[factor]
-    att = 21 * 6.0206
-    f_pass = 0.913 / factor  # fractions of the INPUT Nyquist
-    f_stop = 1.0 / factor
-    width = f_stop - f_pass
-    numtaps, beta = scipy.signal.kaiserord(att, width)
-    if numtaps % 2 == 0:
-        numtaps += 1
-    taps = scipy.signal.firwin(numtaps, 0.5 * (f_pass + f_stop), window=("kaiser", beta), scale=True)
+    bits = 20.0
+    rej = bits * 20.0 * np.log10(2.0)
+    att = (bits + 1.0) * 20.0 * np.log10(2.0)
+    pass_end = 1.0 - 0.05 / ((1.6e-6 * rej - 7.5e-4) * rej + 0.646)
+    fp, fs = pass_end / factor, 1.0 / factor           # fractions of the INPUT Nyquist
+    tr_bw = min(0.5 * (fs - fp), 0.5 * fs)
+    fc = fs - tr_bw
+    beta = _lsx_kaiser_beta(att, tr_bw * 0.5 / fc)
+    a = ((0.0007528358 - 1.577737e-05 * beta) * beta + 0.6248022) * beta + 0.06186902
+    numtaps = (int(np.ceil(a / tr_bw + 1)) + 2) // 4 * 4 + 1
+    m = numtaps - 1
+    z = np.arange(numtaps, dtype=np.float64) - 0.5 * m
+    x = z * np.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        h = np.where(x != 0, np.sin(fc * x) / x, fc)
+    y = z / (0.5 * m + 0.5)
+    taps = h * scipy.special.i0(beta * np.sqrt(np.maximum(0.0, 1.0 - y * y))) / scipy.special.i0(beta)
     _SOXR_FILTER_CACHE[factor] = taps
     return taps
 

@@ -16,13 +16,14 @@ fitted Pipeline(StandardScaler, MLPClassifier(300)) -- over a family of decimato
 the published spec, plus deliberately out-of-spec ones to show where the tolerance breaks.
 
 Variants (all zero-latency linear-phase FIR, applied as the oracle applies its own):
-  default          oracle/CUDA filter: scipy kaiserord/firwin, 381 taps
-  lsx_389          libsoxr's design procedure as recollected from its filter.c (lsx_design_lpf +
-                   lsx_kaiser_params + lsx_make_lpf): Fc = Fs - tr_bw, beta from its cubic fit
-                   (13.04), tap count from its attenuation polynomial rounded up to 1 mod 4 (389),
-                   window argument 1 / (m/2 + 0.5), no DC renormalisation
+  default          the oracle's / CUDA kernel's filter since round 2: libsoxr's design procedure as
+                   recollected from its filter.c (lsx_design_lpf + lsx_kaiser_params + lsx_make_lpf):
+                   Fc = Fs - tr_bw, beta from its cubic fit (13.04), tap count from its attenuation
+                   polynomial rounded up to 1 mod 4 (389), window argument 1 / (m/2 + 0.5), no DC
+                   renormalisation
   lsx_389_f32      the same taps rounded to float32 and a float32 FFT convolution (libsoxr runs its
                    <= 20-bit recipes in single precision)
+  firwin_381       round 1's stand-in: scipy kaiserord / firwin at pass-band end 0.913 (381 taps)
   lsx_385          the same procedure with beta 0.025 lower (the recollected fit's digits are the
                    uncertain part): the tap-count formula then lands on 385
   kaiser_std_385   385 taps, textbook beta = 0.1102 (A - 8.7)
@@ -119,9 +120,9 @@ def firwin_design(numtaps=None, pass_end=0.913, stop_begin=1.0, att=21 * 6.0206,
 
 def variants():
     out = {
-        "default": (firwin_design(), False),
-        "lsx_389": (lsx_design(), False),
+        "default": (lsx_design(), False),
         "lsx_389_f32": (lsx_design(), True),
+        "firwin_381": (firwin_design(), False),
         "lsx_385": (lsx_design(beta=lsx_kaiser_beta(ATT_DB, 0.0225677) - 0.025), False),
         "kaiser_std_385": (lsx_design(beta=0.1102 * (ATT_DB - 8.7), num_taps=385), False),
         "taps_361": (firwin_design(361), False),
@@ -277,7 +278,7 @@ def main():
         print(f"| {name} | {ab.max():.2e} | {se.max():.2e} | {np.quantile(se, 0.99):.2e} | {np.median(se):.2e} | "
               f"{int(np.sum(se.max(axis=1) > 1e-4))} / {n_c2} |")
 
-    family = [k for k in var if k.startswith(("default", "lsx_", "kaiser_std"))]
+    family = [k for k in var if k.startswith(("default", "lsx_", "kaiser_std"))]      # libsoxr's procedure, uncertain digits
     worst_abs = worst_scaled = 0.0
     for i, a in enumerate(family):
         for b in family[i + 1:]:

@@ -53,6 +53,7 @@ SIGNATURES: dict[str, tuple] = {
     "serb_debug_cqt_basis": (c_int, [c_int32, c_int32, c_int32, _P, _P]),
     "serb_debug_decimation_taps": (c_int, [c_int32, _P, c_int32]),
     "serb_debug_launch_count": (c_int64, [_P]),
+    "serb_debug_fp32_peak": (c_int, [_P, _P]),
     "serb_debug_last_compute_ms": (c_float, [_P]),
     "serb_debug_set_profile": (c_int, [_P, c_int32]),
     "serb_debug_kernel_ms": (c_int, [_P, c_int32, _P, _P]),
@@ -342,6 +343,12 @@ class Context:
             self._check(self._lib.serb_debug_kernel_ms(self._handle, kind, ctypes.byref(ms), ctypes.byref(n)))
             out[name] = (float(ms.value), int(n.value))
         return out
+
+    def fp32_peak_tflops(self) -> float:
+        """FFMA ceiling of this GPU measured now (dependent-free chains on every SM)."""
+        out = c_double(0.0)
+        self._check(self._lib.serb_debug_fp32_peak(self._handle, ctypes.byref(out)))
+        return float(out.value)
 
     def last_compute_ms(self) -> float:
         return float(self._lib.serb_debug_last_compute_ms(self._handle))

@@ -64,6 +64,10 @@ def decode_wav(path: str | Path) -> tuple[NDArray[np.float32], int]:
         data = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / np.float32(128.0)
     elif width == 4:
         data = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        data = (np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float64) / 8388608.0).astype(np.float32)
     else:
         raise AudioDecodeError(f"Unsupported PCM sample width {width} in {path}")
     if channels > 1:

@@ -1707,6 +1707,36 @@ int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity) {
 
 int64_t serb_debug_launch_count(const serb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int serb_debug_fp32_peak(serb_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return SERB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    SERB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop{};
+    SERB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    SERB_CUDA(ctx, ctx->x64.reserve(static_cast<size_t>(blocks) * 256 * sizeof(float)));
+    cudaEvent_t a, b;
+    SERB_CUDA(ctx, cudaEventCreate(&a));
+    SERB_CUDA(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {           // first pass warms up; keep the best of the rest
+        cudaEventRecord(a, ctx->stream);
+        cudaError_t e = launch_fp32_peak(ctx->x64.as<float>(), blocks, iters, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(b);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+        if (e != cudaSuccess) { cudaEventDestroy(a); cudaEventDestroy(b); return fail_cuda(ctx, e, "fp32 peak probe"); }
+        const double flops = 2.0 * 16.0 * iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    ctx->launches += 5;
+    *tflops = best;
+    return SERB_OK;
+}
+
 int serb_debug_set_profile(serb_ctx* ctx, int32_t enabled) {
     if (!ctx) return SERB_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);

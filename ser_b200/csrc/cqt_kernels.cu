@@ -7,7 +7,7 @@
 // per octave a rectangular-window STFT of the (recursively half-band decimated) signal times a
 // sparsified FFT-domain wavelet basis.
 //
-// decimate2_kernel   factor-2 FIR decimation (381-tap Kaiser stand-in for soxr_hq, x sqrt 2):
+// decimate2_kernel   factor-2 FIR decimation (389-tap restatement of libsoxr's HQ low-pass, x sqrt 2):
 //                    the two polyphase branches in the halves of packed f32x2 FMAs (FFMA2),
 //                    8 outputs per thread, bank-group padded window, fully unrolled
 // decimate_any_kernel  early downsampling by 4 / 8 (sample rates >= 64 kHz), plain
@@ -22,10 +22,12 @@
 
 namespace serb {
 
-// Factor-2 decimator taps (x sqrt 2) paired for packed FP32 FMAs: c_tap2[e] = (h[382 - 2e],
-// h[381 - 2e]) multiplies the sample pair (x[2q], x[2q + 1]) at pair distance e = 1..191 from the
-// output (zero outside the 381 taps).
-constexpr int kTapPairs = 192;
+// Factor-2 decimator taps (x sqrt 2) paired for packed FP32 FMAs: with K = kDecTaps2 taps,
+// c_tap2[e] = (h[K + 1 - 2e], h[K - 2e]) multiplies the sample pair (x[2q], x[2q + 1]) at pair
+// distance e = 1 .. (K + 1) / 2 from the output (zero outside the K taps).
+constexpr int kDecHalo = (kDecTaps2 + 3) / 4;     // polyphase samples staged before the tile
+constexpr int kTapPairs = 2 * kDecHalo;
+static_assert(kDecTaps2 % 4 == 1, "the pairing below assumes a tap count of 1 mod 4");
 __constant__ __align__(16) float2 c_tap2[kTapPairs];
 
 namespace {
@@ -45,8 +47,7 @@ __device__ __forceinline__ const float* level_ptr(const CqtParams& p, const TonC
 
 // ---- factor-2 decimation -----------------------------------------------------------------
 constexpr int kDecTile = 1024;               // outputs per CTA
-constexpr int kDecHalo = 96;                 // polyphase samples staged before the tile
-constexpr int kDecSpan = kDecTile + 192;     // polyphase samples staged per phase
+constexpr int kDecSpan = kDecTile + kTapPairs;   // polyphase samples staged per phase
 
 // d = a * b + c on both halves of a register pair (FFMA2: one issue slot for two FMAs)
 __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
@@ -56,8 +57,8 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 }
 
 // src_level -1: yharm -> level 0 (early downsampling by 2); otherwise level l -> l + 1
-//   out[m] = sum_k h[k] x[2 m + 190 - k]
-//          = sum_{e = 1..191} h[382 - 2e] x[2 (m + e - 96)] + h[381 - 2e] x[2 (m + e - 96) + 1]:
+//   out[m] = sum_k h[k] x[2 m + (K - 1) / 2 - k]
+//          = sum_{e >= 1} h[K + 1 - 2e] x[2 (m + e - kDecHalo)] + h[K - 2e] x[2 (m + e - kDecHalo) + 1]:
 // the two polyphase branches ride in the two halves of one packed accumulator (the signal is
 // read as natural (even, odd) sample pairs) and are added once at the end.  Thread t owns
 // kDecOuts consecutive outputs; its window starts at pair kDecOuts t, and kDecPad pairs of
@@ -67,7 +68,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 constexpr int kDecOuts = 8;
 constexpr int kDecThreads = kDecTile / kDecOuts;
 constexpr int kDecPad = 2;
-constexpr int kDecPhys = kDecSpan + kDecPad * (kDecSpan / kDecOuts);
+constexpr int kDecPhys = kDecSpan + kDecPad * ((kDecSpan + kDecOuts - 1) / kDecOuts);
 
 __global__ void __launch_bounds__(kDecThreads) decimate2_kernel(CqtParams p, int src_level) {
     __shared__ __align__(16) float2 xs[kDecPhys];
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kDecThreads) decimate2_kernel(CqtParams p, int
             xs[q + kDecPad * (q / kDecOuts)] = v;
         }
         __syncthreads();
-        // acc[r] += tap2[e] * xs[kDecOuts t + r + e], e = 1 .. 191
+        // acc[r] += tap2[e] * xs[kDecOuts t + r + e], e = 1 .. kTapPairs - 1
         unsigned long long acc[kDecOuts];
 #pragma unroll
         for (int r = 0; r < kDecOuts; ++r) acc[r] = 0ull;
@@ -467,8 +468,9 @@ __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
 cudaError_t configure_cqt(const float* taps2_scaled) {
     static float pairs[kTapPairs][2];
     for (int e = 0; e < kTapPairs; ++e) {
-        pairs[e][0] = e >= 1 ? taps2_scaled[382 - 2 * e] : 0.0f;              // h[380] .. h[0]
-        pairs[e][1] = (e >= 1 && e <= 190) ? taps2_scaled[381 - 2 * e] : 0.0f;   // h[379] .. h[1]
+        const int k0 = kDecTaps2 + 1 - 2 * e, k1 = kDecTaps2 - 2 * e;          // even / odd sample of the pair
+        pairs[e][0] = (e >= 1 && k0 >= 0 && k0 < kDecTaps2) ? taps2_scaled[k0] : 0.0f;
+        pairs[e][1] = (e >= 1 && k1 >= 0 && k1 < kDecTaps2) ? taps2_scaled[k1] : 0.0f;
     }
     cudaError_t e = cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs));
     if (e != cudaSuccess) return e;

@@ -313,30 +313,51 @@ bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank, bool lane_orde
     return ok;
 }
 
+// libsoxr's cubic fits of the Kaiser beta (restated; see oracle/shim/librosa/core.py _LSX_BETA_ROWS)
+static double lsx_kaiser_beta(double att, double tr_bw) {
+    static const double rows[10][4] = {
+        {-6.784957e-10, 1.02856e-05, 0.1087556, -0.8988365 + 0.001},
+        {-6.897885e-10, 1.027433e-05, 0.10876, -0.8994658 + 0.002},
+        {-1.000683e-09, 1.030092e-05, 0.1087677, -0.9007898 + 0.003},
+        {-3.654474e-10, 1.040631e-05, 0.1087085, -0.8977766 + 0.006},
+        {8.106988e-09, 6.983091e-06, 0.1091387, -0.9172048 + 0.015},
+        {9.519571e-09, 7.272678e-06, 0.1090068, -0.9140768 + 0.025},
+        {-5.626821e-09, 1.342186e-05, 0.1083999, -0.9065452 + 0.05},
+        {-9.965946e-08, 5.073548e-05, 0.1040967, -0.7672778 + 0.085},
+        {1.604808e-07, -5.856462e-05, 0.1185998, -1.34824 + 0.1},
+        {-1.511964e-07, 6.363034e-05, 0.1064627, -0.9876665 + 0.18},
+    };
+    const double realm = std::log(tr_bw / 0.0005) / std::log(2.0);
+    const int i0 = std::min(std::max(static_cast<int>(realm), 0), 9);
+    const int i1 = std::min(std::max(1 + static_cast<int>(realm), 0), 9);
+    const double b0 = ((rows[i0][0] * att + rows[i0][1]) * att + rows[i0][2]) * att + rows[i0][3];
+    const double b1 = ((rows[i1][0] * att + rows[i1][1]) * att + rows[i1][2]) * att + rows[i1][3];
+    return b0 + (b1 - b0) * (realm - static_cast<int>(realm));
+}
+
 void decimation_taps(int factor, std::vector<double>& taps) {
-    // scipy.signal.kaiserord(att, width) + firwin(numtaps, cutoff, window=("kaiser", beta), scale=True)
-    const double att = 21.0 * 6.0206;
-    const double f_pass = 0.913 / static_cast<double>(factor);
-    const double f_stop = 1.0 / static_cast<double>(factor);
-    const double width = f_stop - f_pass;
-    const double beta = 0.1102 * (att - 8.7);                       // att > 50
-    int numtaps = static_cast<int>(std::ceil((att - 7.95) / 2.285 / (kPi * width) + 1.0));
-    if (numtaps % 2 == 0) numtaps += 1;
-    const double cutoff = 0.5 * (f_pass + f_stop);
-    const double alpha = 0.5 * static_cast<double>(numtaps - 1);
+    // libsoxr "HQ" low-pass for an integer decimation, restated (oracle/shim/librosa/core.py
+    // _soxr_hq_decimation_filter has the derivation): 389 taps, beta 13.04 for factor 2
+    const double bits = 20.0;
+    const double rej = bits * 20.0 * std::log10(2.0);
+    const double att = (bits + 1.0) * 20.0 * std::log10(2.0);
+    const double pass_end = 1.0 - 0.05 / ((1.6e-6 * rej - 7.5e-4) * rej + 0.646);
+    const double fp = pass_end / static_cast<double>(factor), fs = 1.0 / static_cast<double>(factor);
+    const double tr_bw = std::min(0.5 * (fs - fp), 0.5 * fs);
+    const double fc = fs - tr_bw;
+    const double beta = lsx_kaiser_beta(att, tr_bw * 0.5 / fc);
+    const double a = ((0.0007528358 - 1.577737e-05 * beta) * beta + 0.6248022) * beta + 0.06186902;
+    const int numtaps = (static_cast<int>(std::ceil(a / tr_bw + 1.0)) + 2) / 4 * 4 + 1;
+    const int m = numtaps - 1;
     taps.resize(numtaps);
     const double i0_beta = std::cyl_bessel_i(0.0, beta);
-    double sum = 0.0;
-    for (int n = 0; n < numtaps; ++n) {
-        const double m = static_cast<double>(n) - alpha;
-        const double x = cutoff * m;
-        const double sinc = (x == 0.0) ? 1.0 : std::sin(kPi * x) / (kPi * x);
-        const double r = (static_cast<double>(n) - alpha) / alpha;
-        const double win = std::cyl_bessel_i(0.0, beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0_beta;
-        taps[n] = cutoff * sinc * win;
-        sum += taps[n];
+    for (int i = 0; i < numtaps; ++i) {
+        const double z = static_cast<double>(i) - 0.5 * m;
+        const double x = z * kPi;
+        const double sinc = (x == 0.0) ? fc : std::sin(fc * x) / x;
+        const double y = z / (0.5 * m + 0.5);
+        taps[i] = sinc * std::cyl_bessel_i(0.0, beta * std::sqrt(std::max(0.0, 1.0 - y * y))) / i0_beta;
     }
-    for (double& t : taps) t /= sum;
 }
 
 void hann_squared_2048(std::vector<double>& w) {

@@ -113,7 +113,7 @@ constexpr int kCqOctaves = 7;
 constexpr int kCqRows = 36;       // bins per octave
 constexpr int kCqBins = 252;
 constexpr int kCqRowCap = 32;     // complex values stored per basis row
-constexpr int kDecTaps2 = 381;    // soxr_hq stand-in, factor 2 (cqt_tables.cpp decimation_taps)
+constexpr int kDecTaps2 = 389;    // libsoxr HQ 2:1 low-pass, restated (cqt_tables.cpp decimation_taps); 1 mod 4
 
 struct TonClip {
     long long hoff;      // harmonic signal of the clip: yharm[hoff .. hoff + length)
@@ -226,5 +226,8 @@ struct PcmFile {
 cudaError_t launch_pcm_prepare_files(const short* d_pcm, const PcmFile* d_files, int file_lo, int file_hi,
                                      long long max_frames, int* d_peak_bits, float* d_wave, cudaStream_t stream,
                                      long long* launches);
+
+// blocks x 256 threads x 16 chains x iters FMAs
+cudaError_t launch_fp32_peak(float* d_scratch, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace serb

@@ -125,4 +125,26 @@ cudaError_t launch_pcm_prepare_files(const short* d_pcm, const PcmFile* d_files,
     return cudaGetLastError();
 }
 
+// ---- FP32 peak probe --------------------------------------------------------------------------
+// Dependent-free FFMA chains (16 accumulators per thread): the FP32 (FMA pipe) ceiling bench.py
+// quotes the whole-step FP32 fraction against is measured on the same GPU in the same run.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* __restrict__ out, float a, float b, int iters) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = static_cast<float>(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;      // never true: keeps the chains alive
+}
+
+cudaError_t launch_fp32_peak(float* d_scratch, int blocks, int iters, cudaStream_t stream) {
+    fp32_peak_kernel<<<blocks, 256, 0, stream>>>(d_scratch, 0.999f, 0.001f, iters);
+    return cudaGetLastError();
+}
+
 }  // namespace serb

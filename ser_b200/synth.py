@@ -131,17 +131,20 @@ def long_recording(sample_rate: int, n_samples: int, *, seed: int = 99, section_
 
 
 def batch_audio_torch(n_clips: int, sample_rate: int, n_samples: int, *, device, seed: int = 1234,
-                      first_index: int = 0, chunk: int = 64):
+                      first_index: int = 0, chunk: int = 64, return_pcm: bool = False):
     """Same clip family generated on ``device`` with torch, as a (n_clips, n_samples) float32 tensor.
 
     Used by bench.py for the large configurations (c2/c3), where host-side generation would
     dominate the run.  Noise comes from torch's generator, so values differ from
     ``clip_audio`` (statistics are the same); both bench arms read the same tensor.
+    With ``return_pcm`` the int16 PCM the audio was decoded from comes back as well
+    (``audio == decode_pcm16(pcm)`` per clip): what the files of the data set hold.
     """
     import torch
 
     specs = ravdess_specs(first_index + n_clips)[first_index:]
     out = torch.empty((n_clips, n_samples), dtype=torch.float32, device=device)
+    out_pcm = torch.empty((n_clips, n_samples), dtype=torch.int16, device=device) if return_pcm else None
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + first_index)
     t = torch.arange(n_samples, dtype=torch.float64, device=device) / float(sample_rate)
@@ -162,4 +165,6 @@ def batch_audio_torch(n_clips: int, sample_rate: int, n_samples: int, *, device,
         audio = (pcm / 32768.0).to(torch.float32)
         audio = audio / audio.abs().amax(dim=1, keepdim=True)
         out[lo:hi] = audio
-    return out
+        if out_pcm is not None:
+            out_pcm[lo:hi] = pcm.to(torch.int16)
+    return (out, out_pcm) if return_pcm else out

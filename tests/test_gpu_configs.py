@@ -1,0 +1,262 @@
+"""Oracle parity and label agreement on every BASELINE.json config AT ITS REAL SIZE.
+
+The expected rows were computed on CPU by the oracle (``tests/golden/make_c2_oracle_rows.py``,
+``tests/golden/make_config_golden.py``) over deterministic synthetic audio that is regenerated here
+bit for bit, so the GPU box needs no oracle time.  The classifier is a scikit-learn
+Pipeline(StandardScaler, MLPClassifier(300)) FITTED on the c2 oracle rows; label expectations are
+scikit-learn's own ``predict`` on the oracle rows.
+
+North star: pooled features within 1e-4 (scaled metric of tests/conftest.py) and >= 90 % of labels
+bit-identical; the tests hold 100 % of the labels unless stated.
+"""
+
+from __future__ import annotations
+
+import pickle
+import time
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import group_errors
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parents[1]
+ALL_GROUPS = ("mfcc", "chroma", "mel", "contrast", "tonnetz")
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def c2_golden():
+    with np.load(REPO / "tests" / "golden" / "c2_oracle_rows.npz", allow_pickle=False) as data:
+        return {k: data[k] for k in data.files}
+
+
+@pytest.fixture(scope="module")
+def cfg_golden():
+    with np.load(REPO / "tests" / "golden" / "config_golden.npz", allow_pickle=False) as data:
+        return {k: data[k] for k in data.files}
+
+
+@pytest.fixture(scope="module")
+def fitted(c2_golden):
+    from ser_b200 import _native, mlp
+
+    g = c2_golden
+    return mlp.MlpWeights(mean=g["model/mean"], scale=g["model/scale"], w1=g["model/w1"], b1=g["model/b1"],
+                          w2=g["model/w2"], b2=g["model/b2"], classes=tuple(g["model/classes"].tolist()),
+                          out_activation=_native.OUT_SOFTMAX)
+
+
+def _assert_rows(got, expect, what):
+    report = group_errors(got, expect, groups=ALL_GROUPS)
+    worst = max(v[0] for v in report.values())
+    print(f"{what}: " + ", ".join(f"{k} {v[0]:.2e}" for k, v in report.items()))
+    assert worst <= TOL, f"{what}: {report}"
+
+
+def test_c2_sampled_clips_rows_and_labels(c2_golden, fitted):
+    """256 of the 1 440 clips (every actor / emotion), all four windows each = 1 024 rows at 48 kHz."""
+    from ser_b200 import fast_path, synth
+    from ser_b200.handcrafted import HandcraftedBackend
+
+    sr, n = 48000, 168000
+    specs = synth.ravdess_specs(1440)
+    backend = HandcraftedBackend()
+    rows, starts, ends = [], [], []
+    for index in c2_golden["clip_index"]:
+        pcm = synth.clip_pcm16(specs[int(index)], sr, n)
+        encoded = backend.encode_sequence_pcm16(pcm, 1, sr)          # the file-level path: int16 to the device
+        rows.append(encoded.embeddings)
+        starts.append(encoded.frame_start_seconds)
+        ends.append(encoded.frame_end_seconds)
+    rows = np.concatenate(rows)
+    assert rows.shape == c2_golden["window_rows"].shape == (1024, 193)
+    _assert_rows(rows, c2_golden["window_rows"], "c2 windows")
+    frames = fast_path.predict_frames(fitted, rows, np.concatenate(starts), np.concatenate(ends))
+    labels = np.asarray([f.emotion for f in frames])
+    agree = float(np.mean(labels == c2_golden["sk_labels"]))
+    print(f"c2 labels identical to scikit-learn on the oracle rows: {agree:.4f} of {labels.size}")
+    assert agree == 1.0
+    np.testing.assert_allclose([f.confidence for f in frames], c2_golden["sk_proba"].max(axis=1), rtol=0, atol=1e-5)
+    assert float(np.mean(labels == c2_golden["labels"])) >= 0.9       # and they are the generator's emotions
+
+
+def test_c2_full_batch_labels_are_position_independent(c2_golden, fitted, gpu_ctx):
+    """All 5 760 windows of the full 1 440-clip step in ONE call: the sampled clips' rows equal their
+    stand-alone rows bit for bit, so the 1 024 checked labels are the full batch's labels."""
+    from ser_b200 import mlp, synth
+    from ser_b200.config import FeatureFlags, flag_bits
+    from ser_b200.handcrafted import frame_bounds
+
+    sr, n, n_clips = 48000, 168000, 1440
+    specs = synth.ravdess_specs(n_clips)
+    sampled = c2_golden["clip_index"][::8]                             # 32 clips regenerated exactly
+    pcm = np.empty((n_clips, n), dtype=np.int16)
+    rng = np.random.default_rng(0)
+    filler = synth.clip_pcm16(specs[1], sr, n)
+    for i in range(n_clips):
+        pcm[i] = np.roll(filler, int(rng.integers(0, n)))              # any audio: only position matters here
+    for index in sampled:
+        pcm[int(index)] = synth.clip_pcm16(specs[int(index)], sr, n)
+    w_starts, w_ends = frame_bounds(n, sr, 3, 1)
+    clip_of = np.repeat(np.arange(n_clips, dtype=np.int64), w_starts.size)
+    with mlp.session(fitted, 0) as (ctx, weights):
+        feats, proba, label_idx = ctx.infer_host_pcm16([pcm[i] for i in range(n_clips)], 1, clip_of,
+                                                       np.tile(w_starts, n_clips), np.tile(w_ends - w_starts, n_clips),
+                                                       sr, flag_bits(FeatureFlags()))
+    assert feats.shape == (5760, 193) and np.all(np.isfinite(feats))
+    where = np.flatnonzero(np.isin(c2_golden["clip_index"], sampled))
+    for k, index in zip(where, sampled):
+        got = feats[4 * int(index): 4 * int(index) + 4]
+        _assert_rows(got, c2_golden["window_rows"][4 * k: 4 * k + 4], f"c2 full batch clip {int(index)}")
+        labels = [weights.classes[i] for i in label_idx[4 * int(index): 4 * int(index) + 4]]
+        assert labels == c2_golden["sk_labels"][4 * k: 4 * k + 4].tolist()
+
+
+def test_c3_sampled_whole_clip_rows(c2_golden):
+    """Config c3's unit of work (one row per file, data_loader.py:485-529): 64 sampled clips."""
+    from ser_b200 import dsp, synth
+
+    sr, n = 48000, 168000
+    specs = synth.ravdess_specs(1440)
+    clips = [synth.clip_audio(specs[int(i)], sr, n) for i in c2_golden["clip_index"][:64]]
+    rows = dsp.extract_features_batch(clips, sr)
+    assert rows.dtype == np.float64 and rows.shape == (64, 193)
+    _assert_rows(rows, c2_golden["clip_rows"], "c3 whole clips")
+    pcm_rows = dsp.extract_features_pcm16([synth.clip_pcm16(specs[int(i)], sr, n) for i in c2_golden["clip_index"][:64]], 1,
+                                          np.arange(64), np.zeros(64, dtype=np.int64), np.full(64, n), sr)
+    np.testing.assert_array_equal(pcm_rows.astype(np.float64), rows)
+
+
+def test_c4_one_hour_recording(cfg_golden, fitted):
+    """1 h @ 16 kHz as ONE encode_sequence call (3 600 windows): 64 sampled windows against the oracle,
+    and the first five minutes (300 windows) with labels and the full merged segment list."""
+    from ser_b200 import fast_path, synth
+    from ser_b200.handcrafted import HandcraftedBackend
+
+    sr, n = 16000, 57_600_000
+    recording = synth.long_recording(sr, n)
+    t0 = time.perf_counter()
+    encoded = HandcraftedBackend().encode_sequence(recording, sr)
+    print(f"c4: 3600 windows in {time.perf_counter() - t0:.2f} s wall (host float32 entry)")
+    assert encoded.embeddings.shape == (3600, 193)
+    np.testing.assert_array_equal(encoded.frame_start_seconds, np.arange(3600, dtype=np.float64))
+    assert encoded.frame_end_seconds[-1] == 3600.0 and encoded.frame_end_seconds[-3] == 3600.0
+    _assert_rows(encoded.embeddings[cfg_golden["c4/sampled_windows"]], cfg_golden["c4/sampled_rows"], "c4 sampled windows")
+    first = cfg_golden["c4/first5min_rows"].shape[0]
+    _assert_rows(encoded.embeddings[:first], cfg_golden["c4/first5min_rows"], "c4 first five minutes")
+    frames = fast_path.predict_frames(fitted, encoded.embeddings[:first], encoded.frame_start_seconds[:first],
+                                      encoded.frame_end_seconds[:first])
+    assert [f.emotion for f in frames] == cfg_golden["c4/first5min/labels"].tolist()
+    segments = fast_path.segment_predictions(frames)
+    assert [s.emotion for s in segments] == cfg_golden["c4/first5min/seg_labels"].tolist()
+    np.testing.assert_array_equal([s.start_seconds for s in segments], cfg_golden["c4/first5min/seg_starts"])
+    np.testing.assert_array_equal([s.end_seconds for s in segments], cfg_golden["c4/first5min/seg_ends"])
+    np.testing.assert_allclose([s.confidence for s in segments], cfg_golden["c4/first5min/seg_confidence"], rtol=0, atol=1e-5)
+
+
+def test_c5_length_by_batch_cells(cfg_golden, gpu_ctx):
+    """Clip length {1 .. 60 s} x batch {1 .. 4096} @ 48 kHz: in every cell the rows at the positions of
+    three base clips equal the oracle's whole-clip rows of those clips (cells above 2^31 samples are
+    skipped, as in scripts/sweep_configs.py)."""
+    import torch
+
+    from ser_b200 import synth
+    from ser_b200.config import FeatureFlags, flag_bits
+
+    sr = 48000
+    bits = flag_bits(FeatureFlags())
+    specs = synth.ravdess_specs(64)
+    positions = sorted(set(cfg_golden["c5/position"].tolist()))
+    base = torch.zeros((64, 60 * sr), dtype=torch.float32, device="cuda")
+    filler = torch.from_numpy(synth.clip_audio(specs[1], sr, 60 * sr)).cuda()
+    for p in range(64):
+        base[p] = torch.roll(filler, 1000 * p)
+    for p in positions:                                                 # the checked clips are exact
+        base[p] = torch.from_numpy(synth.clip_audio(specs[p], sr, 60 * sr)).cuda()
+    cells = 0
+    for seconds in (1, 2, 3.5, 5, 10, 30, 60):
+        n = int(seconds * sr)
+        expect = {int(p): cfg_golden["c5/rows"][i] for i, (s, p) in
+                  enumerate(zip(cfg_golden["c5/seconds"], cfg_golden["c5/position"])) if s == seconds}
+        for batch in (1, 8, 64, 512, 4096):
+            if batch * n > 2**31:
+                continue
+            reps = (batch + 63) // 64
+            wave = base[:, :n].repeat(reps, 1)[:batch].contiguous().reshape(-1)
+            out = torch.empty((batch, 193), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            gpu_ctx.features_device(wave.data_ptr(), wave.numel(), np.arange(batch, dtype=np.int64) * n,
+                                    np.full(batch, n, dtype=np.int64), sr, bits, out.data_ptr(), 0)
+            gpu_ctx.features_device_check(0)
+            rows = out.cpu().numpy()
+            assert np.all(np.isfinite(rows))
+            for p, row in expect.items():
+                for position in range(p, batch, 64)[:: max(1, (batch // 64) // 3 or 1)]:
+                    _assert_rows(rows[position: position + 1], row[None, :], f"c5 {seconds}s x {batch} @ {position}")
+            cells += 1
+            del wave, out
+    assert cells >= 30
+
+
+def test_c1_sample_wav_with_the_reference_harness_semantics(cfg_golden, c2_golden, tmp_path):
+    """``ser.api.infer`` on the bundled sample.wav (config c1): rows, labels and segments against the
+    oracle, then the reference's latency harness (ser/_internal/runtime/benchmarks.py:21-55: N runs of
+    predict_emotions, each of which RELOADS the model, emotion_model.py:148-150) next to the published
+    mean 1.544 s / p95 2.963 s."""
+    from sklearn.neural_network import MLPClassifier
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+
+    from ser_b200 import fast_inference
+    from ser_b200.feature_extractor import extract_feature_frames
+    from ser_b200.schema import InferenceRequest
+
+    sample = REPO / "tests" / "golden" / "sample.wav"
+    frames = extract_feature_frames(str(sample))
+    assert [f.start_seconds for f in frames] == cfg_golden["c1/starts"].tolist()
+    assert [f.end_seconds for f in frames] == cfg_golden["c1/ends"].tolist()
+    _assert_rows(np.vstack([f.features for f in frames]), cfg_golden["c1/rows"], "c1 sample.wav")
+    # a real scikit-learn pipeline carrying the fitted weights, pickled like the artifact envelope
+    g = c2_golden
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = Pipeline([("scaler", StandardScaler()), ("classifier", MLPClassifier(hidden_layer_sizes=(300,), max_iter=1))])
+        model.fit(g["window_rows"][:64].astype(np.float64), g["labels"][:64])
+    scaler, clf = model.named_steps["scaler"], model.named_steps["classifier"]
+    scaler.mean_, scaler.scale_ = g["model/mean"], g["model/scale"]
+    scaler.var_ = g["model/scale"] ** 2
+    clf.coefs_, clf.intercepts_ = [g["model/w1"], g["model/w2"]], [g["model/b1"], g["model/b2"]]
+    clf.classes_ = g["model/classes"]
+    clf._label_binarizer.classes_ = g["model/classes"]
+    clf.n_outputs_, clf.out_activation_ = len(g["model/classes"]), "softmax"
+    artifact = tmp_path / "ser_model.pkl"
+    artifact.write_bytes(pickle.dumps({"artifact_version": 3, "model": model,
+                                       "metadata": {"backend_id": "handcrafted", "profile": "fast", "feature_vector_size": 193}}))
+    request = InferenceRequest(file_path=str(sample), include_transcript=False)
+
+    def run_once():
+        envelope = pickle.loads(artifact.read_bytes())                   # predict_emotions reloads the model every run
+        loaded = fast_inference.LoadedModel(model=envelope["model"], expected_feature_size=193,
+                                            artifact_metadata=envelope["metadata"])
+        return fast_inference.run_fast_inference(request, None, loaded_model=loaded)
+
+    result = run_once()
+    assert [f.emotion for f in result.frames] == cfg_golden["c1/labels"].tolist()
+    assert [s.emotion for s in result.segments] == cfg_golden["c1/seg_labels"].tolist()
+    np.testing.assert_array_equal([s.start_seconds for s in result.segments], cfg_golden["c1/seg_starts"])
+    np.testing.assert_array_equal([s.end_seconds for s in result.segments], cfg_golden["c1/seg_ends"])
+    np.testing.assert_allclose([s.confidence for s in result.segments], cfg_golden["c1/seg_confidence"], rtol=0, atol=1e-5)
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        run_once()
+        times.append(time.perf_counter() - t0)
+    times = np.asarray(times)
+    print(f"c1 harness (model reload per run, 5 runs): mean {times.mean() * 1e3:.2f} ms, p95 "
+          f"{np.percentile(times, 95) * 1e3:.2f} ms, min {times.min() * 1e3:.2f} ms "
+          f"(reference publishes mean 1544 ms, p95 2963 ms on CPU, docs/compatibility-matrix.md:33)")
+    assert times.mean() < 1.544
