@@ -390,7 +390,7 @@ def run_b200(args) -> None:
         files_pinned.copy_(pcm)
         torch.cuda.synchronize()
         pinned_np = files_pinned.numpy()
-        file_list = [pinned_np[i] for i in range(n_clips)]          # views: one contiguous pinned buffer
+        file_list = pinned_np                                       # (n_files, frames) int16: one contiguous pinned buffer
 
         def e2e_call(files):
             if c3:

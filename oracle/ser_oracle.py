@@ -302,3 +302,40 @@ def predict_frames(weights: MlpWeights, embeddings, starts, ends):
         for i in range(X.shape[0])
     ]
     return frames, segment_predictions(frames)
+
+
+def tuning_margins(audio, sample_rate):
+    """How decisive the two tuning estimates of one clip are: (margin12, margin36).
+
+    ``estimate_tuning`` returns the left edge of the FULLEST of 100 residual bins (Appendix A.6), a
+    discontinuous function of the input: when the two fullest bins hold almost the same number of
+    pitches, one float32 rounding anywhere upstream moves the arg-max and with it the whole chroma
+    filterbank (margin12: chroma_stft on ``|stft(y)|``, dsp.py:113-118) or the whole constant-Q basis
+    (margin36: chroma_cqt on ``harmonic(y)``, dsp.py:138-143).  The margin is the count of the fullest
+    bin minus the count of the runner-up; parity tests treat clips with margin <= 2 as near-ties
+    (tests/test_oracle_sensitivity.py shows the oracle flips on them under 1-ulp input noise).
+    """
+    prepared = pad_audio_for_fft(np.asarray(audio, dtype=np.float32))
+    n_fft = min(prepared.size, 2048)
+
+    def margin(pitch, mag, bins_per_octave):
+        mask = pitch > 0
+        if not mask.any():
+            return 1 << 30
+        threshold = np.median(mag[mask])
+        freqs = pitch[(mag >= threshold) & mask]
+        residual = np.mod(bins_per_octave * librosa.filters.hz_to_octs(freqs), 1.0)
+        residual[residual >= 0.5] -= 1.0
+        counts, _ = np.histogram(residual, np.linspace(-0.5, 0.5, 101))
+        top = np.sort(counts)[::-1]
+        return int(top[0] - top[1])
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        magnitude = np.abs(librosa.stft(prepared, n_fft=n_fft))
+        pitch, mag = librosa.core.piptrack(S=magnitude, sr=sample_rate, n_fft=n_fft)
+        m12 = margin(pitch, mag, 12)
+        harmonic = librosa.effects.harmonic(prepared)
+        pitch, mag = librosa.core.piptrack(y=harmonic, sr=sample_rate)
+        m36 = margin(pitch, mag, 36)
+    return m12, m36

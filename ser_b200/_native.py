@@ -173,6 +173,25 @@ class Context:
     # ---- PCM16 files (N1) ------------------------------------------------------------------
     @staticmethod
     def _pcm16_args(files, channels, clip_file, clip_starts, clip_lengths):
+        if isinstance(files, np.ndarray) and files.ndim == 2:
+            # a batch of equal-length files in one C-contiguous (n_files, frames * channels) int16 array:
+            # pointers and sizes are computed vectorised (no per-file Python work in the caller's loop)
+            if files.dtype != np.int16:
+                raise TypeError(f"PCM16 files must be int16 arrays, got {files.dtype}")
+            block = np.ascontiguousarray(files)
+            n, row = block.shape
+            ch = np.full(n, int(channels), dtype=np.int32) if isinstance(channels, int) else \
+                np.asarray(channels, dtype=np.int32).reshape(-1)
+            if ch.size != n or np.any(ch < 1) or np.any(row % ch != 0):
+                raise ValueError("PCM16 file size is not a multiple of its channel count")
+            frames = (row // ch).astype(np.int64)
+            pointers = (block.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(row * 2)).astype(np.uint64)
+            clip_file = np.ascontiguousarray(clip_file, dtype=np.int64)
+            clip_starts = np.ascontiguousarray(clip_starts, dtype=np.int64)
+            clip_lengths = np.ascontiguousarray(clip_lengths, dtype=np.int64)
+            if not (clip_file.size == clip_starts.size == clip_lengths.size):
+                raise ValueError("clip_file, clip_starts and clip_lengths must have one entry per clip")
+            return [block, pointers], pointers.ctypes.data_as(c_void_p), frames, ch, clip_file, clip_starts, clip_lengths
         arrays = []
         for f in files:
             a = np.asarray(f)
@@ -207,7 +226,7 @@ class Context:
         dim = self._lib.serb_feature_dim(flag_bits)
         out = np.empty((cf.size, dim), dtype=np.float32)
         self._check(self._lib.serb_features_host_pcm16(
-            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), len(keep), _ptr(cf), _ptr(cs), _ptr(cl),
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), frames.size, _ptr(cf), _ptr(cs), _ptr(cl),
             cf.size, int(sample_rate), int(flag_bits), _ptr(out)))
         del keep
         return out
@@ -221,7 +240,7 @@ class Context:
         proba = np.empty((n, max(self._mlp_classes, 1)), dtype=np.float64)
         labels = np.empty(n, dtype=np.int32)
         self._check(self._lib.serb_infer_host_pcm16(
-            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), len(keep), _ptr(cf), _ptr(cs), _ptr(cl),
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), frames.size, _ptr(cf), _ptr(cs), _ptr(cl),
             n, int(sample_rate), int(flag_bits), _ptr(feats), _ptr(proba), _ptr(labels)))
         del keep
         return feats, proba, labels
@@ -292,7 +311,7 @@ class Context:
         outs = [np.empty(int(fr), dtype=np.float32) for fr in frames]
         out_ptrs = (c_void_p * max(len(outs), 1))(*[o.ctypes.data for o in outs])
         self._check(self._lib.serb_prepare_pcm16_files_host(
-            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), len(keep), ctypes.cast(out_ptrs, c_void_p)))
+            self._handle, ctypes.cast(pointers, c_void_p), _ptr(frames), _ptr(ch), frames.size, ctypes.cast(out_ptrs, c_void_p)))
         del keep
         return outs
 

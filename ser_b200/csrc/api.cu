@@ -1146,8 +1146,12 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
             return fail(nullptr, SERB_ERR_UNSUPPORTED, "factor-2 decimation filter length differs from the compiled kernel");
         }
         std::vector<float> taps32(taps.size());
-        for (size_t i = 0; i < taps.size(); ++i) taps32[i] = static_cast<float>(taps[i] * std::sqrt(2.0));
-        CREATE_CHECK(configure_cqt(taps32.data()));
+        std::vector<double> taps64(taps.size());
+        for (size_t i = 0; i < taps.size(); ++i) {
+            taps64[i] = taps[i] * std::sqrt(2.0);
+            taps32[i] = static_cast<float>(taps64[i]);
+        }
+        CREATE_CHECK(configure_cqt(taps32.data(), taps64.data()));
         hann_squared_2048(hsq);
         // behind the 2048 doubles: the overlap-add's window sum of squares where four frames
         // overlap, accumulated in frame order exactly as ola_sample does (float64 add, float32 store)

@@ -28,6 +28,12 @@ namespace serb {
 constexpr int kDecHalo = (kDecTaps2 + 3) / 4;     // polyphase samples staged before the tile
 constexpr int kTapPairs = 2 * kDecHalo;
 static_assert(kDecTaps2 % 4 == 1, "the pairing below assumes a tap count of 1 mod 4");
+// The same taps (x sqrt 2) in float64 for clips shorter than kDecExactBelow samples: their decimated
+// levels are a handful of samples of filter tails whose RATIOS the chroma normalisation reads, so the
+// float32 accumulation error (relative to the largest term) would come out amplified; the oracle's
+// float64 convolution rounded to float32 is reproduced instead (cost: nothing, these clips are tiny).
+__constant__ double c_tap_d[kDecTaps2];
+constexpr int kDecExactBelow = 2048;
 __constant__ __align__(16) float2 c_tap2[kTapPairs];
 
 namespace {
@@ -78,6 +84,17 @@ __global__ void __launch_bounds__(kDecThreads) decimate2_kernel(CqtParams p, int
     const float* src = level_ptr(p, clip, src_level);
     float* dst = p.yoct + p.level_base[src_level + 1] + (clip.off0 >> (src_level + 1));
     const unsigned long long* tap2 = reinterpret_cast<const unsigned long long*>(c_tap2);
+    if (clip.length < kDecExactBelow) {
+        // out[m] = sum_k h[k] x[2 m + (K - 1) / 2 - k] in float64, rounded once
+        for (int m = blockIdx.y * kDecThreads + threadIdx.x; m < len_out; m += gridDim.y * kDecThreads) {
+            const int centre = 2 * m + (kDecTaps2 - 1) / 2;
+            const int k_lo = max(0, centre - (len_in - 1)), k_hi = min(kDecTaps2 - 1, centre);
+            double acc = 0.0;
+            for (int k = k_lo; k <= k_hi; ++k) acc = fma(c_tap_d[k], static_cast<double>(src[centre - k]), acc);
+            dst[m] = static_cast<float>(acc);
+        }
+        return;
+    }
     // grid.y is capped at 65535 tiles: longer signals walk the tiles with a grid stride
     for (int mb = blockIdx.y * kDecTile; mb < len_out; mb += gridDim.y * kDecTile) {
         for (int q = threadIdx.x; q < kDecSpan; q += kDecThreads) {
@@ -465,7 +482,9 @@ __global__ void __launch_bounds__(192) tonnetz_final_kernel(CqtParams p) {
 // per device (called from serb_ctx_create with the device current): opt every instantiation in
 // to the largest dynamic shared memory a launch can ask for, once, so that concurrent contexts
 // never race an attribute change against a launch
-cudaError_t configure_cqt(const float* taps2_scaled) {
+cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_f64) {
+    cudaError_t e0 = cudaMemcpyToSymbol(c_tap_d, taps2_scaled_f64, sizeof(double) * kDecTaps2);
+    if (e0 != cudaSuccess) return e0;
     static float pairs[kTapPairs][2];
     for (int e = 0; e < kTapPairs; ++e) {
         const int k0 = kDecTaps2 + 1 - 2 * e, k1 = kDecTaps2 - 2 * e;          // even / odd sample of the pair

@@ -185,7 +185,7 @@ struct CqtParams {
     int max_len0;                // longest level-0 signal in the chunk
     int max_cq_cols;             // most constant-Q columns of one clip
 };
-cudaError_t configure_cqt(const float* taps2_scaled);   // uploads the factor-2 taps (x sqrt 2) to constant memory
+cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_f64);   // factor-2 taps (x sqrt 2) to constant memory
 cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long long* launches);
 cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long long* launches);
 cudaError_t launch_tonnetz(const CqtParams& p, cudaStream_t stream);

@@ -12,6 +12,9 @@ Writes tests/golden/c2_oracle_rows.npz:
 * ``clip_rows``   (64, 193)   float64  oracle whole-clip ``extract_vector`` rows of the first 64 sampled
                               clips (config c3's unit of work, handcrafted.py:124-137)
 * ``labels``      (1024,)     the emotion of each window's clip (the synthetic generator's label)
+* ``window_margins`` (1024, 2), ``clip_margins`` (64, 2)  ``ser_oracle.tuning_margins``: count of the fullest
+                              tuning-histogram bin minus the runner-up, for chroma_stft's and chroma_cqt's
+                              tuning estimate; <= 2 marks a near-tie whose arg-max one rounding can move
 * ``model/*``                 Pipeline(StandardScaler, MLPClassifier(300)) with the reference's
                               hyper-parameters (ser/_internal/models/training_support.py:87-106) FITTED by
                               scikit-learn on ``window_rows`` -> ``labels``: mean, scale, w1, b1, w2, b2, classes
@@ -57,7 +60,8 @@ def _job(index: int):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         rows, starts, ends = ser_oracle.encode_sequence(audio, SR)
-    return index, rows.astype(np.float32), spec.label
+        margins = [ser_oracle.tuning_margins(audio[a:b], SR) for a, b in ser_oracle.frame_bounds(audio.size, SR)]
+    return index, rows.astype(np.float32), spec.label, np.asarray(margins, dtype=np.int64)
 
 
 def _clip_job(index: int):
@@ -68,7 +72,7 @@ def _clip_job(index: int):
     audio = synth.clip_audio(spec, SR, N_SAMPLES)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return ser_oracle.extract_feature_from_signal(audio, SR)
+        return ser_oracle.extract_feature_from_signal(audio, SR), ser_oracle.tuning_margins(audio, SR)
 
 
 def main() -> None:
@@ -85,8 +89,11 @@ def main() -> None:
     index = sampled_clip_indices(args.clips)
     with mp.get_context("fork").Pool(args.workers) as pool:
         results = pool.map(_job, index.tolist(), chunksize=2)
-        clip_rows = pool.map(_clip_job, index[:64].tolist(), chunksize=2)
+        clip_results = pool.map(_clip_job, index[:64].tolist(), chunksize=2)
+    clip_rows = [r[0] for r in clip_results]
+    clip_margins = np.asarray([r[1] for r in clip_results], dtype=np.int64)
     window_rows = np.concatenate([r[1] for r in results], axis=0)
+    window_margins = np.concatenate([r[3] for r in results], axis=0)
     per_clip = results[0][1].shape[0]
     labels = np.repeat(np.asarray([r[2] for r in results]), per_clip)
     assert window_rows.shape == (args.clips * per_clip, 193)
@@ -100,11 +107,13 @@ def main() -> None:
     classifier, scaler = model.named_steps["classifier"], model.named_steps["scaler"]
     sk_labels, sk_proba = model.predict(x), model.predict_proba(x)
     top2 = np.sort(sk_proba, axis=1)[:, -2:]
+    print(f"near-tie windows (margin <= 2): chroma {int(np.sum(window_margins[:, 0] <= 2))}, "
+          f"tonnetz {int(np.sum(window_margins[:, 1] <= 2))} of {window_margins.shape[0]}")
     print(f"{window_rows.shape[0]} window rows, train accuracy {np.mean(sk_labels == labels):.4f}, "
           f"smallest top-1/top-2 margin {np.min(top2[:, 1] - top2[:, 0]):.3e}, classes {classifier.classes_.tolist()}")
     np.savez_compressed(
         OUT, clip_index=index, window_rows=window_rows, clip_rows=np.stack(clip_rows), labels=labels,
-        sk_labels=sk_labels, sk_proba=sk_proba,
+        sk_labels=sk_labels, sk_proba=sk_proba, window_margins=window_margins, clip_margins=clip_margins,
         **{"model/mean": scaler.mean_, "model/scale": scaler.scale_, "model/w1": classifier.coefs_[0],
            "model/b1": classifier.intercepts_[0], "model/w2": classifier.coefs_[1], "model/b2": classifier.intercepts_[1],
            "model/classes": np.asarray(classifier.classes_), "model/out_activation": np.asarray(classifier.out_activation_)})

@@ -12,6 +12,9 @@ tests/golden/sample.wav (a data file, 140 KB; config c1 names it).
       normalise), window bounds, and -- with the fitted c2 classifier -- labels and segments.
 * c4  1-hour 16 kHz recording (``synth.long_recording(16000, 57_600_000)``): oracle rows of 64 sampled
       windows, and ALL 300 windows of the first five minutes with labels and merged segments.
+Every row comes with ``ser_oracle.tuning_margins`` (``*/margins``, ``*_margins``): the lead of the
+fullest tuning-histogram bin over the runner-up for the two tuning estimates; <= 2 marks a near-tie.
+
 * c5  clip length {1, 2, 3.5, 5, 10, 30, 60} s @ 48 kHz: whole-clip oracle rows of three base clips
       (positions 0, 7, 63 of the 64-clip base set the sweep tiles into every batch size).
 """
@@ -52,7 +55,7 @@ def _window_row(args):
     _limit_threads()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return ser_oracle.extract_feature_from_signal(audio, sr).astype(np.float32)
+        return ser_oracle.extract_feature_from_signal(audio, sr).astype(np.float32), ser_oracle.tuning_margins(audio, sr)
 
 
 def _clip_row(args):
@@ -62,7 +65,7 @@ def _clip_row(args):
     _limit_threads()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return ser_oracle.extract_feature_from_signal(audio, sr)
+        return ser_oracle.extract_feature_from_signal(audio, sr), ser_oracle.tuning_margins(audio, sr)
 
 
 def c5_base_clip(position: int, n_samples: int) -> np.ndarray:
@@ -99,6 +102,9 @@ def main() -> None:
         payload[f"{prefix}/seg_ends"] = np.asarray([s.end_seconds for s in segments])
         payload[f"{prefix}/seg_confidence"] = np.asarray([s.confidence for s in segments])
 
+    def split(results):
+        return np.stack([r[0] for r in results]), np.asarray([r[1] for r in results], dtype=np.int64)
+
     with mp.get_context("fork").Pool(args.workers) as pool:
         # ---- c1: the bundled recording
         sample = Path("/root/reference/sample.wav")
@@ -106,7 +112,7 @@ def main() -> None:
         raw, sr = librosa.load(str(sample), sr=None)
         audio = ser_oracle.prepare_audio_buffer(raw)
         bounds = ser_oracle.frame_bounds(audio.size, sr)
-        rows = np.stack(pool.map(_window_row, [(audio[a:b], sr) for a, b in bounds]))
+        rows, payload["c1/margins"] = split(pool.map(_window_row, [(audio[a:b], sr) for a, b in bounds]))
         starts = np.asarray([a for a, _ in bounds], dtype=np.float64) / float(sr)
         ends = np.asarray([b for _, b in bounds], dtype=np.float64) / float(sr)
         payload.update({"c1/sr": np.asarray(sr), "c1/n_samples": np.asarray(audio.size), "c1/rows": rows,
@@ -119,10 +125,10 @@ def main() -> None:
         bounds = ser_oracle.frame_bounds(recording.size, C4_SR)
         assert len(bounds) == 3600
         sampled = np.unique(np.concatenate([np.linspace(0, 3599, 60).astype(np.int64), [3597, 3598, 3599, 1]]))[:64]
-        rows = np.stack(pool.map(_window_row, [(recording[bounds[i][0]:bounds[i][1]], C4_SR) for i in sampled]))
-        payload.update({"c4/sampled_windows": sampled, "c4/sampled_rows": rows})
+        rows, margins = split(pool.map(_window_row, [(recording[bounds[i][0]:bounds[i][1]], C4_SR) for i in sampled]))
+        payload.update({"c4/sampled_windows": sampled, "c4/sampled_rows": rows, "c4/sampled_margins": margins})
         first = 300
-        rows5 = np.stack(pool.map(_window_row, [(recording[a:b], C4_SR) for a, b in bounds[:first]], chunksize=4))
+        rows5, payload["c4/first5min_margins"] = split(pool.map(_window_row, [(recording[a:b], C4_SR) for a, b in bounds[:first]], chunksize=4))
         starts = np.asarray([a for a, _ in bounds[:first]], dtype=np.float64) / float(C4_SR)
         ends = np.asarray([b for _, b in bounds[:first]], dtype=np.float64) / float(C4_SR)
         payload.update({"c4/first5min_rows": rows5, "c4/first5min_starts": starts, "c4/first5min_ends": ends})
@@ -137,7 +143,7 @@ def main() -> None:
             for position in C5_BASE_CLIPS:
                 jobs.append((c5_base_clip(position, n), C5_SR))
                 keys.append((seconds, position))
-        rows = np.stack(pool.map(_clip_row, jobs))
+        rows, payload["c5/margins"] = split(pool.map(_clip_row, jobs))
         payload.update({"c5/seconds": np.asarray([k[0] for k in keys], dtype=np.float64),
                         "c5/position": np.asarray([k[1] for k in keys], dtype=np.int64), "c5/rows": rows})
         print("c5", rows.shape)

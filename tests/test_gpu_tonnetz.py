@@ -16,7 +16,6 @@ from conftest import group_errors
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
-TOL_TINY_TONNETZ = 5e-3   # clips under 64 samples only, see test_awkward_lengths_match_oracle
 ALL_GROUPS = ("mfcc", "chroma", "mel", "contrast", "tonnetz")
 CASES = ["c16k_3s", "c48k_3p5s", "c22k_2s", "c44k_1s", "c16k_tail_5937", "c16k_2048", "sine16k_1p5s", "silence16k",
          "c16k_short_1500", "c16k_short_1001", "c16k_short_300", "c48k_short_512"]
@@ -319,11 +318,14 @@ def test_awkward_lengths_match_oracle(length):
     spectrum is flat to rounding noise, and the piptrack "peaks" that pick the tuning bin are that
     noise (the discontinuity SURVEY.md section 7 warns about), on the CPU path as much as here.
 
-    Clips shorter than 64 samples (4 ms) get a wider tonnetz bound: their one or two constant-Q
-    columns are L-inf / L1 normalised magnitudes of decimator-filter tails, so float32 rounding
-    noise (1e-7) comes out amplified to 1e-5 .. 2e-3 whatever the summation order of the FIR is
-    (profiles/r01_tiny_lengths_scan.txt: every length 1 .. 64 with two builds of the decimator,
-    scripts/gpu_tiny_lengths.py).  The other four groups keep the 1e-4 bound at every length."""
+    Clips shorter than 64 samples (4 ms): their one or two constant-Q columns are L-inf / L1
+    normalised magnitudes of decimator-filter tails, so a float32 FIR accumulation (rounding
+    relative to the largest term) came out amplified to 1e-5 .. 2e-3 in round 1
+    (profiles/r01_tiny_lengths_scan.txt).  The oracle is stable there
+    (tests/test_oracle_sensitivity.py), so that was this implementation's error: clips under 2 048
+    samples are now decimated with float64 accumulation, like the oracle's convolution.  Their
+    tonnetz means are ~1e-4 in magnitude, which is why the bound for them is 1e-4 scaled OR 1e-6
+    absolute (the noise-like-signal rule); the other four groups keep 1e-4 at every length."""
     from oracle import ser_oracle
     from ser_b200 import dsp, synth
 
@@ -338,8 +340,9 @@ def test_awkward_lengths_match_oracle(length):
     report = group_errors(got, ref, groups=ALL_GROUPS)
     print(length, {k: f"{v[0]:.2e}" for k, v in report.items()})
     for group, (scaled, _raw) in report.items():
-        bound = TOL_TINY_TONNETZ if (group == "tonnetz" and length < 64) else TOL
-        assert scaled <= bound, f"len {length} {group}: {scaled:.3e}"
+        if group == "tonnetz" and length < 64 and float(np.max(np.abs(got[187:] - ref[187:]))) <= 1e-6:
+            continue
+        assert scaled <= TOL, f"len {length} {group}: {scaled:.3e}"
 
 
 @pytest.mark.parametrize("sr", [16000, 22050, 44100])
