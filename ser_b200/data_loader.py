@@ -52,26 +52,27 @@ class _Block:
         self.samples = 0
 
 
-def extract_partition(
-    partition: Sequence[Any],
+def iter_file_features(
+    files: Sequence[tuple[str, float | None, float | None]],
     *,
     feature_flags: FeatureFlags | None = None,
-    handle_sample_failure: Callable[[Any, Exception], bool] | None = None,
-    record_progress: Callable[..., None] | None = None,
     read_audio: Callable[..., tuple[NDArray[np.float32], int]] = read_audio_file,
     read_pcm16: Callable[..., tuple[NDArray[np.int16], int, int] | None] | str | None = "auto",
     extract_batch: Callable[..., NDArray[np.float64]] | None = None,
     device: int = 0,
     max_samples_per_call: int | None = None,
-) -> tuple[NDArray[np.float64], list[str]]:
-    """Feature matrix and labels of one split partition (data_loader.py:485-529).
+):
+    """Yields ``(position, outcome)`` for every ``(path, start_seconds, duration_seconds)`` entry IN
+    ORDER, where ``outcome`` is the float64 feature row of that file or the exception that file raised.
 
-    Failure routing follows the reference, where every sample runs alone inside one ``try``:
-    an error that belongs to a sample -- decode / validation errors, and the deterministic
-    argument errors of a block (``ValueError`` / ``ParameterError``, e.g. librosa's Nyquist check,
-    which every sample of that block would raise on its own) -- goes to ``handle_sample_failure``
-    for that sample.  A batch-level ``RuntimeError`` (CUDA failure, out of memory) is NOT a
-    sample's fault and is re-raised at once instead of being reported as N quarantined samples."""
+    Files are read until a block (per sample rate) holds the per-call sample budget, the block goes to
+    the GPU in one ragged call, its audio is dropped, and the finished prefix is yielded: host memory
+    is O(block), and the consumer sees results while later files are still unread.  Failure routing
+    follows the reference, where every sample runs alone inside one ``try`` (data_loader.py:495-512):
+    an error that belongs to a sample -- decode / validation errors, and the deterministic argument
+    errors of a block (``ValueError`` / ``ParameterError``, e.g. librosa's Nyquist check, which every
+    sample of that block would raise on its own) -- is that sample's outcome.  A batch-level
+    ``RuntimeError`` (CUDA failure, out of memory) is nobody's sample and propagates at once."""
     flags = feature_flags if feature_flags is not None else FeatureFlags()
     if read_pcm16 == "auto":          # the int16 fast path pairs with this package's own file reader only
         read_pcm16 = read_pcm16_file if (read_audio is read_audio_file and extract_batch is None) else None
@@ -87,32 +88,17 @@ def extract_partition(
                                           np.zeros(n, dtype=np.int64), frames, sample_rate, feature_flags=flags,
                                           device=device).astype(np.float64)
 
-    total = len(partition)
-    outcome: list[Any] = [_PENDING] * total       # feature row, or the exception of that sample
+    total = len(files)
+    outcome: list[Any] = [_PENDING] * total
     blocks: dict[tuple[int, bool], _Block] = {}
-    rows: list[NDArray[np.float64]] = []
-    labels: list[str] = []
     cursor = 0
 
-    def drain() -> None:
-        """Hands finished samples on in partition order (progress callbacks keep the reference's order)."""
+    def drain():
         nonlocal cursor
         while cursor < total and outcome[cursor] is not _PENDING:
-            utterance, result = partition[cursor], outcome[cursor]
-            outcome[cursor] = None                 # the row now lives in `rows`
+            result, outcome[cursor] = outcome[cursor], None
             cursor += 1
-            if isinstance(result, Exception):
-                if handle_sample_failure is not None and handle_sample_failure(utterance, result):
-                    if record_progress is not None:
-                        record_progress(processed=cursor, total=total, sample_id=utterance.sample_id)
-                    continue
-                raise result
-            if result.ndim != 1 or result.size <= 0 or not np.all(np.isfinite(result)):
-                raise ValueError(f"Fast feature contract failed for sample {utterance.sample_id!r}.")
-            rows.append(result)
-            labels.append(utterance.require_label())
-            if record_progress is not None:
-                record_progress(processed=cursor, total=total, sample_id=utterance.sample_id)
+            yield cursor - 1, result
 
     def flush(key: tuple[int, bool]) -> None:
         block = blocks.pop(key, None)
@@ -128,13 +114,11 @@ def extract_partition(
             for index, _ in block.items:           # each sample would have raised this on its own
                 outcome[index] = error
         block.items.clear()                        # the audio is dropped here
-        drain()
 
-    for index, utterance in enumerate(partition):
+    for index, (path, start_seconds, duration_seconds) in enumerate(files):
         try:
-            segment = dict(start_seconds=getattr(utterance, "start_seconds", None),
-                           duration_seconds=getattr(utterance, "duration_seconds", None))
-            raw = read_pcm16(str(utterance.audio_path), **segment) if read_pcm16 is not None else None
+            segment = dict(start_seconds=start_seconds, duration_seconds=duration_seconds)
+            raw = read_pcm16(str(path), **segment) if read_pcm16 is not None else None
             if raw is not None:
                 pcm, channels, sample_rate = raw
                 if sample_rate <= 0:
@@ -143,16 +127,17 @@ def extract_partition(
                     raise OSError("Audio file contains no samples.")
                 key, item, size = (int(sample_rate), True), (pcm, int(channels)), pcm.size // channels
             else:
-                audio, sample_rate = read_audio(str(utterance.audio_path), **segment)
+                audio, sample_rate = read_audio(str(path), **segment)
                 clip = _validated(audio, int(sample_rate))
                 key, item, size = (int(sample_rate), False), clip, clip.size
-        except Exception as error:  # noqa: BLE001 - a sample-local failure: the caller's quarantine policy decides
+        except Exception as error:  # noqa: BLE001 - a sample-local failure: the caller's policy decides
             outcome[index] = error
-            drain()
+            yield from drain()
             continue
         block = blocks.get(key)
         if block is not None and block.items and block.samples + size > budget:
             flush(key)
+            yield from drain()
             block = None
         if block is None:
             block = blocks[key] = _Block()
@@ -160,7 +145,45 @@ def extract_partition(
         block.samples += size
     for key in list(blocks):
         flush(key)
-    drain()
+        yield from drain()
+    yield from drain()
+
+
+def extract_partition(
+    partition: Sequence[Any],
+    *,
+    feature_flags: FeatureFlags | None = None,
+    handle_sample_failure: Callable[[Any, Exception], bool] | None = None,
+    record_progress: Callable[..., None] | None = None,
+    read_audio: Callable[..., tuple[NDArray[np.float32], int]] = read_audio_file,
+    read_pcm16: Callable[..., tuple[NDArray[np.int16], int, int] | None] | str | None = "auto",
+    extract_batch: Callable[..., NDArray[np.float64]] | None = None,
+    device: int = 0,
+    max_samples_per_call: int | None = None,
+) -> tuple[NDArray[np.float64], list[str]]:
+    """Feature matrix and labels of one split partition (data_loader.py:485-529): quarantine
+    callback, finite / shape contract and progress records in partition order, over
+    ``iter_file_features``."""
+    total = len(partition)
+    files = [(str(u.audio_path), getattr(u, "start_seconds", None), getattr(u, "duration_seconds", None)) for u in partition]
+    rows: list[NDArray[np.float64]] = []
+    labels: list[str] = []
+    for position, result in iter_file_features(files, feature_flags=feature_flags, read_audio=read_audio,
+                                               read_pcm16=read_pcm16, extract_batch=extract_batch, device=device,
+                                               max_samples_per_call=max_samples_per_call):
+        utterance = partition[position]
+        if isinstance(result, Exception):
+            if handle_sample_failure is not None and handle_sample_failure(utterance, result):
+                if record_progress is not None:
+                    record_progress(processed=position + 1, total=total, sample_id=utterance.sample_id)
+                continue
+            raise result
+        if result.ndim != 1 or result.size <= 0 or not np.all(np.isfinite(result)):
+            raise ValueError(f"Fast feature contract failed for sample {utterance.sample_id!r}.")
+        rows.append(result)
+        labels.append(utterance.require_label())
+        if record_progress is not None:
+            record_progress(processed=position + 1, total=total, sample_id=utterance.sample_id)
     if not rows:
         raise RuntimeError("Fast checked preparation produced an empty split partition.")
     return np.vstack(rows).astype(np.float64, copy=False), labels

@@ -14,7 +14,19 @@ ser._internal.models.emotion_model._fast_predict_emotions_detailed_with_model  (
 ser._internal.data.data_loader.load_checked_fast_data                  ser_b200.data_loader (ragged GPU batches)
 ser._internal.features.feature_extractor._extract_feature_frames_for_settings  16-bit PCM WAV: int16 to the device (N1),
 ser._internal.features.feature_extractor._extract_feature_for_settings         anything else: the reference's reader
+ser._internal.data.data_loader._extract_feature_for_settings                   (same; from-import alias)
+ser._internal.data.data_loader.mp                                              ``Pool`` without a fork (below)
+ser._internal.runtime.fast_public_boundary._fast_worker_entry                 re-installs inside the spawned worker
 =====================================================================  =========================================
+
+Process boundaries.  The reference's spawn-isolated fast worker (``SER_FAST_PROCESS_ISOLATION=1``,
+fast_public_boundary.py:251-277) starts a fresh interpreter, where no patch exists; its target is
+therefore swapped for ``spawned_fast_worker_entry`` (module-level, picklable by name), which calls
+``install()`` in the child -- the CUDA context is created lazily there -- and then runs the
+reference's own entry.  The reference's legacy training loader forks a ``multiprocessing.Pool``
+(data_loader.py:374-379): a CUDA context does not survive a fork, so that module's ``mp`` is
+replaced by an object whose ``Pool`` runs ``process_file`` over the files IN THIS PROCESS, feeding
+them to the GPU in ragged blocks (same results, same ``imap_unordered`` interface, no fork).
 
 ``ser.api.infer``, ``ser --file``, ``ser --train`` and ``run_fast_inference`` keep their
 signatures; the registry hook ``"handcrafted"`` still resolves
@@ -26,6 +38,7 @@ signatures; the registry hook ``"handcrafted"`` still resolves
 from __future__ import annotations
 
 import importlib
+import os
 from typing import Any
 
 from . import data_loader as _data_loader
@@ -36,6 +49,92 @@ from .handcrafted import HandcraftedBackend as _GpuBackend
 from .handcrafted import frame_bounds
 
 _originals: list[tuple[Any, str, Any]] = []
+_DEVICE_ENV = "SERB_INSTALL_DEVICE"
+
+
+def spawned_fast_worker_entry(payload, connection) -> None:
+    """Target of the reference's spawn-isolated fast worker after ``install()``: patches the fresh
+    interpreter, then hands over to the reference's own ``_fast_worker_entry``."""
+    install(device=int(os.environ.get(_DEVICE_ENV, "0")))
+    boundary = importlib.import_module("ser._internal.runtime.fast_public_boundary")
+    original = next(value for owner, name, value in _originals if owner is boundary and name == "_fast_worker_entry")
+    original(payload, connection)
+
+
+class _InProcessPool:
+    """``multiprocessing.Pool`` stand-in for ser/_internal/data/data_loader.py:374-379: no fork (a CUDA
+    context does not survive one).  ``imap_unordered(partial(process_file, ...), files)`` is recognised
+    and served in ragged GPU blocks; any other callable is mapped serially."""
+
+    def __init__(self, ref_loader, device: int, _processes=None) -> None:
+        self._ref_loader = ref_loader
+        self._device = device
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc) -> bool:
+        return False
+
+    def imap_unordered(self, fn, files, chunksize: int = 1):
+        keywords = getattr(fn, "keywords", None) or {}
+        target = getattr(fn, "func", None)
+        wanted = {"observed_emotions", "emotion_map", "feature_flags", "audio_read_config"}
+        if target is not self._ref_loader.process_file or not wanted <= set(keywords) or getattr(fn, "args", ()):
+            return (fn(file) for file in files)
+        return self._process_files(list(files), **{k: keywords[k] for k in wanted})
+
+    map = imap = imap_unordered
+
+    def _process_files(self, files, *, observed_emotions, emotion_map, feature_flags, audio_read_config):
+        # process_file (data_loader.py:241-292) with the feature call batched: label filter first,
+        # then one streamed GPU pass over the accepted files
+        loader = self._ref_loader
+        result_type = loader.ProcessFileResult
+        results: list[Any] = [None] * len(files)
+        accepted: list[int] = []
+        emotions: dict[int, str] = {}
+        for i, file in enumerate(files):
+            name = os.path.basename(file)
+            code = loader._extract_emotion_code(name)
+            if code is None:
+                results[i] = result_type(sample=None, error=f"Skipping file with unexpected name format (missing emotion code): {name}")
+                continue
+            emotion = emotion_map.get(code)
+            if not emotion or emotion not in observed_emotions:
+                results[i] = result_type(sample=None, error=None)
+                continue
+            accepted.append(i)
+            emotions[i] = emotion
+
+        def read_audio(path, *, start_seconds=None, duration_seconds=None):
+            return loader.read_audio_file(path, start_seconds=start_seconds, duration_seconds=duration_seconds,
+                                          audio_read_config=audio_read_config)
+
+        entries = [(files[i], None, None) for i in accepted]
+        for position, outcome in _data_loader.iter_file_features(entries, feature_flags=feature_flags, read_audio=read_audio,
+                                                                 read_pcm16=read_pcm16_file, device=self._device):
+            i = accepted[position]
+            if isinstance(outcome, Exception):
+                results[i] = result_type(sample=None, error=f"Failed to process file {files[i]}: {outcome}")
+            else:
+                results[i] = result_type(sample=(outcome, emotions[i]), error=None)
+        return iter(results)
+
+
+class _ForkFreeMultiprocessing:
+    """What ``data_loader.mp`` becomes: everything of ``multiprocessing`` except that ``Pool`` does not fork."""
+
+    def __init__(self, real, ref_loader, device: int) -> None:
+        self._real = real
+        self._ref_loader = ref_loader
+        self._device = device
+
+    def Pool(self, processes=None, *args, **kwargs):  # noqa: N802 - multiprocessing's name
+        return _InProcessPool(self._ref_loader, self._device, processes)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
 
 
 def _swap(owner: Any, name: str, value: Any) -> None:
@@ -154,6 +253,13 @@ def install(device: int = 0) -> list[str]:
 
     _swap(ref_features, "_extract_feature_frames_for_settings", extract_feature_frames_for_settings)
     _swap(ref_features, "_extract_feature_for_settings", extract_feature_for_settings)
+    if hasattr(ref_data_loader, "_extract_feature_for_settings"):
+        _swap(ref_data_loader, "_extract_feature_for_settings", extract_feature_for_settings)
+    if hasattr(ref_data_loader, "mp"):
+        _swap(ref_data_loader, "mp", _ForkFreeMultiprocessing(ref_data_loader.mp, ref_data_loader, device))
+    ref_boundary = importlib.import_module("ser._internal.runtime.fast_public_boundary")
+    os.environ[_DEVICE_ENV] = str(int(device))
+    _swap(ref_boundary, "_fast_worker_entry", spawned_fast_worker_entry)
     _swap(ref_data_loader, "load_checked_fast_data", load_checked_fast_data)
     _swap(ref_dsp, "extract_feature_from_signal", extract_feature_from_signal)
     _swap(ref_features, "_extract_feature_from_signal", extract_feature_from_signal)
