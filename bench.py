@@ -398,8 +398,22 @@ def run_b200(args) -> None:
                 return rows, None, None
             return ctx.infer_host_pcm16(files, 1, clip_of, w_starts, lengths, sr, bits, want_features=False)
 
+        rank_rows = [0] * world
+        if info.distributed:
+            import torch.distributed as dist
+
+            dist.all_gather_object(rank_rows, n_rows)
+        else:
+            rank_rows = [n_rows]
+
+        def to_rank0(f_host, p_host, l_host):
+            # the small per-row results go to rank 0 (north_star: "only the small per-clip feature vectors are
+            # gathered to the host"): one padded tensor gather, GPU to GPU under NCCL
+            local = f_host if c3 else np.concatenate([p_host, l_host[:, None].astype(np.float64)], axis=1)
+            return multi_gpu.gather_rows(info, local, total_rows, counts=rank_rows)
+
         def e2e_timed(files, steps):
-            e2e_call(files)                                          # warm the staging buffers
+            to_rank0(*e2e_call(files))                               # warm the staging buffers and the gather's channels
             barrier()
             t0 = time.perf_counter()
             chain = []
@@ -407,9 +421,7 @@ def run_b200(args) -> None:
             for _ in range(steps):
                 f_host, p_host, l_host = e2e_call(files)
                 chain.append(ctx.last_compute_ms())
-                # the small per-row results go to rank 0 inside the timed region (north_star)
-                local = f_host if c3 else np.concatenate([p_host, l_host[:, None].astype(np.float64)], axis=1)
-                gathered = multi_gpu.gather_rows(info, local, total_rows)
+                gathered = to_rank0(f_host, p_host, l_host)         # inside the timed region
             elapsed = max_over_ranks(time.perf_counter() - t0)
             barrier()
             return elapsed, float(np.median(chain)), (f_host, p_host, l_host), gathered

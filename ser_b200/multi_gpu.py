@@ -79,19 +79,33 @@ def my_clip_range(info: RankInfo, lengths: np.ndarray) -> tuple[int, int]:
     return shard_bounds(lengths, info.world)[info.rank]
 
 
-def gather_rows(info: RankInfo, local_rows: np.ndarray, n_total: int) -> np.ndarray | None:
-    """Concatenates every rank's (n_i, dim) block in rank order on rank 0 (None elsewhere)."""
+def gather_rows(info: RankInfo, local_rows: np.ndarray, n_total: int, *, counts: list[int] | None = None,
+                device=None) -> np.ndarray | None:
+    """Concatenates every rank's (n_i, dim) block in rank order on rank 0 (None elsewhere).
+
+    One tensor collective (``dist.gather`` of blocks padded to the largest rank's row count), not an
+    object collective: no pickling, and on NCCL the blocks travel GPU to GPU.  ``counts`` (rows per rank)
+    is known to callers that sharded the work themselves; when absent it is exchanged first.
+    ``device`` is where the collective runs: "cuda" for NCCL, "cpu" for gloo (default: by backend)."""
     local_rows = np.ascontiguousarray(local_rows)
     if not info.distributed:
         assert local_rows.shape[0] == n_total
         return local_rows
+    import torch
     import torch.distributed as dist
 
-    blocks: list = [None] * info.world if info.rank == 0 else None
-    dist.gather_object(local_rows, blocks, dst=0)
+    if device is None:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    if counts is None:
+        counts = [0] * info.world
+        dist.all_gather_object(counts, int(local_rows.shape[0]))
+    if sum(counts) != n_total:
+        raise RuntimeError(f"ranks hold {sum(counts)} rows, expected {n_total}")
+    most = max(counts)
+    block = torch.zeros((most,) + local_rows.shape[1:], dtype=torch.from_numpy(local_rows[:0]).dtype, device=device)
+    block[: local_rows.shape[0]].copy_(torch.from_numpy(local_rows), non_blocking=False)
+    blocks = [torch.empty_like(block) for _ in range(info.world)] if info.rank == 0 else None
+    dist.gather(block, blocks, dst=0)
     if info.rank != 0:
         return None
-    out = np.concatenate(blocks, axis=0)
-    if out.shape[0] != n_total:
-        raise RuntimeError(f"gathered {out.shape[0]} rows, expected {n_total}")
-    return out
+    return np.concatenate([b[:c].cpu().numpy() for b, c in zip(blocks, counts)], axis=0)
