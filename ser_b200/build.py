@@ -29,6 +29,7 @@ SOURCES = [
     "short_kernel.cu",
     "hpss_kernels.cu",
     "cqt_kernels.cu",
+    "decimate_mma.cu",
     "mlp_kernel.cu",
     "pcm_kernels.cu",
     "api.cu",

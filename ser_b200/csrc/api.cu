@@ -97,7 +97,9 @@ struct serb_ctx {
     // host-entry staging
     DevBuf wave, out, proba, labels, x64, pcm, pcm_max, pcm_files, pcm_peaks;
     // tonnetz chain
-    DevBuf hann_sq, cq_twiddles;
+    DevBuf hann_sq, cq_twiddles, dec_toeplitz;
+    int n_sms = 0;
+    bool dec_mma = true;        // factor-2 decimation on tcgen05 (SERB_DECIMATE=ffma keeps the FFMA2 kernel)
     DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
@@ -361,7 +363,7 @@ struct LongList {
 struct TonChunk {
     int clip_lo, clip_hi;       // range in the request-wide TonClip array
     int seg_lo, n_segs;
-    int n_cols, n_tiles, cq_rows, max_len0, max_cq_cols, n_parts;
+    int n_cols, n_tiles, cq_rows, max_len0, max_cq_cols, n_parts, max_length, n_dec_exact;
     long long total0, max_end;
 };
 
@@ -407,13 +409,16 @@ int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur,
     for (int t0 = 0; t0 < a.n_cols; t0 += ctx->harm_seg) tp.segs.push_back(make_int2(local, t0));
     tp.clips.push_back(c);
     tp.clips_b.push_back(b);
-    cur.total0 += (len0 + 127) / 128 * 128;
+    // 512-sample granules keep every level of every clip 32-byte aligned (off0 >> 6 is a multiple of 8)
+    cur.total0 += (len0 + 511) / 512 * 512;
     cur.n_cols = std::max(cur.n_cols, a.col_base + a.n_cols);
     cur.n_tiles = std::max(cur.n_tiles, a.tile_base + (a.n_cols + kColsPerTile - 1) / kColsPerTile);
     cur.n_segs = static_cast<int>(tp.segs.size()) - cur.seg_lo;
     cur.cq_rows += cq;
     cur.n_parts += (cq + kTonTile - 1) / kTonTile;
     cur.max_len0 = std::max(cur.max_len0, c.len0);
+    cur.max_length = std::max(cur.max_length, c.length);
+    cur.n_dec_exact += c.length < kDecExactBelow;
     cur.max_cq_cols = std::max(cur.max_cq_cols, cq);
     cur.max_end = std::max(cur.max_end, a.start + a.length);
     cur.clip_hi += 1;
@@ -555,6 +560,10 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.off_tonnetz = off.tonnetz;
     qp.max_len0 = c.max_len0;
     qp.max_cq_cols = c.max_cq_cols;
+    qp.max_length = c.max_length;
+    qp.n_dec_exact = c.n_dec_exact;
+    qp.dec_toeplitz = ctx->dec_mma ? ctx->dec_toeplitz.ptr : nullptr;
+    qp.n_sms = ctx->n_sms;
     { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
@@ -1152,6 +1161,13 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
             taps32[i] = static_cast<float>(taps64[i]);
         }
         CREATE_CHECK(configure_cqt(taps32.data(), taps64.data()));
+        CREATE_CHECK(configure_decimate_mma());
+        std::vector<unsigned char> toeplitz(decimate_mma_table_bytes());
+        decimate_mma_table(taps64.data(), toeplitz.data());
+        CREATE_CHECK(ctx->dec_toeplitz.reserve(toeplitz.size()));
+        CREATE_CHECK(cudaMemcpy(ctx->dec_toeplitz.ptr, toeplitz.data(), toeplitz.size(), cudaMemcpyHostToDevice));
+        CREATE_CHECK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device_ordinal));
+        if (const char* env = std::getenv("SERB_DECIMATE")) ctx->dec_mma = std::string(env) != "ffma";
         hann_squared_2048(hsq);
         // behind the 2048 doubles: the overlap-add's window sum of squares where four frames
         // overlap, accumulated in frame order exactly as ola_sample does (float64 add, float32 store)
@@ -1220,7 +1236,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
                       &ctx->tile_chroma, &ctx->peaks, &ctx->peak_count, &ctx->clips, &ctx->short_clips,
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->pcm_files, &ctx->pcm_peaks, &ctx->mlp.mean, &ctx->mlp.scale,
-                      &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles,
+                      &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles, &ctx->dec_toeplitz,
                       &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag, &ctx->ton_part,
                       &ctx->long_idx, &ctx->long_state, &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
                       &ctx->ton_tile_clip})

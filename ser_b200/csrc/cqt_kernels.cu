@@ -33,7 +33,6 @@ static_assert(kDecTaps2 % 4 == 1, "the pairing below assumes a tap count of 1 mo
 // float32 accumulation error (relative to the largest term) would come out amplified; the oracle's
 // float64 convolution rounded to float32 is reproduced instead (cost: nothing, these clips are tiny).
 __constant__ double c_tap_d[kDecTaps2];
-constexpr int kDecExactBelow = 2048;
 __constant__ __align__(16) float2 c_tap2[kTapPairs];
 
 namespace {
@@ -76,9 +75,11 @@ constexpr int kDecThreads = kDecTile / kDecOuts;
 constexpr int kDecPad = 2;
 constexpr int kDecPhys = kDecSpan + kDecPad * ((kDecSpan + kDecOuts - 1) / kDecOuts);
 
-__global__ void __launch_bounds__(kDecThreads) decimate2_kernel(CqtParams p, int src_level) {
+// exact_only: the clips of at least kDecExactBelow samples are left to decimate2_mma_kernel
+__global__ void __launch_bounds__(kDecThreads) decimate2_kernel(CqtParams p, int src_level, int exact_only) {
     __shared__ __align__(16) float2 xs[kDecPhys];
     const TonClip clip = p.clips[blockIdx.x];
+    if (exact_only && clip.length >= kDecExactBelow) return;
     const int len_in = src_level < 0 ? clip.length : level_length(clip.len0, src_level);
     const int len_out = (len_in + 1) >> 1;
     const float* src = level_ptr(p, clip, src_level);
@@ -544,12 +545,36 @@ static cudaError_t launch_cqt_group(CqtParams p, int first, int count, cudaStrea
     return cudaGetLastError();
 }
 
+// one factor-2 stage: the tensor-core kernel for the long clips (when its operand table is there)
+// plus the float64 path for the clips below kDecExactBelow samples, else the FFMA2 kernel for all
+static cudaError_t launch_decimate2(const CqtParams& p, int src_level, int max_len_in, cudaStream_t stream, long long* n) {
+    const int max_out = (max_len_in + 1) >> 1;
+    const dim3 grid(p.n_clips, min(65535, (max_out + kDecTile - 1) / kDecTile));
+    if (p.dec_toeplitz == nullptr) {
+        decimate2_kernel<<<grid, kDecThreads, 0, stream>>>(p, src_level, 0);
+        ++*n;
+        return cudaGetLastError();
+    }
+    if (p.n_dec_exact < p.n_clips) {
+        cudaError_t e = launch_decimate2_mma(p, src_level, max_len_in, p.dec_toeplitz, p.n_sms, stream);
+        if (e != cudaSuccess) return e;
+        ++*n;
+    }
+    if (p.n_dec_exact > 0) {
+        // the short clips only: their levels are at most kDecExactBelow / 2 outputs long
+        const dim3 small(p.n_clips, min(static_cast<int>(grid.y), (kDecExactBelow / 2 + kDecThreads - 1) / kDecThreads));
+        decimate2_kernel<<<small, kDecThreads, 0, stream>>>(p, src_level, 1);
+        ++*n;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long long* launches) {
     if (p.n_clips <= 0) return cudaSuccess;
     long long n = 0;
+    cudaError_t e;
     if (p.early_factor == 2) {
-        decimate2_kernel<<<dim3(p.n_clips, min(65535, (p.max_len0 + kDecTile - 1) / kDecTile)), kDecThreads, 0, stream>>>(p, -1);
-        ++n;
+        if ((e = launch_decimate2(p, -1, p.max_length, stream, &n)) != cudaSuccess) return e;
     } else if (p.early_factor > 2) {
         const int tiles = min(4096, (p.max_len0 + 255) / 256);
         decimate_any_kernel<<<dim3(p.n_clips, tiles), 256, 0, stream>>>(p);
@@ -557,9 +582,8 @@ cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long lon
     }
     int len = p.max_len0;
     for (int level = 0; level + 1 < kCqOctaves; ++level) {
+        if ((e = launch_decimate2(p, level, len, stream, &n)) != cudaSuccess) return e;
         len = (len + 1) >> 1;
-        decimate2_kernel<<<dim3(p.n_clips, min(65535, (len + kDecTile - 1) / kDecTile)), kDecThreads, 0, stream>>>(p, level);
-        ++n;
     }
     if (launches) *launches += n;
     return cudaGetLastError();

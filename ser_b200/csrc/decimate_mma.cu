@@ -1,0 +1,419 @@
+// Factor-2 decimation of the constant-Q recursion as a banded-Toeplitz GEMM on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Arithmetic to reproduce (oracle/shim/librosa/core.py:_soxr_hq_decimate, resample(scale=True)):
+//   out[m] = sum_{k < K} h[k] x[2 m + (K - 1) / 2 - k],   K = 389, h = sqrt(2) x the HQ low-pass.
+//
+// GEMM view.  128 consecutive outputs of one signal (a "window") read 643 consecutive samples;
+// written as D[128 x N] = T[128 x 656] . X[656 x N], T is the banded Toeplitz matrix of the taps
+// and every column of X is the sample span of another window.  float32 accuracy comes from three
+// bf16 terms per operand (x = x0 + x1 + x2, h = h0 + h1 + h2, 8 mantissa bits each) and the six
+// products of total order <= 2 (x0 h0 | x0 h1, x1 h0 | x1 h1, x0 h2, x2 h0), accumulated in float32:
+// the leading product in one TMEM accumulator, the five small ones in a second (their sum is 2^-8
+// of the result, so the tensor core's truncating accumulate costs them nothing), added once in
+// the epilogue.
+//
+// Layouts (both operands K-major, no swizzle: 8 x 16-byte core matrices, UMMA "INTERLEAVE"):
+// * T depends on (2 row - column) only.  With the output ROWS REVERSED (row i' = output 127 - i')
+//   core matrix (r', c) depends on u = 2 r' + c alone, so the whole 128 x 656 operand is 112 core
+//   matrices (14 KB per bf16 term) addressed with SBO = 2 cores, LBO = 1 core: it stays resident in
+//   shared memory for the life of the CTA and costs no traffic.
+// * X: the N = 8 R columns are 8 "lanes" (core-matrix rows) x R consecutive windows.  Lane a holds
+//   one contiguous span of one signal as 16-byte chunks of 8 samples, chunk q at 128 q + 16 a;
+//   window rn of the lane starts 32 chunks after window rn - 1, so core matrix (rn, c) is chunk
+//   32 rn + c: SBO = 32 cores, LBO = 1 core, and the overlapping windows share their samples
+//   (6 bytes of shared memory per input sample instead of 15).
+// A CTA (one per SM, persistent) loops over tiles of 8 lanes: eight producer warps load float32
+// samples, split them into the three bf16 terms and store the chunks; one thread issues the
+// 41 K-slabs x 6 products = 246 tcgen05.mma (M 128, N 8 R, K 16); four epilogue warps read the two
+// accumulators (tcgen05.ld), add them and store float32 outputs, overlapped with the next tile
+// through a second pair of accumulators.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace serb {
+
+namespace {
+
+constexpr int kDmR = 12;                               // windows per lane
+constexpr int kDmN = 8 * kDmR;                         // MMA N
+constexpr int kDmWin = 128;                            // outputs per window = MMA M
+constexpr int kDmSlabs = 41;                           // K = 16 x 41 = 656 >= 643 + left padding
+constexpr int kDmHalf = (kDecTaps2 - 1) / 2;           // 194
+constexpr int kDmLeft = 200;                           // window sample 0 = x[2 m0 - kDmLeft] (multiple of 8)
+constexpr int kDmKoff = 2 * (kDmWin - 1) + kDmHalf + kDmLeft;   // tap index = kDmKoff - 8 u - 2 a - b
+constexpr int kDmCoresA = 2 * (kDmWin / 8 - 1) + 2 * kDmSlabs;  // 112 distinct core matrices of T
+constexpr int kDmChunks = 32 * (kDmR - 1) + 2 * kDmSlabs;       // 16-byte chunks per lane
+constexpr int kDmABytes = kDmCoresA * 128;
+constexpr int kDmBBytes = kDmChunks * 128;
+constexpr int kDmSegOut = kDmWin * kDmR;               // outputs per lane segment
+static_assert(kDmLeft % 8 == 0 && kDmLeft >= kDmHalf, "left padding");
+static_assert(kDmKoff < 16 * kDmSlabs, "the last tap must fall inside the last K slab");
+static_assert(kDmHalf + kDmLeft - (kDecTaps2 - 1) >= 0, "the first tap must fall inside the first K slab");
+static_assert(kDmN % 16 == 0 && kDmN <= 256, "tcgen05.mma M = 128 needs N % 16 == 0");
+static_assert(4 * kDmN <= 512, "two pairs of accumulators must fit the 512 TMEM columns");
+
+constexpr int kDmProducerWarps = 15;
+constexpr int kDmChunkIters = (8 * kDmChunks + 32 * kDmProducerWarps - 1) / (32 * kDmProducerWarps);   // chunks per producer thread
+constexpr int kDmThreads = 32 * (1 + 4 + kDmProducerWarps);
+constexpr int kDmProducers = 32 * kDmProducerWarps;
+constexpr size_t kDmSmem = 3 * kDmABytes + 3 * kDmBBytes + 128;
+
+struct DmLaneInfo {
+    const float* src;
+    float* dst;
+    int len_in, len_out, m0, active;
+};
+
+__device__ __forceinline__ int dm_level_length(int len0, int level) {
+    int n = len0;
+    for (int i = 0; i < level; ++i) n = (n + 1) >> 1;
+    return n;
+}
+
+// lane a of tile `tile` = segment (8 tile + a) of the launch: clip (segment / segs_per_clip),
+// outputs [m0, m0 + kDmSegOut) of that clip's destination level
+__device__ __forceinline__ DmLaneInfo dm_lane_info(const CqtParams& p, int src_level, int segs_per_clip, int tile, int a) {
+    DmLaneInfo li{};
+    const int g = 8 * tile + a;
+    const int c = g / segs_per_clip;
+    if (c >= p.n_clips) return li;
+    const TonClip clip = p.clips[c];
+    if (clip.length < kDecExactBelow) return li;         // float64 path (decimate2_kernel)
+    li.len_in = src_level < 0 ? clip.length : dm_level_length(clip.len0, src_level);
+    li.len_out = (li.len_in + 1) >> 1;
+    li.m0 = (g - c * segs_per_clip) * kDmSegOut;
+    if (li.m0 >= li.len_out) return li;
+    li.src = (src_level < 0 || (src_level == 0 && p.early_factor == 1)) ? p.yharm + clip.hoff
+                                                                        : p.yoct + p.level_base[src_level] + (clip.off0 >> src_level);
+    li.dst = p.yoct + p.level_base[src_level + 1] + (clip.off0 >> (src_level + 1));
+    li.active = 1;
+    return li;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// A phase that never completes is a protocol bug: trap instead of hanging the device.  The
+// waiting roles that are not on the critical path back off between polls (kSleepNs), so that
+// their polling does not take issue slots from the warp that feeds the tensor core.
+template <int kSleepNs>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (kSleepNs > 0) __nanosleep(kSleepNs);
+        if ((spins & 4095u) == 4095u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();          // seconds, not microseconds
+        }
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc], bf16 x bf16 -> f32
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 consecutive TMEM columns of this thread's lane (32 lanes x 32 bit per warp)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor: start >> 4 in
+// bits [0,14), leading (K) byte offset >> 4 in [16,30), stride (M/N) byte offset >> 4 in [32,46),
+// version 1 in [46,48), layout type 0 in [61,64))
+__device__ __forceinline__ uint64_t dm_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+           (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A and B bf16, both K-major
+constexpr uint32_t kDmIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kDmN >> 3) << 17) |
+                              (static_cast<uint32_t>(kDmWin >> 4) << 24);
+
+// eight float32 samples -> the three bf16 terms, 16 bytes each (element b at byte 2 b)
+__device__ __forceinline__ void dm_split8(const float4& lo, const float4& hi, uint4& s0, uint4& s1, uint4& s2) {
+    const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        const float2 f0 = __bfloat1622float2(h0);
+        const float ra = x[2 * i] - f0.x, rb = x[2 * i + 1] - f0.y;          // exact
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn(ra, rb);
+        const float2 f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(ra - f1.x, rb - f1.y);
+        w0[i] = *reinterpret_cast<const uint32_t*>(&h0);
+        w1[i] = *reinterpret_cast<const uint32_t*>(&h1);
+        w2[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    s0 = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    s1 = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    s2 = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kDmThreads, 1)
+decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles, const uint4* __restrict__ toeplitz) {
+    extern __shared__ __align__(128) unsigned char dm_smem[];
+    unsigned char* sm_a = dm_smem;                               // [3][kDmABytes]
+    unsigned char* sm_b = dm_smem + 3 * kDmABytes;               // [3][kDmBBytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dm_smem + 3 * kDmABytes + 3 * kDmBBytes);
+    // bars[0] b_full, [1] b_empty, [2..3] d_full, [4..5] d_empty; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    __shared__ DmLaneInfo epi_info[4][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < 3 * kDmABytes / 16; i += kDmThreads) reinterpret_cast<uint4*>(sm_a)[i] = toeplitz[i];
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars[0]), kDmProducers);
+        mbar_init(smem_u32(&bars[1]), 1);
+        mbar_init(smem_u32(&bars[2]), 1);
+        mbar_init(smem_u32(&bars[3]), 1);
+        mbar_init(smem_u32(&bars[4]), 128);
+        mbar_init(smem_u32(&bars[5]), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the Toeplitz operand, written with generic stores
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_full = smem_u32(&bars[0]), b_empty = smem_u32(&bars[1]);
+
+    if (warp == 0) {
+        // ---- MMA issue: the whole warp walks the tiles, one elected lane issues ----
+        const uint32_t a_addr = smem_u32(sm_a), b_addr = smem_u32(sm_b);
+        // descriptors of K slab 0; slab s is 256 bytes (two core matrices) further in both operands
+        uint64_t ad[3], bd[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            ad[t] = dm_desc(a_addr + t * kDmABytes, 128, 256);
+            bd[t] = dm_desc(b_addr + t * kDmBBytes, 128, 32 * 128);
+        }
+        int n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            const int buf = n & 1, use = n >> 1;
+            mbar_wait<0>(smem_u32(&bars[4 + buf]), (use & 1) ^ 1);      // accumulators drained by the epilogue
+            mbar_wait<0>(b_full, n & 1);                               // samples staged
+            tc_fence_after();
+            const uint32_t d_main = tmem_base + buf * 2 * kDmN, d_small = d_main + kDmN;
+            if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < kDmSlabs; ++s) {
+                    const uint64_t o = 16ull * s;                  // (256 s) >> 4 in the start-address field
+                    tc_mma(d_main, ad[0] + o, bd[0] + o, kDmIdesc, s > 0);
+                    tc_mma(d_small, ad[1] + o, bd[1] + o, kDmIdesc, s > 0);
+                    tc_mma(d_small, ad[2] + o, bd[0] + o, kDmIdesc, 1);
+                    tc_mma(d_small, ad[0] + o, bd[2] + o, kDmIdesc, 1);
+                    tc_mma(d_small, ad[1] + o, bd[0] + o, kDmIdesc, 1);
+                    tc_mma(d_small, ad[0] + o, bd[1] + o, kDmIdesc, 1);
+                }
+                tc_commit(b_empty);                      // the staged samples may be overwritten
+                tc_commit(smem_u32(&bars[2 + buf]));     // the accumulators are complete
+            }
+            __syncwarp();
+        }
+    } else if (warp <= 4) {
+        // ---- epilogue: TMEM lane quarter (warp & 3), row i' = output 127 - i' of every window ----
+        const int quarter = warp & 3;
+        DmLaneInfo* info = epi_info[warp - 1];
+        const int mrow = kDmWin - 1 - (32 * quarter + lane);
+        int n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            const int buf = n & 1, use = n >> 1;
+            if (lane < 8) info[lane] = dm_lane_info(p, src_level, segs_per_clip, tile, lane);
+            __syncwarp();
+            // per lane of the tile: where this thread's row lands and how many outputs are left there
+            float* dptr[8];
+            int left[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const DmLaneInfo li = info[a];
+                dptr[a] = li.dst + li.m0 + mrow;
+                left[a] = li.active ? li.len_out - li.m0 - mrow : 0;
+            }
+            mbar_wait<64>(smem_u32(&bars[2 + buf]), use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) + buf * 2 * kDmN;
+#pragma unroll 2
+            for (int g = 0; g < kDmN / 16; ++g) {
+                float v[16], w[16];
+                tc_ld16(taddr + 16 * g, v);
+                tc_ld16(taddr + kDmN + 16 * g, w);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int off = kDmWin * (2 * g + (j >> 3));          // window rn = 2 g + j / 8 of lane j % 8
+                    if (off < left[j & 7]) dptr[j & 7][off] = v[j] + w[j];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars[4 + buf]));
+            __syncwarp();
+        }
+    } else {
+        // ---- producers: thread = (lane a, chunks q0 + kDmProducers / 8 * it) ----
+        // The samples of tile n + 1 are loaded into registers while the tensor core works on tile n
+        // (the operand buffer is single: 6 bytes x 2 samples per output fill the shared memory), so
+        // that only the split into bf16 terms and the stores sit between two tiles' MMAs.
+        const int pt = tid - 160, a = pt & 7, q0 = pt >> 3;
+        unsigned char* dst0 = sm_b + 16 * a;
+        float4 lo[kDmChunkIters], hi[kDmChunkIters];
+        auto load_tile = [&](int tile) -> int {
+            const DmLaneInfo li = dm_lane_info(p, src_level, segs_per_clip, tile, a);
+            if (!li.active) return 0;
+            const int sbase = 2 * li.m0 - kDmLeft;
+            const bool aligned = (reinterpret_cast<uintptr_t>(li.src) & 31) == 0;
+#pragma unroll
+            for (int it = 0; it < kDmChunkIters; ++it) {
+                const int q = q0 + (kDmProducers / 8) * it;
+                const int s = sbase + 8 * q;
+                if (q >= kDmChunks) continue;
+                if (aligned && s >= 0 && s + 8 <= li.len_in) {
+                    lo[it] = __ldg(reinterpret_cast<const float4*>(li.src + s));
+                    hi[it] = __ldg(reinterpret_cast<const float4*>(li.src + s + 4));
+                } else {
+                    float x[8];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) x[b] = (s + b >= 0 && s + b < li.len_in) ? li.src[s + b] : 0.0f;
+                    lo[it] = make_float4(x[0], x[1], x[2], x[3]);
+                    hi[it] = make_float4(x[4], x[5], x[6], x[7]);
+                }
+            }
+            return 1;
+        };
+        int n = 0;
+        int active = blockIdx.x < n_tiles ? load_tile(blockIdx.x) : 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            mbar_wait<32>(b_empty, (n & 1) ^ 1);
+            if (active) {
+#pragma unroll
+                for (int it = 0; it < kDmChunkIters; ++it) {
+                    const int q = q0 + (kDmProducers / 8) * it;
+                    if (q >= kDmChunks) continue;
+                    uint4 s0, s1, s2;
+                    dm_split8(lo[it], hi[it], s0, s1, s2);
+                    unsigned char* d = dst0 + 128 * q;
+                    *reinterpret_cast<uint4*>(d) = s0;
+                    *reinterpret_cast<uint4*>(d + kDmBBytes) = s1;
+                    *reinterpret_cast<uint4*>(d + 2 * kDmBBytes) = s2;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(b_full);
+            if (tile + static_cast<int>(gridDim.x) < n_tiles) active = load_tile(tile + gridDim.x);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+namespace {
+
+uint16_t bf16_rn(double v, double* back) {
+    const float f = static_cast<float>(v);
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    const uint32_t rounded = u + 0x7fffu + ((u >> 16) & 1u);     // round to nearest even on the top 16 bits
+    const uint16_t h = static_cast<uint16_t>(rounded >> 16);
+    const uint32_t w = static_cast<uint32_t>(h) << 16;
+    float g;
+    std::memcpy(&g, &w, 4);
+    *back = static_cast<double>(g);
+    return h;
+}
+
+}  // namespace
+
+size_t decimate_mma_table_bytes() { return 3 * kDmABytes; }
+
+// taps (x sqrt 2, float64) -> [3 terms][112 core matrices][8 rows][8 columns] bf16
+void decimate_mma_table(const double* taps2_scaled, unsigned char* out) {
+    uint16_t* t = reinterpret_cast<uint16_t*>(out);
+    for (int u = 0; u < kDmCoresA; ++u)
+        for (int a = 0; a < 8; ++a)
+            for (int b = 0; b < 8; ++b) {
+                const int k = kDmKoff - 8 * u - 2 * a - b;
+                const double h = (k >= 0 && k < kDecTaps2) ? taps2_scaled[k] : 0.0;
+                double b0, b1, b2;
+                const uint16_t h0 = bf16_rn(h, &b0);
+                const uint16_t h1 = bf16_rn(h - b0, &b1);
+                const uint16_t h2 = bf16_rn(h - b0 - b1, &b2);
+                const size_t at = (static_cast<size_t>(u) * 8 + a) * 8 + b;
+                t[at] = h0;
+                t[kDmABytes / 2 + at] = h1;
+                t[2 * (kDmABytes / 2) + at] = h2;
+            }
+}
+
+cudaError_t configure_decimate_mma() {
+    return cudaFuncSetAttribute(decimate2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDmSmem));
+}
+
+// level src_level -> src_level + 1 (src_level -1: yharm -> level 0) for every clip of at least
+// kDecExactBelow samples; max_len_in = longest source signal of the launch
+cudaError_t launch_decimate2_mma(const CqtParams& p, int src_level, int max_len_in, const void* d_toeplitz, int n_sms,
+                                 cudaStream_t stream) {
+    const int max_out = (max_len_in + 1) >> 1;
+    const int segs_per_clip = (max_out + kDmSegOut - 1) / kDmSegOut;
+    const long long segs = static_cast<long long>(p.n_clips) * segs_per_clip;
+    if (segs <= 0) return cudaSuccess;
+    if (segs > 0x3fffffffll) return cudaErrorInvalidValue;
+    const int n_tiles = static_cast<int>((segs + 7) / 8);
+    const int grid = n_tiles < n_sms ? n_tiles : n_sms;
+    decimate2_mma_kernel<<<grid, kDmThreads, kDmSmem, stream>>>(p, src_level, segs_per_clip, n_tiles,
+                                                                static_cast<const uint4*>(d_toeplitz));
+    return cudaGetLastError();
+}
+
+}  // namespace serb

@@ -114,6 +114,7 @@ constexpr int kCqRows = 36;       // bins per octave
 constexpr int kCqBins = 252;
 constexpr int kCqRowCap = 32;     // complex values stored per basis row
 constexpr int kDecTaps2 = 389;    // libsoxr HQ 2:1 low-pass, restated (cqt_tables.cpp decimation_taps); 1 mod 4
+constexpr int kDecExactBelow = 2048;   // clips shorter than this decimate in float64 (cqt_kernels.cu)
 
 struct TonClip {
     long long hoff;      // harmonic signal of the clip: yharm[hoff .. hoff + length)
@@ -184,9 +185,19 @@ struct CqtParams {
     int dim, off_tonnetz;
     int max_len0;                // longest level-0 signal in the chunk
     int max_cq_cols;             // most constant-Q columns of one clip
+    int max_length;              // longest full-rate signal in the chunk
+    int n_dec_exact;             // clips shorter than kDecExactBelow samples (float64 decimation)
+    const void* dec_toeplitz;    // bf16 Toeplitz operand of decimate2_mma_kernel (decimate_mma_table)
+    int n_sms;
 };
 cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_f64);   // factor-2 taps (x sqrt 2) to constant memory
 cudaError_t launch_decimations(const CqtParams& p, cudaStream_t stream, long long* launches);
+// decimate_mma.cu: the factor-2 decimation on tcgen05 (clips of at least kDecExactBelow samples)
+size_t decimate_mma_table_bytes();
+void decimate_mma_table(const double* taps2_scaled, unsigned char* out);
+cudaError_t configure_decimate_mma();
+cudaError_t launch_decimate2_mma(const CqtParams& p, int src_level, int max_len_in, const void* d_toeplitz, int n_sms,
+                                 cudaStream_t stream);
 cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long long* launches);
 cudaError_t launch_tonnetz(const CqtParams& p, cudaStream_t stream);
 
