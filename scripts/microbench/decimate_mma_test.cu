@@ -16,6 +16,9 @@
 #include "kernels.h"
 
 using namespace serb;
+#ifdef DM_TRACE
+namespace serb { void* decimate_mma_trace_ptr(); }
+#endif
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); std::exit(1); } } while (0)
 
@@ -120,6 +123,24 @@ int main(int argc, char** argv) {
     }
     CK(cudaDeviceSynchronize());
 
+#ifdef DM_TRACE
+    {
+        // one more level-0 launch, then the clock stamps of CTA 0
+        std::vector<long long> tr(4096 * 16, 0);
+        void* sym = serb::decimate_mma_trace_ptr();
+        CK(cudaMemset(sym, 0, tr.size() * 8));
+        CK(launch_decimate2_mma(pb, -1, max_length, d_table, n_sms, 0));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(tr.data(), sym, tr.size() * 8, cudaMemcpyDeviceToHost));
+        std::printf("CTA 0, clocks.  per group: [wait for the staged group | issue] ; producer warp 5 group 0: released at, stored at ; epilogue warp 1: accumulators full at, drained at\n");
+        for (int n = 0; n < 10 && tr[n * 16] != 0; ++n) {
+            const long long* t = &tr[n * 16];
+            std::printf("%2d: start %7lld |", n, t[0] - tr[0]);
+            for (int g = 0; g < 4; ++g) std::printf(" g%d wait %5lld issue %5lld |", g, t[3 * g + 1] - t[3 * g], t[3 * g + 2] - t[3 * g + 1]);
+            std::printf(" loop top %7lld | prod g0 stored %7lld | epi %7lld .. %7lld\n", t[12] - tr[0], t[13] - tr[0], t[14] - tr[0], t[15] - tr[0]);
+        }
+    }
+#endif
     std::vector<float> ya(oct_floats), yb(oct_floats);
     CK(cudaMemcpy(ya.data(), d_yoct_a, oct_floats * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(yb.data(), d_yoct_b, oct_floats * 4, cudaMemcpyDeviceToHost));
@@ -130,6 +151,8 @@ int main(int argc, char** argv) {
     int bad = 0;
     for (int level = 0; level < kCqOctaves; ++level) {
         double worst_a = 0, worst_b = 0, worst_ab = 0;
+        double bias_a = 0, bias_b = 0, sq_a = 0, sq_b = 0;      // signed relative error where |out| > peak / 10
+        long long n_big = 0;
         for (int ci : check) {
             if (ci >= n_clips) continue;
             const TonClip& c = clips[ci];
@@ -162,10 +185,16 @@ int main(int argc, char** argv) {
                 worst_b = std::max(worst_b, std::fabs(ob[m] - rb[m]) / peak);
                 worst_ab = std::max(worst_ab, std::fabs(static_cast<double>(oa[m]) - ob[m]) / peak);
                 if (!std::isfinite(ob[m])) ++bad;
+                if (std::fabs(rb[m]) > 0.1 * peak && std::fabs(ra[m]) > 0.1 * peak) {
+                    const double ea = (oa[m] - ra[m]) / ra[m], eb = (ob[m] - rb[m]) / rb[m];
+                    bias_a += ea; bias_b += eb; sq_a += ea * ea; sq_b += eb * eb; ++n_big;
+                }
             }
         }
         std::printf("level %d: max |out - f64 FIR of own input| / peak   FFMA2 %.3e   tcgen05 %.3e   | FFMA2 vs tcgen05 chain %.3e\n",
                     level, worst_a, worst_b, worst_ab);
+        if (n_big) std::printf("         signed relative error on large outputs: FFMA2 mean %+.2e rms %.2e   tcgen05 mean %+.2e rms %.2e  (%lld outputs)\n",
+                               bias_a / n_big, std::sqrt(sq_a / n_big), bias_b / n_big, std::sqrt(sq_b / n_big), n_big);
     }
     // bit-identity of equal signals at different batch positions (clips 0 and 4)
     if (n_clips > 4 && clips[0].length == clips[4].length) {

@@ -51,6 +51,11 @@ constexpr int kDmChunks = 32 * (kDmR - 1) + 2 * kDmSlabs;       // 16-byte chunk
 constexpr int kDmABytes = kDmCoresA * 128;
 constexpr int kDmBBytes = kDmChunks * 128;
 constexpr int kDmSegOut = kDmWin * kDmR;               // outputs per lane segment
+// K slabs [kDmCentral0, kDmCentral1) hold the centre tap of some row: row i (output i) has it at
+// window sample 2 i + kDmLeft, i = 0 .. 127
+constexpr int kDmCentral0 = kDmLeft / 16;
+constexpr int kDmCentral1 = (2 * (kDmWin - 1) + kDmLeft) / 16 + 1;
+static_assert(kDmSlabs - kDmCentral1 <= kDmCentral0, "the outer-slab loop pairs slab t with slab kDmSlabs - 1 - t");
 static_assert(kDmLeft % 8 == 0 && kDmLeft >= kDmHalf, "left padding");
 static_assert(kDmKoff < 16 * kDmSlabs, "the last tap must fall inside the last K slab");
 static_assert(kDmHalf + kDmLeft - (kDecTaps2 - 1) >= 0, "the first tap must fall inside the first K slab");
@@ -58,10 +63,19 @@ static_assert(kDmN % 16 == 0 && kDmN <= 256, "tcgen05.mma M = 128 needs N % 16 =
 static_assert(4 * kDmN <= 512, "two pairs of accumulators must fit the 512 TMEM columns");
 
 constexpr int kDmProducerWarps = 15;
-constexpr int kDmChunkIters = (8 * kDmChunks + 32 * kDmProducerWarps - 1) / (32 * kDmProducerWarps);   // chunks per producer thread
 constexpr int kDmThreads = 32 * (1 + 4 + kDmProducerWarps);
 constexpr int kDmProducers = 32 * kDmProducerWarps;
 constexpr size_t kDmSmem = 3 * kDmABytes + 3 * kDmBBytes + 128;
+
+#ifdef DM_TRACE
+// per-tile clock64 stamps of CTA 0 (scripts/microbench/decimate_mma_test -DDM_TRACE): [tile][8]
+__device__ long long dm_trace[4096 * 16];
+#define DM_STAMP(n, slot) do { if (blockIdx.x == 0 && (n) < 4096 && (threadIdx.x & 31) == 0) dm_trace[(n) * 16 + (slot)] = clock64(); } while (0)
+#define DM_STAMP1(n, slot) do { if (blockIdx.x == 0 && (n) < 4096) dm_trace[(n) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DM_STAMP(n, slot) do { } while (0)
+#define DM_STAMP1(n, slot) do { } while (0)
+#endif
 
 struct DmLaneInfo {
     const float* src;
@@ -193,25 +207,39 @@ __device__ __forceinline__ void dm_split8(const float4& lo, const float4& hi, ui
 
 }  // namespace
 
+// Chunk q of a lane is read by the K slabs s with (2 s) mod 32 == q mod 32 rounded down to even, i.e.
+// by slabs s, s + 16, s + 32 only.  The 41 slabs therefore fall into kDmGroups groups that read
+// disjoint quarters of the operand buffer (group of slab s = (s mod 16) / 4, group of chunk q =
+// (q mod 32) / 8): the single buffer works as a four-stage ring -- while the tensor core runs the
+// slabs of group g + 1 of tile n, the producers already write group g of tile n + 1.
+constexpr int kDmGroups = 4;
+constexpr int kDmBlk = (kDmChunks + 31) / 32;                       // 32-chunk blocks per lane
+constexpr int kDmGroupTasks = 8 * 8 * kDmBlk;                       // (lane, chunk) tasks per group, tail included
+constexpr int kDmGroupIters = (kDmGroupTasks + kDmProducers - 1) / kDmProducers;
+__host__ __device__ constexpr int dm_slab_group(int s) { return (s % 16) / 4; }
+
 __global__ void __launch_bounds__(kDmThreads, 1)
 decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles, const uint4* __restrict__ toeplitz) {
     extern __shared__ __align__(128) unsigned char dm_smem[];
     unsigned char* sm_a = dm_smem;                               // [3][kDmABytes]
     unsigned char* sm_b = dm_smem + 3 * kDmABytes;               // [3][kDmBBytes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(dm_smem + 3 * kDmABytes + 3 * kDmBBytes);
-    // bars[0] b_full, [1] b_empty, [2..3] d_full, [4..5] d_empty; then the TMEM base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    // bars[0..3] group full, [4..7] group empty, [8..9] accumulators full, [10..11] accumulators
+    // empty; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     __shared__ DmLaneInfo epi_info[4][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < 3 * kDmABytes / 16; i += kDmThreads) reinterpret_cast<uint4*>(sm_a)[i] = toeplitz[i];
     if (tid == 0) {
-        mbar_init(smem_u32(&bars[0]), kDmProducers);
-        mbar_init(smem_u32(&bars[1]), 1);
-        mbar_init(smem_u32(&bars[2]), 1);
-        mbar_init(smem_u32(&bars[3]), 1);
-        mbar_init(smem_u32(&bars[4]), 128);
-        mbar_init(smem_u32(&bars[5]), 128);
+        for (int g = 0; g < kDmGroups; ++g) {
+            mbar_init(smem_u32(&bars[g]), kDmProducerWarps);
+            mbar_init(smem_u32(&bars[4 + g]), 1);
+        }
+        mbar_init(smem_u32(&bars[8]), 1);
+        mbar_init(smem_u32(&bars[9]), 1);
+        mbar_init(smem_u32(&bars[10]), 4);
+        mbar_init(smem_u32(&bars[11]), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -223,7 +251,6 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t b_full = smem_u32(&bars[0]), b_empty = smem_u32(&bars[1]);
 
     if (warp == 0) {
         // ---- MMA issue: the whole warp walks the tiles, one elected lane issues ----
@@ -235,29 +262,50 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
             ad[t] = dm_desc(a_addr + t * kDmABytes, 128, 256);
             bd[t] = dm_desc(b_addr + t * kDmBBytes, 128, 32 * 128);
         }
-        int n = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-            const int buf = n & 1, use = n >> 1;
-            mbar_wait<0>(smem_u32(&bars[4 + buf]), (use & 1) ^ 1);      // accumulators drained by the epilogue
-            mbar_wait<0>(b_full, n & 1);                               // samples staged
-            tc_fence_after();
-            const uint32_t d_main = tmem_base + buf * 2 * kDmN, d_small = d_main + kDmN;
-            if (elect_one()) {
+        // one elected lane does all the waiting and issuing; the other lanes park at the warp barrier
+        if (elect_one()) {
+            int n = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+                const int buf = n & 1, use = n >> 1;
+                DM_STAMP1(n, 12);
+                mbar_wait<0>(smem_u32(&bars[10 + buf]), (use & 1) ^ 1);      // accumulators drained by the epilogue
+                const uint32_t d_main = tmem_base + buf * 2 * kDmN, d_small = d_main + kDmN;
+                // The tensor core's float32 accumulate truncates, so every add at full magnitude costs
+                // up to an ulp, always towards zero.  The leading product x0 h0 of the CENTRAL slabs --
+                // where every row's main lobe lies -- goes to d_main; its outer slabs (side lobes: a few
+                // per cent of the result) and the five small products of all slabs go to d_small.
+                // Within a slab the six MMAs stay together: they share three A and three B tiles, and
+                // the operand fetch, not the MMA rate, is what paces the pipe at N = 96.
 #pragma unroll
-                for (int s = 0; s < kDmSlabs; ++s) {
-                    const uint64_t o = 16ull * s;                  // (256 s) >> 4 in the start-address field
-                    tc_mma(d_main, ad[0] + o, bd[0] + o, kDmIdesc, s > 0);
-                    tc_mma(d_small, ad[1] + o, bd[1] + o, kDmIdesc, s > 0);
-                    tc_mma(d_small, ad[2] + o, bd[0] + o, kDmIdesc, 1);
-                    tc_mma(d_small, ad[0] + o, bd[2] + o, kDmIdesc, 1);
-                    tc_mma(d_small, ad[1] + o, bd[0] + o, kDmIdesc, 1);
-                    tc_mma(d_small, ad[0] + o, bd[1] + o, kDmIdesc, 1);
+                for (int g = 0; g < kDmGroups; ++g) {
+                    DM_STAMP1(n, 3 * g);
+                    mbar_wait<0>(smem_u32(&bars[g]), n & 1);                 // group g of this tile staged
+                    DM_STAMP1(n, 3 * g + 1);
+                    tc_fence_after();
+                    auto slab = [](uint64_t d, int s) { return d + 16ull * s; };     // (256 s) >> 4 in the start-address field
+                    bool first_small = (g == 0), first_main = true;
+#pragma unroll
+                    for (int s = 0; s < kDmSlabs; ++s) {
+                        if (dm_slab_group(s) != g) continue;
+                        const bool central = s >= kDmCentral0 && s < kDmCentral1;
+                        tc_mma(d_small, slab(ad[1], s), slab(bd[1], s), kDmIdesc, !first_small);
+                        first_small = false;
+                        tc_mma(d_small, slab(ad[2], s), slab(bd[0], s), kDmIdesc, 1);
+                        // the first central slab of the tile is slab 16, in group 0
+                        tc_mma(central ? d_main : d_small, slab(ad[0], s), slab(bd[0], s), kDmIdesc,
+                               !(central && g == 0 && first_main));
+                        if (central) first_main = false;
+                        tc_mma(d_small, slab(ad[0], s), slab(bd[2], s), kDmIdesc, 1);
+                        tc_mma(d_small, slab(ad[1], s), slab(bd[0], s), kDmIdesc, 1);
+                        tc_mma(d_small, slab(ad[0], s), slab(bd[1], s), kDmIdesc, 1);
+                    }
+                    tc_commit(smem_u32(&bars[4 + g]));                    // group g may be overwritten
+                    if (g == kDmGroups - 1) tc_commit(smem_u32(&bars[8 + buf]));     // the accumulators are complete
+                    DM_STAMP1(n, 3 * g + 2);
                 }
-                tc_commit(b_empty);                      // the staged samples may be overwritten
-                tc_commit(smem_u32(&bars[2 + buf]));     // the accumulators are complete
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp <= 4) {
         // ---- epilogue: TMEM lane quarter (warp & 3), row i' = output 127 - i' of every window ----
         const int quarter = warp & 3;
@@ -277,7 +325,8 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
                 dptr[a] = li.dst + li.m0 + mrow;
                 left[a] = li.active ? li.len_out - li.m0 - mrow : 0;
             }
-            mbar_wait<64>(smem_u32(&bars[2 + buf]), use & 1);
+            mbar_wait<64>(smem_u32(&bars[8 + buf]), use & 1);
+            if (warp == 1) DM_STAMP(n, 14);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) + buf * 2 * kDmN;
 #pragma unroll 2
@@ -293,59 +342,73 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
                 }
             }
             tc_fence_before();
-            mbar_arrive(smem_u32(&bars[4 + buf]));
             __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[10 + buf]));
+            if (warp == 1) DM_STAMP(n, 15);
         }
     } else {
-        // ---- producers: thread = (lane a, chunks q0 + kDmProducers / 8 * it) ----
-        // The samples of tile n + 1 are loaded into registers while the tensor core works on tile n
-        // (the operand buffer is single: 6 bytes x 2 samples per output fill the shared memory), so
-        // that only the split into bf16 terms and the stores sit between two tiles' MMAs.
-        const int pt = tid - 160, a = pt & 7, q0 = pt >> 3;
-        unsigned char* dst0 = sm_b + 16 * a;
-        float4 lo[kDmChunkIters], hi[kDmChunkIters];
+        // ---- producers ----
+        // Task t of group g = (lane a = t % 8, chunk q = 32 (t / 64) + 8 g + (t / 8) % 8); a thread owns
+        // tasks pt + kDmProducers k.  The samples of tile n + 1 are loaded into registers as soon as
+        // the thread has stored its part of tile n, i.e. while the tensor core still works on tile n,
+        // so that only the split into bf16 terms and the stores wait for a group to be released.
+        const int pt = tid - 160;
+        float4 lo[kDmGroups][kDmGroupIters], hi[kDmGroups][kDmGroupIters];
+        auto task_chunk = [&](int g, int k) -> int {
+            const int t = pt + kDmProducers * k;
+            return t < kDmGroupTasks ? 32 * (t >> 6) + 8 * g + ((t >> 3) & 7) : kDmChunks;
+        };
         auto load_tile = [&](int tile) -> int {
+            const int a = pt & 7;
             const DmLaneInfo li = dm_lane_info(p, src_level, segs_per_clip, tile, a);
             if (!li.active) return 0;
             const int sbase = 2 * li.m0 - kDmLeft;
             const bool aligned = (reinterpret_cast<uintptr_t>(li.src) & 31) == 0;
 #pragma unroll
-            for (int it = 0; it < kDmChunkIters; ++it) {
-                const int q = q0 + (kDmProducers / 8) * it;
-                const int s = sbase + 8 * q;
-                if (q >= kDmChunks) continue;
-                if (aligned && s >= 0 && s + 8 <= li.len_in) {
-                    lo[it] = __ldg(reinterpret_cast<const float4*>(li.src + s));
-                    hi[it] = __ldg(reinterpret_cast<const float4*>(li.src + s + 4));
-                } else {
-                    float x[8];
+            for (int g = 0; g < kDmGroups; ++g)
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) x[b] = (s + b >= 0 && s + b < li.len_in) ? li.src[s + b] : 0.0f;
-                    lo[it] = make_float4(x[0], x[1], x[2], x[3]);
-                    hi[it] = make_float4(x[4], x[5], x[6], x[7]);
+                for (int k = 0; k < kDmGroupIters; ++k) {
+                    const int q = task_chunk(g, k);
+                    const int s = sbase + 8 * q;
+                    if (q >= kDmChunks) continue;
+                    if (aligned && s >= 0 && s + 8 <= li.len_in) {
+                        lo[g][k] = __ldg(reinterpret_cast<const float4*>(li.src + s));
+                        hi[g][k] = __ldg(reinterpret_cast<const float4*>(li.src + s + 4));
+                    } else {
+                        float x[8];
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) x[b] = (s + b >= 0 && s + b < li.len_in) ? li.src[s + b] : 0.0f;
+                        lo[g][k] = make_float4(x[0], x[1], x[2], x[3]);
+                        hi[g][k] = make_float4(x[4], x[5], x[6], x[7]);
+                    }
                 }
-            }
             return 1;
         };
+        unsigned char* dst0 = sm_b + 16 * (pt & 7);
         int n = 0;
         int active = blockIdx.x < n_tiles ? load_tile(blockIdx.x) : 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-            mbar_wait<32>(b_empty, (n & 1) ^ 1);
-            if (active) {
 #pragma unroll
-                for (int it = 0; it < kDmChunkIters; ++it) {
-                    const int q = q0 + (kDmProducers / 8) * it;
-                    if (q >= kDmChunks) continue;
-                    uint4 s0, s1, s2;
-                    dm_split8(lo[it], hi[it], s0, s1, s2);
-                    unsigned char* d = dst0 + 128 * q;
-                    *reinterpret_cast<uint4*>(d) = s0;
-                    *reinterpret_cast<uint4*>(d + kDmBBytes) = s1;
-                    *reinterpret_cast<uint4*>(d + 2 * kDmBBytes) = s2;
+            for (int g = 0; g < kDmGroups; ++g) {
+                mbar_wait<32>(smem_u32(&bars[4 + g]), (n & 1) ^ 1);
+                if (active) {
+#pragma unroll
+                    for (int k = 0; k < kDmGroupIters; ++k) {
+                        const int q = task_chunk(g, k);
+                        if (q >= kDmChunks) continue;
+                        uint4 s0, s1, s2;
+                        dm_split8(lo[g][k], hi[g][k], s0, s1, s2);
+                        unsigned char* d = dst0 + 128 * q;
+                        *reinterpret_cast<uint4*>(d) = s0;
+                        *reinterpret_cast<uint4*>(d + kDmBBytes) = s1;
+                        *reinterpret_cast<uint4*>(d + 2 * kDmBBytes) = s2;
+                    }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[g]));
+                if (warp == 5 && g == 0) DM_STAMP(n, 13);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(b_full);
             if (tile + static_cast<int>(gridDim.x) < n_tiles) active = load_tile(tile + gridDim.x);
         }
     }
@@ -374,6 +437,14 @@ uint16_t bf16_rn(double v, double* back) {
 }
 
 }  // namespace
+
+#ifdef DM_TRACE
+void* decimate_mma_trace_ptr() {
+    void* sym = nullptr;
+    cudaGetSymbolAddress(&sym, dm_trace);
+    return sym;
+}
+#endif
 
 size_t decimate_mma_table_bytes() { return 3 * kDmABytes; }
 

@@ -52,6 +52,13 @@ def fitted(c2_golden):
 
 NEAR_TIE = 2          # ser_oracle.tuning_margins: fullest tuning bin leads the runner-up by <= 2 pitches
 MAX_FLIP_FRACTION = 0.005
+# Tonnetz components are means of cancelling terms; where one sits at 1e-3 of the group's largest the
+# scaled metric reads float32 rounding noise: the ORACLE's own first sample.wav window moves by 7e-5
+# scaled = 1.5e-7 absolute under 1-ulp input noise (tests/test_oracle_sensitivity.py::
+# test_sample_wav_small_tonnetz_components_sit_at_the_oracles_own_noise_floor), and three float32
+# decimators of this repo scatter 6e-5 .. 1.5e-4 on that one component.  A tonnetz row therefore
+# passes at 1e-4 scaled OR 3e-7 absolute (2 x the oracle's measured spread, 2.5 float32 epsilons).
+TONNETZ_ABS = 3e-7
 
 
 def _assert_rows(got, expect, what, margins=None):
@@ -68,6 +75,8 @@ def _assert_rows(got, expect, what, margins=None):
     for column, group in ((0, "chroma"), (1, "tonnetz"), (None, "mfcc"), (None, "mel"), (None, "contrast")):
         per_row = np.asarray([group_errors(got[i], expect[i], groups=(group,))[group][0] for i in range(got.shape[0])])
         bad = per_row > TOL
+        if group == "tonnetz":
+            bad &= np.max(np.abs(got[:, 187:193] - expect[:, 187:193]), axis=1) > TONNETZ_ABS
         if column is not None and margins is not None:
             near = np.atleast_2d(margins)[:, column] <= NEAR_TIE
             assert not np.any(bad & ~near), f"{what}: {group} off on well-conditioned rows {np.flatnonzero(bad & ~near)[:8]}: {per_row[bad & ~near][:8]}"
