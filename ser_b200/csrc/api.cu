@@ -102,7 +102,8 @@ struct serb_ctx {
     bool dec_mma = true;        // factor-2 decimation on tcgen05 (SERB_DECIMATE=ffma keeps the FFMA2 kernel)
     DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
     DevBuf long_idx, long_state;
-    DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_tuning, ton_tile_clip;
+    DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_runs, ton_tuning, ton_tile_clip;
+    bool istft_fused = true;    // inverse STFT + overlap-add in one kernel (SERB_ISTFT=split keeps the two HBM-bound kernels)
     int harm_seg = 512;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
     std::vector<int> last_short_rows;
@@ -363,6 +364,7 @@ struct LongList {
 struct TonChunk {
     int clip_lo, clip_hi;       // range in the request-wide TonClip array
     int seg_lo, n_segs;
+    int run_lo, n_runs;         // (clip, first column) per kIstftRun columns: work items of istft_ola_kernel
     int n_cols, n_tiles, cq_rows, max_len0, max_cq_cols, n_parts, max_length, n_dec_exact;
     long long total0, max_end;
 };
@@ -371,6 +373,7 @@ struct TonPlan {
     std::vector<TonClip> clips;
     std::vector<ClipDev> clips_b;   // the harmonic signals as STFT clips (tuning pass)
     std::vector<int2> segs;
+    std::vector<int2> runs;
     std::vector<TonChunk> chunks;
 };
 
@@ -378,6 +381,7 @@ TonChunk ton_open_chunk(const TonPlan& tp) {
     TonChunk c{};
     c.clip_lo = c.clip_hi = static_cast<int>(tp.clips.size());
     c.seg_lo = static_cast<int>(tp.segs.size());
+    c.run_lo = static_cast<int>(tp.runs.size());
     return c;
 }
 
@@ -407,6 +411,7 @@ int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur,
     b.length = c.length;
     const int local = static_cast<int>(tp.clips.size()) - cur.clip_lo;
     for (int t0 = 0; t0 < a.n_cols; t0 += ctx->harm_seg) tp.segs.push_back(make_int2(local, t0));
+    for (int t0 = 0; t0 < a.n_cols; t0 += kIstftRun) tp.runs.push_back(make_int2(local, t0));
     tp.clips.push_back(c);
     tp.clips_b.push_back(b);
     // 512-sample granules keep every level of every clip 32-byte aligned (off0 >> 6 is a multiple of 8)
@@ -414,6 +419,7 @@ int ton_add_clip(serb_ctx* ctx, const CqtPlan& plan, TonPlan& tp, TonChunk& cur,
     cur.n_cols = std::max(cur.n_cols, a.col_base + a.n_cols);
     cur.n_tiles = std::max(cur.n_tiles, a.tile_base + (a.n_cols + kColsPerTile - 1) / kColsPerTile);
     cur.n_segs = static_cast<int>(tp.segs.size()) - cur.seg_lo;
+    cur.n_runs = static_cast<int>(tp.runs.size()) - cur.run_lo;
     cur.cq_rows += cq;
     cur.n_parts += (cq + kTonTile - 1) / kTonTile;
     cur.max_len0 = std::max(cur.max_len0, c.len0);
@@ -440,7 +446,7 @@ int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cuda
     SERB_CUDA(ctx, ctx->spill.reserve(col_f * sizeof(float)));
     SERB_CUDA(ctx, ctx->cspec.reserve(col_f * sizeof(float2)));
     SERB_CUDA(ctx, ctx->perc.reserve(col_f * sizeof(float)));
-    SERB_CUDA(ctx, ctx->frames.reserve(static_cast<size_t>(max_cols) * kNFft * sizeof(float)));
+    if (!ctx->istft_fused) SERB_CUDA(ctx, ctx->frames.reserve(static_cast<size_t>(max_cols) * kNFft * sizeof(float)));
     SERB_CUDA(ctx, ctx->yharm.reserve((static_cast<size_t>(max_total0) * fe + 64) * sizeof(float)));
     SERB_CUDA(ctx, ctx->yoct.reserve((static_cast<size_t>(max_total0) * 2 + 64) * sizeof(float)));
     SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(std::max(max_cq, 1)) * kCqBins * sizeof(float)));
@@ -453,6 +459,7 @@ int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cuda
     if ((rc = upload(ctx, ctx->ton_clips, tp.clips.data(), tp.clips.size(), stream))) return rc;
     if ((rc = upload(ctx, ctx->ton_clips_b, tp.clips_b.data(), tp.clips_b.size(), stream))) return rc;
     if ((rc = upload(ctx, ctx->ton_segs, tp.segs.data(), tp.segs.size(), stream))) return rc;
+    if ((rc = upload(ctx, ctx->ton_runs, tp.runs.data(), tp.runs.size(), stream))) return rc;
     return SERB_OK;
 }
 
@@ -512,9 +519,15 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     op.hann_sq = ctx->hann_sq.as<double>();
     op.wss4 = reinterpret_cast<const float*>(ctx->hann_sq.as<double>() + 2048);
     op.yharm = ctx->yharm.as<float>();
-    { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream)); }
-    { ProfScope ps(ctx, 9, stream); SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream)); }
-    ctx->launches += 2;
+    if (ctx->istft_fused) {
+        ProfScope ps(ctx, 8, stream);
+        SERB_CUDA(ctx, launch_istft_ola(ip, op, ctx->ton_runs.as<int2>() + c.run_lo, c.n_runs, ctx->n_sms, stream));
+        ctx->launches += 1;
+    } else {
+        { ProfScope ps(ctx, 8, stream); SERB_CUDA(ctx, launch_istft(ip, c.n_cols, stream)); }
+        { ProfScope ps(ctx, 9, stream); SERB_CUDA(ctx, launch_ola(op, c.n_tiles, stream)); }
+        ctx->launches += 2;
+    }
     // 4. tuning of the harmonic signal (36 bins per octave)
     sp.wave = ctx->yharm.as<float>();
     sp.clips = d_b;
@@ -1168,6 +1181,7 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         CREATE_CHECK(cudaMemcpy(ctx->dec_toeplitz.ptr, toeplitz.data(), toeplitz.size(), cudaMemcpyHostToDevice));
         CREATE_CHECK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device_ordinal));
         if (const char* env = std::getenv("SERB_DECIMATE")) ctx->dec_mma = std::string(env) != "ffma";
+        if (const char* env = std::getenv("SERB_ISTFT")) ctx->istft_fused = std::string(env) != "split";
         hann_squared_2048(hsq);
         // behind the 2048 doubles: the overlap-add's window sum of squares where four frames
         // overlap, accumulated in frame order exactly as ola_sample does (float64 add, float32 store)
@@ -1238,7 +1252,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->pcm_files, &ctx->pcm_peaks, &ctx->mlp.mean, &ctx->mlp.scale,
                       &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles, &ctx->dec_toeplitz,
                       &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag, &ctx->ton_part,
-                      &ctx->long_idx, &ctx->long_state, &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_tuning,
+                      &ctx->long_idx, &ctx->long_state, &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_runs, &ctx->ton_tuning,
                       &ctx->ton_tile_clip})
         b->release();
     for (auto& kv : ctx->sr_tables) {

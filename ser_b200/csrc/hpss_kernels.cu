@@ -280,12 +280,13 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(IstftParams p, int n_cols
             const int k = 32 * n1 + lane;
             const float2 x = X[k];
             const float m = M[k];
-            v[n1] = make_float2(x.x * m, x.y * m);
+            // rounded products: the reference holds (S * mask) * phase as complex64 before the inverse FFT
+            v[n1] = make_float2(__fmul_rn(x.x, m), __fmul_rn(x.y, m));
             buf[n1 * 33 + lane] = v[n1];
         }
         float nyq = 0.0f;   // X[1024] (real)
         if (lane == 0) {
-            nyq = X[1024].x * M[1024];
+            nyq = __fmul_rn(X[1024].x, M[1024]);
             v[0].y = 0.0f;   // irfft ignores the imaginary part of the DC bin
         }
         __syncwarp();
@@ -385,8 +386,208 @@ __global__ void __launch_bounds__(256) ola_kernel(OlaParams p) {
     }
 }
 
+// ---- inverse STFT fused with the overlap-add ---------------------------------------------
+// One warp walks a RUN of consecutive columns of one clip and keeps the three unfinished hop
+// blocks of the overlap-add in registers, so the windowed frames never go to memory (the split
+// kernels above move 16 KB per column through HBM for them).  The inverse FFT leaves lane l with
+// frame samples 64 k2 + 2 l + {0, 1}, k2 = 0 .. 31: the quarter of the frame (hop block) is a
+// REGISTER index, so "add quarter q of this frame to block t + q" is plain register arithmetic.
+// Block b = sum of quarter (b - t) of frames t = b - 3 .. b, added in frame order exactly as
+// ola_kernel does: ((f[b-3] + f[b-2]) + f[b-1]) + f[b], so yharm is bit-identical to the split
+// kernels'.  A run recomputes the three frames before its first column (3 / kIstftRun extra work).
+constexpr int kIstftWarps = 8;
+constexpr int kIstftStageX = 1026;     // float2 per staged spectrum row (1025 used; 16-byte multiple)
+constexpr int kIstftStageM = 1028;     // floats per staged mask row
+// per warp: the staged column (spectrum + mask, landed by a bulk copy) and the transpose buffer of
+// the two-step FFT.  Eight warps per SM with 255 registers each: the transform (64 registers), the
+// three unfinished overlap-add blocks (48) and the epilogue fit without spills.  Measured
+// alternatives (c2 step): twelve warps of 168 registers that reuse the staged column as transpose
+// buffer, keep two blocks in shared memory and prefetch later, 5.42 ms; twelve warps with plain
+// global loads and spills, 6.55 ms; this layout, 4.62 ms; the split kernels, 3.38 + 1.50 ms.
+struct IstftOlaWarp {
+    struct { float2 x[kIstftStageX]; float m[kIstftStageM]; } in;
+    float2 buf[32 * 33];
+};
+struct IstftOlaSmem {
+    float2 tw[32][32];                 // W_1024^(k1 n2)
+    float2 tw2[1024];                  // (cos, sin) 2 pi k / 2048
+    float4 win[32];
+    float2 wss4[kHop / 2];             // 1 / window sum of squares where four frames overlap, by n mod 512
+    unsigned long long bar[kIstftWarps];
+    IstftOlaWarp w[kIstftWarps];
+};
+static_assert(sizeof(IstftOlaSmem) <= 227 * 1024, "istft_ola_kernel shared memory");
+
+__device__ __forceinline__ void istft_stage_column(IstftOlaWarp& w, unsigned long long* bar, const float2* X, const float* M) {
+    const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+    constexpr uint32_t bytes_x = 1025 * 8 + 8, bytes_m = 1025 * 4 + 12;       // 16-byte multiples inside the 1032-element rows
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes_x + bytes_m) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(w.in.x))), "l"(X), "r"(bytes_x), "r"(b) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(w.in.m))), "l"(M), "r"(bytes_m), "r"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(kIstftWarps * 32, 1) istft_ola_kernel(IstftParams p, OlaParams o, const int2* __restrict__ runs, int n_runs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftOlaSmem& sm = *reinterpret_cast<IstftOlaSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 2048; i += kIstftWarps * 32) reinterpret_cast<float2*>(&sm.tw[0][0])[i] = p.tables[i];
+    for (int i = tid; i < kHop / 2; i += kIstftWarps * 32) {
+        const float2 w = reinterpret_cast<const float2*>(o.wss4)[i];
+        sm.wss4[i] = make_float2(1.0f / w.x, 1.0f / w.y);       // reciprocals, see emit()
+    }
+    if (tid < 32) {
+        float ws0, wc0, ws1, wc1;
+        sincospif(static_cast<float>(2 * tid) * (2.0f / 2048.0f), &ws0, &wc0);
+        sincospif(static_cast<float>(2 * tid + 1) * (2.0f / 2048.0f), &ws1, &wc1);
+        sm.win[tid] = make_float4(wc0, ws0, wc1, ws1);
+    }
+    if (tid < kIstftWarps) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&sm.bar[tid]))));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    IstftOlaWarp& ws = sm.w[warp];
+    float2* buf = ws.buf;
+    const float4 wa = sm.win[lane];
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&sm.bar[warp]));
+    uint32_t parity = 0;
+    const int n_warps = gridDim.x * kIstftWarps;
+    for (int item = blockIdx.x * kIstftWarps + warp; item < n_runs; item += n_warps) {
+        const int2 run = runs[item];
+        const TonClip clip = o.clips[run.x];
+        const int T = clip.n_cols;
+        const int t_first = run.y, t_last = min(run.y + kIstftRun, T) - 1;
+        const int t_begin = max(0, t_first - 3);
+        float* y = o.yharm + clip.hoff;
+        const float2* Xc = p.cspec + static_cast<long long>(clip.col_base) * kSpillStride;
+        const float* Mc = p.mask + static_cast<long long>(clip.col_base) * kSpillStride;
+        // block b of the clip: padded samples m = 512 b + j, output n = m - 1024; lane owns
+        // j = 64 k + 2 lane + {0, 1}, k = 0 .. 7
+        auto emit = [&](int b, const float2 (&acc)[8]) {
+            const int n0 = kHop * b - kNFft / 2 + 2 * lane;
+            if (b < 2 || n0 - 2 * lane >= clip.length) return;
+            const bool full = b >= 3 && b <= T - 1;             // all four frames exist: tabulated window sum
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int n = n0 + 64 * k;
+                float2 w;
+                if (full) {
+                    // interior: the tabulated window sum (1.5 up to rounding) as a reciprocal -- sixteen
+                    // true divisions per lane and column were 13 % of this kernel's issue slots; the
+                    // product is within one ulp of the reference's quotient
+                    const float2 r = sm.wss4[32 * k + lane];
+                    const float2 out = make_float2(acc[k].x * r.x, acc[k].y * r.y);
+                    if (n + 1 < clip.length) *reinterpret_cast<float2*>(y + n) = out;
+                    else if (n < clip.length) y[n] = out.x;
+                    continue;
+                } else {
+                    // librosa's window_sumsquare: float64 add, float32 store, frame by frame
+                    w = make_float2(0.0f, 0.0f);
+                    const int m = n + kNFft / 2;
+                    for (int t = max(0, b - 3); t <= min(T - 1, b); ++t) {
+                        w.x = static_cast<float>(static_cast<double>(w.x) + o.hann_sq[m - t * kHop]);
+                        w.y = static_cast<float>(static_cast<double>(w.y) + o.hann_sq[m + 1 - t * kHop]);
+                    }
+                }
+                float2 out;
+                out.x = w.x > FLT_MIN ? acc[k].x / w.x : acc[k].x;
+                out.y = w.y > FLT_MIN ? acc[k].y / w.y : acc[k].y;
+                if (n + 1 < clip.length) *reinterpret_cast<float2*>(y + n) = out;
+                else if (n < clip.length) y[n] = out.x;
+            }
+        };
+        float2 a1[8], a2[8], a3[8];      // blocks t + 1, t + 2, t + 3 after frame t
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a1[k] = a2[k] = a3[k] = make_float2(0.0f, 0.0f);
+        if (lane == 0) istft_stage_column(ws, &sm.bar[warp], Xc + static_cast<long long>(t_begin) * kSpillStride,
+                                          Mc + static_cast<long long>(t_begin) * kSpillStride);
+        for (int t = t_begin; t <= t_last; ++t) {
+            // wait for the column's spectrum and mask
+            {
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                parity ^= 1u;
+            }
+            // conj(Z[k]), Z[k] = E[k] + i O[k] of the masked spectrum A = (S * mask) * phase:
+            // 2E = A + conj P, 2O = (A - conj P) e^{+i 2 pi k / 2048}, P = A[1024 - k]; k = 32 n1 + lane
+            float2 v[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const int k = 32 * n1 + lane, kp = 1024 - k;
+                const float2 x = ws.in.x[k], xp = ws.in.x[kp];
+                const float m = ws.in.m[k], mp = ws.in.m[kp];
+                // rounded products: the reference holds (S * mask) * phase as complex64 before the inverse FFT
+                float ax = __fmul_rn(x.x, m), ay = __fmul_rn(x.y, m);
+                float px = __fmul_rn(xp.x, mp), py = __fmul_rn(xp.y, mp);
+                if (k == 0) { ay = 0.0f; py = 0.0f; }      // irfft ignores the imaginary parts of the DC and Nyquist bins
+                const float ex = ax + px, ey = ay - py;      // A + conj P
+                const float dx = ax - px, dy = ay + py;      // A - conj P
+                const float2 w = sm.tw2[k];
+                const float ox = dx * w.x - dy * w.y;            // (dx + i dy)(cos + i sin)
+                const float oy = dx * w.y + dy * w.x;
+                v[n1] = make_float2(ex - oy, -(ey + ox));
+            }
+            __syncwarp();
+            // the staged column is in registers: the next one lands while this one is transformed
+            if (lane == 0 && t < t_last)
+                istft_stage_column(ws, &sm.bar[warp], Xc + static_cast<long long>(t + 1) * kSpillStride,
+                                   Mc + static_cast<long long>(t + 1) * kSpillStride);
+            fft32(v);
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                float2 yv = v[k1];
+                if (k1 > 0) {
+                    const float2 w = sm.tw[k1][lane];
+                    yv = make_float2(fmaf(yv.x, w.x, -yv.y * w.y), fmaf(yv.x, w.y, yv.y * w.x));
+                }
+                buf[k1 * 33 + lane] = yv;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) v[n2] = buf[lane * 33 + n2];
+            __syncwarp();
+            fft32(v);
+            // windowed frame samples 64 k2 + 2 lane + {0, 1} (the arithmetic of istft_kernel; the
+            // rounded products are what ola_kernel adds, so no multiply may fuse into the adds below)
+            constexpr float scale = 1.0f / 2048.0f;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) {
+                const float ca = cos32(k2), sa = sin32(k2);
+                const float w0 = fmaf(-0.5f * ca, wa.x, fmaf(0.5f * sa, wa.y, 0.5f));
+                const float w1 = fmaf(-0.5f * ca, wa.z, fmaf(0.5f * sa, wa.w, 0.5f));
+                v[k2] = make_float2(__fmul_rn(__fmul_rn(v[k2].x, scale), w0), __fmul_rn(__fmul_rn(-v[k2].y, scale), w1));
+            }
+            if (t >= t_first) {
+                float2 done[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) done[k] = make_float2(__fadd_rn(a1[k].x, v[k].x), __fadd_rn(a1[k].y, v[k].y));
+                emit(t, done);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a1[k] = make_float2(__fadd_rn(a2[k].x, v[8 + k].x), __fadd_rn(a2[k].y, v[8 + k].y));
+                a2[k] = make_float2(__fadd_rn(a3[k].x, v[16 + k].x), __fadd_rn(a3[k].y, v[16 + k].y));
+                a3[k] = v[24 + k];
+            }
+        }
+        if (t_last == T - 1) {     // the clip's tail: blocks that fewer than four frames reach
+            emit(T, a1);
+            emit(T + 1, a2);
+            emit(T + 2, a3);
+        }
+    }
+}
+
 // ---- launchers ---------------------------------------------------------------------------
 cudaError_t configure_hpss() {
+    cudaError_t e = cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(IstftOlaSmem)));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(IstftSmem)));
 }
@@ -411,6 +612,14 @@ cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream) 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = min((n_cols + 7) / 8, 2 * sms);
     istft_kernel<<<grid, 256, sizeof(IstftSmem), stream>>>(p, n_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_istft_ola(const IstftParams& p, const OlaParams& o, const int2* runs, int n_runs, int n_sms,
+                             cudaStream_t stream) {
+    if (n_runs <= 0) return cudaSuccess;
+    const int grid = min((n_runs + kIstftWarps - 1) / kIstftWarps, n_sms);
+    istft_ola_kernel<<<grid, kIstftWarps * 32, sizeof(IstftOlaSmem), stream>>>(p, o, runs, n_runs);
     return cudaGetLastError();
 }
 

@@ -160,6 +160,10 @@ cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t strea
 cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_cols, cudaStream_t stream);
 cudaError_t launch_ola(const OlaParams& p, int n_tiles, cudaStream_t stream);
+// inverse STFT and overlap-add in one kernel: runs = (clip, first column) per kIstftRun columns
+constexpr int kIstftRun = 48;
+cudaError_t launch_istft_ola(const IstftParams& p, const OlaParams& o, const int2* runs, int n_runs, int n_sms,
+                             cudaStream_t stream);
 
 struct CqRow { int start; int count; float scale; int bin; };
 struct CqtParams {

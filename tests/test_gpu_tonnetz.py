@@ -427,3 +427,78 @@ def test_sharded_extraction_matches_single_device(golden):
     devices = list(range(_native.device_count()))
     got = extract_features_sharded(wave, starts, lengths, 16000, devices=devices)
     np.testing.assert_array_equal(got, expected)
+
+
+def _context_with_env(**env):
+    """A second context whose kernel choices come from the environment at creation time."""
+    import os
+
+    from ser_b200 import _native
+
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return _native.Context(0)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _ragged_batch(sr):
+    from ser_b200 import synth
+
+    lengths = [sr * 3, sr * 3 - 17, 2048, 2049, 4096 + 511, 512 * 48 - 1, 512 * 48, 512 * 48 + 1, 512 * 97 + 300, 512, 700, sr]
+    return [synth.clip_audio(synth.ClipSpec(30 + i, 3 + i, 1 + i % 7), sr, n) for i, n in enumerate(lengths)]
+
+
+@pytest.mark.parametrize("sr", [16000, 48000])
+def test_fused_inverse_stft_against_the_split_kernels(gpu_ctx, sr):
+    """istft_ola_kernel keeps the overlap-add in registers: same frame arithmetic, same order of the
+    four adds as istft_kernel + ola_kernel (SERB_ISTFT=split), but the compiler contracts other
+    multiply-adds of the spectrum preparation and the interior window sum is applied as a reciprocal,
+    so samples may differ in the last bit (measured: 43 % of them by one ulp, none by more than
+    1.8e-7 of the peak).  Held to 3e-7 of the peak at run boundaries (48 columns), clip ends and
+    short clips; tuning identical; rows within 1e-5 scaled."""
+    split = _context_with_env(SERB_ISTFT="split")
+    try:
+        clips = _ragged_batch(sr)
+        for clip in clips:
+            a = gpu_ctx.debug_tonnetz_stages(clip, sr)
+            b = split.debug_tonnetz_stages(clip, sr)
+            assert np.max(np.abs(a["yharm"] - b["yharm"])) <= 3e-7 * np.max(np.abs(b["yharm"])), clip.size
+            assert a["tuning_index"] == b["tuning_index"]
+            assert np.max(np.abs(a["cqmag"] - b["cqmag"])) <= 5e-6 * np.max(b["cqmag"])
+        bits = 0x1F
+        report = group_errors(gpu_ctx.features_host_clips(clips, sr, bits), split.features_host_clips(clips, sr, bits),
+                              groups=ALL_GROUPS)
+        assert all(v[0] <= 1e-5 for v in report.values()), report
+    finally:
+        split.close()
+
+
+def test_tensor_core_decimator_against_the_ffma2_kernel(gpu_ctx):
+    """decimate2_mma_kernel (tcgen05, three bf16 terms per operand) and decimate2_kernel (FFMA2) are two
+    float32 evaluations of the same 389-tap sums: constant-Q magnitudes agree to 5e-6 of their maximum
+    (each is within that of the float64 oracle, test_tonnetz_stages_match_oracle), tuning identical,
+    and a clip gives the same bits wherever it sits in a batch."""
+    sr = 48000
+    ffma = _context_with_env(SERB_DECIMATE="ffma")
+    try:
+        clips = _ragged_batch(sr)
+        for clip in clips[:6]:
+            a = gpu_ctx.debug_tonnetz_stages(clip, sr)
+            b = ffma.debug_tonnetz_stages(clip, sr)
+            assert np.array_equal(a["yharm"], b["yharm"])
+            assert a["tuning_index"] == b["tuning_index"]
+            assert np.max(np.abs(a["cqmag"] - b["cqmag"])) <= 5e-6 * np.max(b["cqmag"])
+        bits = 0x1F
+        rows = gpu_ctx.features_host_clips(clips, sr, bits)
+        again = gpu_ctx.features_host_clips(clips[::-1], sr, bits)[::-1]
+        assert np.array_equal(rows, again)                       # batch position does not matter
+        report = group_errors(rows, ffma.features_host_clips(clips, sr, bits), groups=ALL_GROUPS)
+        assert all(v[0] <= TOL for v in report.values()), report
+    finally:
+        ffma.close()
