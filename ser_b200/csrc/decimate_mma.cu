@@ -28,6 +28,15 @@
 // 41 K-slabs x 6 products = 246 tcgen05.mma (M 128, N 8 R, K 16); four epilogue warps read the two
 // accumulators (tcgen05.ld), add them and store float32 outputs, overlapped with the next tile
 // through a second pair of accumulators.
+//
+// Measured on a B200 (scripts/microbench/decimate_mma_test, 1 440 clips of 144 000 samples, all seven
+// stages): 1.46 ms against 2.57 ms for the FFMA2 kernel.  With the producers' and the epilogue's
+// work compiled out (MMAs only) the same launches take 1.26 ms, so the kernel runs at 86 % of what
+// its MMA sequence allows: 246 MMAs take ~14 000 clocks per tile (57 per MMA where the N = 96 rate
+// would be 48), paced by the operand fetch -- a slab's six MMAs read three A and three B tiles,
+// 21 KB, at ~62 bytes per clock (an order that does not keep a slab's products together is twice as
+// slow) -- and the SM clock settles near 1.4-1.5 GHz under this load.  N = 128 would balance fetch
+// and MMA rate but needs 216 KB for the samples alone.
 #include <cuda_bf16.h>
 
 #include <cmath>
@@ -217,6 +226,8 @@ constexpr int kDmBlk = (kDmChunks + 31) / 32;                       // 32-chunk 
 constexpr int kDmGroupTasks = 8 * 8 * kDmBlk;                       // (lane, chunk) tasks per group, tail included
 constexpr int kDmGroupIters = (kDmGroupTasks + kDmProducers - 1) / kDmProducers;
 __host__ __device__ constexpr int dm_slab_group(int s) { return (s % 16) / 4; }
+// issue order of group 0 is slabs 0..3, 16..19, 32..35: slab 0 opens d_small, slab 16 must be the first central one
+static_assert(kDmCentral0 > 3 && kDmCentral0 <= 16 && kDmCentral1 > 16, "first MMA into d_main");
 
 __global__ void __launch_bounds__(kDmThreads, 1)
 decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles, const uint4* __restrict__ toeplitz) {
@@ -276,28 +287,31 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
                 // per cent of the result) and the five small products of all slabs go to d_small.
                 // Within a slab the six MMAs stay together: they share three A and three B tiles, and
                 // the operand fetch, not the MMA rate, is what paces the pipe at N = 96.
-#pragma unroll
+#pragma unroll 1
                 for (int g = 0; g < kDmGroups; ++g) {
                     DM_STAMP1(n, 3 * g);
                     mbar_wait<0>(smem_u32(&bars[g]), n & 1);                 // group g of this tile staged
                     DM_STAMP1(n, 3 * g + 1);
                     tc_fence_after();
-                    auto slab = [](uint64_t d, int s) { return d + 16ull * s; };     // (256 s) >> 4 in the start-address field
-                    bool first_small = (g == 0), first_main = true;
-#pragma unroll
-                    for (int s = 0; s < kDmSlabs; ++s) {
-                        if (dm_slab_group(s) != g) continue;
-                        const bool central = s >= kDmCentral0 && s < kDmCentral1;
-                        tc_mma(d_small, slab(ad[1], s), slab(bd[1], s), kDmIdesc, !first_small);
-                        first_small = false;
-                        tc_mma(d_small, slab(ad[2], s), slab(bd[0], s), kDmIdesc, 1);
-                        // the first central slab of the tile is slab 16, in group 0
-                        tc_mma(central ? d_main : d_small, slab(ad[0], s), slab(bd[0], s), kDmIdesc,
-                               !(central && g == 0 && first_main));
-                        if (central) first_main = false;
-                        tc_mma(d_small, slab(ad[0], s), slab(bd[2], s), kDmIdesc, 1);
-                        tc_mma(d_small, slab(ad[1], s), slab(bd[0], s), kDmIdesc, 1);
-                        tc_mma(d_small, slab(ad[0], s), slab(bd[1], s), kDmIdesc, 1);
+                    // rolled on purpose: 246 unrolled MMAs with their descriptor arithmetic are 12 KB of
+                    // straight-line code that the issuing warp's instruction cache loses to the producer
+                    // and epilogue warps between tiles
+#pragma unroll 1
+                    for (int o = 0; o < 48; o += 16) {
+#pragma unroll 1
+                        for (int j = 0; j < 4; ++j) {
+                            const int s = 4 * g + j + o;
+                            if (s >= kDmSlabs) break;
+                            const uint64_t off = 16ull * s;                  // (256 s) >> 4 in the start-address field
+                            const bool central = s >= kDmCentral0 && s < kDmCentral1;
+                            // the tile's first MMA into d_small is slab 0's, into d_main slab 16's (both group 0)
+                            tc_mma(d_small, ad[1] + off, bd[1] + off, kDmIdesc, s != 0);
+                            tc_mma(d_small, ad[2] + off, bd[0] + off, kDmIdesc, 1);
+                            tc_mma(central ? d_main : d_small, ad[0] + off, bd[0] + off, kDmIdesc, s != 16);
+                            tc_mma(d_small, ad[0] + off, bd[2] + off, kDmIdesc, 1);
+                            tc_mma(d_small, ad[1] + off, bd[0] + off, kDmIdesc, 1);
+                            tc_mma(d_small, ad[0] + off, bd[1] + off, kDmIdesc, 1);
+                        }
                     }
                     tc_commit(smem_u32(&bars[4 + g]));                    // group g may be overwritten
                     if (g == kDmGroups - 1) tc_commit(smem_u32(&bars[8 + buf]));     // the accumulators are complete
