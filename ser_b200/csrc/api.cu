@@ -100,7 +100,8 @@ struct serb_ctx {
     DevBuf hann_sq, cq_twiddles, dec_toeplitz;
     int n_sms = 0;
     bool dec_mma = true;        // factor-2 decimation on tcgen05 (SERB_DECIMATE=ffma keeps the FFMA2 kernel)
-    DevBuf cspec, perc, frames, yharm, yoct, cqmag, ton_part;
+    DevBuf cspec, perc, frames, yharm, yoct, cqmag, cq_chroma, ton_part;
+    bool keep_cqmag = false;    // serb_debug_tonnetz_stages: also write the 252-wide constant-Q magnitudes
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_runs, ton_tuning, ton_tile_clip;
     bool istft_fused = true;    // inverse STFT + overlap-add in one kernel (SERB_ISTFT=split keeps the two HBM-bound kernels)
@@ -449,7 +450,8 @@ int ton_reserve_and_upload(serb_ctx* ctx, SrTables* tab, const TonPlan& tp, cuda
     if (!ctx->istft_fused) SERB_CUDA(ctx, ctx->frames.reserve(static_cast<size_t>(max_cols) * kNFft * sizeof(float)));
     SERB_CUDA(ctx, ctx->yharm.reserve((static_cast<size_t>(max_total0) * fe + 64) * sizeof(float)));
     SERB_CUDA(ctx, ctx->yoct.reserve((static_cast<size_t>(max_total0) * 2 + 64) * sizeof(float)));
-    SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(std::max(max_cq, 1)) * kCqBins * sizeof(float)));
+    if (ctx->keep_cqmag) SERB_CUDA(ctx, ctx->cqmag.reserve(static_cast<size_t>(std::max(max_cq, 1)) * kCqBins * sizeof(float)));
+    SERB_CUDA(ctx, ctx->cq_chroma.reserve(static_cast<size_t>(std::max(max_cq, 1)) * kCqOctaves * 12 * sizeof(float)));
     SERB_CUDA(ctx, ctx->ton_part.reserve(static_cast<size_t>(std::max(max_parts, 1)) * 6 * sizeof(double)));
     SERB_CUDA(ctx, ctx->ton_tile_clip.reserve(static_cast<size_t>(std::max(max_tiles, 1)) * sizeof(int)));
     SERB_CUDA(ctx, ctx->peaks.reserve(static_cast<size_t>(max_cols) * tab->peak_cap * sizeof(float2)));
@@ -566,7 +568,8 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.rows = tab->cq_rows.as<CqRow>();
     qp.vals = tab->cq_vals.as<float2>();
     qp.twiddles = ctx->cq_twiddles.as<float2>();
-    qp.cqmag = ctx->cqmag.as<float>();
+    qp.cqmag = ctx->keep_cqmag ? ctx->cqmag.as<float>() : nullptr;
+    qp.cq_chroma = ctx->cq_chroma.as<float>();
     qp.ton_part = ctx->ton_part.as<double>();
     qp.out = d_out;
     qp.dim = off.dim;
@@ -1251,7 +1254,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
                       &ctx->tuning, &ctx->short_tuning, &ctx->status, &ctx->wave, &ctx->out, &ctx->proba,
                       &ctx->labels, &ctx->x64, &ctx->pcm, &ctx->pcm_max, &ctx->pcm_files, &ctx->pcm_peaks, &ctx->mlp.mean, &ctx->mlp.scale,
                       &ctx->mlp.w1, &ctx->mlp.b1, &ctx->mlp.w2, &ctx->mlp.b2, &ctx->hann_sq, &ctx->cq_twiddles, &ctx->dec_toeplitz,
-                      &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag, &ctx->ton_part,
+                      &ctx->cspec, &ctx->perc, &ctx->frames, &ctx->yharm, &ctx->yoct, &ctx->cqmag, &ctx->cq_chroma, &ctx->ton_part,
                       &ctx->long_idx, &ctx->long_state, &ctx->ton_clips, &ctx->ton_clips_a, &ctx->ton_clips_b, &ctx->ton_segs, &ctx->ton_runs, &ctx->ton_tuning,
                       &ctx->ton_tile_clip})
         b->release();
@@ -1677,8 +1680,10 @@ int serb_debug_tonnetz_stages(serb_ctx* ctx, const float* h_wave, int64_t n, int
     SERB_CUDA(ctx, cudaMemsetAsync(ctx->status.ptr, 0, sizeof(int), ctx->stream));
     SERB_CUDA(ctx, cudaMemcpyAsync(ctx->wave.ptr, h_wave, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t start = 0, length = n;
+    ctx->keep_cqmag = h_cqmag != nullptr;
     rc = run_features(ctx, ctx->wave.as<float>(), n, &start, &length, 1, sample_rate, SERB_FLAG_TONNETZ,
                       ctx->out.as<float>(), ctx->stream, [](long long) {});
+    ctx->keep_cqmag = false;
     if (rc) return rc;
     const long long plen = std::max<long long>(n, 512);
     int cq = 0x7fffffff;

@@ -192,6 +192,8 @@ struct CqtSmemHead {
     float2 buf[kCqtWarps][32 * kCqtBufPitch]; // per-warp transpose buffer, then the column spectra
     float2 vals[kCqRows][kCqtValPitch];       // sparse basis rows of this (tuning, octave)
     CqRow rows[kCqRows];
+    float mags[kCqtWarps][2 * kCqRows];       // scaled magnitudes of two of the warp's columns, by bin within the octave
+                                              // (two CTAs per SM leave room for no more)
     int cmax;                                 // widest staged row, rounded up to a multiple of four
     int bin_lo, bin_hi;                       // smallest and largest first bin of the staged rows
 };
@@ -331,6 +333,10 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         // Rows 0..31: lane = row, all G columns of the warp at once (one basis load feeds G
         // products: shared-memory bandwidth is what bounds this kernel).  Rows 32..35: lane =
         // (row, column).
+        float mval[G];      // rows 0..31: this lane's row, every column
+        int mbin;
+        float mag4;         // rows 32..35: this lane's (row, column), valid on the lanes with part == 0
+        int bin4, g4;
         {
             const CqRow row = sm.rows[lane];
             const float2* b = sm.vals[lane];
@@ -353,12 +359,12 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
             }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                if (lc0 + g < n_here) {
-                    float mag;
-                    asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr[g], cr[g], ci[g] * ci[g])));
-                    p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mag * row.scale;
-                }
+                float mag;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr[g], cr[g], ci[g] * ci[g])));
+                mval[g] = mag * row.scale;
+                if (p.cqmag && lc0 + g < n_here) p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mval[g];
             }
+            mbin = row.bin % kCqRows;
         }
         {
             // rows 32..35 for all G columns: every (row, column) is shared by P = 8 / G lanes that
@@ -381,10 +387,34 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
                 cr += __shfl_xor_sync(0xffffffffu, cr, o);
                 ci += __shfl_xor_sync(0xffffffffu, ci, o);
             }
-            if (part == 0 && lc0 + g < n_here) {
-                float mag;
-                asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(cr, cr, ci * ci)));
-                p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mag * row.scale;
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(mag4) : "f"(fmaf(cr, cr, ci * ci)));
+            mag4 *= row.scale;
+            bin4 = part == 0 ? row.bin % kCqRows : -1;
+            g4 = g;
+            if (p.cqmag && part == 0 && lc0 + g < n_here) p.cqmag[(clip.cq_base + t_block + lc0 + g) * kCqBins + row.bin] = mag4;
+        }
+        __syncwarp();
+        // this octave's share of the chroma fold (filters.cq_to_chroma, 36 bins per octave: chroma c <-
+        // bins 3 c - 1, 3 c, 3 c + 1 of the octave, the first wrapping to bin 35): 12 floats per column
+        // instead of 36 magnitudes, so the 252-wide constant-Q matrix never goes to memory
+        {
+            const int oct_slot = sm.rows[0].bin / kCqRows;
+            float* ms = sm.mags[warp];
+#pragma unroll
+            for (int g0 = 0; g0 < G; g0 += 2) {            // two columns per pass
+#pragma unroll
+                for (int g = g0; g < g0 + 2 && g < G; ++g) ms[(g - g0) * kCqRows + mbin] = mval[g];
+                if (bin4 >= 0 && g4 >= g0 && g4 < g0 + 2) ms[(g4 - g0) * kCqRows + bin4] = mag4;
+                __syncwarp();
+                if (lane < 24) {
+                    const int g = g0 + lane / 12, c = lane % 12;
+                    if (g < G && lc0 + g < n_here) {
+                        const float* m = ms + (g - g0) * kCqRows;
+                        const float sum = (m[(3 * c + kCqRows - 1) % kCqRows] + m[3 * c]) + m[3 * c + 1];
+                        p.cq_chroma[(static_cast<size_t>(clip.cq_base) + t_block + lc0 + g) * (kCqOctaves * 12) + oct_slot * 12 + c] = sum;
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
 // per-clip reduction in tile order (tonnetz_final_kernel), so long clips spread over many CTAs
 // and every clip's result is independent of the batch around it
 __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
-    __shared__ __align__(16) float mags[8][256];
+    __shared__ __align__(16) float mags[8][kCqOctaves * 12];
     __shared__ double phi[6][12];
     __shared__ double part[8][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -415,26 +445,21 @@ __global__ void __launch_bounds__(128) tonnetz_kernel(CqtParams p) {
         phi[q][c] = ((q < 4) ? 1.0 : 0.5) * cospi(vv);
     }
     __syncthreads();
-    // chroma c <- constant-Q bins 36 o + fold[j], j = 0..2 (filters.cq_to_chroma, bins_per_octave 36)
-    int fold[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) fold[j] = (3 * min(hl, 11) - 1 + j + 36) % 36;
+    // chroma c = sum over the octaves (lowest first) of cqt_kernel's per-octave folds
     double acc = 0.0;   // lanes 0..5 of each half: running sum of tonnetz row `hl` over the half's columns
     for (int tb = t_lo + 2 * warp; tb < t_hi; tb += 8) {
         const int t = tb + half;
         const bool valid = t < t_hi;
-        // one row of 252 magnitudes = 63 16-byte pieces
-        const float4* row = reinterpret_cast<const float4*>(p.cqmag + (static_cast<size_t>(clip.cq_base) + (valid ? t : tb)) * kCqBins);
+        // one row of 7 x 12 chroma shares = 21 16-byte pieces
+        const float4* row = reinterpret_cast<const float4*>(p.cq_chroma + (static_cast<size_t>(clip.cq_base) + (valid ? t : tb)) * (kCqOctaves * 12));
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (hl + 16 * i < kCqBins / 4) reinterpret_cast<float4*>(mags[slot])[hl + 16 * i] = row[hl + 16 * i];
+        for (int i = 0; i < 2; ++i)
+            if (hl + 16 * i < kCqOctaves * 3) reinterpret_cast<float4*>(mags[slot])[hl + 16 * i] = row[hl + 16 * i];
         __syncwarp();
         float ch = 0.0f;
         if (hl < 12) {
 #pragma unroll
-            for (int o = 0; o < kCqOctaves; ++o)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) ch += mags[slot][36 * o + fold[j]];
+            for (int o = 0; o < kCqOctaves; ++o) ch += mags[slot][12 * o + hl];
         }
         __syncwarp();
         // util.normalize(norm=inf) then util.normalize(norm=1): float32 values, float64 lengths
@@ -500,7 +525,7 @@ cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_
     return cudaFuncSetAttribute(cqt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem));
 }
 
-constexpr int kCqtSpanBudget = 8960;    // staged signal floats per CTA (two CTAs per SM)
+constexpr int kCqtSpanBudget = 8384;    // staged signal floats per CTA (two CTAs per SM)
 
 // columns per CTA and dynamic shared memory of one octave's launch
 template <int R>

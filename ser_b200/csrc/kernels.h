@@ -183,7 +183,8 @@ struct CqtParams {
     const float2* vals;          // [100][7][36][kCqRowCap]
     const float2* twiddles;      // W_N^j (cos, -sin), j < N, for N = 128, 256, 512, 1024 back to back, then
                                  // (cos, sin) 2 pi k / (2N), k < N, for the same N
-    float* cqmag;                // [cq rows][252]
+    float* cqmag;                // [cq rows][252] scaled magnitudes: debug output only, NULL on the product path
+    float* cq_chroma;            // [cq rows][7 octaves][12]: every octave's share of the chroma fold
     double* ton_part;            // [partial slots][6] tonnetz sums per kTonTile columns
     float* out;                  // [rows][dim]
     int dim, off_tonnetz;
