@@ -68,6 +68,16 @@ class ParameterError(Exception):
     (e.g. spectral_contrast's Nyquist check, ser/_internal/utils/dsp.py:127-136)."""
 
 
+class UnsupportedConfigurationError(NotImplementedError):
+    """SERB_ERR_UNSUPPORTED: the input is valid for the reference but outside what the CUDA path
+    implements -- today the ~5.5 % of sample rates (e.g. 20.5-20.8, 33.1-33.6, 40.9-41.6,
+    66.1-67.2 kHz; none of 8 / 11.025 / 16 / 22.05 / 24 / 32 / 44.1 / 48 / 96 kHz) whose constant-Q
+    plan (early-downsampling count or FFT size) would depend on the per-clip tuning estimate.
+    Deliberately NOT a ValueError: callers that treat ValueError as "bad audio" (the reference's
+    run_fast_inference does) must not mistake it for one; route such files to the reference's own
+    CPU path or resample them."""
+
+
 def load_library() -> ctypes.CDLL:
     """Loads libser_b200.so once; raises RuntimeError with build instructions if it is absent."""
     global _lib
@@ -97,6 +107,8 @@ def _raise(lib, ctx, code: int) -> None:
     text = message.decode("utf-8", "replace") if message else f"ser_b200 error {code}"
     if code == -5:
         raise ParameterError(text)
+    if code == -7:
+        raise UnsupportedConfigurationError(text)
     if code < 0:
         raise ValueError(text)
     raise RuntimeError(text)

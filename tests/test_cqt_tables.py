@@ -61,3 +61,15 @@ def test_cqt_plan_and_basis_match_oracle(sr):
 def test_cqt_plan_rejects_rates_below_the_top_wavelet():
     assert _native.debug_cqt_plan(8000)["status"] == 1      # librosa: wavelet basis exceeds Nyquist
     assert _native.debug_cqt_plan(96000)["early_factor"] == 4
+
+
+def test_tuning_dependent_plans_are_reported_as_unsupported_not_as_bad_input():
+    """~5.5 % of sample rates have a constant-Q plan that depends on the tuning estimate
+    (status 2).  They must surface as UnsupportedConfigurationError (a NotImplementedError), never as
+    the ValueError the runtime boundary reads as "bad audio"."""
+    assert _native.debug_cqt_plan(20600)["status"] == 2
+    assert _native.debug_cqt_plan(41000)["status"] == 2
+    for sr in (8000 * 2, 11025 * 2, 24000, 32000, 44100, 48000, 96000):
+        assert _native.debug_cqt_plan(sr)["status"] == 0, sr
+    assert issubclass(_native.UnsupportedConfigurationError, NotImplementedError)
+    assert not issubclass(_native.UnsupportedConfigurationError, ValueError)

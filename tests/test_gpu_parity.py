@@ -176,6 +176,13 @@ def test_error_behaviour_matches_reference():
         dsp.extract_feature_from_signal(good, 8000, feature_flags=_flags187())
     ok = dsp.extract_feature_from_signal(good, 8000, feature_flags=FeatureFlags(contrast=False, tonnetz=False))
     assert ok.shape == (180,)
+    # a sample rate whose constant-Q plan depends on the tuning estimate: valid for the reference,
+    # unsupported here -- NOT a ValueError, and the 187-d groups still work
+    from ser_b200 import _native
+
+    with pytest.raises(_native.UnsupportedConfigurationError, match="tuning estimate"):
+        dsp.extract_feature_from_signal(good, 20600)
+    assert dsp.extract_feature_from_signal(good, 20600, feature_flags=_flags187()).shape == (187,)
 
 
 def test_mlp_matches_sklearn_golden(golden, gpu_ctx):
