@@ -104,6 +104,7 @@ struct serb_ctx {
     bool keep_cqmag = false;    // serb_debug_tonnetz_stages: also write the 252-wide constant-Q magnitudes
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_runs, ton_tuning, ton_tile_clip;
+    bool cqt_shared = true;     // low octaves share the first FFT stage between frames (SERB_CQT=percolumn turns it off)
     bool istft_fused = true;    // inverse STFT + overlap-add in one kernel (SERB_ISTFT=split keeps the two HBM-bound kernels)
     int harm_seg = 512;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
@@ -580,6 +581,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.n_dec_exact = c.n_dec_exact;
     qp.dec_toeplitz = ctx->dec_mma ? ctx->dec_toeplitz.ptr : nullptr;
     qp.n_sms = ctx->n_sms;
+    qp.cqt_no_shared = ctx->cqt_shared ? 0 : 1;
     { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
@@ -1185,6 +1187,7 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         CREATE_CHECK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device_ordinal));
         if (const char* env = std::getenv("SERB_DECIMATE")) ctx->dec_mma = std::string(env) != "ffma";
         if (const char* env = std::getenv("SERB_ISTFT")) ctx->istft_fused = std::string(env) != "split";
+        if (const char* env = std::getenv("SERB_CQT")) ctx->cqt_shared = std::string(env) != "percolumn";
         hann_squared_2048(hsq);
         // behind the 2048 doubles: the overlap-add's window sum of squares where four frames
         // overlap, accumulated in frame order exactly as ola_sample does (float64 add, float32 store)

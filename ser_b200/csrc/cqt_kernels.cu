@@ -202,16 +202,25 @@ struct CqtSmemHead {
 // columns touch is staged once in shared memory (zero padded at the clip ends), together with
 // the 36 sparse basis rows of the clip's tuning; after one barrier every warp works alone:
 // G = 32 / R columns per iteration, R complex points per lane per column (N = 32 R = n_fft / 2).
-template <int R>
-__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int octave_arg) {
+//
+// SHARED (octaves whose hop is at most 16 samples): neighbouring frames overlap by more than 98 %,
+// and step A of the transform -- the R-point DFT over n1 of z[ct + 32 n1 + l] -- depends on the
+// absolute position m = ct + l only.  The CTA computes D~[m][k1] = W_N^(m k1) sum_n1 z[m + 32 n1]
+// W_R^(n1 k1) ONCE for its span (a few hundred m instead of 32 per column), and a column is
+//   Z[k1 + R k2] = W_N^(-ct k1) sum_l W_32^(l k2) D~[ct + l][k1]:
+// 32 loads, one 32-point DFT and one constant phase per lane.  No frame loads, no step A, no
+// transpose: the shared-memory traffic of the transform drops from 12 to 4 KB per column and
+// its arithmetic by two fifths.
+template <int R, bool SHARED>
+__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int oct_first) {
     constexpr int G = 32 / R;
     constexpr int N = 32 * R;
     extern __shared__ __align__(16) unsigned char cqt_smem_raw[];
     CqtSmemHead& sm = *reinterpret_cast<CqtSmemHead*>(cqt_smem_raw);
     float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(CqtSmemHead));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // one launch per octave, or all octaves of equal FFT size in one launch (blockIdx.z)
-    const int octave = octave_arg >= 0 ? octave_arg : static_cast<int>(blockIdx.z);
+    // consecutive octaves of equal FFT size share a launch (blockIdx.z)
+    const int octave = oct_first + static_cast<int>(blockIdx.z);
     const int cols_per_block = p.cq_cols_per_block[octave];
     const TonClip clip = p.clips[blockIdx.x];
     const int t_block = blockIdx.y * cols_per_block;
@@ -259,10 +268,48 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     const int k2_lo = sm.bin_lo / R, k2_hi = min(31, (sm.bin_hi + cmax - 1) / R);
     const int g2 = lane / R, k1 = lane % R;
     const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
-
-    for (int lc0 = warp * G; lc0 < n_here; lc0 += kCqtWarps * G) {
-        // frames (rectangular window): z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane
+    // SHARED: D~[k1][m] behind the staged span, row pitch = 1 mod 16 so that the sixteen k1 of a
+    // half warp read sixteen different bank pairs.  The table covers `sub_cols` columns at a time
+    // (the CTA's columns in sub-blocks, two CTA barriers each), so that the CTA keeps the long
+    // column run that amortises the staging of the basis.
+    const int h2 = hop >> 1;
+    const int sub_cols = SHARED ? p.cq_sub_cols[octave] : cols_per_block;
+    const int dpitch = ((sub_cols - 1) * h2 + 32 + 15) / 16 * 16 + 1;
+    float2* dt = reinterpret_cast<float2*>(sig_s + (((cols_per_block - 1) * hop + 2 * N + 3) & ~3));
+    for (int sb = 0; sb < n_here; sb += sub_cols) {
+    const int sub_end = min(sb + sub_cols, n_here);
+    if constexpr (SHARED) {
+        if (sb) __syncthreads();                       // the previous sub-block's readers are done
+        const int m_range = (sub_end - sb - 1) * h2 + 32;
+        const float* base = sig_s + 2 * sb * h2;       // complex sample 0 of the sub-block
+        for (int m = tid; m < m_range; m += kCqtWarps * 32) {
+            float2 y[R];
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) y[n1] = *reinterpret_cast<const float2*>(base + 2 * (m + 32 * n1));
+            fft_small<R>(y);
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                float2 z = y[q];
+                if (q > 0) {
+                    const float2 w = twa[(m * q) & (N - 1)];
+                    z = make_float2(fmaf(z.x, w.x, -z.y * w.y), fmaf(z.x, w.y, z.y * w.x));
+                }
+                dt[q * dpitch + m] = z;
+            }
+        }
+        __syncthreads();
+    }
+    for (int lc0 = sb + warp * G; lc0 < sub_end; lc0 += kCqtWarps * G) {
         float2 v[32];
+        if constexpr (SHARED) {
+            // lane = (column g2, k1): the 32 table entries of this column's span, then the DFT over l
+            const int ct = (min(lc0 + g2, sub_end - 1) - sb) * h2;     // relative to the sub-block's table
+            const float2* drow = dt + k1 * dpitch + ct;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) v[l] = drow[l];
+        } else {
+        // frames (rectangular window): z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane
+
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int lc = min(lc0 + g, n_here - 1);       // surplus columns repeat the last one (not stored)
@@ -303,8 +350,19 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
             v[n2 + 1] = make_float2(q2.z, q2.w);
         }
         __syncwarp();
+        }
         // step B: 32-point DFT over n2; lane = (column g2, k1): v[k2] = Z[k1 + R k2]
         fft32(v);
+        if constexpr (SHARED) {
+            // the column's constant phase W_N^(-ct k1) = conj(twa[ct k1])
+            const int ct = (min(lc0 + g2, sub_end - 1) - sb) * h2;
+            const float2 w = twa[(ct * k1) & (N - 1)];
+            if (k1 > 0) {
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2)
+                    v[k2] = make_float2(fmaf(v[k2].x, w.x, v[k2].y * w.y), fmaf(v[k2].y, w.x, -v[k2].x * w.y));
+            }
+        }
         float2* xs = buf + g2 * (N + 1);
         // in groups of four register indices (one warp-uniform branch per group, so that the
         // twiddle loads and shuffles of a group are in flight together); the up to three surplus
@@ -419,6 +477,7 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
         }
         __syncwarp();
     }
+    }
 }
 
 // ---- chroma fold + tonnetz ---------------------------------------------------------------
@@ -519,17 +578,25 @@ cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_
     }
     cudaError_t e = cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs));
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cqt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cqt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cqt_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem))) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(cqt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCqtMaxSmem));
+    const int smem = static_cast<int>(kCqtMaxSmem);
+    if ((e = cudaFuncSetAttribute(cqt_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(cqt_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 constexpr int kCqtSpanBudget = 8384;    // staged signal floats per CTA (two CTAs per SM)
+constexpr int kCqtSharedMaxHop = 16;    // octaves with a hop up to this share the first FFT stage (n_fft 1024 only)
+
+static bool cqt_octave_shared(const CqtParams& p, int octave) {
+    const int hop = p.hop0 >> octave;
+    return p.n_fft[octave] == 1024 && (hop & 1) == 0 && hop <= kCqtSharedMaxHop && !p.cqt_no_shared;
+}
 
 // columns per CTA and dynamic shared memory of one octave's launch
 template <int R>
-static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block, size_t& bytes) {
+static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block, int& sub_cols, size_t& bytes) {
     constexpr int G = 32 / R;
     constexpr int N = 32 * R;
     const int hop = p.hop0 >> octave;
@@ -540,33 +607,34 @@ static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block
     cols_per_block = per_iter * iters;
     const size_t span = static_cast<size_t>(cols_per_block - 1) * hop + 2 * N;
     bytes = sizeof(CqtSmemHead) + span * sizeof(float);
+    if (cqt_octave_shared(p, octave)) {
+        // the first-stage table takes what the span leaves of the budget: R rows of
+        // ((sub - 1) hop / 2 + 32, rounded up to 1 mod 16) float2 for `sub` columns at a time
+        const size_t span_bytes = ((span + 3) & ~size_t(3)) * sizeof(float);
+        auto table = [&](int sub) { return static_cast<size_t>(R) * (((sub - 1) * (hop / 2) + 32 + 15) / 16 * 16 + 1) * sizeof(float2); };
+        int sub = per_iter;
+        for (int c = per_iter; c <= cols_per_block; c += per_iter)
+            if (span_bytes + table(c) <= kCqtSpanBudget * sizeof(float)) sub = c;
+        sub_cols = sub;
+        bytes = sizeof(CqtSmemHead) + span_bytes + table(sub);
+    }
 }
 
-// octaves [first, first + count) share the FFT size 64 R: one launch, blockIdx.z = octave - first
-// is not needed because the kernel takes the octave from blockIdx.z only when count covers all
-template <int R>
+// octaves [first, first + count) share the FFT size 64 R and the kernel variant: one launch,
+// blockIdx.z = octave - first
+template <int R, bool SHARED>
 static cudaError_t launch_cqt_group(CqtParams p, int first, int count, cudaStream_t stream) {
     size_t max_bytes = 0;
     int min_cols = 1 << 30;
     for (int o = first; o < first + count; ++o) {
         size_t bytes;
-        cqt_octave_shape<R>(p, o, p.cq_cols_per_block[o], bytes);
+        cqt_octave_shape<R>(p, o, p.cq_cols_per_block[o], p.cq_sub_cols[o], bytes);
         max_bytes = max(max_bytes, bytes);
         min_cols = min(min_cols, p.cq_cols_per_block[o]);
     }
     if (max_bytes > kCqtMaxSmem) return cudaErrorInvalidConfiguration;
-    if (first == 0 && count == kCqOctaves) {
-        dim3 grid(p.n_clips, (p.max_cq_cols + min_cols - 1) / min_cols, kCqOctaves);
-        cqt_kernel<R><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, -1);
-    } else {
-        for (int o = first; o < first + count; ++o) {
-            size_t bytes;
-            int cols;
-            cqt_octave_shape<R>(p, o, cols, bytes);
-            dim3 grid(p.n_clips, (p.max_cq_cols + cols - 1) / cols);
-            cqt_kernel<R><<<grid, kCqtWarps * 32, bytes, stream>>>(p, o);
-        }
-    }
+    dim3 grid(p.n_clips, (p.max_cq_cols + min_cols - 1) / min_cols, count);
+    cqt_kernel<R, SHARED><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, first);
     return cudaGetLastError();
 }
 
@@ -618,19 +686,24 @@ cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long lon
     if (p.n_clips <= 0) return cudaSuccess;
     cudaError_t e = cudaSuccess;
     long long n = 0;
-    // maximal runs of octaves with one FFT size (all seven at the common sample rates)
+    // maximal runs of octaves with one FFT size and one kernel variant (at the common sample rates:
+    // the top octaves with per-column transforms, the bottom ones sharing the first stage)
     for (int first = 0; first < kCqOctaves;) {
+        const bool shared = cqt_octave_shared(p, first);
         int count = 1;
-        while (first + count < kCqOctaves && p.n_fft[first + count] == p.n_fft[first]) ++count;
+        while (first + count < kCqOctaves && p.n_fft[first + count] == p.n_fft[first] &&
+               cqt_octave_shared(p, first + count) == shared)
+            ++count;
         switch (p.n_fft[first]) {
-            case 256: e = launch_cqt_group<4>(p, first, count, stream); break;
-            case 512: e = launch_cqt_group<8>(p, first, count, stream); break;
-            case 1024: e = launch_cqt_group<16>(p, first, count, stream); break;
-            case 2048: e = launch_cqt_group<32>(p, first, count, stream); break;
+            case 256: e = launch_cqt_group<4, false>(p, first, count, stream); break;
+            case 512: e = launch_cqt_group<8, false>(p, first, count, stream); break;
+            case 1024: e = shared ? launch_cqt_group<16, true>(p, first, count, stream)
+                                  : launch_cqt_group<16, false>(p, first, count, stream); break;
+            case 2048: e = launch_cqt_group<32, false>(p, first, count, stream); break;
             default: return cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return e;
-        n += (first == 0 && count == kCqOctaves) ? 1 : count;
+        ++n;
         first += count;
     }
     if (launches) *launches += n;

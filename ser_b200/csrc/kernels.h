@@ -177,6 +177,7 @@ struct CqtParams {
     int hop0;                    // hop of level 0
     int n_fft[kCqOctaves];
     int cq_cols_per_block[kCqOctaves];   // filled by the launcher
+    int cq_sub_cols[kCqOctaves];         // columns per first-stage table of the shared-stage kernel (launcher)
     const float* early_taps;     // [n_early_taps] (scaled by sqrt(early_factor)); NULL if factor 1
     int n_early_taps;
     const CqRow* rows;           // [100][7][36]
@@ -192,6 +193,7 @@ struct CqtParams {
     int max_cq_cols;             // most constant-Q columns of one clip
     int max_length;              // longest full-rate signal in the chunk
     int n_dec_exact;             // clips shorter than kDecExactBelow samples (float64 decimation)
+    int cqt_no_shared;           // 1: every octave takes the per-column transform (SERB_CQT=percolumn, A/B tests)
     const void* dec_toeplitz;    // bf16 Toeplitz operand of decimate2_mma_kernel (decimate_mma_table)
     int n_sms;
 };

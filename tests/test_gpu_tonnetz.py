@@ -502,3 +502,27 @@ def test_tensor_core_decimator_against_the_ffma2_kernel(gpu_ctx):
         assert all(v[0] <= TOL for v in report.values()), report
     finally:
         ffma.close()
+
+
+@pytest.mark.parametrize("sr", [16000, 22050, 48000])
+def test_shared_first_fft_stage_against_the_per_column_transform(gpu_ctx, sr):
+    """The low constant-Q octaves (hop <= 16 samples) compute step A of the transform once per CTA
+    span instead of once per column (cqt_kernel<16, true>); SERB_CQT=percolumn keeps every octave on
+    the per-column transform.  Same mathematics, twiddles applied in another order: magnitudes agree
+    to 2e-6 of their maximum, rows to 1e-5 scaled, at block edges and clip ends alike."""
+    percol = _context_with_env(SERB_CQT="percolumn")
+    try:
+        clips = _ragged_batch(sr)
+        for clip in clips:
+            a = gpu_ctx.debug_tonnetz_stages(clip, sr)
+            b = percol.debug_tonnetz_stages(clip, sr)
+            assert np.array_equal(a["yharm"], b["yharm"])
+            assert a["tuning_index"] == b["tuning_index"]
+            assert a["cqmag"].shape == b["cqmag"].shape
+            assert np.max(np.abs(a["cqmag"] - b["cqmag"])) <= 2e-6 * max(np.max(b["cqmag"]), 1e-30), clip.size
+        bits = 0x1F
+        report = group_errors(gpu_ctx.features_host_clips(clips, sr, bits), percol.features_host_clips(clips, sr, bits),
+                              groups=ALL_GROUPS)
+        assert all(v[0] <= 1e-5 for v in report.values()), report
+    finally:
+        percol.close()
