@@ -51,7 +51,7 @@ GROUPS = {"mfcc": (0, 40), "chroma": (40, 52), "mel": (52, 180), "contrast": (18
 KERNEL_NAMES = {
     "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
     "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
-    "istft": "istft_kernel", "ola": "ola_kernel", "decimate": "decimate2_kernel", "cqt": "cqt_kernel",
+    "istft": "istft_ola_kernel", "ola": "ola_kernel", "decimate": "decimate2_mma_kernel", "cqt": "cqt_kernel",
     "tonnetz": "tonnetz_kernel", "pcm_prepare": "pcm_file_scale_kernel",
 }
 TONNETZ = os.environ.get("SERB_BENCH_TONNETZ", "1") == "1"   # the build implements all five groups (193-d)
@@ -513,6 +513,8 @@ def run_b200(args) -> None:
         "bound_source": bounds.get("source"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_source": bounds.get("traffic_source"), "peak_source": peak_src,
+        "chain_dram_bytes_per_stft_column": kernel_bounds().get("_chain", {}).get("dram_bytes_per_stft_column"),
+        "chain_dram_source": kernel_bounds().get("_chain", {}).get("source"),
         "algorithmic_bytes_per_launch": alg_bytes_step / max(dom_n, 1), "launches_per_step": dom_n,
         "avg_launch_ms": dom_ms / max(dom_n, 1),
         "kernel_ms_per_step": {k: v[0] for k, v in kms.items()},
