@@ -150,9 +150,11 @@ def test_median_filter_short_axis_restatement(n_cols):
         idx = [i if i < n_cols else period - 1 - i for i in idx]       # d c b a | a b c d | d c b a
         expect[:, t] = np.median(mag[:, idx], axis=1)
     assert np.array_equal(ours, expect)
+    # scipy: authoritative only where the axis is not much shorter than the kernel.  Below that its
+    # 1-D rank filter returns run-to-run different values on this image (see the next test) -- two
+    # runs can even agree with each other and still be wrong, so agreement is recorded, not asserted.
     first = median_filter(mag, size=(1, 31), mode="reflect")
-    second = median_filter(mag.copy(order="F"), size=(1, 31), mode="reflect")
-    if np.array_equal(first, second, equal_nan=True) and np.all(np.isfinite(first)):
+    if n_cols >= 12:
         assert np.array_equal(ours, first)
 
 
@@ -172,11 +174,12 @@ def test_scipy_short_axis_median_instability_is_why_the_restatement_exists(recor
         assert np.all(np.isfinite(ours))
         a = median_filter(mag, size=(1, 31), mode="reflect")
         b = median_filter(mag.copy(order="F"), size=(1, 31), mode="reflect")
-        if np.array_equal(a, b, equal_nan=True) and np.all(np.isfinite(a)):
-            assert np.array_equal(a, ours)
-        else:
+        # the restatement itself is pinned by the per-element definition in the test above; scipy's
+        # answer is compared for the record only (it may differ from itself between two runs, and two
+        # wrong runs may coincide, so neither equality nor inequality is asserted)
+        if not (np.array_equal(a, b, equal_nan=True) and np.array_equal(a, ours)):
             unstable += 1
-    record_property("scipy_unstable_trials_of_60", unstable)
+    record_property("scipy_unstable_or_different_trials_of_60", unstable)
 
 
 def test_softmask_definition():
