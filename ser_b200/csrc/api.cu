@@ -80,7 +80,8 @@ struct serb_ctx {
     std::mutex mu;
     std::string err;
     long long launches = 0;
-    int chunk_cols = 262144;
+    int chunk_cols = 1048576;   // STFT columns per launch chain (SERB_CHUNK_COLS): 21 KB of scratch per column, 22 GB at most;
+                                // 262 144 cost 1.3 ms more per c2 step in launch tails (gpurun_out sweep)
     int ramp_start = 32768;     // first chunk of a host-buffer call (SERB_RAMP_START), then x ramp_factor_x10 / 10 per chunk
     int ramp_factor_x10 = 30;   // SERB_RAMP_FACTOR_X10
     bool ramp_chunks = false;   // set by the host-buffer entries for the duration of one call
@@ -1147,7 +1148,7 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
     ctx->device = device_ordinal;
     if (const char* env = std::getenv("SERB_CHUNK_COLS")) {
         const int v = std::atoi(env);
-        if (v >= 64) ctx->chunk_cols = v;
+        if (v >= 64) ctx->chunk_cols = std::min(v, 1 << 20);    // int element indices stay below 2^31 up to here
     }
     if (const char* env = std::getenv("SERB_HARM_SEG")) { const int v = std::atoi(env); if (v >= 16) ctx->harm_seg = v; }
     if (const char* env = std::getenv("SERB_RAMP_START")) { const int v = std::atoi(env); if (v >= 1024) ctx->ramp_start = v; }
