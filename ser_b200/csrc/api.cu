@@ -82,8 +82,8 @@ struct serb_ctx {
     long long launches = 0;
     int chunk_cols = 1048576;   // STFT columns per launch chain (SERB_CHUNK_COLS): 21 KB of scratch per column, 22 GB at most;
                                 // 262 144 cost 1.3 ms more per c2 step in launch tails (gpurun_out sweep)
-    int ramp_start = 32768;     // first chunk of a host-buffer call (SERB_RAMP_START), then x ramp_factor_x10 / 10 per chunk
-    int ramp_factor_x10 = 30;   // SERB_RAMP_FACTOR_X10
+    int ramp_start = 65536;     // first chunk of a host-buffer call (SERB_RAMP_START), then x ramp_factor_x10 / 10 per chunk
+    int ramp_factor_x10 = 40;   // SERB_RAMP_FACTOR_X10 (profiles/r02_ramp_sweep_pcm16.txt)
     bool ramp_chunks = false;   // set by the host-buffer entries for the duration of one call
     float last_ms = 0.f;
     bool timed = false;
