@@ -48,7 +48,7 @@ namespace serb {
 
 namespace {
 
-constexpr int kDmR = 12;                               // windows per lane
+constexpr int kDmR = 14;                               // windows per lane
 constexpr int kDmN = 8 * kDmR;                         // MMA N
 constexpr int kDmWin = 128;                            // outputs per window = MMA M
 constexpr int kDmSlabs = 41;                           // K = 16 x 41 = 656 >= 643 + left padding
@@ -58,6 +58,15 @@ constexpr int kDmKoff = 2 * (kDmWin - 1) + kDmHalf + kDmLeft;   // tap index = k
 constexpr int kDmCoresA = 2 * (kDmWin / 8 - 1) + 2 * kDmSlabs;  // 112 distinct core matrices of T
 constexpr int kDmChunks = 32 * (kDmR - 1) + 2 * kDmSlabs;       // 16-byte chunks per lane
 constexpr int kDmABytes = kDmCoresA * 128;
+// Core matrix u of T holds taps kDmKoff - 8 u - [0, 21]: all zero before kDmAFirst and after kDmALast,
+// so the three bf16 terms' tables overlap on their zero cores (term t starts kDmAStride bytes after
+// term t - 1): 35 KB instead of 42, which is what lets N = 112 windows fit the shared memory.
+constexpr int kDmAFirst = (kDmKoff - 21 - (kDecTaps2 - 1) + 7) / 8;     // first core with a non-zero tap
+constexpr int kDmALast = kDmKoff / 8;                                   // last one
+constexpr int kDmAOverlap = (kDmAFirst < kDmCoresA - 1 - kDmALast) ? kDmAFirst : kDmCoresA - 1 - kDmALast;
+constexpr int kDmAStride = (kDmCoresA - kDmAOverlap) * 128;
+constexpr int kDmATotal = 2 * kDmAStride + kDmABytes;
+static_assert(kDmAFirst > 0 && kDmALast < kDmCoresA - 1 && kDmAOverlap > 0, "zero cores at both ends of the Toeplitz table");
 constexpr int kDmBBytes = kDmChunks * 128;
 constexpr int kDmSegOut = kDmWin * kDmR;               // outputs per lane segment
 // K slabs [kDmCentral0, kDmCentral1) hold the centre tap of some row: row i (output i) has it at
@@ -74,7 +83,8 @@ static_assert(4 * kDmN <= 512, "two pairs of accumulators must fit the 512 TMEM 
 constexpr int kDmProducerWarps = 15;
 constexpr int kDmThreads = 32 * (1 + 4 + kDmProducerWarps);
 constexpr int kDmProducers = 32 * kDmProducerWarps;
-constexpr size_t kDmSmem = 3 * kDmABytes + 3 * kDmBBytes + 128;
+constexpr size_t kDmSmem = kDmATotal + 3 * kDmBBytes + 128;
+static_assert(kDmSmem + 1024 <= 227 * 1024, "decimate2_mma_kernel shared memory");
 
 #ifdef DM_TRACE
 // per-tile clock64 stamps of CTA 0 (scripts/microbench/decimate_mma_test -DDM_TRACE): [tile][8]
@@ -232,16 +242,16 @@ static_assert(kDmCentral0 > 3 && kDmCentral0 <= 16 && kDmCentral1 > 16, "first M
 __global__ void __launch_bounds__(kDmThreads, 1)
 decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles, const uint4* __restrict__ toeplitz) {
     extern __shared__ __align__(128) unsigned char dm_smem[];
-    unsigned char* sm_a = dm_smem;                               // [3][kDmABytes]
-    unsigned char* sm_b = dm_smem + 3 * kDmABytes;               // [3][kDmBBytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dm_smem + 3 * kDmABytes + 3 * kDmBBytes);
+    unsigned char* sm_a = dm_smem;                               // three overlapped tables, kDmAStride apart
+    unsigned char* sm_b = dm_smem + kDmATotal;                   // [3][kDmBBytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dm_smem + kDmATotal + 3 * kDmBBytes);
     // bars[0..3] group full, [4..7] group empty, [8..9] accumulators full, [10..11] accumulators
     // empty; then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     __shared__ DmLaneInfo epi_info[4][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int i = tid; i < 3 * kDmABytes / 16; i += kDmThreads) reinterpret_cast<uint4*>(sm_a)[i] = toeplitz[i];
+    for (int i = tid; i < kDmATotal / 16; i += kDmThreads) reinterpret_cast<uint4*>(sm_a)[i] = toeplitz[i];
     if (tid == 0) {
         for (int g = 0; g < kDmGroups; ++g) {
             mbar_init(smem_u32(&bars[g]), kDmProducerWarps);
@@ -270,7 +280,7 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
         uint64_t ad[3], bd[3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            ad[t] = dm_desc(a_addr + t * kDmABytes, 128, 256);
+            ad[t] = dm_desc(a_addr + t * kDmAStride, 128, 256);
             bd[t] = dm_desc(b_addr + t * kDmBBytes, 128, 32 * 128);
         }
         // one elected lane does all the waiting and issuing; the other lanes park at the warp barrier
@@ -363,55 +373,45 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
     } else {
         // ---- producers ----
         // Task t of group g = (lane a = t % 8, chunk q = 32 (t / 64) + 8 g + (t / 8) % 8); a thread owns
-        // tasks pt + kDmProducers k.  The samples of tile n + 1 are loaded into registers as soon as
-        // the thread has stored its part of tile n, i.e. while the tensor core still works on tile n,
-        // so that only the split into bf16 terms and the stores wait for a group to be released.
-        const int pt = tid - 160;
-        float4 lo[kDmGroups][kDmGroupIters], hi[kDmGroups][kDmGroupIters];
-        auto task_chunk = [&](int g, int k) -> int {
-            const int t = pt + kDmProducers * k;
-            return t < kDmGroupTasks ? 32 * (t >> 6) + 8 * g + ((t >> 3) & 7) : kDmChunks;
-        };
-        auto load_tile = [&](int tile) -> int {
-            const int a = pt & 7;
+        // tasks pt + kDmProducers k.  A group is refilled (load float32, split, store) as soon as the
+        // tensor core releases it and is needed again a whole tile later, so the loads' latency is
+        // off the critical path and nothing is prefetched into registers.
+        const int pt = tid - 160, a = pt & 7;
+        unsigned char* dst0 = sm_b + 16 * a;
+        int n = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
             const DmLaneInfo li = dm_lane_info(p, src_level, segs_per_clip, tile, a);
-            if (!li.active) return 0;
             const int sbase = 2 * li.m0 - kDmLeft;
             const bool aligned = (reinterpret_cast<uintptr_t>(li.src) & 31) == 0;
-#pragma unroll
-            for (int g = 0; g < kDmGroups; ++g)
-#pragma unroll
-                for (int k = 0; k < kDmGroupIters; ++k) {
-                    const int q = task_chunk(g, k);
-                    const int s = sbase + 8 * q;
-                    if (q >= kDmChunks) continue;
-                    if (aligned && s >= 0 && s + 8 <= li.len_in) {
-                        lo[g][k] = __ldg(reinterpret_cast<const float4*>(li.src + s));
-                        hi[g][k] = __ldg(reinterpret_cast<const float4*>(li.src + s + 4));
-                    } else {
-                        float x[8];
-#pragma unroll
-                        for (int b = 0; b < 8; ++b) x[b] = (s + b >= 0 && s + b < li.len_in) ? li.src[s + b] : 0.0f;
-                        lo[g][k] = make_float4(x[0], x[1], x[2], x[3]);
-                        hi[g][k] = make_float4(x[4], x[5], x[6], x[7]);
-                    }
-                }
-            return 1;
-        };
-        unsigned char* dst0 = sm_b + 16 * (pt & 7);
-        int n = 0;
-        int active = blockIdx.x < n_tiles ? load_tile(blockIdx.x) : 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-#pragma unroll
+#pragma unroll 1
             for (int g = 0; g < kDmGroups; ++g) {
                 mbar_wait<32>(smem_u32(&bars[4 + g]), (n & 1) ^ 1);
-                if (active) {
+                if (li.active) {
+                    float4 lo[kDmGroupIters], hi[kDmGroupIters];
 #pragma unroll
                     for (int k = 0; k < kDmGroupIters; ++k) {
-                        const int q = task_chunk(g, k);
-                        if (q >= kDmChunks) continue;
+                        const int t = pt + kDmProducers * k;
+                        const int q = 32 * (t >> 6) + 8 * g + ((t >> 3) & 7);
+                        const int s = sbase + 8 * q;
+                        if (t >= kDmGroupTasks || q >= kDmChunks) continue;
+                        if (aligned && s >= 0 && s + 8 <= li.len_in) {
+                            lo[k] = __ldg(reinterpret_cast<const float4*>(li.src + s));
+                            hi[k] = __ldg(reinterpret_cast<const float4*>(li.src + s + 4));
+                        } else {
+                            float x[8];
+#pragma unroll
+                            for (int b = 0; b < 8; ++b) x[b] = (s + b >= 0 && s + b < li.len_in) ? li.src[s + b] : 0.0f;
+                            lo[k] = make_float4(x[0], x[1], x[2], x[3]);
+                            hi[k] = make_float4(x[4], x[5], x[6], x[7]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kDmGroupIters; ++k) {
+                        const int t = pt + kDmProducers * k;
+                        const int q = 32 * (t >> 6) + 8 * g + ((t >> 3) & 7);
+                        if (t >= kDmGroupTasks || q >= kDmChunks) continue;
                         uint4 s0, s1, s2;
-                        dm_split8(lo[g][k], hi[g][k], s0, s1, s2);
+                        dm_split8(lo[k], hi[k], s0, s1, s2);
                         unsigned char* d = dst0 + 128 * q;
                         *reinterpret_cast<uint4*>(d) = s0;
                         *reinterpret_cast<uint4*>(d + kDmBBytes) = s1;
@@ -423,7 +423,6 @@ decimate2_mma_kernel(CqtParams p, int src_level, int segs_per_clip, int n_tiles,
                 if (lane == 0) mbar_arrive(smem_u32(&bars[g]));
                 if (warp == 5 && g == 0) DM_STAMP(n, 13);
             }
-            if (tile + static_cast<int>(gridDim.x) < n_tiles) active = load_tile(tile + gridDim.x);
         }
     }
     tc_fence_before();
@@ -460,10 +459,11 @@ void* decimate_mma_trace_ptr() {
 }
 #endif
 
-size_t decimate_mma_table_bytes() { return 3 * kDmABytes; }
+size_t decimate_mma_table_bytes() { return kDmATotal; }
 
-// taps (x sqrt 2, float64) -> [3 terms][112 core matrices][8 rows][8 columns] bf16
+// taps (x sqrt 2, float64) -> three overlapped tables of [112 core matrices][8 rows][8 columns] bf16
 void decimate_mma_table(const double* taps2_scaled, unsigned char* out) {
+    std::memset(out, 0, kDmATotal);
     uint16_t* t = reinterpret_cast<uint16_t*>(out);
     for (int u = 0; u < kDmCoresA; ++u)
         for (int a = 0; a < 8; ++a)
@@ -475,9 +475,13 @@ void decimate_mma_table(const double* taps2_scaled, unsigned char* out) {
                 const uint16_t h1 = bf16_rn(h - b0, &b1);
                 const uint16_t h2 = bf16_rn(h - b0 - b1, &b2);
                 const size_t at = (static_cast<size_t>(u) * 8 + a) * 8 + b;
-                t[at] = h0;
-                t[kDmABytes / 2 + at] = h1;
-                t[2 * (kDmABytes / 2) + at] = h2;
+                // overlapped tables: a core outside [kDmAFirst, kDmALast] is zero in every term, and only
+                // such cores share storage
+                if (u >= kDmAFirst && u <= kDmALast) {
+                    t[at] = h0;
+                    t[kDmAStride / 2 + at] = h1;
+                    t[2 * (kDmAStride / 2) + at] = h2;
+                }
             }
 }
 
