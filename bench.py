@@ -443,9 +443,15 @@ def run_b200(args) -> None:
             assert np.array_equal(l_host, dev_labels), "PCM16 host-entry labels differ from the device path"
         # the same call from pageable memory (what a numpy caller of the Python API passes)
         pageable = [np.array(pinned_np[i]) for i in range(n_clips)]
-        elapsed_p, chain_p, _, _ = e2e_timed(pageable, 2)
+        elapsed_p, chain_p, last_p, _ = e2e_timed(pageable, 2)
+        if c3:
+            assert np.array_equal(last_p[0], dev_feats), "rows from pageable memory differ from the device path"
+        else:
+            assert np.array_equal(last_p[2], dev_labels), "labels from pageable memory differ from the device path"
         e2e["pageable"] = {"value": audio_seconds_step * 2 / elapsed_p, "unit": UNIT, "ms_per_step": 1e3 * elapsed_p / 2,
-                           "device_chain_ms": chain_p, "input": "one pageable int16 numpy array per file"}
+                           "device_chain_ms": chain_p,
+                           "input": "one pageable int16 numpy array per file, gathered into pinned slots by the "
+                                    "library's staging threads (csrc/host_stage.h)"}
         del pageable
         if not c3:
             # round 1's float32 entry, for continuity: 4 bytes per sample over PCIe

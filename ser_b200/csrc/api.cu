@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "cqt_tables.h"
 #include "filterbanks.h"
+#include "host_stage.h"
 #include "kernels.h"
 
 namespace {
@@ -85,6 +86,13 @@ struct serb_ctx {
     int ramp_start = 65536;     // first chunk of a host-buffer call (SERB_RAMP_START), then x ramp_factor_x10 / 10 per chunk
     int ramp_factor_x10 = 40;   // SERB_RAMP_FACTOR_X10 (profiles/r02_ramp_sweep_pcm16.txt)
     bool ramp_chunks = false;   // set by the host-buffer entries for the duration of one call
+    // pageable caller memory goes through a ring of pinned slots filled by stage_threads host threads
+    // (host_stage.h; SERB_STAGE_THREADS, 0 = hand pageable pointers to cudaMemcpyAsync as they are).  The
+    // gather runs at a few times the chain's consumption rate, not at PCIe speed, so the ramp is gentler.
+    StageRing stage_ring;
+    int stage_threads = 4;
+    int ramp_factor_pageable_x10 = 20;   // SERB_RAMP_FACTOR_PAGEABLE_X10
+    bool ramp_pageable = false; // this call's sources are pageable (set with ramp_chunks)
     float last_ms = 0.f;
     bool timed = false;
 
@@ -264,7 +272,8 @@ int plan(serb_ctx* ctx, long long n_wave, const int64_t* starts, const int64_t* 
             // H2D from pinned memory runs about three times faster than the chain consumes columns, so
             // each chunk may be three times the previous one without starving
             long long ramp = ctx->ramp_start;
-            for (size_t i = 0; i < std::min<size_t>(index, 12) && ramp < ctx->chunk_cols; ++i) ramp = ramp * ctx->ramp_factor_x10 / 10;
+            const int factor_x10 = ctx->ramp_pageable ? ctx->ramp_factor_pageable_x10 : ctx->ramp_factor_x10;
+            for (size_t i = 0; i < std::min<size_t>(index, 12) && ramp < ctx->chunk_cols; ++i) ramp = ramp * factor_x10 / 10;
             limit = std::min(limit, ramp);
         }
         if (limit >= ctx->chunk_cols) {
@@ -857,13 +866,26 @@ int check_status(serb_ctx* ctx, cudaStream_t stream) {
 // first chunk: every small table upload of the call has been issued by then, so none of them sits
 // behind a gigabyte of waveform in the H2D copy engine's queue.  operator()(max_end) makes the
 // compute stream wait for the piece holding sample (max_end - 1).
+// whether this call's host sources go through the pinned ring (the first source decides; a wrong
+// guess only costs speed, never correctness)
+bool use_stage_ring(serb_ctx* ctx, const void* first_source) {
+    if (ctx->stage_threads <= 0 || !first_source || !host_pointer_is_pageable(first_source)) return false;
+    if (ctx->stage_ring.ensure(ctx->stage_threads) != cudaSuccess) {
+        cudaGetLastError();      // no pinned memory to be had: plain copies
+        return false;
+    }
+    return true;
+}
+
 struct PieceWaiter {
     serb_ctx* ctx;
     cudaStream_t stream;
     const float* h_wave;
     long long n_wave;
+    bool staged = false;           // pageable source: pieces are gathered into pinned slots as the chunks ask for them
     long long piece = 8LL << 20;   // samples per piece (32 MiB)
     int n_pieces = 0;
+    int enqueued = 0;
     int waited = -1;
     bool started = false;
     cudaError_t error = cudaSuccess;
@@ -872,18 +894,30 @@ struct PieceWaiter {
         n_pieces = static_cast<int>((n_wave + piece - 1) / piece);
         // the previous call's kernels may still read ctx->wave
         if ((error = cudaEventRecord(ctx->ev_done, ctx->stream)) != cudaSuccess) return;
-        if ((error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0)) != cudaSuccess) return;
-        for (int i = 0; i < n_pieces; ++i) {
-            const long long lo = i * piece, hi = std::min(n_wave, lo + piece);
-            if ((error = cudaMemcpyAsync(ctx->wave.as<float>() + lo, h_wave + lo, (hi - lo) * sizeof(float),
-                                         cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess) return;
-            if ((error = cudaEventRecord(ctx->piece_events[i], ctx->copy_stream)) != cudaSuccess) return;
+        error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0);
+    }
+    void enqueue_through(int last) {
+        for (; enqueued <= last && error == cudaSuccess; ++enqueued) {
+            const long long lo = enqueued * piece, hi = std::min(n_wave, lo + piece);
+            if (staged) {
+                StagedWriter writer{&ctx->stage_ring, ctx->copy_stream};
+                if ((error = writer.add(ctx->wave.as<float>() + lo, h_wave + lo, (hi - lo) * sizeof(float))) != cudaSuccess) return;
+                if ((error = writer.flush()) != cudaSuccess) return;
+            } else if ((error = cudaMemcpyAsync(ctx->wave.as<float>() + lo, h_wave + lo, (hi - lo) * sizeof(float),
+                                                cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess) {
+                return;
+            }
+            error = cudaEventRecord(ctx->piece_events[enqueued], ctx->copy_stream);
         }
     }
     void operator()(long long max_end) {
         if (!started) start();
         if (n_pieces == 0 || error != cudaSuccess) return;
         int idx = static_cast<int>(std::min<long long>((std::max<long long>(max_end, 1) - 1) / piece, n_pieces - 1));
+        // pinned sources: every copy is enqueued at once (they are asynchronous); pageable ones: up to the
+        // piece this chunk needs, the host gathering the next pieces while the chunk's kernels run
+        enqueue_through(staged ? idx : n_pieces - 1);
+        if (error != cudaSuccess) return;
         if (idx > waited) {
             cudaStreamWaitEvent(stream, ctx->piece_events[idx], 0);
             waited = idx;
@@ -903,6 +937,7 @@ int ensure_piece_events(serb_ctx* ctx, int n_pieces) {
 int stage_wave(serb_ctx* ctx, const float* h_wave, long long n_wave, PieceWaiter& waiter) {
     SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
     waiter = PieceWaiter{ctx, ctx->stream, h_wave, n_wave};
+    waiter.staged = n_wave > 0 && use_stage_ring(ctx, h_wave);
     return ensure_piece_events(ctx, static_cast<int>((n_wave + waiter.piece - 1) / waiter.piece));
 }
 
@@ -920,6 +955,7 @@ struct ClipStager {
     long long n_clips;
     long long next_clip = 0;      // first clip not yet enqueued
     long long enqueued_end = 0;   // wave offset covered by the enqueued copies
+    bool staged = false;          // pageable clips: gathered into pinned slots (host_stage.h)
     int n_pieces = 0;
     bool started = false;
     cudaError_t error = cudaSuccess;
@@ -934,15 +970,19 @@ struct ClipStager {
         constexpr long long kPiece = 8LL << 20;   // samples per piece (32 MiB)
         while (enqueued_end < max_end && next_clip < n_clips) {
             long long in_piece = 0;
+            StagedWriter writer{&ctx->stage_ring, ctx->copy_stream};
             while (next_clip < n_clips && in_piece < kPiece) {
                 const long long len = lengths[next_clip];
-                if ((error = cudaMemcpyAsync(ctx->wave.as<float>() + (*starts)[next_clip], clips[next_clip],
-                                             static_cast<size_t>(len) * sizeof(float), cudaMemcpyHostToDevice,
-                                             ctx->copy_stream)) != cudaSuccess) return;
+                float* dst = ctx->wave.as<float>() + (*starts)[next_clip];
+                if (staged) error = writer.add(dst, clips[next_clip], static_cast<size_t>(len) * sizeof(float));
+                else error = cudaMemcpyAsync(dst, clips[next_clip], static_cast<size_t>(len) * sizeof(float),
+                                             cudaMemcpyHostToDevice, ctx->copy_stream);
+                if (error != cudaSuccess) return;
                 enqueued_end = (*starts)[next_clip] + len;
                 in_piece += len;
                 ++next_clip;
             }
+            if (staged && (error = writer.flush()) != cudaSuccess) return;
             if (n_pieces >= static_cast<int>(ctx->piece_events.size())) {
                 cudaEvent_t ev;
                 if ((error = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return;
@@ -983,6 +1023,7 @@ struct PcmStager {
     long long max_frames;
     int next_file = 0;            // first file whose copy is not enqueued yet
     int prepared = 0;             // first file not yet converted
+    bool staged = false;          // pageable files: gathered into pinned slots (host_stage.h)
     int n_pieces = 0;
     bool started = false;
     cudaError_t error = cudaSuccess;
@@ -998,6 +1039,7 @@ struct PcmStager {
         constexpr long long kPiece = 16LL << 20;   // int16 samples per piece (32 MiB)
         while (next_file < n_files && lay[next_file].wave_off < max_end) {
             long long in_piece = 0;
+            StagedWriter writer{&ctx->stage_ring, ctx->copy_stream};
             while (next_file < n_files && in_piece < kPiece) {
                 // extend a run while host and device layouts stay contiguous
                 int run_hi = next_file + 1;
@@ -1008,12 +1050,15 @@ struct PcmStager {
                     run_samples += lay[run_hi].frames * lay[run_hi].channels;
                     ++run_hi;
                 }
-                if ((error = cudaMemcpyAsync(ctx->pcm.as<short>() + lay[next_file].pcm_off, files[next_file],
-                                             static_cast<size_t>(run_samples) * sizeof(int16_t), cudaMemcpyHostToDevice,
-                                             ctx->copy_stream)) != cudaSuccess) return;
+                short* dst = ctx->pcm.as<short>() + lay[next_file].pcm_off;
+                if (staged) error = writer.add(dst, files[next_file], static_cast<size_t>(run_samples) * sizeof(int16_t));
+                else error = cudaMemcpyAsync(dst, files[next_file], static_cast<size_t>(run_samples) * sizeof(int16_t),
+                                             cudaMemcpyHostToDevice, ctx->copy_stream);
+                if (error != cudaSuccess) return;
                 in_piece += run_samples;
                 next_file = run_hi;
             }
+            if (staged && (error = writer.flush()) != cudaSuccess) return;
             if (n_pieces >= static_cast<int>(ctx->piece_events.size())) {
                 cudaEvent_t ev;
                 if ((error = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return;
@@ -1087,10 +1132,13 @@ int run_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_
     int rc = upload(ctx, ctx->pcm_files, layout.data(), layout.size(), ctx->stream);
     if (rc) return rc;
     PcmStager stager{ctx, ctx->stream, h_files, &layout, max_frames};
+    stager.staged = n_files > 0 && use_stage_ring(ctx, h_files[0]);
+    ctx->ramp_pageable = stager.staged;
     ctx->ramp_chunks = true;
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts.data(), clip_lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, stager);
     ctx->ramp_chunks = false;
+    ctx->ramp_pageable = false;
     if (!rc && stager.error != cudaSuccess) rc = fail_cuda(ctx, stager.error, "PCM16 staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips == 0 || dim == 0) { SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SERB_OK; }
@@ -1153,6 +1201,15 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
     if (const char* env = std::getenv("SERB_HARM_SEG")) { const int v = std::atoi(env); if (v >= 16) ctx->harm_seg = v; }
     if (const char* env = std::getenv("SERB_RAMP_START")) { const int v = std::atoi(env); if (v >= 1024) ctx->ramp_start = v; }
     if (const char* env = std::getenv("SERB_RAMP_FACTOR_X10")) { const int v = std::atoi(env); if (v >= 11 && v <= 100) ctx->ramp_factor_x10 = v; }
+    if (const char* env = std::getenv("SERB_RAMP_FACTOR_PAGEABLE_X10")) { const int v = std::atoi(env); if (v >= 11 && v <= 100) ctx->ramp_factor_pageable_x10 = v; }
+    {
+        // staging threads: half the host's cores shared between the visible GPUs (one rank per GPU), 2 .. 8
+        int n_gpus = 1;
+        if (cudaGetDeviceCount(&n_gpus) != cudaSuccess || n_gpus < 1) { cudaGetLastError(); n_gpus = 1; }
+        const int cores = static_cast<int>(std::thread::hardware_concurrency());
+        ctx->stage_threads = std::max(2, std::min(8, cores / (2 * n_gpus)));
+    }
+    if (const char* env = std::getenv("SERB_STAGE_THREADS")) { const int v = std::atoi(env); if (v >= 0 && v <= 64) ctx->stage_threads = v; }
     ctx->timed = true;
 #define CREATE_CHECK(call)                                                                     \
     do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { int rc2 = fail_cuda(nullptr, e2, #call); delete ctx; return rc2; } } while (0)
@@ -1269,6 +1326,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
             b->release();
     }
     for (cudaEvent_t ev : ctx->piece_events) cudaEventDestroy(ev);
+    ctx->stage_ring.destroy();
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     cudaEventDestroy(ctx->ev_done);
@@ -1310,10 +1368,12 @@ int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const
     int rc = stage_wave(ctx, h_wave, n_wave, waiter);
     if (rc) return rc;
     SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
+    ctx->ramp_pageable = waiter.staged;
     ctx->ramp_chunks = true;
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, waiter);
     ctx->ramp_chunks = false;
+    ctx->ramp_pageable = false;
     if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips > 0 && dim > 0)
@@ -1342,10 +1402,13 @@ int serb_features_host_clips(serb_ctx* ctx, const float* const* h_clips, const i
     SERB_CUDA(ctx, ctx->wave.reserve(std::max<long long>(n_wave, 1) * sizeof(float) + 64));
     SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
     ClipStager stager{ctx, ctx->stream, h_clips, lengths, &starts, n_clips};
+    stager.staged = n_clips > 0 && use_stage_ring(ctx, h_clips[0]);
+    ctx->ramp_pageable = stager.staged;
     ctx->ramp_chunks = true;
     int rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts.data(), lengths, n_clips, sample_rate, flag_bits,
                           ctx->out.as<float>(), ctx->stream, stager);
     ctx->ramp_chunks = false;
+    ctx->ramp_pageable = false;
     if (!rc && stager.error != cudaSuccess) rc = fail_cuda(ctx, stager.error, "clip staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips > 0 && dim > 0)
@@ -1440,10 +1503,12 @@ int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const in
     SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
     SERB_CUDA(ctx, ctx->proba.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * m.n_classes, 1) * sizeof(double)));
     SERB_CUDA(ctx, ctx->labels.reserve(std::max<size_t>(static_cast<size_t>(n_clips), 1) * sizeof(int)));
+    ctx->ramp_pageable = waiter.staged;
     ctx->ramp_chunks = true;
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, waiter);
     ctx->ramp_chunks = false;
+    ctx->ramp_pageable = false;
     if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips == 0) return SERB_OK;

@@ -1,0 +1,96 @@
+"""Pageable caller memory (plain numpy, what every caller of the Python mirror passes) travels
+through the pinned staging ring of ``csrc/host_stage.h``; pinned memory goes to the copy engine as
+it is; ``SERB_STAGE_THREADS=0`` hands pageable pointers to ``cudaMemcpyAsync`` unchanged.  All three
+must give bit-identical rows -- staging moves bytes, nothing else -- including files that span several
+32 MiB slots, files whose sizes leave alignment gaps in the device layout, and more files than slots.
+
+Reference side: numpy arrays from soundfile / librosa.load (ser/_internal/utils/audio_utils.py:63-113).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SR = 16000
+BITS = 15          # mfcc + chroma + mel + contrast: the staging path is the same for every flag set
+
+
+def _pinned(array: np.ndarray) -> np.ndarray:
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(array)).pin_memory()
+    return t.numpy()
+
+
+@pytest.fixture()
+def unstaged_ctx(monkeypatch):
+    from ser_b200 import _native
+
+    monkeypatch.setenv("SERB_STAGE_THREADS", "0")
+    ctx = _native.Context(0)
+    yield ctx
+    ctx.close()
+
+
+def _pcm_files(rng):
+    sizes = [40001, 7, 2049, 123457, 5000, 99999, 31, 64000] * 3
+    return [rng.integers(-20000, 20000, size=n).astype(np.int16) for n in sizes]
+
+
+def test_pcm16_files_pageable_pinned_and_unstaged_rows_are_identical(gpu_ctx, unstaged_ctx):
+    rng = np.random.default_rng(5)
+    files = _pcm_files(rng)
+    usable = [i for i, f in enumerate(files) if f.size >= 2048]
+    clip_file = np.asarray(usable, dtype=np.int64)
+    starts = np.zeros(len(usable), dtype=np.int64)
+    lengths = np.asarray([files[i].size for i in usable], dtype=np.int64)
+    staged = gpu_ctx.features_host_pcm16(files, 1, clip_file, starts, lengths, SR, BITS)
+    pinned = gpu_ctx.features_host_pcm16([_pinned(f) for f in files], 1, clip_file, starts, lengths, SR, BITS)
+    plain = unstaged_ctx.features_host_pcm16(files, 1, clip_file, starts, lengths, SR, BITS)
+    assert np.all(np.isfinite(staged))
+    np.testing.assert_array_equal(staged, pinned)
+    np.testing.assert_array_equal(staged, plain)
+
+
+def test_one_file_larger_than_a_staging_slot(gpu_ctx, unstaged_ctx):
+    # 20 M int16 samples = 40 MB: two slots; windows at both ends and across the slot boundary
+    rng = np.random.default_rng(6)
+    big = rng.integers(-12000, 12000, size=20_000_000).astype(np.int16)
+    boundary = (32 << 20) // 2
+    starts = np.asarray([0, boundary - 24000, boundary - 1, big.size - 48000], dtype=np.int64)
+    lengths = np.full(starts.size, 48000, dtype=np.int64)
+    clip_file = np.zeros(starts.size, dtype=np.int64)
+    staged = gpu_ctx.features_host_pcm16([big], 1, clip_file, starts, lengths, SR, BITS)
+    plain = unstaged_ctx.features_host_pcm16([big], 1, clip_file, starts, lengths, SR, BITS)
+    np.testing.assert_array_equal(staged, plain)
+
+
+def test_float32_buffer_and_clip_list_entries(gpu_ctx, unstaged_ctx):
+    rng = np.random.default_rng(7)
+    # one buffer of 10 M samples (40 MB: two pieces, two slots) with windows over the piece boundary
+    wave = (0.3 * rng.standard_normal(10_000_000)).astype(np.float32)
+    piece = 8 << 20
+    starts = np.asarray([0, piece - 30000, piece - 2048, wave.size - 64000], dtype=np.int64)
+    lengths = np.asarray([64000, 60000, 4096, 64000], dtype=np.int64)
+    staged = gpu_ctx.features_host(wave, starts, lengths, SR, BITS)
+    pinned = gpu_ctx.features_host(_pinned(wave), starts, lengths, SR, BITS)
+    plain = unstaged_ctx.features_host(wave, starts, lengths, SR, BITS)
+    np.testing.assert_array_equal(staged, pinned)
+    np.testing.assert_array_equal(staged, plain)
+    # a list of separately allocated clips of ragged lengths (the training loader's shape)
+    clips = [(0.2 * rng.standard_normal(n)).astype(np.float32) for n in (2048, 2051, 48000, 16001, 100003, 4097) * 4]
+    staged = gpu_ctx.features_host_clips(clips, SR, BITS)
+    plain = unstaged_ctx.features_host_clips(clips, SR, BITS)
+    np.testing.assert_array_equal(staged, plain)
+
+
+def test_non_finite_audio_is_still_reported_through_the_ring(gpu_ctx):
+    wave = np.zeros(9_000_000, dtype=np.float32)
+    wave[8_500_000] = np.nan                      # in the second piece
+    starts = np.asarray([0, 8_400_000], dtype=np.int64)
+    lengths = np.asarray([48000, 200_000], dtype=np.int64)
+    with pytest.raises(ValueError, match="not finite"):
+        gpu_ctx.features_host(wave, starts, lengths, SR, BITS)
