@@ -293,6 +293,10 @@ def run_b200(args) -> None:
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: ser_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # host side of this rank next to its GPU (pinned buffers, staging threads); the CPU baseline leg
+    # below gets the whole machine back
+    numa = multi_gpu.bind_host_to_gpu(local_rank)
+    full_affinity = numa.pop("restore", None) if numa else None
     multi_gpu.init_process_group(info, "nccl", device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -418,10 +422,16 @@ def run_b200(args) -> None:
             t0 = time.perf_counter()
             chain = []
             gathered = None
+            trace = os.environ.get("SERB_BENCH_TRACE") == "1"
             for _ in range(steps):
+                ta = time.perf_counter()
                 f_host, p_host, l_host = e2e_call(files)
+                tb = time.perf_counter()
                 chain.append(ctx.last_compute_ms())
                 gathered = to_rank0(f_host, p_host, l_host)         # inside the timed region
+                if trace:
+                    print(f"[trace] rank {rank}: call {1e3 * (tb - ta):.2f} ms (device chain {chain[-1]:.2f}), "
+                          f"gather {1e3 * (time.perf_counter() - tb):.2f} ms", file=sys.stderr, flush=True)
             elapsed = max_over_ranks(time.perf_counter() - t0)
             barrier()
             return elapsed, float(np.median(chain)), (f_host, p_host, l_host), gathered
@@ -436,7 +446,8 @@ def run_b200(args) -> None:
                "input": "int16 PCM in pinned host memory (serb_infer_host_pcm16: decode scaling, peak normalisation, "
                         "features and classifier on the device)" if not c3 else
                         "int16 PCM in pinned host memory (serb_features_host_pcm16)",
-               "gathered_rows_on_rank0": None if gathered is None else int(gathered.shape[0])}
+               "gathered_rows_on_rank0": None if gathered is None else int(gathered.shape[0]),
+               "host_binding": numa}
         if c3:
             assert np.array_equal(f_host, dev_feats), "PCM16 host-entry rows differ from the device path"
         else:
@@ -541,6 +552,8 @@ def run_b200(args) -> None:
     # ---- CPU baseline on the box's host cores + parity of the GPU rows against it, rank 0 at N=1 ----
     cpu_baseline = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if full_affinity:
+            os.sched_setaffinity(0, full_affinity)      # the CPU arm runs on every host core
         cores = min(os.cpu_count() or 1, 32)
         per = args.cpu_clips or min(n_clips, max(2 * cores, 8) if TONNETZ else 4 * cores)
         sample_clips = wave[: per * n_samples].reshape(per, n_samples).cpu().numpy()

@@ -1203,11 +1203,11 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
     if (const char* env = std::getenv("SERB_RAMP_FACTOR_X10")) { const int v = std::atoi(env); if (v >= 11 && v <= 100) ctx->ramp_factor_x10 = v; }
     if (const char* env = std::getenv("SERB_RAMP_FACTOR_PAGEABLE_X10")) { const int v = std::atoi(env); if (v >= 11 && v <= 100) ctx->ramp_factor_pageable_x10 = v; }
     {
-        // staging threads: half the host's cores shared between the visible GPUs (one rank per GPU), 2 .. 8
+        // staging threads: the host's cores shared between the visible GPUs (one rank per GPU), 2 .. 8
         int n_gpus = 1;
         if (cudaGetDeviceCount(&n_gpus) != cudaSuccess || n_gpus < 1) { cudaGetLastError(); n_gpus = 1; }
         const int cores = static_cast<int>(std::thread::hardware_concurrency());
-        ctx->stage_threads = std::max(2, std::min(8, cores / (2 * n_gpus)));
+        ctx->stage_threads = std::max(2, std::min(8, cores / n_gpus));
     }
     if (const char* env = std::getenv("SERB_STAGE_THREADS")) { const int v = std::atoi(env); if (v >= 0 && v <= 64) ctx->stage_threads = v; }
     ctx->timed = true;

@@ -33,6 +33,36 @@ def rank_info() -> RankInfo:
                     int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def bind_host_to_gpu(local_rank: int) -> dict | None:
+    """Moves the calling thread (and the threads it starts later) onto the CPU cores NVML names as
+    closest to GPU ``local_rank``, so that the pinned buffers this rank allocates afterwards -- and
+    the staging threads of ``csrc/host_stage.h`` -- sit on the GPU's own NUMA node.  With eight
+    ranks each pulling ~0.5 GB per step out of host memory, copies that cross the socket
+    interconnect are what bends the end-to-end scaling curve.  ``SERB_NUMA_BIND=0`` turns it off.
+    Returns what was done (for the bench line), or None when disabled."""
+    if os.environ.get("SERB_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_getaffinity"):
+        return None
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(props, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        else:
+            visible = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(visible[local_rank]) if visible else local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+    except Exception as exc:  # no NVML, a cpuset that excludes the ideal cores, ...: stay where we are
+        return {"bound": False, "why": f"{type(exc).__name__}: {exc}"[:120], "cpus": len(before)}
+    after = sorted(os.sched_getaffinity(0))
+    return {"bound": after != before, "cpus": len(after), "cpus_before": len(before),
+            "first_cpu": after[0] if after else None, "restore": before}
+
+
 def init_process_group(info: RankInfo, backend: str, device=None) -> None:
     if not info.distributed:
         return
