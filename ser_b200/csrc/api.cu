@@ -910,6 +910,18 @@ struct PieceWaiter {
             error = cudaEventRecord(ctx->piece_events[enqueued], ctx->copy_stream);
         }
     }
+    // every enqueued copy is ordered before whatever follows on the compute stream (a call that planned
+    // no chunk at all never waited for the prefetched piece, and the caller's buffer must not be in
+    // flight when the entry returns)
+    void finish() {
+        if (enqueued > 0) cudaStreamWaitEvent(stream, ctx->piece_events[enqueued - 1], 0);
+    }
+    // before the host plans the chain: the first piece of a pinned source starts crossing PCIe now
+    void prefetch() {
+        if (staged || n_wave <= 0) return;
+        if (!started) start();
+        if (n_pieces > 0 && error == cudaSuccess) enqueue_through(0);
+    }
     void operator()(long long max_end) {
         if (!started) start();
         if (n_pieces == 0 || error != cudaSuccess) return;
@@ -1027,46 +1039,65 @@ struct PcmStager {
     int n_pieces = 0;
     bool started = false;
     cudaError_t error = cudaSuccess;
+    void begin() {
+        if (started) return;
+        started = true;
+        // the previous call's kernels may still read ctx->pcm / ctx->wave
+        if ((error = cudaEventRecord(ctx->ev_done, ctx->stream)) != cudaSuccess) return;
+        error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0);
+    }
+    // one piece of about 32 MiB: whole files from next_file on, one event
+    void enqueue_piece() {
+        const std::vector<PcmFile>& lay = *layout;
+        const int n_files = static_cast<int>(lay.size());
+        constexpr long long kPiece = 16LL << 20;   // int16 samples per piece (32 MiB)
+        long long in_piece = 0;
+        StagedWriter writer{&ctx->stage_ring, ctx->copy_stream};
+        while (next_file < n_files && in_piece < kPiece) {
+            // extend a run while host and device layouts stay contiguous
+            int run_hi = next_file + 1;
+            long long run_samples = lay[next_file].frames * lay[next_file].channels;
+            while (run_hi < n_files && in_piece + run_samples < kPiece &&
+                   files[run_hi] == files[run_hi - 1] + lay[run_hi - 1].frames * lay[run_hi - 1].channels &&
+                   lay[run_hi].pcm_off == lay[run_hi - 1].pcm_off + lay[run_hi - 1].frames * lay[run_hi - 1].channels) {
+                run_samples += lay[run_hi].frames * lay[run_hi].channels;
+                ++run_hi;
+            }
+            short* dst = ctx->pcm.as<short>() + lay[next_file].pcm_off;
+            if (staged) error = writer.add(dst, files[next_file], static_cast<size_t>(run_samples) * sizeof(int16_t));
+            else error = cudaMemcpyAsync(dst, files[next_file], static_cast<size_t>(run_samples) * sizeof(int16_t),
+                                         cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (error != cudaSuccess) return;
+            in_piece += run_samples;
+            next_file = run_hi;
+        }
+        if (staged && (error = writer.flush()) != cudaSuccess) return;
+        if (n_pieces >= static_cast<int>(ctx->piece_events.size())) {
+            cudaEvent_t ev;
+            if ((error = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return;
+            ctx->piece_events.push_back(ev);
+        }
+        if ((error = cudaEventRecord(ctx->piece_events[n_pieces], ctx->copy_stream)) != cudaSuccess) return;
+        ++n_pieces;
+    }
+    void finish() {       // see PieceWaiter::finish
+        if (n_pieces > 0) cudaStreamWaitEvent(stream, ctx->piece_events[n_pieces - 1], 0);
+    }
+    // Called before the host plans the launch chain: the first piece (about the first chunk of the ramp)
+    // crosses PCIe while the host builds its clip tables, instead of after.  Pinned sources only -- a
+    // pageable piece is gathered by this very thread.
+    void prefetch() {
+        if (staged || layout->empty()) return;
+        begin();
+        if (error == cudaSuccess) enqueue_piece();
+    }
     void operator()(long long max_end) {
         if (error != cudaSuccess) return;
         const std::vector<PcmFile>& lay = *layout;
         const int n_files = static_cast<int>(lay.size());
-        if (!started) {
-            started = true;
-            if ((error = cudaEventRecord(ctx->ev_done, ctx->stream)) != cudaSuccess) return;
-            if ((error = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0)) != cudaSuccess) return;
-        }
-        constexpr long long kPiece = 16LL << 20;   // int16 samples per piece (32 MiB)
-        while (next_file < n_files && lay[next_file].wave_off < max_end) {
-            long long in_piece = 0;
-            StagedWriter writer{&ctx->stage_ring, ctx->copy_stream};
-            while (next_file < n_files && in_piece < kPiece) {
-                // extend a run while host and device layouts stay contiguous
-                int run_hi = next_file + 1;
-                long long run_samples = lay[next_file].frames * lay[next_file].channels;
-                while (run_hi < n_files && in_piece + run_samples < kPiece &&
-                       files[run_hi] == files[run_hi - 1] + lay[run_hi - 1].frames * lay[run_hi - 1].channels &&
-                       lay[run_hi].pcm_off == lay[run_hi - 1].pcm_off + lay[run_hi - 1].frames * lay[run_hi - 1].channels) {
-                    run_samples += lay[run_hi].frames * lay[run_hi].channels;
-                    ++run_hi;
-                }
-                short* dst = ctx->pcm.as<short>() + lay[next_file].pcm_off;
-                if (staged) error = writer.add(dst, files[next_file], static_cast<size_t>(run_samples) * sizeof(int16_t));
-                else error = cudaMemcpyAsync(dst, files[next_file], static_cast<size_t>(run_samples) * sizeof(int16_t),
-                                             cudaMemcpyHostToDevice, ctx->copy_stream);
-                if (error != cudaSuccess) return;
-                in_piece += run_samples;
-                next_file = run_hi;
-            }
-            if (staged && (error = writer.flush()) != cudaSuccess) return;
-            if (n_pieces >= static_cast<int>(ctx->piece_events.size())) {
-                cudaEvent_t ev;
-                if ((error = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return;
-                ctx->piece_events.push_back(ev);
-            }
-            if ((error = cudaEventRecord(ctx->piece_events[n_pieces], ctx->copy_stream)) != cudaSuccess) return;
-            ++n_pieces;
-        }
+        begin();
+        while (error == cudaSuccess && next_file < n_files && lay[next_file].wave_off < max_end) enqueue_piece();
+        if (error != cudaSuccess) return;
         if (prepared < next_file) {
             if ((error = cudaStreamWaitEvent(stream, ctx->piece_events[n_pieces - 1], 0)) != cudaSuccess) return;
             ProfScope ps(ctx, 13, stream);
@@ -1135,10 +1166,12 @@ int run_pcm16(serb_ctx* ctx, const int16_t* const* h_files, const int64_t* file_
     stager.staged = n_files > 0 && use_stage_ring(ctx, h_files[0]);
     ctx->ramp_pageable = stager.staged;
     ctx->ramp_chunks = true;
+    if (n_clips > 0) stager.prefetch();
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts.data(), clip_lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, stager);
     ctx->ramp_chunks = false;
     ctx->ramp_pageable = false;
+    stager.finish();
     if (!rc && stager.error != cudaSuccess) rc = fail_cuda(ctx, stager.error, "PCM16 staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips == 0 || dim == 0) { SERB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SERB_OK; }
@@ -1370,10 +1403,12 @@ int serb_features_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const
     SERB_CUDA(ctx, ctx->out.reserve(std::max<size_t>(static_cast<size_t>(n_clips) * dim, 1) * sizeof(float)));
     ctx->ramp_pageable = waiter.staged;
     ctx->ramp_chunks = true;
+    if (n_clips > 0) waiter.prefetch();
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, waiter);
     ctx->ramp_chunks = false;
     ctx->ramp_pageable = false;
+    waiter.finish();
     if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips > 0 && dim > 0)
@@ -1505,10 +1540,12 @@ int serb_infer_host(serb_ctx* ctx, const float* h_wave, int64_t n_wave, const in
     SERB_CUDA(ctx, ctx->labels.reserve(std::max<size_t>(static_cast<size_t>(n_clips), 1) * sizeof(int)));
     ctx->ramp_pageable = waiter.staged;
     ctx->ramp_chunks = true;
+    if (n_clips > 0) waiter.prefetch();
     rc = run_features(ctx, ctx->wave.as<float>(), n_wave, starts, lengths, n_clips, sample_rate, flag_bits,
                       ctx->out.as<float>(), ctx->stream, waiter);
     ctx->ramp_chunks = false;
     ctx->ramp_pageable = false;
+    waiter.finish();
     if (!rc && waiter.error != cudaSuccess) rc = fail_cuda(ctx, waiter.error, "waveform staging");
     if (rc) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (n_clips == 0) return SERB_OK;
