@@ -410,30 +410,44 @@ def run_b200(args) -> None:
         else:
             rank_rows = [n_rows]
 
-        def to_rank0(f_host, p_host, l_host):
-            # the small per-row results go to rank 0 (north_star: "only the small per-clip feature vectors are
-            # gathered to the host"): one padded tensor gather, GPU to GPU under NCCL
-            local = f_host if c3 else np.concatenate([p_host, l_host[:, None].astype(np.float64)], axis=1)
-            return multi_gpu.gather_rows(info, local, total_rows, counts=rank_rows)
+        def local_block(f_host, p_host, l_host):
+            # the small per-row results that go to rank 0 (north_star: "only the small per-clip feature vectors
+            # are gathered to the host")
+            return f_host if c3 else np.concatenate([p_host, l_host[:, None].astype(np.float64)], axis=1)
+
+        # one padded tensor gather per step, GPU to GPU under NCCL, double-buffered: step i's rows travel (and
+        # rank 0 waits for the slowest rank) while step i + 1 computes; the last step's rows are collected
+        # before the clock stops, so every row is on rank 0 inside the timed region
+        gatherer = multi_gpu.RowGatherer(info, rank_rows, (dim,) if c3 else (n_classes + 1,),
+                                         np.float32 if c3 else np.float64)
 
         def e2e_timed(files, steps):
-            to_rank0(*e2e_call(files))                               # warm the staging buffers and the gather's channels
+            for _ in range(3):     # warm-up: staging buffers, the gather's channels, and the clocks after the idle gap
+                gatherer.collect(gatherer.submit(local_block(*e2e_call(files))))
             barrier()
             t0 = time.perf_counter()
             chain = []
             gathered = None
+            pending = None
             trace = os.environ.get("SERB_BENCH_TRACE") == "1"
             for _ in range(steps):
                 ta = time.perf_counter()
                 f_host, p_host, l_host = e2e_call(files)
                 tb = time.perf_counter()
                 chain.append(ctx.last_compute_ms())
-                gathered = to_rank0(f_host, p_host, l_host)         # inside the timed region
+                ticket = gatherer.submit(local_block(f_host, p_host, l_host))
+                if pending is not None:
+                    gathered = gatherer.collect(pending)
+                pending = ticket
                 if trace:
                     print(f"[trace] rank {rank}: call {1e3 * (tb - ta):.2f} ms (device chain {chain[-1]:.2f}), "
                           f"gather {1e3 * (time.perf_counter() - tb):.2f} ms", file=sys.stderr, flush=True)
+            gathered = gatherer.collect(pending)                    # inside the timed region
             elapsed = max_over_ranks(time.perf_counter() - t0)
             barrier()
+            if rank == 0:
+                assert gathered.shape[0] == total_rows, "rank 0 does not hold every rank's rows"
+                assert np.array_equal(gathered[:n_rows], local_block(f_host, p_host, l_host)), "gathered rows differ"
             return elapsed, float(np.median(chain)), (f_host, p_host, l_host), gathered
 
         e2e_steps = max(2, min(args.steps, 5))

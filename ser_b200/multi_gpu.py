@@ -139,3 +139,100 @@ def gather_rows(info: RankInfo, local_rows: np.ndarray, n_total: int, *, counts:
     if info.rank != 0:
         return None
     return np.concatenate([b[:c].cpu().numpy() for b, c in zip(blocks, counts)], axis=0)
+
+
+class RowGatherer:
+    """Double-buffered gather of per-rank row blocks to rank 0, off the critical path.
+
+    ``submit(rows)`` starts the gather of this step's rows (pinned staging -> device block -> one
+    ``dist.gather`` -> one device-to-host copy on rank 0, all on a side stream) and returns a ticket;
+    ``collect(ticket)`` waits for it and returns the concatenated rows on rank 0 (None elsewhere).
+    A caller that collects step i after submitting step i + 1 overlaps the exchange -- and rank 0's
+    wait for the slowest rank -- with the next step's compute; every row still reaches rank 0 inside
+    the caller's timed region as long as the last ticket is collected before the clock stops.
+    On gloo (CPU tests) the same protocol runs on ``async_op`` work handles.  Counts (rows per rank)
+    and the row shape are fixed at construction; two tickets may be in flight."""
+
+    def __init__(self, info: RankInfo, counts: list[int], row_shape: tuple[int, ...], dtype=np.float64,
+                 device: str | None = None) -> None:
+        self.info = info
+        self.counts = [int(c) for c in counts]
+        self.row_shape = tuple(int(d) for d in row_shape)
+        self.dtype = np.dtype(dtype)
+        self._submitted = 0
+        self._slots: list[dict] = []
+        if not info.distributed:
+            self._slots = [{"rows": None}, {"rows": None}]
+            return
+        import torch
+        import torch.distributed as dist
+
+        if device is None:
+            device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        self.device = device
+        self.cuda = device != "cpu"
+        tdtype = torch.from_numpy(np.zeros(0, dtype=self.dtype)).dtype
+        most = max(self.counts)
+        shape = (most,) + self.row_shape
+        self.side = torch.cuda.Stream() if self.cuda else None
+        for _ in range(2):
+            slot = {
+                "host_in": torch.zeros(shape, dtype=tdtype, pin_memory=self.cuda),
+                "block": torch.zeros(shape, dtype=tdtype, device=device),
+                "all": torch.zeros((info.world,) + shape, dtype=tdtype, device=device) if info.rank == 0 else None,
+                "host_out": torch.zeros((info.world,) + shape, dtype=tdtype, pin_memory=self.cuda) if info.rank == 0 else None,
+                "event": torch.cuda.Event() if self.cuda else None,
+                "work": None,
+                "busy": False,
+            }
+            self._slots.append(slot)
+
+    def submit(self, local_rows: np.ndarray) -> int:
+        ticket = self._submitted
+        self._submitted += 1
+        slot = self._slots[ticket & 1]
+        local_rows = np.ascontiguousarray(local_rows, dtype=self.dtype)
+        if not self.info.distributed:
+            slot["rows"] = local_rows
+            return ticket
+        import torch
+        import torch.distributed as dist
+
+        if slot["busy"]:
+            raise RuntimeError("RowGatherer: collect the ticket two steps back before submitting again")
+        n = self.counts[self.info.rank]
+        if local_rows.shape != (n,) + self.row_shape:
+            raise ValueError(f"rank {self.info.rank} submits {local_rows.shape}, expected {(n,) + self.row_shape}")
+        slot["host_in"][:n].copy_(torch.from_numpy(local_rows))
+        gather_list = list(slot["all"].unbind(0)) if self.info.rank == 0 else None
+        if self.cuda:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                slot["block"].copy_(slot["host_in"], non_blocking=True)
+                dist.gather(slot["block"], gather_list, dst=0)
+                if self.info.rank == 0:
+                    slot["host_out"].copy_(slot["all"], non_blocking=True)
+                slot["event"].record(self.side)
+        else:
+            slot["block"].copy_(slot["host_in"])
+            slot["work"] = dist.gather(slot["block"], gather_list, dst=0, async_op=True)
+        slot["busy"] = True
+        return ticket
+
+    def collect(self, ticket: int) -> np.ndarray | None:
+        slot = self._slots[ticket & 1]
+        if not self.info.distributed:
+            return slot["rows"]
+        if not slot["busy"]:
+            raise RuntimeError("RowGatherer: ticket already collected")
+        if self.cuda:
+            slot["event"].synchronize()
+        else:
+            slot["work"].wait()
+            if self.info.rank == 0:
+                slot["host_out"].copy_(slot["all"])
+        slot["busy"] = False
+        if self.info.rank != 0:
+            return None
+        out = slot["host_out"].numpy()
+        return np.concatenate([out[r, :c] for r, c in enumerate(self.counts)], axis=0)

@@ -51,6 +51,19 @@ def _worker(rank: int, world: int, port: int, queue) -> None:
         multi_gpu.barrier(info)
         slowest = multi_gpu.max_over_ranks(info, 10.0 + rank)
         gathered = multi_gpu.gather_rows(info, rows, lengths.size)
+        # the double-buffered gatherer: two steps in flight, collected one step late
+        bounds = multi_gpu.shard_bounds(lengths, world)
+        gatherer = multi_gpu.RowGatherer(info, [b - a for a, b in bounds], rows.shape[1:])
+        t0 = gatherer.submit(rows)
+        t1 = gatherer.submit(rows * 2.0)
+        first = gatherer.collect(t0)
+        t2 = gatherer.submit(rows * 3.0)
+        second, third = gatherer.collect(t1), gatherer.collect(t2)
+        if rank == 0:
+            assert np.array_equal(first, gathered) and np.array_equal(second, 2.0 * gathered)
+            assert np.array_equal(third, 3.0 * gathered)
+        else:
+            assert first is None and second is None and third is None
         queue.put((rank, lo, hi, slowest, None if gathered is None else gathered.tolist()))
     finally:
         multi_gpu.destroy_process_group(info)
@@ -87,3 +100,5 @@ def test_single_process_helpers_are_no_ops():
     assert multi_gpu.max_over_ranks(info, 3.5) == 3.5
     rows = np.zeros((4, 2))
     assert multi_gpu.gather_rows(info, rows, 4) is rows
+    gatherer = multi_gpu.RowGatherer(info, [4], (2,))
+    assert np.array_equal(gatherer.collect(gatherer.submit(rows + 1.0)), rows + 1.0)
