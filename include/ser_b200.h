@@ -215,6 +215,11 @@ int serb_debug_cqt_plan(int32_t sample_rate, int32_t* out10);
  * row (may be NULL).  Host only. */
 int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis,
                          float* out_scale36);
+/* the same basis as cqt16_kernel holds it (rows in sets over the union of their bins, csrc/cqt_tables.h
+ * CqtSetBank), expanded back to [36 x (1 + n_fft/2) x 2]: must equal serb_debug_cqt_basis.  Host only;
+ * SERB_ERR_UNSUPPORTED when the basis does not fit the layout (the lane = row kernels run then). */
+int serb_debug_cqt_set_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis,
+                             float* out_scale36);
 /* decimation filter (soxr_hq stand-in) for an integer factor 2..8; returns the tap count
  * (> 0) and, when out is non-NULL and capacity suffices, the taps.  Host only. */
 int serb_debug_decimation_taps(int32_t factor, double* out, int32_t capacity);

@@ -51,6 +51,7 @@ SIGNATURES: dict[str, tuple] = {
     "serb_debug_tonnetz_stages": (c_int, [_P, _P, c_int64, c_int32, _P, _P, _P, c_int64, _P, _P]),
     "serb_debug_cqt_plan": (c_int, [c_int32, _P]),
     "serb_debug_cqt_basis": (c_int, [c_int32, c_int32, c_int32, _P, _P]),
+    "serb_debug_cqt_set_basis": (c_int, [c_int32, c_int32, c_int32, _P, _P]),
     "serb_debug_decimation_taps": (c_int, [c_int32, _P, c_int32]),
     "serb_debug_launch_count": (c_int64, [_P]),
     "serb_debug_fp32_peak": (c_int, [_P, _P]),
@@ -415,6 +416,20 @@ def debug_cqt_basis(sample_rate: int, tuning_index: int, octave: int) -> tuple[n
     code = load_library().serb_debug_cqt_basis(int(sample_rate), int(tuning_index), int(octave), _ptr(basis), _ptr(scale))
     if code != 0:
         raise ValueError(f"serb_debug_cqt_basis failed with {code}")
+    return basis[..., 0] + 1j * basis[..., 1], scale
+
+
+def debug_cqt_set_basis(sample_rate: int, tuning_index: int, octave: int) -> tuple[np.ndarray, np.ndarray] | None:
+    """The same basis expanded from the column-mapped layout cqt16_kernel reads (None if it does not fit)."""
+    plan = debug_cqt_plan(sample_rate)
+    n_bins = 1 + plan["n_fft"][octave] // 2
+    basis = np.zeros((36, n_bins, 2), dtype=np.float32)
+    scale = np.zeros(36, dtype=np.float32)
+    code = load_library().serb_debug_cqt_set_basis(int(sample_rate), int(tuning_index), int(octave), _ptr(basis), _ptr(scale))
+    if code == -7:
+        return None
+    if code != 0:
+        raise ValueError(f"serb_debug_cqt_set_basis failed with {code}")
     return basis[..., 0] + 1j * basis[..., 1], scale
 
 

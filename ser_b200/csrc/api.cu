@@ -58,6 +58,8 @@ struct SrTables {
     bool cqt_ready = false;
     CqtPlan plan;
     DevBuf cq_rows, cq_vals, early_taps;
+    DevBuf cq_sets;         // [100][7] CqSetBank: the rows mapped lane = column (cqt16_kernel), if the basis fits
+    bool cq_sets_ok = false;
     int n_early_taps = 0;
 };
 
@@ -114,6 +116,7 @@ struct serb_ctx {
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_runs, ton_tuning, ton_tile_clip;
     bool cqt_shared = true;     // low octaves share the first FFT stage between frames (SERB_CQT=percolumn turns it off)
+    bool cqt_cols = true;       // n_fft 1024 octaves multiply the rows lane = column (SERB_CQT=rows keeps the lane = row kernels)
     bool istft_fused = true;    // inverse STFT + overlap-add in one kernel (SERB_ISTFT=split keeps the two HBM-bound kernels)
     int harm_seg = 512;
     std::vector<int> last_tuning_rows;   // out_row per main clip, in clips-array order
@@ -331,6 +334,11 @@ int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
     std::vector<CqRow> rows(static_cast<size_t>(kNTunings) * kCqtBins);
     std::vector<float> vals(static_cast<size_t>(kNTunings) * kCqtBins * kCqtRowCap * 2);
     std::vector<int> ok(kNTunings, 1);
+    static_assert(sizeof(CqtSetBank) == sizeof(CqSetBank) && sizeof(CqtSet) == sizeof(CqSet), "host and device layouts of the row sets");
+    bool any_1024 = false;
+    for (int i = 0; i < kCqtOctaves; ++i) any_1024 = any_1024 || plan.n_fft[i] == 1024;
+    std::vector<CqtSetBank> sets(any_1024 ? static_cast<size_t>(kNTunings) * kCqtOctaves : 0);
+    std::vector<int> sets_ok(kNTunings, any_1024 ? 1 : 0);
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::thread> workers;
     for (unsigned w = 0; w < hw; ++w)
@@ -344,6 +352,7 @@ int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
                 }
                 std::memcpy(vals.data() + static_cast<size_t>(t) * kCqtBins * kCqtRowCap * 2, bank.vals.data(),
                             bank.vals.size() * sizeof(float));
+                if (any_1024) sets_ok[t] = cqt_set_banks(plan, t, sets.data() + static_cast<size_t>(t) * kCqtOctaves) ? 1 : 0;
             }
         });
     for (std::thread& th : workers) th.join();
@@ -352,6 +361,9 @@ int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
     int rc;
     if ((rc = upload(ctx, tab->cq_rows, rows.data(), rows.size(), ctx->stream))) return rc;
     if ((rc = upload(ctx, tab->cq_vals, vals.data(), vals.size(), ctx->stream))) return rc;
+    tab->cq_sets_ok = any_1024;
+    for (int t = 0; t < kNTunings; ++t) tab->cq_sets_ok = tab->cq_sets_ok && sets_ok[t];
+    if (tab->cq_sets_ok && (rc = upload(ctx, tab->cq_sets, sets.data(), sets.size(), ctx->stream))) return rc;
     std::vector<float> taps32;
     if (plan.early_factor > 2) {
         std::vector<double> taps;
@@ -578,6 +590,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.n_early_taps = tab->n_early_taps;
     qp.rows = tab->cq_rows.as<CqRow>();
     qp.vals = tab->cq_vals.as<float2>();
+    qp.set_banks = (ctx->cqt_cols && tab->cq_sets_ok) ? tab->cq_sets.as<CqSetBank>() : nullptr;
     qp.twiddles = ctx->cq_twiddles.as<float2>();
     qp.cqmag = ctx->keep_cqmag ? ctx->cqmag.as<float>() : nullptr;
     qp.cq_chroma = ctx->cq_chroma.as<float>();
@@ -1278,7 +1291,10 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         CREATE_CHECK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device_ordinal));
         if (const char* env = std::getenv("SERB_DECIMATE")) ctx->dec_mma = std::string(env) != "ffma";
         if (const char* env = std::getenv("SERB_ISTFT")) ctx->istft_fused = std::string(env) != "split";
-        if (const char* env = std::getenv("SERB_CQT")) ctx->cqt_shared = std::string(env) != "percolumn";
+        if (const char* env = std::getenv("SERB_CQT")) {
+            ctx->cqt_shared = std::string(env) != "percolumn";
+            ctx->cqt_cols = std::string(env) != "rows" && std::string(env) != "percolumn";
+        }
         hann_squared_2048(hsq);
         // behind the 2048 doubles: the overlap-add's window sum of squares where four frames
         // overlap, accumulated in frame order exactly as ola_sample does (float64 add, float32 store)
@@ -1355,7 +1371,7 @@ void serb_ctx_destroy(serb_ctx* ctx) {
     for (auto& kv : ctx->sr_tables) {
         SrTables& t = kv.second;
         for (DevBuf* b : {&t.chroma_banks, &t.mel_start, &t.mel_count, &t.mel_offset, &t.mel_weights, &t.mel_points,
-                          &t.cq_rows, &t.cq_vals, &t.early_taps})
+                          &t.cq_rows, &t.cq_vals, &t.cq_sets, &t.early_taps})
             b->release();
     }
     for (cudaEvent_t ev : ctx->piece_events) cudaEventDestroy(ev);
@@ -1817,6 +1833,36 @@ int serb_debug_cqt_plan(int32_t sample_rate, int32_t* out10) {
     out10[1] = plan.early_factor;
     out10[2] = plan.hop0;
     for (int i = 0; i < kCqtOctaves; ++i) out10[3 + i] = plan.n_fft[i];
+    return SERB_OK;
+}
+
+int serb_debug_cqt_set_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis, float* out_scale36) {
+    if (sample_rate <= 0 || tuning_index < 0 || tuning_index >= kNTunings || octave < 0 || octave >= kCqtOctaves || !out_basis)
+        return SERB_ERR_INVALID_ARG;
+    CqtPlan plan;
+    cqt_plan(sample_rate, plan);
+    if (plan.status != 0) return SERB_ERR_UNSUPPORTED;
+    std::vector<CqtSetBank> banks(kCqtOctaves);
+    if (!cqt_set_banks(plan, tuning_index, banks.data())) return SERB_ERR_UNSUPPORTED;
+    // the column-mapped layout expanded back to [36][1 + n_fft/2] complex64, exactly as cqt16_kernel reads it
+    const CqtSetBank& sb = banks[octave];
+    const int n_bins = 1 + plan.n_fft[octave] / 2;
+    std::memset(out_basis, 0, static_cast<size_t>(kCqtBpo) * n_bins * 2 * sizeof(float));
+    for (int s = 0; s < kCqtSets; ++s) {
+        const CqtSet& set = sb.sets[s];
+        const int rpad = s < 4 ? 4 : 2;
+        for (int q = 0; q < set.nrows; ++q) {
+            const int j = set.bin[q] % kCqtBpo;
+            if (out_scale36) out_scale36[j] = set.scale[q];
+            for (int b = 0; b < set.ulen; ++b) {
+                const int k = sb.bin_lo + set.u0 + b;
+                if (k < 0 || k >= n_bins) return SERB_ERR_UNSUPPORTED;
+                const size_t at = static_cast<size_t>(set.off) + static_cast<size_t>(b) * rpad + q;
+                out_basis[(static_cast<size_t>(j) * n_bins + k) * 2] = sb.vals[2 * at];
+                out_basis[(static_cast<size_t>(j) * n_bins + k) * 2 + 1] = sb.vals[2 * at + 1];
+            }
+        }
+    }
     return SERB_OK;
 }
 

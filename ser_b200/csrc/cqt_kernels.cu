@@ -480,6 +480,246 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     }
 }
 
+// ---- n_fft = 1024 octaves with the rows mapped lane = column ---------------------------------
+// Same transform as cqt_kernel<16, SHARED>; what differs is the product with the sparse rows.  There
+// the lane is a ROW: every lane walks its own row of the basis and its own window of the spectrum
+// (all loads distinct: 45 % of the kernel's shared-memory wavefronts, 2.1 of its 8.5 ms per c2 step,
+// every row padded to the widest).  Here the CTA's eight warps transform 16 columns, leave the bins the
+// rows read ([bin_lo, bin_lo + n_bins), about 100 of 513) in shared memory column-major, and after a
+// CTA barrier the lane is a COLUMN: half warp s holds row set s (CqSetBank: three or two consecutive
+// rows over the union of their bins) for the 16 columns, so one spectrum load feeds every row of
+// the set, the basis values are warp-uniform 16-byte loads, and every row runs its own length.
+// Magnitudes meet in a [16 columns][36] buffer; after a second barrier 192 threads fold them into the
+// octave's 12 chroma shares while the other warps already transform the next 16 columns.
+//
+// Column c of warp w's pair lives at Xw[c * kC16Pitch + (bin - bin_lo)] inside warp w's own
+// transpose region (free between its exchange and the next iteration's); the regions are 8720
+// bytes apart (16 mod 128) and kC16Pitch = 1 mod 16, so the 16 lanes of a half warp read 16 different
+// 8-byte bank slots.
+constexpr int kC16Pitch = kCqSetMaxBins + 1;            // float2 between a warp's two columns
+constexpr int kC16MagPitch = kCqRows + 1;
+// float2 per warp: the 32 x 34 transpose buffer + the 16-byte bank shift; the shared-stage variant has no
+// transpose and keeps the two columns only (2 x 129 x 8 bytes = 16 mod 128 as well)
+template <bool SHARED> constexpr int kC16Region = SHARED ? 2 * kC16Pitch : 32 * kCqtBufPitch + 2;
+static_assert(2 * kC16Pitch <= 32 * kCqtBufPitch, "both columns' bins fit the warp's transpose region");
+static_assert((kC16Region<true> * 8) % 128 == 16 && (kC16Region<false> * 8) % 128 == 16, "bank shift between the warps' regions");
+
+template <bool SHARED>
+struct Cqt16Head {
+    float2 buf[kCqtWarps * kC16Region<SHARED>];
+    CqSetBank bank;
+    float mags[16][kC16MagPitch];
+};
+
+template <bool SHARED>
+__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, int oct_first) {
+    constexpr int R = 16, G = 2, N = 512;
+    extern __shared__ __align__(16) unsigned char cqt_smem_raw[];
+    Cqt16Head<SHARED>& sm = *reinterpret_cast<Cqt16Head<SHARED>*>(cqt_smem_raw);
+    float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(Cqt16Head<SHARED>));
+    constexpr int kRegion = kC16Region<SHARED>;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int octave = oct_first + static_cast<int>(blockIdx.z);
+    const int cols_per_block = p.cq_cols_per_block[octave];
+    const TonClip clip = p.clips[blockIdx.x];
+    const int t_block = blockIdx.y * cols_per_block;
+    if (t_block >= clip.cq_cols) return;
+    const int n_here = min(cols_per_block, clip.cq_cols - t_block);
+    const int tuning = p.tuning_idx[blockIdx.x];
+    const float* sig = level_ptr(p, clip, octave);
+    const int len = level_length(clip.len0, octave);
+    const int hop = p.hop0 >> octave;
+    // ---- stage the span and the rows ----
+    const int s0 = t_block * hop - N;
+    const int span = (n_here - 1) * hop + 2 * N;
+    for (int i = tid; i < span; i += kCqtWarps * 32) {
+        const int j = s0 + i;
+        const bool inside = j >= 0 && j < len;
+        const float* src = inside ? sig + j : sig;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sig_s + i))),
+                     "l"(src), "r"(inside ? 4 : 0) : "memory");
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.set_banks + static_cast<size_t>(tuning) * kCqOctaves + octave);
+        for (int i = tid; i < static_cast<int>(sizeof(CqSetBank) / 16); i += kCqtWarps * 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(reinterpret_cast<uint4*>(&sm.bank) + i))),
+                         "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const float2* twa = p.twiddles + (N - 128);            // W_N^j = (cos, -sin)
+    const float2* twb = p.twiddles + 1920 + (N - 128);     // (cos, sin) 2 pi k / (2N)
+    float2* buf = sm.buf + warp * kRegion;
+    const int bin_lo = sm.bank.bin_lo, n_bins = sm.bank.n_bins;
+    const int k2_lo = bin_lo / R, k2_hi = min(31, (bin_lo + n_bins - 1) / R);
+    const int g2 = lane / R, k1 = lane % R;
+    const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
+    // this thread's part of the row product: half warp = row set, lane = column
+    const int set_idx = tid >> 4, col16 = tid & 15;
+    const CqSet set = sm.bank.sets[set_idx];
+    const float2* xcol = sm.buf + (col16 >> 1) * kRegion + (col16 & 1) * kC16Pitch + set.u0;
+    const float2* bvals = sm.bank.vals + set.off;
+    const int oct_slot = sm.bank.sets[0].bin[0] / kCqRows;
+    // first-stage table of the shared variant (see cqt_kernel)
+    const int h2 = hop >> 1;
+    const int sub_cols = SHARED ? p.cq_sub_cols[octave] : cols_per_block;
+    const int dpitch = ((sub_cols - 1) * h2 + 32 + 15) / 16 * 16 + 1;
+    float2* dt = reinterpret_cast<float2*>(sig_s + (((cols_per_block - 1) * hop + 2 * N + 3) & ~3));
+    for (int sb = 0; sb < n_here; sb += sub_cols) {
+        const int sub_end = min(sb + sub_cols, n_here);
+        if constexpr (SHARED) {
+            if (sb) __syncthreads();                       // the previous sub-block's table readers are done
+            const int m_range = (sub_end - sb - 1) * h2 + 32;
+            const float* base = sig_s + 2 * sb * h2;
+            for (int m = tid; m < m_range; m += kCqtWarps * 32) {
+                float2 y[R];
+#pragma unroll
+                for (int n1 = 0; n1 < R; ++n1) y[n1] = *reinterpret_cast<const float2*>(base + 2 * (m + 32 * n1));
+                fft_small<R>(y);
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    float2 z = y[q];
+                    if (q > 0) {
+                        const float2 w = twa[(m * q) & (N - 1)];
+                        z = make_float2(fmaf(z.x, w.x, -z.y * w.y), fmaf(z.x, w.y, z.y * w.x));
+                    }
+                    dt[q * dpitch + m] = z;
+                }
+            }
+            __syncthreads();
+        }
+        // every warp runs every iteration (CTA barriers inside): surplus columns repeat the last one
+        for (int it0 = sb; it0 < sub_end; it0 += kCqtWarps * G) {
+            const int lc0 = it0 + warp * G;
+            float2 v[32];
+            if constexpr (SHARED) {
+                const int ct = (min(lc0 + g2, sub_end - 1) - sb) * h2;
+                const float2* drow = dt + k1 * dpitch + ct;
+#pragma unroll
+                for (int l = 0; l < 32; ++l) v[l] = drow[l];
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int lc = min(lc0 + g, n_here - 1);
+                    const float* frame = sig_s + lc * hop;
+                    if (hop & 1) {
+#pragma unroll
+                        for (int n1 = 0; n1 < R; ++n1)
+                            v[g * R + n1] = make_float2(frame[2 * (32 * n1 + lane)], frame[2 * (32 * n1 + lane) + 1]);
+                    } else {
+#pragma unroll
+                        for (int n1 = 0; n1 < R; ++n1)
+                            v[g * R + n1] = *reinterpret_cast<const float2*>(frame + 2 * (32 * n1 + lane));
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) fft_small<R>(v + g * R);
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        float2 y = v[g * R + q];
+                        if (q > 0) {
+                            const float2 w = twa[lane * q];
+                            y = make_float2(fmaf(y.x, w.x, -y.y * w.y), fmaf(y.x, w.y, y.y * w.x));
+                        }
+                        buf[(g * R + q) * kCqtBufPitch + lane] = y;
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2 += 2) {
+                    const float4 q2 = *reinterpret_cast<const float4*>(&buf[lane * kCqtBufPitch + n2]);
+                    v[n2] = make_float2(q2.x, q2.y);
+                    v[n2 + 1] = make_float2(q2.z, q2.w);
+                }
+                __syncwarp();
+            }
+            fft32(v);
+            if constexpr (SHARED) {
+                const int ct = (min(lc0 + g2, sub_end - 1) - sb) * h2;
+                const float2 w = twa[(ct * k1) & (N - 1)];
+                if (k1 > 0) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; ++k2)
+                        v[k2] = make_float2(fmaf(v[k2].x, w.x, v[k2].y * w.y), fmaf(v[k2].y, w.x, -v[k2].x * w.y));
+                }
+            }
+            // real-input split for the bins the rows read, into this warp's column-major pair
+            float2* xw = buf + g2 * kC16Pitch - bin_lo;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) {
+                if ((k2 | 3) < k2_lo || (k2 & ~3) > k2_hi) continue;        // warp-uniform, same for a group of four
+                float px = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
+                float py = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
+                if (k1 == 0) { px = v[(32 - k2) & 31].x; py = v[(32 - k2) & 31].y; }
+                const float2 pc = make_float2(px, -py);
+                const float2 e = cadd(v[k2], pc), d = csub(v[k2], pc);
+                const int k = k1 + R * k2;
+                const float2 w = twb[k];
+                const float wx = fmaf(w.x, d.y, -(w.y * d.x));
+                const float wy = fmaf(w.x, -d.x, -(w.y * d.y));
+                if (k >= bin_lo && k < bin_lo + n_bins) xw[k] = cscale(cadd(e, make_float2(wx, wy)), 0.5f);
+            }
+            // Nyquist bin X[N] = Re Z[0] - Im Z[0], only if a row reaches it
+            if (bin_lo + n_bins > N && k1 == 0) xw[N] = make_float2(v[0].x - v[0].y, 0.0f);
+            __syncthreads();                               // A: the 16 columns' bins are in place
+            const int n_valid = min(kCqtWarps * G, sub_end - it0);
+            {
+                float mag[3];
+                if (warp < 2) {
+                    // three rows per set, stored [bin][4]
+                    float cr[3] = {0.f, 0.f, 0.f}, ci[3] = {0.f, 0.f, 0.f};
+                    const float4* b4 = reinterpret_cast<const float4*>(bvals);
+                    for (int b = 0; b < set.ulen; ++b) {
+                        const float2 xv = xcol[b];
+                        const float4 b01 = b4[2 * b], b23 = b4[2 * b + 1];
+                        cr[0] = fmaf(b01.x, xv.x, fmaf(-b01.y, xv.y, cr[0])); ci[0] = fmaf(b01.x, xv.y, fmaf(b01.y, xv.x, ci[0]));
+                        cr[1] = fmaf(b01.z, xv.x, fmaf(-b01.w, xv.y, cr[1])); ci[1] = fmaf(b01.z, xv.y, fmaf(b01.w, xv.x, ci[1]));
+                        cr[2] = fmaf(b23.x, xv.x, fmaf(-b23.y, xv.y, cr[2])); ci[2] = fmaf(b23.x, xv.y, fmaf(b23.y, xv.x, ci[2]));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) asm("sqrt.approx.f32 %0, %1;" : "=f"(mag[q]) : "f"(fmaf(cr[q], cr[q], ci[q] * ci[q])));
+                } else {
+                    float cr[2] = {0.f, 0.f}, ci[2] = {0.f, 0.f};
+                    const float4* b4 = reinterpret_cast<const float4*>(bvals);
+                    for (int b = 0; b < set.ulen; ++b) {
+                        const float2 xv = xcol[b];
+                        const float4 b01 = b4[b];
+                        cr[0] = fmaf(b01.x, xv.x, fmaf(-b01.y, xv.y, cr[0])); ci[0] = fmaf(b01.x, xv.y, fmaf(b01.y, xv.x, ci[0]));
+                        cr[1] = fmaf(b01.z, xv.x, fmaf(-b01.w, xv.y, cr[1])); ci[1] = fmaf(b01.z, xv.y, fmaf(b01.w, xv.x, ci[1]));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) asm("sqrt.approx.f32 %0, %1;" : "=f"(mag[q]) : "f"(fmaf(cr[q], cr[q], ci[q] * ci[q])));
+                    mag[2] = 0.0f;
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (q < set.nrows) {
+                        const float mv = mag[q] * set.scale[q];
+                        sm.mags[col16][set.bin[q] % kCqRows] = mv;
+                        if (p.cqmag && col16 < n_valid) p.cqmag[(clip.cq_base + t_block + it0 + col16) * kCqBins + set.bin[q]] = mv;
+                    }
+                }
+            }
+            __syncthreads();                               // B: every row has read the bins (the transpose regions are free
+                                                           // again) and the 16 x 36 magnitudes are complete
+            // this octave's share of the chroma fold (filters.cq_to_chroma, 36 bins per octave: chroma c <- bins
+            // 3 c - 1, 3 c, 3 c + 1 of the octave, the first wrapping to bin 35); the next iteration's rows write
+            // sm.mags only after its barrier A, which these threads reach after the fold
+            if (tid < 192) {
+                const int g = tid / 12, c = tid % 12;
+                if (g < n_valid) {
+                    const float* m = sm.mags[g];
+                    const float sum = (m[(3 * c + kCqRows - 1) % kCqRows] + m[3 * c]) + m[3 * c + 1];
+                    p.cq_chroma[(static_cast<size_t>(clip.cq_base) + t_block + it0 + g) * (kCqOctaves * 12) + oct_slot * 12 + c] = sum;
+                }
+            }
+        }
+    }
+}
+
 // ---- chroma fold + tonnetz ---------------------------------------------------------------
 // one CTA per (clip, kTonTile columns): partial sums of the six tonnetz rows in float64, then a
 // per-clip reduction in tile order (tonnetz_final_kernel), so long clips spread over many CTAs
@@ -583,6 +823,8 @@ cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_
     if ((e = cudaFuncSetAttribute(cqt_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqt16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(cqt_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
@@ -618,6 +860,58 @@ static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block
         sub_cols = sub;
         bytes = sizeof(CqtSmemHead) + span_bytes + table(sub);
     }
+}
+
+// cqt16_kernel: columns per CTA, columns per first-stage table and dynamic shared memory of one octave
+constexpr size_t kCqt16Budget = (227 * 1024 - 2048) / 2;     // per CTA, two CTAs per SM
+constexpr int kCqt16SharedMaxHop = 32;   // at hop 64 the table costs as many first-stage transforms as the frames do
+
+static bool cqt16_octave_shared(const CqtParams& p, int octave) {
+    const int hop = p.hop0 >> octave;
+    return p.n_fft[octave] == 1024 && (hop & 1) == 0 && hop <= kCqt16SharedMaxHop && !p.cqt_no_shared;
+}
+
+template <bool SHARED>
+static void cqt16_octave_shape(const CqtParams& p, int octave, int& cols_per_block, int& sub_cols, size_t& bytes) {
+    constexpr int N = 512, per_iter = 16;
+    const int hop = p.hop0 >> octave;
+    const size_t room = kCqt16Budget - sizeof(Cqt16Head<SHARED>);
+    auto span_bytes = [&](int cols) { return ((static_cast<size_t>(cols - 1) * hop + 2 * N + 3) & ~size_t(3)) * sizeof(float); };
+    auto table = [&](int sub) { return static_cast<size_t>(16) * (((sub - 1) * (hop / 2) + 32 + 15) / 16 * 16 + 1) * sizeof(float2); };
+    for (int iters = 8; iters >= 1; --iters) {
+        const int cols = per_iter * iters;
+        if (!SHARED) {
+            if (span_bytes(cols) <= room || iters == 1) {
+                cols_per_block = cols; sub_cols = cols; bytes = sizeof(Cqt16Head<SHARED>) + span_bytes(cols);
+                return;
+            }
+            continue;
+        }
+        int sub = 0;
+        for (int c = per_iter; c <= cols; c += per_iter)
+            if (span_bytes(cols) + table(c) <= room) sub = c;
+        if (sub > 0 || iters == 1) {
+            if (sub == 0) sub = per_iter;
+            cols_per_block = cols; sub_cols = sub; bytes = sizeof(Cqt16Head<SHARED>) + span_bytes(cols) + table(sub);
+            return;
+        }
+    }
+}
+
+template <bool SHARED>
+static cudaError_t launch_cqt16_group(CqtParams p, int first, int count, cudaStream_t stream) {
+    size_t max_bytes = 0;
+    int min_cols = 1 << 30;
+    for (int o = first; o < first + count; ++o) {
+        size_t bytes;
+        cqt16_octave_shape<SHARED>(p, o, p.cq_cols_per_block[o], p.cq_sub_cols[o], bytes);
+        max_bytes = max(max_bytes, bytes);
+        min_cols = min(min_cols, p.cq_cols_per_block[o]);
+    }
+    if (max_bytes > kCqtMaxSmem) return cudaErrorInvalidConfiguration;
+    dim3 grid(p.n_clips, (p.max_cq_cols + min_cols - 1) / min_cols, count);
+    cqt16_kernel<SHARED><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, first);
+    return cudaGetLastError();
 }
 
 // octaves [first, first + count) share the FFT size 64 R and the kernel variant: one launch,
@@ -689,11 +983,19 @@ cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long lon
     // maximal runs of octaves with one FFT size and one kernel variant (at the common sample rates:
     // the top octaves with per-column transforms, the bottom ones sharing the first stage)
     for (int first = 0; first < kCqOctaves;) {
-        const bool shared = cqt_octave_shared(p, first);
+        const bool cols16 = p.set_banks != nullptr && p.n_fft[first] == 1024;      // lane = column rows (cqt16_kernel)
+        const bool shared = cols16 ? cqt16_octave_shared(p, first) : cqt_octave_shared(p, first);
         int count = 1;
         while (first + count < kCqOctaves && p.n_fft[first + count] == p.n_fft[first] &&
-               cqt_octave_shared(p, first + count) == shared)
+               (cols16 ? cqt16_octave_shared(p, first + count) : cqt_octave_shared(p, first + count)) == shared)
             ++count;
+        if (cols16) {
+            e = shared ? launch_cqt16_group<true>(p, first, count, stream) : launch_cqt16_group<false>(p, first, count, stream);
+            if (e != cudaSuccess) return e;
+            ++n;
+            first += count;
+            continue;
+        }
         switch (p.n_fft[first]) {
             case 256: e = launch_cqt_group<4, false>(p, first, count, stream); break;
             case 512: e = launch_cqt_group<8, false>(p, first, count, stream); break;

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <complex>
 
 #include "filterbanks.h"
@@ -311,6 +312,56 @@ bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank, bool lane_orde
         if (lane_order) lane_order_octave(bank, i);
     }
     return ok;
+}
+
+bool cqt_set_banks(const CqtPlan& plan, int tuning_idx, CqtSetBank* out7) {
+    CqtBank bank;
+    if (!cqt_bank(plan, tuning_idx, bank, /*lane_order=*/false)) return false;
+    for (int i = 0; i < kCqtOctaves; ++i) {
+        CqtSetBank& sb = out7[i];
+        std::memset(&sb, 0, sizeof(sb));
+        const CqtRow* rows = bank.rows.data() + static_cast<size_t>(i) * kCqtBpo;
+        const float* vals = bank.vals.data() + static_cast<size_t>(i) * kCqtBpo * kCqtRowCap * 2;
+        int lo = 1 << 30, hi = 0;
+        for (int j = 0; j < kCqtBpo; ++j)
+            if (rows[j].count > 0) { lo = std::min(lo, rows[j].start); hi = std::max(hi, rows[j].start + rows[j].count); }
+        if (hi <= lo) { lo = 0; hi = 1; }
+        if (hi - lo > kCqtSetMaxBins) return false;
+        sb.bin_lo = lo;
+        sb.n_bins = hi - lo;
+        int off = 0, row = 0;
+        for (int s = 0; s < kCqtSets; ++s) {
+            const int nrows = s < 4 ? 3 : 2, rpad = s < 4 ? 4 : 2;
+            int u0 = 1 << 30, u1 = 0;
+            for (int q = 0; q < nrows; ++q)
+                if (rows[row + q].count > 0) {
+                    u0 = std::min(u0, rows[row + q].start);
+                    u1 = std::max(u1, rows[row + q].start + rows[row + q].count);
+                }
+            if (u1 <= u0) { u0 = lo; u1 = lo; }
+            CqtSet& set = sb.sets[s];
+            set.u0 = static_cast<int16_t>(u0 - lo);
+            set.ulen = static_cast<int16_t>(u1 - u0);
+            set.off = static_cast<int16_t>(off);
+            set.nrows = static_cast<int16_t>(nrows);
+            if (off + (u1 - u0) * rpad > kCqtSetValCap) return false;
+            for (int q = 0; q < 4; ++q) { set.bin[q] = -1; set.scale[q] = 0.0f; }
+            for (int q = 0; q < nrows; ++q) {
+                const CqtRow& r = rows[row + q];
+                set.bin[q] = static_cast<int16_t>(r.bin);
+                set.scale[q] = r.scale;
+                for (int k = 0; k < r.count; ++k) {
+                    const size_t at = static_cast<size_t>(off) + static_cast<size_t>(r.start + k - u0) * rpad + q;
+                    sb.vals[2 * at] = vals[(static_cast<size_t>(row + q) * kCqtRowCap + k) * 2];
+                    sb.vals[2 * at + 1] = vals[(static_cast<size_t>(row + q) * kCqtRowCap + k) * 2 + 1];
+                }
+            }
+            off += (u1 - u0) * rpad;
+            off = (off + 1) & ~1;          // sets start on 16-byte boundaries
+            row += nrows;
+        }
+    }
+    return true;
 }
 
 // libsoxr's cubic fits of the Kaiser beta (restated; see oracle/shim/librosa/core.py _LSX_BETA_ROWS)

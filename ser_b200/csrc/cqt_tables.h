@@ -48,6 +48,26 @@ void cqt_plan(int sample_rate, CqtPlan& plan);
 // the kernel's lane = row reads of the spectrum are shared-memory bank-conflict free; otherwise
 // rows stay in bin order.
 bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank, bool lane_order = true);
+// Column-mapped layout of the same rows for cqt16_kernel (lane = column): the 36 rows of an octave in
+// frequency order, cut into 16 sets of consecutive rows -- four sets of three (the narrow low rows),
+// twelve sets of two -- each stored over the union of its rows' bins as [bin][2 or 4 rows] complex64
+// (zero where a row does not reach), so that one spectrum value feeds every row of the set and the
+// basis values are warp-uniform loads.  u0 is relative to bin_lo, the lowest bin any row reads.
+constexpr int kCqtSets = 16;
+constexpr int kCqtSetValCap = 1536;               // complex values per (tuning, octave) record
+constexpr int kCqtSetMaxBins = 128;               // bins [bin_lo, bin_lo + n_bins) the kernel keeps per column
+struct CqtSet {
+    int16_t u0, ulen, off, nrows;                 // first bin - bin_lo, bins, first value in vals[], rows (2 or 3)
+    int16_t bin[4];                               // output bins 0..251 (-1: padding row)
+    float scale[4];                               // 1 / sqrt(wavelet length)
+};
+struct CqtSetBank {
+    int32_t bin_lo, n_bins, reserved[2];
+    CqtSet sets[kCqtSets];
+    float vals[kCqtSetValCap * 2];
+};
+// one record per octave (out7[0..6]); false if the basis does not fit the layout's capacities
+bool cqt_set_banks(const CqtPlan& plan, int tuning_idx, CqtSetBank* out7);
 // dense basis of one octave, [36][1 + n_fft/2] complex64 (tests)
 void cqt_basis_dense(const CqtPlan& plan, int tuning_idx, int octave, std::vector<float>& out);
 

@@ -166,6 +166,12 @@ cudaError_t launch_istft_ola(const IstftParams& p, const OlaParams& o, const int
                              cudaStream_t stream);
 
 struct CqRow { int start; int count; float scale; int bin; };
+// column-mapped rows of one (tuning, octave) for cqt16_kernel: same layout as CqtSetBank (cqt_tables.h)
+constexpr int kCqSets = 16;
+constexpr int kCqSetValCap = 1536;
+constexpr int kCqSetMaxBins = 128;
+struct CqSet { short u0, ulen, off, nrows; short bin[4]; float scale[4]; };
+struct CqSetBank { int bin_lo, n_bins, reserved[2]; CqSet sets[kCqSets]; float2 vals[kCqSetValCap]; };
 struct CqtParams {
     const TonClip* clips;
     int n_clips;
@@ -182,6 +188,7 @@ struct CqtParams {
     int n_early_taps;
     const CqRow* rows;           // [100][7][36]
     const float2* vals;          // [100][7][36][kCqRowCap]
+    const CqSetBank* set_banks;  // [100][7] column-mapped rows (n_fft 1024 octaves take cqt16_kernel); NULL: lane = row kernels only
     const float2* twiddles;      // W_N^j (cos, -sin), j < N, for N = 128, 256, 512, 1024 back to back, then
                                  // (cos, sin) 2 pi k / (2N), k < N, for the same N
     float* cqmag;                // [cq rows][252] scaled magnitudes: debug output only, NULL on the product path

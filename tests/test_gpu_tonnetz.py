@@ -526,3 +526,28 @@ def test_shared_first_fft_stage_against_the_per_column_transform(gpu_ctx, sr):
         assert all(v[0] <= 1e-5 for v in report.values()), report
     finally:
         percol.close()
+
+
+@pytest.mark.parametrize("sr", [22050, 44100, 48000])
+def test_column_mapped_rows_against_the_row_mapped_kernels(gpu_ctx, sr):
+    """n_fft = 1024 octaves multiply the sparse rows with the lane as a COLUMN (cqt16_kernel: 16 columns
+    per CTA iteration, row sets over the union of their bins); SERB_CQT=rows keeps the lane = row kernels.
+    Same products in another summation order: magnitudes agree to 2e-6 of their maximum, rows to 1e-5
+    scaled, for ragged clips (partial last iterations, clip ends inside a block) and in any batch order."""
+    rows_ctx = _context_with_env(SERB_CQT="rows")
+    try:
+        clips = _ragged_batch(sr)
+        for clip in clips:
+            a = gpu_ctx.debug_tonnetz_stages(clip, sr)
+            b = rows_ctx.debug_tonnetz_stages(clip, sr)
+            assert np.array_equal(a["yharm"], b["yharm"])
+            assert a["tuning_index"] == b["tuning_index"]
+            assert a["cqmag"].shape == b["cqmag"].shape
+            assert np.max(np.abs(a["cqmag"] - b["cqmag"])) <= 2e-6 * max(np.max(b["cqmag"]), 1e-30), clip.size
+        bits = 0x1F
+        rows = gpu_ctx.features_host_clips(clips, sr, bits)
+        assert np.array_equal(rows, gpu_ctx.features_host_clips(clips[::-1], sr, bits)[::-1])
+        report = group_errors(rows, rows_ctx.features_host_clips(clips, sr, bits), groups=ALL_GROUPS)
+        assert all(v[0] <= 1e-5 for v in report.values()), report
+    finally:
+        rows_ctx.close()
