@@ -116,6 +116,8 @@ struct serb_ctx {
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_runs, ton_tuning, ton_tile_clip;
     bool cqt_shared = true;     // low octaves share the first FFT stage between frames (SERB_CQT=percolumn turns it off)
+    int cqt16_max_hop = 32;     // cqt16_kernel: largest hop that shares the first FFT stage (at 64 the table costs as many
+                                // first-stage transforms as the frames do); SERB_CQT16_MAXHOP
     bool cqt_cols = true;       // n_fft 1024 octaves multiply the rows lane = column (SERB_CQT=rows keeps the lane = row kernels)
     bool istft_fused = true;    // inverse STFT + overlap-add in one kernel (SERB_ISTFT=split keeps the two HBM-bound kernels)
     int harm_seg = 512;
@@ -605,6 +607,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.dec_toeplitz = ctx->dec_mma ? ctx->dec_toeplitz.ptr : nullptr;
     qp.n_sms = ctx->n_sms;
     qp.cqt_no_shared = ctx->cqt_shared ? 0 : 1;
+    qp.cqt16_shared_max_hop = ctx->cqt16_max_hop;
     { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
@@ -1291,6 +1294,7 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         CREATE_CHECK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device_ordinal));
         if (const char* env = std::getenv("SERB_DECIMATE")) ctx->dec_mma = std::string(env) != "ffma";
         if (const char* env = std::getenv("SERB_ISTFT")) ctx->istft_fused = std::string(env) != "split";
+        if (const char* env = std::getenv("SERB_CQT16_MAXHOP")) { const int v = std::atoi(env); if (v >= 0 && v <= 256) ctx->cqt16_max_hop = v; }
         if (const char* env = std::getenv("SERB_CQT")) {
             ctx->cqt_shared = std::string(env) != "percolumn";
             ctx->cqt_cols = std::string(env) != "rows" && std::string(env) != "percolumn";

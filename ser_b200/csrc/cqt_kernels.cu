@@ -496,7 +496,9 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
 // transpose region (free between its exchange and the next iteration's); the regions are 8720
 // bytes apart (16 mod 128) and kC16Pitch = 1 mod 16, so the 16 lanes of a half warp read 16 different
 // 8-byte bank slots.
-constexpr int kC16Pitch = kCqSetMaxBins + 1;            // float2 between a warp's two columns
+// float2 between a warp's two columns: the split writes whole groups of four register indices (64 bins), and
+// at most 128 bins starting anywhere touch three such groups; 193 = 1 mod 16
+constexpr int kC16Pitch = 3 * 64 + 1;
 constexpr int kC16MagPitch = kCqRows + 1;
 // float2 per warp: the 32 x 34 transpose buffer + the 16-byte bank shift; the shared-stage variant has no
 // transpose and keeps the two columns only (2 x 129 x 8 bytes = 16 mod 128 as well)
@@ -532,12 +534,30 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
     // ---- stage the span and the rows ----
     const int s0 = t_block * hop - N;
     const int span = (n_here - 1) * hop + 2 * N;
-    for (int i = tid; i < span; i += kCqtWarps * 32) {
-        const int j = s0 + i;
-        const bool inside = j >= 0 && j < len;
-        const float* src = inside ? sig + j : sig;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sig_s + i))),
-                     "l"(src), "r"(inside ? 4 : 0) : "memory");
+    if (((s0 | span) & 3) == 0 && (reinterpret_cast<uintptr_t>(sig) & 15) == 0) {
+        // 16 bytes per request where the four samples lie inside the clip, else sample by sample
+        for (int i = 4 * tid; i < span; i += 4 * kCqtWarps * 32) {
+            const int j = s0 + i;
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(sig_s + i));
+            if (j >= 0 && j + 3 < len) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(sig + j) : "memory");
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool inside = j + u >= 0 && j + u < len;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * u), "l"(inside ? sig + j + u : sig),
+                                 "r"(inside ? 4 : 0) : "memory");
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < span; i += kCqtWarps * 32) {
+            const int j = s0 + i;
+            const bool inside = j >= 0 && j < len;
+            const float* src = inside ? sig + j : sig;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sig_s + i))),
+                         "l"(src), "r"(inside ? 4 : 0) : "memory");
+        }
     }
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.set_banks + static_cast<size_t>(tuning) * kCqOctaves + octave);
@@ -554,12 +574,13 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
     float2* buf = sm.buf + warp * kRegion;
     const int bin_lo = sm.bank.bin_lo, n_bins = sm.bank.n_bins;
     const int k2_lo = bin_lo / R, k2_hi = min(31, (bin_lo + n_bins - 1) / R);
+    const int x_base = R * (k2_lo & ~3);                   // bin held at index 0 of a column
     const int g2 = lane / R, k1 = lane % R;
     const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
     // this thread's part of the row product: half warp = row set, lane = column
     const int set_idx = tid >> 4, col16 = tid & 15;
     const CqSet set = sm.bank.sets[set_idx];
-    const float2* xcol = sm.buf + (col16 >> 1) * kRegion + (col16 & 1) * kC16Pitch + set.u0;
+    const float2* xcol = sm.buf + (col16 >> 1) * kRegion + (col16 & 1) * kC16Pitch + (bin_lo - x_base) + set.u0;
     const float2* bvals = sm.bank.vals + set.off;
     const int oct_slot = sm.bank.sets[0].bin[0] / kCqRows;
     // first-stage table of the shared variant (see cqt_kernel)
@@ -640,14 +661,18 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
             if constexpr (SHARED) {
                 const int ct = (min(lc0 + g2, sub_end - 1) - sb) * h2;
                 const float2 w = twa[(ct * k1) & (N - 1)];
+                // only the register indices the split reads: k2 of the needed groups and their mirrors 31 - k2
                 if (k1 > 0) {
 #pragma unroll
-                    for (int k2 = 0; k2 < 32; ++k2)
+                    for (int k2 = 0; k2 < 32; ++k2) {
+                        const int m2 = 31 - k2;
+                        if (((k2 | 3) < k2_lo || (k2 & ~3) > k2_hi) && ((m2 | 3) < k2_lo || (m2 & ~3) > k2_hi)) continue;
                         v[k2] = make_float2(fmaf(v[k2].x, w.x, v[k2].y * w.y), fmaf(v[k2].y, w.x, -v[k2].x * w.y));
+                    }
                 }
             }
             // real-input split for the bins the rows read, into this warp's column-major pair
-            float2* xw = buf + g2 * kC16Pitch - bin_lo;
+            float2* xw = buf + g2 * kC16Pitch - x_base;
 #pragma unroll
             for (int k2 = 0; k2 < 32; ++k2) {
                 if ((k2 | 3) < k2_lo || (k2 & ~3) > k2_hi) continue;        // warp-uniform, same for a group of four
@@ -660,10 +685,10 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
                 const float2 w = twb[k];
                 const float wx = fmaf(w.x, d.y, -(w.y * d.x));
                 const float wy = fmaf(w.x, -d.x, -(w.y * d.y));
-                if (k >= bin_lo && k < bin_lo + n_bins) xw[k] = cscale(cadd(e, make_float2(wx, wy)), 0.5f);
+                xw[k] = cscale(cadd(e, make_float2(wx, wy)), 0.5f);   // surplus bins of the group are written and never read
             }
             // Nyquist bin X[N] = Re Z[0] - Im Z[0], only if a row reaches it
-            if (bin_lo + n_bins > N && k1 == 0) xw[N] = make_float2(v[0].x - v[0].y, 0.0f);
+            if (bin_lo + n_bins > N && k1 == 0) xw[N] = make_float2(v[0].x - v[0].y, 0.0f);   // N - x_base <= 192
             __syncthreads();                               // A: the 16 columns' bins are in place
             const int n_valid = min(kCqtWarps * G, sub_end - it0);
             {
@@ -864,11 +889,10 @@ static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block
 
 // cqt16_kernel: columns per CTA, columns per first-stage table and dynamic shared memory of one octave
 constexpr size_t kCqt16Budget = (227 * 1024 - 2048) / 2;     // per CTA, two CTAs per SM
-constexpr int kCqt16SharedMaxHop = 32;   // at hop 64 the table costs as many first-stage transforms as the frames do
 
 static bool cqt16_octave_shared(const CqtParams& p, int octave) {
     const int hop = p.hop0 >> octave;
-    return p.n_fft[octave] == 1024 && (hop & 1) == 0 && hop <= kCqt16SharedMaxHop && !p.cqt_no_shared;
+    return p.n_fft[octave] == 1024 && (hop & 1) == 0 && hop <= p.cqt16_shared_max_hop && !p.cqt_no_shared;
 }
 
 template <bool SHARED>

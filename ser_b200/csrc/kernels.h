@@ -201,6 +201,7 @@ struct CqtParams {
     int max_length;              // longest full-rate signal in the chunk
     int n_dec_exact;             // clips shorter than kDecExactBelow samples (float64 decimation)
     int cqt_no_shared;           // 1: every octave takes the per-column transform (SERB_CQT=percolumn, A/B tests)
+    int cqt16_shared_max_hop;    // cqt16_kernel: octaves with a hop up to this share the first FFT stage (SERB_CQT16_MAXHOP)
     const void* dec_toeplitz;    // bf16 Toeplitz operand of decimate2_mma_kernel (decimate_mma_table)
     int n_sms;
 };
