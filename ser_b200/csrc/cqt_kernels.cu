@@ -521,10 +521,14 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
     float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(Cqt16Head<SHARED>));
     constexpr int kRegion = kC16Region<SHARED>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int octave = oct_first + static_cast<int>(blockIdx.z);
+    // blockIdx.y walks the launch's octaves one after the other, each with its own number of column blocks
+    // (an octave whose blocks hold 128 columns does not launch the 18 blocks a 16-column octave needs)
+    int oct_in_launch = 0, block_lo = 0;
+    while (static_cast<int>(blockIdx.y) >= p.cq_block_end[oct_in_launch]) block_lo = p.cq_block_end[oct_in_launch++];
+    const int octave = oct_first + oct_in_launch;
     const int cols_per_block = p.cq_cols_per_block[octave];
     const TonClip clip = p.clips[blockIdx.x];
-    const int t_block = blockIdx.y * cols_per_block;
+    const int t_block = (static_cast<int>(blockIdx.y) - block_lo) * cols_per_block;
     if (t_block >= clip.cq_cols) return;
     const int n_here = min(cols_per_block, clip.cq_cols - t_block);
     const int tuning = p.tuning_idx[blockIdx.x];
@@ -925,15 +929,25 @@ static void cqt16_octave_shape(const CqtParams& p, int octave, int& cols_per_blo
 template <bool SHARED>
 static cudaError_t launch_cqt16_group(CqtParams p, int first, int count, cudaStream_t stream) {
     size_t max_bytes = 0;
-    int min_cols = 1 << 30;
+    int blocks = 0;
     for (int o = first; o < first + count; ++o) {
         size_t bytes;
         cqt16_octave_shape<SHARED>(p, o, p.cq_cols_per_block[o], p.cq_sub_cols[o], bytes);
         max_bytes = max(max_bytes, bytes);
-        min_cols = min(min_cols, p.cq_cols_per_block[o]);
+        blocks += (p.max_cq_cols + p.cq_cols_per_block[o] - 1) / p.cq_cols_per_block[o];
+        p.cq_block_end[o - first] = blocks;
     }
-    if (max_bytes > kCqtMaxSmem) return cudaErrorInvalidConfiguration;
-    dim3 grid(p.n_clips, (p.max_cq_cols + min_cols - 1) / min_cols, count);
+    for (int i = count; i < kCqOctaves; ++i) p.cq_block_end[i] = 0x7fffffff;
+    if (blocks > 65535 && count > 1) {
+        // hours-long clips: one octave per launch keeps grid.y inside its limit
+        for (int o = first; o < first + count; ++o) {
+            const cudaError_t e = launch_cqt16_group<SHARED>(p, o, 1, stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    if (max_bytes > kCqtMaxSmem || blocks > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid(p.n_clips, blocks, 1);
     cqt16_kernel<SHARED><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, first);
     return cudaGetLastError();
 }

@@ -184,6 +184,7 @@ struct CqtParams {
     int n_fft[kCqOctaves];
     int cq_cols_per_block[kCqOctaves];   // filled by the launcher
     int cq_sub_cols[kCqOctaves];         // columns per first-stage table of the shared-stage kernel (launcher)
+    int cq_block_end[kCqOctaves];        // cqt16_kernel: blockIdx.y < cq_block_end[i] belongs to the launch's i-th octave (launcher)
     const float* early_taps;     // [n_early_taps] (scaled by sqrt(early_factor)); NULL if factor 1
     int n_early_taps;
     const CqRow* rows;           // [100][7][36]
