@@ -51,7 +51,7 @@ GROUPS = {"mfcc": (0, 40), "chroma": (40, 52), "mel": (52, 180), "contrast": (18
 KERNEL_NAMES = {
     "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
     "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
-    "istft": "istft_ola_kernel", "ola": "ola_kernel", "decimate": "decimate2_mma_kernel", "cqt": "cqt_kernel",
+    "istft": "istft_ola_kernel", "ola": "ola_kernel", "decimate": "decimate2_mma_kernel", "cqt": "cqt16_kernel",
     "tonnetz": "tonnetz_kernel", "pcm_prepare": "pcm_file_scale_kernel",
 }
 TONNETZ = os.environ.get("SERB_BENCH_TONNETZ", "1") == "1"   # the build implements all five groups (193-d)
@@ -523,7 +523,9 @@ def run_b200(args) -> None:
     dom = max(kms, key=lambda k: kms[k][0])
     dom_ms, dom_n = kms[dom]
     # the library brackets the decimation launches of a chunk (and the two tonnetz kernels) with one
-    # event pair: count kernel launches, not brackets (the constant-Q kernel is one launch per chunk)
+    # event pair: count kernel launches, not brackets.  The constant-Q bracket holds the kernel's two
+    # instantiations (per-column octaves, shared-stage octaves) and is reported as ONE launch of the
+    # kernel: together they pass over the step's algorithmic bytes once.
     dom_n *= {"decimate": 7 if sr >= 33400 else 6, "tonnetz": 2}.get(dom, 1)
     total_cols = int(np.sum(1 + lengths // 512))
     # algorithmic bytes: every input sample once (float32 at boundary B1/B2) + every output row once
