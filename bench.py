@@ -51,7 +51,7 @@ GROUPS = {"mfcc": (0, 40), "chroma": (40, 52), "mel": (52, 180), "contrast": (18
 KERNEL_NAMES = {
     "stft": "stft_kernel", "tuning": "tuning_kernel", "proj": "proj_kernel", "pool": "pool_kernel",
     "short": "short_kernel", "mlp": "mlp_kernel", "hpss_harm": "hpss_harm_kernel", "hpss_perc": "hpss_perc_kernel",
-    "istft": "istft_ola_kernel", "ola": "ola_kernel", "decimate": "decimate2_mma_kernel", "cqt": "cqt16_kernel",
+    "istft": "istft_ola_kernel", "ola": "ola_kernel", "decimate": "decimate2_mma_kernel", "cqt": "cqtc_kernel",
     "tonnetz": "tonnetz_kernel", "pcm_prepare": "pcm_file_scale_kernel",
 }
 TONNETZ = os.environ.get("SERB_BENCH_TONNETZ", "1") == "1"   # the build implements all five groups (193-d)

@@ -215,7 +215,7 @@ int serb_debug_cqt_plan(int32_t sample_rate, int32_t* out10);
  * row (may be NULL).  Host only. */
 int serb_debug_cqt_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis,
                          float* out_scale36);
-/* the same basis as cqt16_kernel holds it (rows in sets over the union of their bins, csrc/cqt_tables.h
+/* the same basis as cqtc_kernel holds it (rows in sets over the union of their bins, csrc/cqt_tables.h
  * CqtSetBank), expanded back to [36 x (1 + n_fft/2) x 2]: must equal serb_debug_cqt_basis.  Host only;
  * SERB_ERR_UNSUPPORTED when the basis does not fit the layout (the lane = row kernels run then). */
 int serb_debug_cqt_set_basis(int32_t sample_rate, int32_t tuning_index, int32_t octave, float* out_basis,

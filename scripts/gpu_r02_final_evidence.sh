@@ -10,9 +10,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-fi
 echo "list exit $?"
 CMD2="python bench.py --clips 288 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
 $CMD2 > gpurun_out/lt_plain2.json 2> gpurun_out/lt_plain2.err &&
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:^(cqt16_kernel|cqt_kernel|decimate|stft_kernel|hpss_|istft|ola_kernel|proj_kernel|tuning|tune_long|tonnetz|pool_kernel|mlp_kernel|expand_tiles)' -c 600 --csv --log-file gpurun_out/chain_traffic.csv $CMD2 > gpurun_out/lt_traffic.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:^(cqtc_kernel|cqt_kernel|decimate|stft_kernel|hpss_|istft|ola_kernel|proj_kernel|tuning|tune_long|tonnetz|pool_kernel|mlp_kernel|expand_tiles)' -c 600 --csv --log-file gpurun_out/chain_traffic.csv $CMD2 > gpurun_out/lt_traffic.log 2>&1
 echo "traffic exit $?"
-ncu --set full --clock-control none --import-source on -k regex:cqt16_kernel -s 6 -c 2 -o gpurun_out/prof_cqt16 -f $CMD2 > gpurun_out/ncu_full_cqt16.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cqtc_kernel -s 6 -c 2 -o gpurun_out/prof_cqt16 -f $CMD2 > gpurun_out/ncu_full_cqt16.log 2>&1
 echo "cqt16 exit $?"
 ncu --set full --clock-control none --import-source on -k regex:decimate2_mma -s 21 -c 1 -o gpurun_out/prof_dec_mma -f $CMD2 > gpurun_out/ncu_full_dec.log 2>&1
 echo "dec exit $?"

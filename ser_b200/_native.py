@@ -420,7 +420,7 @@ def debug_cqt_basis(sample_rate: int, tuning_index: int, octave: int) -> tuple[n
 
 
 def debug_cqt_set_basis(sample_rate: int, tuning_index: int, octave: int) -> tuple[np.ndarray, np.ndarray] | None:
-    """The same basis expanded from the column-mapped layout cqt16_kernel reads (None if it does not fit)."""
+    """The same basis expanded from the column-mapped layout cqtc_kernel reads (None if it does not fit)."""
     plan = debug_cqt_plan(sample_rate)
     n_bins = 1 + plan["n_fft"][octave] // 2
     basis = np.zeros((36, n_bins, 2), dtype=np.float32)

@@ -58,7 +58,7 @@ struct SrTables {
     bool cqt_ready = false;
     CqtPlan plan;
     DevBuf cq_rows, cq_vals, early_taps;
-    DevBuf cq_sets;         // [100][7] CqSetBank: the rows mapped lane = column (cqt16_kernel), if the basis fits
+    DevBuf cq_sets;         // [100][7] CqSetBank: the rows mapped lane = column (cqtc_kernel), if the basis fits
     bool cq_sets_ok = false;
     int n_early_taps = 0;
 };
@@ -116,8 +116,8 @@ struct serb_ctx {
     DevBuf long_idx, long_state;
     DevBuf ton_clips, ton_clips_a, ton_clips_b, ton_segs, ton_runs, ton_tuning, ton_tile_clip;
     bool cqt_shared = true;     // low octaves share the first FFT stage between frames (SERB_CQT=percolumn turns it off)
-    int cqt16_max_hop = 32;     // cqt16_kernel: largest hop that shares the first FFT stage (at 64 the table costs as many
-                                // first-stage transforms as the frames do); SERB_CQT16_MAXHOP
+    int cqtc_max_hop = 32;     // cqtc_kernel: largest hop that shares the first FFT stage (at 64 the table costs as many
+                                // first-stage transforms as the frames do); SERB_CQT_SHARED_MAXHOP
     bool cqt_cols = true;       // n_fft 1024 octaves multiply the rows lane = column (SERB_CQT=rows keeps the lane = row kernels)
     bool istft_fused = true;    // inverse STFT + overlap-add in one kernel (SERB_ISTFT=split keeps the two HBM-bound kernels)
     int harm_seg = 512;
@@ -178,6 +178,10 @@ struct ProfScope {
     }
 };
 
+// Small per-call tables travel as pageable copies on purpose: the call returns once the copy engine has taken
+// them, i.e. right behind the first waveform piece.  Asynchronous copies from a pinned arena were measured
+// and dropped: the host then enqueues every later 32 MiB piece within a millisecond, the copy engine
+// alternates between the two streams, and each small table waits for one more piece (chain start 8 ms late).
 template <typename T>
 int upload(serb_ctx* ctx, DevBuf& buf, const T* host, size_t count, cudaStream_t stream) {
     SERB_CUDA(ctx, buf.reserve(std::max<size_t>(count, 1) * sizeof(T)));
@@ -337,8 +341,8 @@ int get_cqt_tables(serb_ctx* ctx, SrTables* tab) {
     std::vector<float> vals(static_cast<size_t>(kNTunings) * kCqtBins * kCqtRowCap * 2);
     std::vector<int> ok(kNTunings, 1);
     static_assert(sizeof(CqtSetBank) == sizeof(CqSetBank) && sizeof(CqtSet) == sizeof(CqSet), "host and device layouts of the row sets");
-    bool any_1024 = false;
-    for (int i = 0; i < kCqtOctaves; ++i) any_1024 = any_1024 || plan.n_fft[i] == 1024;
+    bool any_1024 = false;      // octaves with an FFT size cqtc_kernel is built for (1024, 512)
+    for (int i = 0; i < kCqtOctaves; ++i) any_1024 = any_1024 || plan.n_fft[i] == 1024 || plan.n_fft[i] == 512;
     std::vector<CqtSetBank> sets(any_1024 ? static_cast<size_t>(kNTunings) * kCqtOctaves : 0);
     std::vector<int> sets_ok(kNTunings, any_1024 ? 1 : 0);
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -607,7 +611,7 @@ int ton_run_chunk(serb_ctx* ctx, SrTables* tab, int sr, const Offsets& off, floa
     qp.dec_toeplitz = ctx->dec_mma ? ctx->dec_toeplitz.ptr : nullptr;
     qp.n_sms = ctx->n_sms;
     qp.cqt_no_shared = ctx->cqt_shared ? 0 : 1;
-    qp.cqt16_shared_max_hop = ctx->cqt16_max_hop;
+    qp.cqtc_shared_max_hop = ctx->cqtc_max_hop;
     { ProfScope ps(ctx, 10, stream); SERB_CUDA(ctx, launch_decimations(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 11, stream); SERB_CUDA(ctx, launch_cqt_octaves(qp, stream, &ctx->launches)); }
     { ProfScope ps(ctx, 12, stream); SERB_CUDA(ctx, launch_tonnetz(qp, stream)); }
@@ -1294,7 +1298,7 @@ int serb_ctx_create(int device_ordinal, serb_ctx** out_ctx) {
         CREATE_CHECK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device_ordinal));
         if (const char* env = std::getenv("SERB_DECIMATE")) ctx->dec_mma = std::string(env) != "ffma";
         if (const char* env = std::getenv("SERB_ISTFT")) ctx->istft_fused = std::string(env) != "split";
-        if (const char* env = std::getenv("SERB_CQT16_MAXHOP")) { const int v = std::atoi(env); if (v >= 0 && v <= 256) ctx->cqt16_max_hop = v; }
+        if (const char* env = std::getenv("SERB_CQT_SHARED_MAXHOP")) { const int v = std::atoi(env); if (v >= 0 && v <= 256) ctx->cqtc_max_hop = v; }
         if (const char* env = std::getenv("SERB_CQT")) {
             ctx->cqt_shared = std::string(env) != "percolumn";
             ctx->cqt_cols = std::string(env) != "rows" && std::string(env) != "percolumn";
@@ -1848,7 +1852,7 @@ int serb_debug_cqt_set_basis(int32_t sample_rate, int32_t tuning_index, int32_t 
     if (plan.status != 0) return SERB_ERR_UNSUPPORTED;
     std::vector<CqtSetBank> banks(kCqtOctaves);
     if (!cqt_set_banks(plan, tuning_index, banks.data())) return SERB_ERR_UNSUPPORTED;
-    // the column-mapped layout expanded back to [36][1 + n_fft/2] complex64, exactly as cqt16_kernel reads it
+    // the column-mapped layout expanded back to [36][1 + n_fft/2] complex64, exactly as cqtc_kernel reads it
     const CqtSetBank& sb = banks[octave];
     const int n_bins = 1 + plan.n_fft[octave] / 2;
     std::memset(out_basis, 0, static_cast<size_t>(kCqtBpo) * n_bins * 2 * sizeof(float));

@@ -480,46 +480,51 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt_kernel(CqtParams p, int
     }
 }
 
-// ---- n_fft = 1024 octaves with the rows mapped lane = column ---------------------------------
-// Same transform as cqt_kernel<16, SHARED>; what differs is the product with the sparse rows.  There
+// ---- n_fft = 1024 / 512 octaves with the rows mapped lane = column ------------------------------
+// Same transform as cqt_kernel<R, SHARED>; what differs is the product with the sparse rows.  There
 // the lane is a ROW: every lane walks its own row of the basis and its own window of the spectrum
 // (all loads distinct: 45 % of the kernel's shared-memory wavefronts, 2.1 of its 8.5 ms per c2 step,
-// every row padded to the widest).  Here the CTA's eight warps transform 16 columns, leave the bins the
-// rows read ([bin_lo, bin_lo + n_bins), about 100 of 513) in shared memory column-major, and after a
-// CTA barrier the lane is a COLUMN: half warp s holds row set s (CqSetBank: three or two consecutive
-// rows over the union of their bins) for the 16 columns, so one spectrum load feeds every row of
-// the set, the basis values are warp-uniform 16-byte loads, and every row runs its own length.
-// Magnitudes meet in a [16 columns][36] buffer; after a second barrier 192 threads fold them into the
-// octave's 12 chroma shares while the other warps already transform the next 16 columns.
+// every row padded to the widest).  Here the CTA's eight warps transform CI = 16 (n_fft 1024) or 32
+// (512) columns, leave the bins the rows read ([bin_lo, bin_lo + n_bins), about 100 of 513) in
+// shared memory column-major, and after a CTA barrier the lane is a COLUMN: CI consecutive threads
+// hold one row set (CqSetBank: three or two consecutive rows over the union of their bins), so one
+// spectrum load feeds every row of the set, the basis values are warp-uniform 16-byte loads, and
+// every row runs its own length.  Magnitudes meet in a [CI columns][36] buffer; after a second
+// barrier they are folded into the octave's 12 chroma shares while the other warps already
+// transform the next CI columns.
 //
-// Column c of warp w's pair lives at Xw[c * kC16Pitch + (bin - bin_lo)] inside warp w's own
-// transpose region (free between its exchange and the next iteration's); the regions are 8720
-// bytes apart (16 mod 128) and kC16Pitch = 1 mod 16, so the 16 lanes of a half warp read 16 different
+// Column c of warp w's G = 32 / R columns lives at Xw[c * kCcPitch + (bin - x_base)] inside warp w's
+// own transpose region (free between its exchange and the next iteration's); the regions are
+// 8 G bytes mod 128 apart and kCcPitch = 1 mod 16, so 16 consecutive lanes read 16 different
 // 8-byte bank slots.
-// float2 between a warp's two columns: the split writes whole groups of four register indices (64 bins), and
-// at most 128 bins starting anywhere touch three such groups; 193 = 1 mod 16
-constexpr int kC16Pitch = 3 * 64 + 1;
-constexpr int kC16MagPitch = kCqRows + 1;
-// float2 per warp: the 32 x 34 transpose buffer + the 16-byte bank shift; the shared-stage variant has no
-// transpose and keeps the two columns only (2 x 129 x 8 bytes = 16 mod 128 as well)
-template <bool SHARED> constexpr int kC16Region = SHARED ? 2 * kC16Pitch : 32 * kCqtBufPitch + 2;
-static_assert(2 * kC16Pitch <= 32 * kCqtBufPitch, "both columns' bins fit the warp's transpose region");
-static_assert((kC16Region<true> * 8) % 128 == 16 && (kC16Region<false> * 8) % 128 == 16, "bank shift between the warps' regions");
+// float2 between two columns of a warp: the split writes whole groups of four register indices (4 R bins),
+// and at most 128 bins starting anywhere touch 128 / (4 R) + 1 such groups; 193 and 161 are 1 mod 16
+template <int R> constexpr int kCcPitch = (128 / (4 * R) + 1) * 4 * R + 1;
+constexpr int kCcMagPitch = kCqRows + 1;
+// float2 per warp: the 32 x 34 transpose buffer + the bank shift of 8 G bytes; the shared-stage variant has
+// no transpose and keeps the G columns only (G x pitch x 8 bytes = 8 G mod 128 as well)
+template <int R, bool SHARED> constexpr int kCcRegion = SHARED ? (32 / R) * kCcPitch<R> : 32 * kCqtBufPitch + 32 / R;
+static_assert(4 * kCcPitch<8> <= 32 * kCqtBufPitch && 2 * kCcPitch<16> <= 32 * kCqtBufPitch, "the columns' bins fit the warp's transpose region");
+static_assert((kCcRegion<16, true> * 8) % 128 == 16 && (kCcRegion<16, false> * 8) % 128 == 16 &&
+              (kCcRegion<8, true> * 8) % 128 == 32 && (kCcRegion<8, false> * 8) % 128 == 32, "bank shift between the warps' regions");
 
-template <bool SHARED>
-struct Cqt16Head {
-    float2 buf[kCqtWarps * kC16Region<SHARED>];
+template <int R, bool SHARED>
+struct CqtcHead {
+    float2 buf[kCqtWarps * kCcRegion<R, SHARED>];
     CqSetBank bank;
-    float mags[16][kC16MagPitch];
+    float mags[kCqtWarps * (32 / R)][kCcMagPitch];
 };
 
-template <bool SHARED>
-__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, int oct_first) {
-    constexpr int R = 16, G = 2, N = 512;
+template <int R, bool SHARED>
+__global__ void __launch_bounds__(kCqtWarps * 32, 2) cqtc_kernel(CqtParams p, int oct_first) {
+    constexpr int G = 32 / R, N = 32 * R;
+    constexpr int CI = kCqtWarps * G;                      // columns per CTA iteration: 16 (n_fft 1024) or 32 (512)
+    constexpr int kSetsPerThread = kCqSets * CI / (kCqtWarps * 32);
+    constexpr int kPitch = kCcPitch<R>;
     extern __shared__ __align__(16) unsigned char cqt_smem_raw[];
-    Cqt16Head<SHARED>& sm = *reinterpret_cast<Cqt16Head<SHARED>*>(cqt_smem_raw);
-    float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(Cqt16Head<SHARED>));
-    constexpr int kRegion = kC16Region<SHARED>;
+    CqtcHead<R, SHARED>& sm = *reinterpret_cast<CqtcHead<R, SHARED>*>(cqt_smem_raw);
+    float* sig_s = reinterpret_cast<float*>(cqt_smem_raw + sizeof(CqtcHead<R, SHARED>));
+    constexpr int kRegion = kCcRegion<R, SHARED>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // blockIdx.y walks the launch's octaves one after the other, each with its own number of column blocks
     // (an octave whose blocks hold 128 columns does not launch the 18 blocks a 16-column octave needs)
@@ -581,11 +586,10 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
     const int x_base = R * (k2_lo & ~3);                   // bin held at index 0 of a column
     const int g2 = lane / R, k1 = lane % R;
     const int src = (k1 == 0) ? lane : g2 * R + (R - k1);
-    // this thread's part of the row product: half warp = row set, lane = column
-    const int set_idx = tid >> 4, col16 = tid & 15;
-    const CqSet set = sm.bank.sets[set_idx];
-    const float2* xcol = sm.buf + (col16 >> 1) * kRegion + (col16 & 1) * kC16Pitch + (bin_lo - x_base) + set.u0;
-    const float2* bvals = sm.bank.vals + set.off;
+    // this thread's part of the row product: lane = column, CI consecutive threads share a row set (a half
+    // warp holds one set at n_fft 1024; a warp walks two sets one after the other at n_fft 512)
+    const int set0 = (tid / CI) * kSetsPerThread, col = tid % CI;
+    const float2* xcol0 = sm.buf + (col / G) * kRegion + (col % G) * kPitch + (bin_lo - x_base);
     const int oct_slot = sm.bank.sets[0].bin[0] / kCqRows;
     // first-stage table of the shared variant (see cqt_kernel)
     const int h2 = hop >> 1;
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
                 }
             }
             // real-input split for the bins the rows read, into this warp's column-major pair
-            float2* xw = buf + g2 * kC16Pitch - x_base;
+            float2* xw = buf + g2 * kPitch - x_base;
 #pragma unroll
             for (int k2 = 0; k2 < 32; ++k2) {
                 if ((k2 | 3) < k2_lo || (k2 & ~3) > k2_hi) continue;        // warp-uniform, same for a group of four
@@ -692,15 +696,18 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
                 xw[k] = cscale(cadd(e, make_float2(wx, wy)), 0.5f);   // surplus bins of the group are written and never read
             }
             // Nyquist bin X[N] = Re Z[0] - Im Z[0], only if a row reaches it
-            if (bin_lo + n_bins > N && k1 == 0) xw[N] = make_float2(v[0].x - v[0].y, 0.0f);   // N - x_base <= 192
+            if (bin_lo + n_bins > N && k1 == 0) xw[N] = make_float2(v[0].x - v[0].y, 0.0f);   // N - x_base < kPitch
             __syncthreads();                               // A: the 16 columns' bins are in place
-            const int n_valid = min(kCqtWarps * G, sub_end - it0);
-            {
+            const int n_valid = min(CI, sub_end - it0);
+#pragma unroll
+            for (int si = 0; si < kSetsPerThread; ++si) {
+                const CqSet set = sm.bank.sets[set0 + si];
+                const float2* xcol = xcol0 + set.u0;
+                const float4* b4 = reinterpret_cast<const float4*>(sm.bank.vals + set.off);
                 float mag[3];
                 if (warp < 2) {
                     // three rows per set, stored [bin][4]
                     float cr[3] = {0.f, 0.f, 0.f}, ci[3] = {0.f, 0.f, 0.f};
-                    const float4* b4 = reinterpret_cast<const float4*>(bvals);
                     for (int b = 0; b < set.ulen; ++b) {
                         const float2 xv = xcol[b];
                         const float4 b01 = b4[2 * b], b23 = b4[2 * b + 1];
@@ -712,7 +719,6 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
                     for (int q = 0; q < 3; ++q) asm("sqrt.approx.f32 %0, %1;" : "=f"(mag[q]) : "f"(fmaf(cr[q], cr[q], ci[q] * ci[q])));
                 } else {
                     float cr[2] = {0.f, 0.f}, ci[2] = {0.f, 0.f};
-                    const float4* b4 = reinterpret_cast<const float4*>(bvals);
                     for (int b = 0; b < set.ulen; ++b) {
                         const float2 xv = xcol[b];
                         const float4 b01 = b4[b];
@@ -727,8 +733,8 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
                 for (int q = 0; q < 3; ++q) {
                     if (q < set.nrows) {
                         const float mv = mag[q] * set.scale[q];
-                        sm.mags[col16][set.bin[q] % kCqRows] = mv;
-                        if (p.cqmag && col16 < n_valid) p.cqmag[(clip.cq_base + t_block + it0 + col16) * kCqBins + set.bin[q]] = mv;
+                        sm.mags[col][set.bin[q] % kCqRows] = mv;
+                        if (p.cqmag && col < n_valid) p.cqmag[(clip.cq_base + t_block + it0 + col) * kCqBins + set.bin[q]] = mv;
                     }
                 }
             }
@@ -737,13 +743,11 @@ __global__ void __launch_bounds__(kCqtWarps * 32, 2) cqt16_kernel(CqtParams p, i
             // this octave's share of the chroma fold (filters.cq_to_chroma, 36 bins per octave: chroma c <- bins
             // 3 c - 1, 3 c, 3 c + 1 of the octave, the first wrapping to bin 35); the next iteration's rows write
             // sm.mags only after its barrier A, which these threads reach after the fold
-            if (tid < 192) {
-                const int g = tid / 12, c = tid % 12;
-                if (g < n_valid) {
-                    const float* m = sm.mags[g];
-                    const float sum = (m[(3 * c + kCqRows - 1) % kCqRows] + m[3 * c]) + m[3 * c + 1];
-                    p.cq_chroma[(static_cast<size_t>(clip.cq_base) + t_block + it0 + g) * (kCqOctaves * 12) + oct_slot * 12 + c] = sum;
-                }
+            for (int i = tid; i < 12 * n_valid; i += kCqtWarps * 32) {
+                const int g = i / 12, c = i % 12;
+                const float* m = sm.mags[g];
+                const float sum = (m[(3 * c + kCqRows - 1) % kCqRows] + m[3 * c]) + m[3 * c + 1];
+                p.cq_chroma[(static_cast<size_t>(clip.cq_base) + t_block + it0 + g) * (kCqOctaves * 12) + oct_slot * 12 + c] = sum;
             }
         }
     }
@@ -852,8 +856,10 @@ cudaError_t configure_cqt(const float* taps2_scaled, const double* taps2_scaled_
     if ((e = cudaFuncSetAttribute(cqt_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(cqt_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cqt16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(cqt16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqtc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqtc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqtc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(cqtc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(cqt_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
@@ -891,26 +897,27 @@ static void cqt_octave_shape(const CqtParams& p, int octave, int& cols_per_block
     }
 }
 
-// cqt16_kernel: columns per CTA, columns per first-stage table and dynamic shared memory of one octave
-constexpr size_t kCqt16Budget = (227 * 1024 - 2048) / 2;     // per CTA, two CTAs per SM
+// cqtc_kernel: columns per CTA, columns per first-stage table and dynamic shared memory of one octave
+constexpr size_t kCqtcBudget = (227 * 1024 - 2048) / 2;     // per CTA, two CTAs per SM
 
-static bool cqt16_octave_shared(const CqtParams& p, int octave) {
+static bool cqtc_fft_size(int n_fft) { return n_fft == 1024 || n_fft == 512; }
+static bool cqtc_octave_shared(const CqtParams& p, int octave) {
     const int hop = p.hop0 >> octave;
-    return p.n_fft[octave] == 1024 && (hop & 1) == 0 && hop <= p.cqt16_shared_max_hop && !p.cqt_no_shared;
+    return cqtc_fft_size(p.n_fft[octave]) && (hop & 1) == 0 && hop <= p.cqtc_shared_max_hop && !p.cqt_no_shared;
 }
 
-template <bool SHARED>
-static void cqt16_octave_shape(const CqtParams& p, int octave, int& cols_per_block, int& sub_cols, size_t& bytes) {
-    constexpr int N = 512, per_iter = 16;
+template <int R, bool SHARED>
+static void cqtc_octave_shape(const CqtParams& p, int octave, int& cols_per_block, int& sub_cols, size_t& bytes) {
+    constexpr int N = 32 * R, per_iter = kCqtWarps * (32 / R);
     const int hop = p.hop0 >> octave;
-    const size_t room = kCqt16Budget - sizeof(Cqt16Head<SHARED>);
+    const size_t room = kCqtcBudget - sizeof(CqtcHead<R, SHARED>);
     auto span_bytes = [&](int cols) { return ((static_cast<size_t>(cols - 1) * hop + 2 * N + 3) & ~size_t(3)) * sizeof(float); };
-    auto table = [&](int sub) { return static_cast<size_t>(16) * (((sub - 1) * (hop / 2) + 32 + 15) / 16 * 16 + 1) * sizeof(float2); };
-    for (int iters = 8; iters >= 1; --iters) {
+    auto table = [&](int sub) { return static_cast<size_t>(R) * (((sub - 1) * (hop / 2) + 32 + 15) / 16 * 16 + 1) * sizeof(float2); };
+    for (int iters = 128 / per_iter; iters >= 1; --iters) {
         const int cols = per_iter * iters;
         if (!SHARED) {
             if (span_bytes(cols) <= room || iters == 1) {
-                cols_per_block = cols; sub_cols = cols; bytes = sizeof(Cqt16Head<SHARED>) + span_bytes(cols);
+                cols_per_block = cols; sub_cols = cols; bytes = sizeof(CqtcHead<R, SHARED>) + span_bytes(cols);
                 return;
             }
             continue;
@@ -920,19 +927,19 @@ static void cqt16_octave_shape(const CqtParams& p, int octave, int& cols_per_blo
             if (span_bytes(cols) + table(c) <= room) sub = c;
         if (sub > 0 || iters == 1) {
             if (sub == 0) sub = per_iter;
-            cols_per_block = cols; sub_cols = sub; bytes = sizeof(Cqt16Head<SHARED>) + span_bytes(cols) + table(sub);
+            cols_per_block = cols; sub_cols = sub; bytes = sizeof(CqtcHead<R, SHARED>) + span_bytes(cols) + table(sub);
             return;
         }
     }
 }
 
-template <bool SHARED>
-static cudaError_t launch_cqt16_group(CqtParams p, int first, int count, cudaStream_t stream) {
+template <int R, bool SHARED>
+static cudaError_t launch_cqtc_group(CqtParams p, int first, int count, cudaStream_t stream) {
     size_t max_bytes = 0;
     int blocks = 0;
     for (int o = first; o < first + count; ++o) {
         size_t bytes;
-        cqt16_octave_shape<SHARED>(p, o, p.cq_cols_per_block[o], p.cq_sub_cols[o], bytes);
+        cqtc_octave_shape<R, SHARED>(p, o, p.cq_cols_per_block[o], p.cq_sub_cols[o], bytes);
         max_bytes = max(max_bytes, bytes);
         blocks += (p.max_cq_cols + p.cq_cols_per_block[o] - 1) / p.cq_cols_per_block[o];
         p.cq_block_end[o - first] = blocks;
@@ -941,14 +948,14 @@ static cudaError_t launch_cqt16_group(CqtParams p, int first, int count, cudaStr
     if (blocks > 65535 && count > 1) {
         // hours-long clips: one octave per launch keeps grid.y inside its limit
         for (int o = first; o < first + count; ++o) {
-            const cudaError_t e = launch_cqt16_group<SHARED>(p, o, 1, stream);
+            const cudaError_t e = launch_cqtc_group<R, SHARED>(p, o, 1, stream);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
     }
     if (max_bytes > kCqtMaxSmem || blocks > 65535) return cudaErrorInvalidConfiguration;
     dim3 grid(p.n_clips, blocks, 1);
-    cqt16_kernel<SHARED><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, first);
+    cqtc_kernel<R, SHARED><<<grid, kCqtWarps * 32, max_bytes, stream>>>(p, first);
     return cudaGetLastError();
 }
 
@@ -1021,14 +1028,17 @@ cudaError_t launch_cqt_octaves(const CqtParams& p, cudaStream_t stream, long lon
     // maximal runs of octaves with one FFT size and one kernel variant (at the common sample rates:
     // the top octaves with per-column transforms, the bottom ones sharing the first stage)
     for (int first = 0; first < kCqOctaves;) {
-        const bool cols16 = p.set_banks != nullptr && p.n_fft[first] == 1024;      // lane = column rows (cqt16_kernel)
-        const bool shared = cols16 ? cqt16_octave_shared(p, first) : cqt_octave_shared(p, first);
+        const bool cols = p.set_banks != nullptr && cqtc_fft_size(p.n_fft[first]);      // lane = column rows (cqtc_kernel)
+        const bool shared = cols ? cqtc_octave_shared(p, first) : cqt_octave_shared(p, first);
         int count = 1;
         while (first + count < kCqOctaves && p.n_fft[first + count] == p.n_fft[first] &&
-               (cols16 ? cqt16_octave_shared(p, first + count) : cqt_octave_shared(p, first + count)) == shared)
+               (cols ? cqtc_octave_shared(p, first + count) : cqt_octave_shared(p, first + count)) == shared)
             ++count;
-        if (cols16) {
-            e = shared ? launch_cqt16_group<true>(p, first, count, stream) : launch_cqt16_group<false>(p, first, count, stream);
+        if (cols) {
+            if (p.n_fft[first] == 1024)
+                e = shared ? launch_cqtc_group<16, true>(p, first, count, stream) : launch_cqtc_group<16, false>(p, first, count, stream);
+            else
+                e = shared ? launch_cqtc_group<8, true>(p, first, count, stream) : launch_cqtc_group<8, false>(p, first, count, stream);
             if (e != cudaSuccess) return e;
             ++n;
             first += count;

@@ -48,7 +48,7 @@ void cqt_plan(int sample_rate, CqtPlan& plan);
 // the kernel's lane = row reads of the spectrum are shared-memory bank-conflict free; otherwise
 // rows stay in bin order.
 bool cqt_bank(const CqtPlan& plan, int tuning_idx, CqtBank& bank, bool lane_order = true);
-// Column-mapped layout of the same rows for cqt16_kernel (lane = column): the 36 rows of an octave in
+// Column-mapped layout of the same rows for cqtc_kernel (lane = column): the 36 rows of an octave in
 // frequency order, cut into 16 sets of consecutive rows -- four sets of three (the narrow low rows),
 // twelve sets of two -- each stored over the union of its rows' bins as [bin][2 or 4 rows] complex64
 // (zero where a row does not reach), so that one spectrum value feeds every row of the set and the

@@ -166,7 +166,7 @@ cudaError_t launch_istft_ola(const IstftParams& p, const OlaParams& o, const int
                              cudaStream_t stream);
 
 struct CqRow { int start; int count; float scale; int bin; };
-// column-mapped rows of one (tuning, octave) for cqt16_kernel: same layout as CqtSetBank (cqt_tables.h)
+// column-mapped rows of one (tuning, octave) for cqtc_kernel: same layout as CqtSetBank (cqt_tables.h)
 constexpr int kCqSets = 16;
 constexpr int kCqSetValCap = 1536;
 constexpr int kCqSetMaxBins = 128;
@@ -184,12 +184,12 @@ struct CqtParams {
     int n_fft[kCqOctaves];
     int cq_cols_per_block[kCqOctaves];   // filled by the launcher
     int cq_sub_cols[kCqOctaves];         // columns per first-stage table of the shared-stage kernel (launcher)
-    int cq_block_end[kCqOctaves];        // cqt16_kernel: blockIdx.y < cq_block_end[i] belongs to the launch's i-th octave (launcher)
+    int cq_block_end[kCqOctaves];        // cqtc_kernel: blockIdx.y < cq_block_end[i] belongs to the launch's i-th octave (launcher)
     const float* early_taps;     // [n_early_taps] (scaled by sqrt(early_factor)); NULL if factor 1
     int n_early_taps;
     const CqRow* rows;           // [100][7][36]
     const float2* vals;          // [100][7][36][kCqRowCap]
-    const CqSetBank* set_banks;  // [100][7] column-mapped rows (n_fft 1024 octaves take cqt16_kernel); NULL: lane = row kernels only
+    const CqSetBank* set_banks;  // [100][7] column-mapped rows (n_fft 1024 octaves take cqtc_kernel); NULL: lane = row kernels only
     const float2* twiddles;      // W_N^j (cos, -sin), j < N, for N = 128, 256, 512, 1024 back to back, then
                                  // (cos, sin) 2 pi k / (2N), k < N, for the same N
     float* cqmag;                // [cq rows][252] scaled magnitudes: debug output only, NULL on the product path
@@ -202,7 +202,7 @@ struct CqtParams {
     int max_length;              // longest full-rate signal in the chunk
     int n_dec_exact;             // clips shorter than kDecExactBelow samples (float64 decimation)
     int cqt_no_shared;           // 1: every octave takes the per-column transform (SERB_CQT=percolumn, A/B tests)
-    int cqt16_shared_max_hop;    // cqt16_kernel: octaves with a hop up to this share the first FFT stage (SERB_CQT16_MAXHOP)
+    int cqtc_shared_max_hop;    // cqtc_kernel: octaves with a hop up to this share the first FFT stage (SERB_CQT_SHARED_MAXHOP)
     const void* dec_toeplitz;    // bf16 Toeplitz operand of decimate2_mma_kernel (decimate_mma_table)
     int n_sms;
 };

@@ -76,11 +76,11 @@ def test_tuning_dependent_plans_are_reported_as_unsupported_not_as_bad_input():
 
 
 def test_column_mapped_row_sets_expand_to_the_same_basis():
-    """cqt16_kernel reads the rows as 16 sets over the union of their bins (csrc/cqt_tables.cpp
+    """cqtc_kernel reads the rows as 16 sets over the union of their bins (csrc/cqt_tables.cpp
     cqt_set_banks); expanded back they must be the sparsified basis itself, value for value."""
     from ser_b200 import _native
 
-    for sr in (22050, 32000, 44100, 48000, 96000):
+    for sr in (11025, 16000, 22050, 32000, 44100, 48000, 96000):
         for tuning in (0, 37, 99):
             for octave in (0, 3, 6):
                 dense, scale = _native.debug_cqt_basis(sr, tuning, octave)
