@@ -102,3 +102,22 @@ def test_single_process_helpers_are_no_ops():
     assert multi_gpu.gather_rows(info, rows, 4) is rows
     gatherer = multi_gpu.RowGatherer(info, [4], (2,))
     assert np.array_equal(gatherer.collect(gatherer.submit(rows + 1.0)), rows + 1.0)
+
+
+def test_host_binding_is_optional_and_never_raises(monkeypatch):
+    """bind_host_to_gpu moves the process next to its GPU where NVML names such cores; without a GPU (this
+    container), without NVML or inside a restrictive cpuset it reports why and leaves the affinity alone."""
+    import os
+
+    from ser_b200 import multi_gpu
+
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("SERB_NUMA_BIND", "0")
+    assert multi_gpu.bind_host_to_gpu(0) is None
+    monkeypatch.setenv("SERB_NUMA_BIND", "1")
+    report = multi_gpu.bind_host_to_gpu(0)
+    assert isinstance(report, dict) and "bound" in report and report["cpus"] >= 1
+    if not report["bound"]:
+        assert os.sched_getaffinity(0) == before
+    else:                                     # a GPU box: undo for the tests that follow
+        os.sched_setaffinity(0, report["restore"])
