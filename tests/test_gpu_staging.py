@@ -94,3 +94,36 @@ def test_non_finite_audio_is_still_reported_through_the_ring(gpu_ctx):
     lengths = np.asarray([48000, 200_000], dtype=np.int64)
     with pytest.raises(ValueError, match="not finite"):
         gpu_ctx.features_host(wave, starts, lengths, SR, BITS)
+
+
+def test_two_contexts_on_two_threads_give_the_single_caller_rows(gpu_ctx):
+    """A server overlaps calls by giving every host thread its own context (own scratch, own streams);
+    contexts share nothing but the device, so rows are bit-identical to one caller's
+    (bench.py: e2e.two_callers; INTEGRATION.md section on threads)."""
+    import threading
+
+    from ser_b200 import _native
+
+    rng = np.random.default_rng(9)
+    files = [rng.integers(-15000, 15000, size=n).astype(np.int16) for n in (48000, 80000, 36001, 64000) * 6]
+    clip_file = np.arange(len(files), dtype=np.int64)
+    starts = np.zeros(len(files), dtype=np.int64)
+    lengths = np.asarray([f.size for f in files], dtype=np.int64)
+    bits = 0x1F
+    expected = gpu_ctx.features_host_pcm16(files, 1, clip_file, starts, lengths, SR, bits)
+    other = _native.Context(0)
+    out = {}
+
+    def run(name, ctx):
+        out[name] = [ctx.features_host_pcm16(files, 1, clip_file, starts, lengths, SR, bits) for _ in range(4)]
+
+    try:
+        threads = [threading.Thread(target=run, args=("a", gpu_ctx)), threading.Thread(target=run, args=("b", other))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        other.close()
+    for rows in out["a"] + out["b"]:
+        np.testing.assert_array_equal(rows, expected)
