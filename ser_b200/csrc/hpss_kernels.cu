@@ -168,10 +168,18 @@ __device__ __forceinline__ float harm_mask(float h, float q) {
 // medians in hand it overwrites the frequency median with the soft mask (12 bytes of traffic per
 // bin; istft_kernel applies the mask to the complex spectrum as it loads it).
 __global__ void __launch_bounds__(256, 2) hpss_harm_kernel(HpssParams p) {
-    const int2 seg = p.segs[blockIdx.x];
+    // 1025 bins = four blocks of 256 and one bin: the last block row takes that bin for 256 SEGMENTS per CTA
+    // (one segment per thread) instead of one nearly empty CTA per segment holding half an SM's slots
+    static_assert((kNBins - 1) % 256 == 0 && kNBins - 1 == 16 * 64, "the last bin is the only one outside whole 256-thread blocks");
+    int seg_index = blockIdx.x;
+    int f = blockIdx.y * blockDim.x + threadIdx.x;
+    if (blockIdx.y == gridDim.y - 1) {
+        seg_index = blockIdx.x * blockDim.x + threadIdx.x;
+        f = kNBins - 1;
+        if (seg_index >= static_cast<int>(gridDim.x)) return;
+    }
+    const int2 seg = p.segs[seg_index];
     const TonClip clip = p.clips[seg.x];
-    const int f = blockIdx.y * blockDim.x + threadIdx.x;
-    if (f >= kNBins) return;
     const int T = clip.n_cols;
     const int t0 = seg.y;
     const int t1 = min(t0 + p.seg_len, T);
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(256, 2) hpss_harm_kernel(HpssParams p) {
         // rows are addressed straight off one base pointer (immediate offsets): the reflection and
         // clamp arithmetic of the general path is integer work on the same ALU pipe the min/max
         // instructions saturate.
-        const bool interior = (t + 2 * kMedBlock + 15 <= T) && (t + kMedBlock <= t1);    // warp-uniform
+        const bool interior = (t + 2 * kMedBlock + 15 <= T) && (t + kMedBlock <= t1);    // warp-uniform (but for the last bin's CTAs)
         float pq[kMedBlock];
         if (interior) {
             const float* s_row = src + static_cast<long long>(t + kMedBlock + 15) * kSpillStride;
@@ -247,10 +255,21 @@ __device__ __forceinline__ void perc_load8(const float* __restrict__ src, int po
 __global__ void __launch_bounds__(256, 2) hpss_perc_kernel(HpssParams p, int n_cols) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int col = 2 * warp + (lane >> 4);
+    // 1025 bins = 16 runs of 64 and one bin.  The main warps take the runs (two columns per warp, eight
+    // blocks per lane); the last bin of every column is one more block, done by tail warps with one
+    // column per lane -- a ninth block on one lane in sixteen would idle the other fifteen for it.
+    const int main_warps = (n_cols + 1) >> 1;
+    int col, f0, f1;
+    if (warp < main_warps) {
+        col = 2 * warp + (lane >> 4);
+        f0 = (lane & 15) * kPercRun;
+        f1 = f0 + kPercRun;
+    } else {
+        col = (warp - main_warps) * 32 + lane;
+        f0 = kNBins - 1;
+        f1 = kNBins;
+    }
     if (col >= n_cols) return;
-    const int f0 = (lane & 15) * kPercRun;
-    const int f1 = ((lane & 15) == 15) ? kNBins : f0 + kPercRun;
     const float one = p.one;
     const float* src = p.mag + static_cast<long long>(col) * kSpillStride;
     float* dst = p.perc + static_cast<long long>(col) * kSpillStride;
@@ -645,7 +664,7 @@ cudaError_t launch_hpss_harm(const HpssParams& p, int n_segs, cudaStream_t strea
 
 cudaError_t launch_hpss_perc(const HpssParams& p, int n_cols, cudaStream_t stream) {
     if (n_cols <= 0) return cudaSuccess;
-    const int warps = (n_cols + 1) / 2;                     // two columns per warp
+    const int warps = (n_cols + 1) / 2 + (n_cols + 31) / 32;   // two columns per warp, then the last bin of 32 columns per warp
     hpss_perc_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(p, n_cols);
     return cudaGetLastError();
 }
