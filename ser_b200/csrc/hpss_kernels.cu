@@ -11,11 +11,13 @@
 // ola_kernel        overlap-add in frame order / window sum-of-squares -> harmonic signal
 //
 // The medians are computed eight positions at a time.  The eight windows of 31 share a core of
-// 24 values, sorted once by a network (132 compare-exchanges); the other seven values of each
-// window form a small sorted set that slides by one replace per position; the median is the
-// rank-15 element of the two sorted sets, eight max and seven min.  About 70 min/max/compare per
-// output and no window fill, against 124 (plus the fill) for a sliding sorted window of 31.
-// The work is ALU-bound (FMNMX), not memory-bound.
+// 24 values -- three aligned groups of eight, two of them shared with the next block: groups are
+// sorted once, the merge of two groups serves two blocks, and a 16 + 8 merge pruned to the ranks
+// the selection reads finishes a block (66.5 compare-exchanges instead of the 132 of a 24-value
+// sort); the other seven values of each window form a small sorted set that slides by one replace
+// per position; the median is the rank-15 element of the two sorted sets, seven max and seven
+// min.  About 51 min/max/compare per output and no window fill, against 124 (plus the fill) for a
+// sliding sorted window of 31.  The work is ALU-bound (FMNMX), not memory-bound.
 #include <cfloat>
 
 #include "fft.cuh"
