@@ -127,3 +127,35 @@ def test_two_contexts_on_two_threads_give_the_single_caller_rows(gpu_ctx):
         other.close()
     for rows in out["a"] + out["b"]:
         np.testing.assert_array_equal(rows, expected)
+
+
+@pytest.mark.parametrize("sr", [16000, 48000])
+def test_device_entry_writes_its_rows_and_nothing_else(gpu_ctx, sr):
+    """compute-sanitizer is not available on the pool, so the caller-owned buffers get guard regions: the
+    device entry must fill exactly rows [0, n) of ``d_out`` and leave the waveform and the bytes around the
+    output untouched, for a ragged batch that exercises partial tiles, partial constant-Q blocks (both
+    kernel variants) and short clips."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    sizes = [2048, 2049, 4095, 7777, sr, 3 * sr + 123, 513, 100, 5 * sr, 2 * sr - 1]
+    clips = [(0.25 * rng.standard_normal(n)).astype(np.float32) for n in sizes]
+    starts = np.cumsum([0] + sizes[:-1]).astype(np.int64)
+    lengths = np.asarray(sizes, dtype=np.int64)
+    flat = np.concatenate(clips)
+    guard = 1024
+    wave = torch.full((flat.size + 2 * guard,), 7.5, dtype=torch.float32, device="cuda")
+    wave[guard:guard + flat.size] = torch.from_numpy(flat).cuda()
+    before = wave.clone()
+    n, dim, pad_rows = len(sizes), 193, 3
+    out = torch.full(((n + 2 * pad_rows) * dim,), -123.0, dtype=torch.float32, device="cuda")
+    body = out[pad_rows * dim:(pad_rows + n) * dim]
+    torch.cuda.synchronize()
+    gpu_ctx.features_device(wave[guard:].data_ptr(), flat.size, starts, lengths, sr, 0x1F, body.data_ptr(), 0)
+    gpu_ctx.features_device_check(0)
+    torch.cuda.synchronize()
+    assert torch.equal(wave, before)
+    assert bool((out[: pad_rows * dim] == -123.0).all()) and bool((out[(pad_rows + n) * dim:] == -123.0).all())
+    rows = body.reshape(n, dim).cpu().numpy()
+    assert np.all(np.isfinite(rows))
+    np.testing.assert_array_equal(rows, gpu_ctx.features_host(flat, starts, lengths, sr, 0x1F))
