@@ -120,7 +120,8 @@ __device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[
     __syncwarp();
     fft32(v);  // over n2 -> Z[lane + 32 k2] in v[k2]
 
-    // real-input split, scaled by 2:  2 X[k] = (Z[k] + conj Z[M-k]) + W_2048^k (-i)(Z[k] - conj Z[M-k])
+    // real-input split:  2 X[k] = (Z[k] + conj Z[M-k]) + W_2048^k (-i)(Z[k] - conj Z[M-k]); the frame came in
+    // halved (see the window), so the right-hand side is X[k] itself
     const int src = (32 - lane) & 31;
     float* sbuf = reinterpret_cast<float*>(buf);
     float cmax = 0.0f;
@@ -137,15 +138,15 @@ __device__ __forceinline__ float column_fft(float2 (&v)[32], const float2 (*tw)[
         const float wy = fmaf(w.x, -d.x, -(w.y * d.y));    // w.x O.y - w.y O.x
         const float2 x2 = cadd(e, make_float2(wx, wy));
         const float xr = x2.x, xi = x2.y;
-        const float mag = 0.5f * sqrt_approx(fmaf(xr, xr, xi * xi));
-        if (crow) crow[lane + 32 * k2] = cscale(x2, 0.5f);
+        const float mag = sqrt_approx(fmaf(xr, xr, xi * xi));
+        if (crow) crow[lane + 32 * k2] = x2;
         if (row) row[lane + 32 * k2] = mag;
         sbuf[lane + 32 * k2] = mag;
         cmax = fmaxf(cmax, mag);
         if (k2 == 0 && lane == 0) {
             const float nr = e.x - wx, ni = e.y - wy;
-            const float nyq = 0.5f * sqrt_approx(fmaf(nr, nr, ni * ni));
-            if (crow) crow[1024] = make_float2(0.5f * nr, 0.5f * ni);
+            const float nyq = sqrt_approx(fmaf(nr, nr, ni * ni));
+            if (crow) crow[1024] = make_float2(nr, ni);
             if (row) row[1024] = nyq;
             sbuf[1024] = nyq;
             cmax = fmaxf(cmax, nyq);
@@ -253,8 +254,11 @@ __global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(StftParams p, int
                 const float2 x = *reinterpret_cast<const float2*>(frame + 64 * n1 + 2 * lane);
                 bad |= !isfinite(x.x) | !isfinite(x.y);   // dsp.py:94 finite check, folded into the load
                 const float ca = cos32(n1), sa = sin32(n1);
-                const float w0 = fmaf(-0.5f * ca, wc0, fmaf(0.5f * sa, ws0, 0.5f));
-                const float w1 = fmaf(-0.5f * ca, wc1, fmaf(0.5f * sa, ws1, 0.5f));
+                // HALF the Hann window: the real-input split below yields 2 X of what it is fed, so feeding
+                // x w / 2 gives X itself and spares a multiply per bin for |X| and one for the complex spill.
+                // Scaling by a power of two commutes with every rounding on the way: the same bits as before.
+                const float w0 = fmaf(-0.25f * ca, wc0, fmaf(0.25f * sa, ws0, 0.25f));
+                const float w1 = fmaf(-0.25f * ca, wc1, fmaf(0.25f * sa, ws1, 0.25f));
                 v[n1] = make_float2(x.x * w0, x.y * w1);
             }
             if (bad) sm.bad = 1;
