@@ -54,3 +54,25 @@ def group_errors(actual: np.ndarray, expected: np.ndarray, groups=("mfcc", "chro
         raw = float(np.max(np.abs(a - b) / denom)) if a.size else 0.0
         report[name] = (scaled, raw)
     return report
+
+
+def binary_model_and_inputs():
+    """A fitted two-class Pipeline(StandardScaler, MLPClassifier(300)): scikit-learn then uses ONE logistic
+    output unit (training_support.py:87-106 builds the same pipeline whatever the label set is)."""
+    from sklearn.neural_network import MLPClassifier
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((300, 193)) * (1.0 + 5.0 * rng.random(193))
+    y = np.where(x[:, 0] / np.std(x[:, 0]) + 0.5 * x[:, 7] / np.std(x[:, 7]) + 0.1 * rng.standard_normal(300) > 0, "happy", "sad")
+    model = Pipeline([("scaler", StandardScaler()),
+                      ("classifier", MLPClassifier(hidden_layer_sizes=(300,), max_iter=40, random_state=3))])
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # ConvergenceWarning: 40 iterations are plenty for a test
+        model.fit(x, y)
+    assert model.named_steps["classifier"].out_activation_ == "logistic"
+    x_eval = rng.standard_normal((64, 193)) * (1.0 + 5.0 * rng.random(193))
+    return model, x_eval

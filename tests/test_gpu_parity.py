@@ -284,3 +284,18 @@ def test_clip_list_entry_errors_and_empty_batch(gpu_ctx):
     np.testing.assert_array_equal(rows[0], dsp.extract_feature_from_signal(good, 16000))
     np.testing.assert_array_equal(rows[1], dsp.extract_feature_from_signal(good[:700], 16000))
     assert _native.device_count() >= 1
+
+
+def test_binary_logistic_classifier_matches_sklearn(gpu_ctx):
+    """Two emotion classes: scikit-learn's MLPClassifier has a single logistic output unit and
+    predict_proba returns [1 - p, p] (fast_path.py:48,181 call the same methods for any label set).
+    The fused kernel's SERB_OUT_LOGISTIC branch against the real fitted model."""
+    from ser_b200 import mlp
+    from conftest import binary_model_and_inputs
+
+    model, x_eval = binary_model_and_inputs()
+    labels, proba = mlp.predict(model, x_eval)
+    assert proba.shape == (64, 2)
+    assert labels == model.predict(x_eval).tolist()
+    np.testing.assert_allclose(proba, model.predict_proba(x_eval), rtol=0, atol=1e-12)
+    assert set(labels) == {"happy", "sad"}                     # both classes occur in the evaluation set

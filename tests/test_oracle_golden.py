@@ -80,3 +80,15 @@ def test_segment_merge_matches_reference_fast_path(golden):
     np.testing.assert_array_equal([s.start_seconds for s in segments], golden["fast/seg_starts"])
     np.testing.assert_array_equal([s.end_seconds for s in segments], golden["fast/seg_ends"])
     np.testing.assert_allclose([s.confidence for s in segments], golden["fast/seg_conf"], rtol=1e-12)
+
+
+def test_binary_logistic_restatement_matches_sklearn():
+    from oracle import ser_oracle
+
+    from conftest import binary_model_and_inputs
+
+    model, x_eval = binary_model_and_inputs()
+    weights = ser_oracle.mlp_weights_from_sklearn(model)
+    assert weights.out_activation == "logistic" and len(weights.classes) == 2
+    np.testing.assert_allclose(ser_oracle.mlp_predict_proba(weights, x_eval), model.predict_proba(x_eval), rtol=0, atol=1e-12)
+    assert list(ser_oracle.mlp_predict(weights, x_eval)) == model.predict(x_eval).tolist()
