@@ -125,7 +125,10 @@ struct StageRing {
         cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&base), kSlotBytes * kSlots, cudaHostAllocDefault);
         if (e != cudaSuccess) { base = nullptr; return e; }
         for (int i = 0; i < kSlots; ++i)
-            if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) {
+                destroy();          // nothing half-built stays behind for the next call to trust
+                return e;
+            }
         pool = new CopyPool(std::max(1, threads));
         return cudaSuccess;
     }
@@ -133,8 +136,11 @@ struct StageRing {
         delete pool;
         pool = nullptr;
         if (!base) return;
-        for (int i = 0; i < kSlots; ++i)
+        for (int i = 0; i < kSlots; ++i) {
             if (done[i]) cudaEventDestroy(done[i]);
+            done[i] = nullptr;
+            in_flight[i] = false;
+        }
         cudaFreeHost(base);
         base = nullptr;
     }
