@@ -87,3 +87,16 @@ def test_column_mapped_row_sets_expand_to_the_same_basis():
                 expanded = _native.debug_cqt_set_basis(sr, tuning, octave)
                 assert expanded is not None, (sr, tuning, octave)
                 assert np.array_equal(expanded[0], dense) and np.array_equal(expanded[1], scale)
+
+
+def test_median_networks_header_is_what_the_generator_emits():
+    """csrc/median_net.cuh (the sorting / merging networks of the block medians) is generated; the generator
+    checks every network on all sorted 0-1 inputs (the 0-1 principle) before printing it, so equality with
+    the committed header means the kernels run verified networks."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    repo = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(repo / "scripts" / "gen" / "median_net.py")], capture_output=True, text=True, check=True)
+    assert out.stdout == (repo / "ser_b200" / "csrc" / "median_net.cuh").read_text()
