@@ -69,3 +69,31 @@ def test_host_tables_match_oracle(sr):
     assert np.max(np.abs(dct - ref)) < 1e-7
     win = _native.debug_filterbank(3, sr, 2048)
     assert np.max(np.abs(win - scipy.signal.get_window("hann", 2048, fftbins=True))) < 1e-7
+
+
+def test_every_context_entry_rejects_a_null_context():
+    """An entry handed a NULL context reports SERB_ERR_INVALID_ARG before it reads any other
+    argument (no device, no crash): what a binding sees when serb_ctx_create failed and its
+    result was used anyway."""
+    import ctypes
+
+    lib = _native.load_library()
+    checked = 0
+    for name, (restype, argtypes) in _native.SIGNATURES.items():
+        if not argtypes or argtypes[0] is not _native._P or name in ("serb_ctx_destroy", "serb_last_error"):
+            continue
+        args = [None] + [t() if not hasattr(t, "contents") and t is not _native._P else None for t in argtypes[1:]]
+        result = getattr(lib, name)(*args)
+        if restype is ctypes.c_int:
+            expected = 0 if name == "serb_mlp_n_classes" else -1   # SERB_ERR_INVALID_ARG
+            assert result == expected, f"{name}(NULL, ...) returned {result}"
+        checked += 1
+    assert checked >= 20
+    lib.serb_ctx_destroy(None)                                   # a no-op, as free(NULL)
+    assert isinstance(lib.serb_last_error(None), bytes)          # the creation error text
+
+
+def test_ctx_create_without_out_pointer_is_an_argument_error():
+    lib = _native.load_library()
+    assert lib.serb_ctx_create(0, None) == -1
+    assert b"out_ctx" in lib.serb_last_error(None)
