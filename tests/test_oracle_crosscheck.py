@@ -3,9 +3,11 @@ this image and were not written here: torchaudio (slaney mel bank, DCT-II, dB sc
 (``stft`` / ``istft`` in float64), scipy (``ndimage.median_filter``, ``fftpack.dct``,
 ``signal.get_window``) and ``transformers.audio_utils`` (a port of librosa's chroma / mel banks).
 
-Nothing in the image cross-checks piptrack / estimate_tuning, HPSS as a whole, the constant-Q
-transform or libsoxr; those stay restatement-only and are bounded by
-scripts/soxr_sensitivity_study.py and tests/test_oracle_sensitivity.py instead.
+No third-party implementation of piptrack / estimate_tuning, HPSS as a whole, the constant-Q
+transform or libsoxr ships in the image; tests/test_oracle_definitions.py recomputes the first three
+from their definitions by a second route (time-domain constant-Q at the full rate, torch + scipy
+HPSS, explicit piptrack loops), libsoxr stays restatement-only and is bounded
+by scripts/soxr_sensitivity_study.py and tests/test_oracle_sensitivity.py.
 CPU only; every check runs in seconds.
 """
 
