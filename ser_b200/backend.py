@@ -13,25 +13,34 @@ import numpy as np
 from numpy.typing import NDArray
 
 
+def _reject(rules) -> None:
+    """Raises ``ValueError`` with the text of the first rule whose predicate holds.  Rules are
+    evaluated lazily and in order: a later predicate may rely on the earlier ones having passed
+    (the order, and therefore which text a doubly-invalid value gets, is the reference's)."""
+    for violated, text in rules:
+        if violated():
+            raise ValueError(text)
+
+
 @dataclass(frozen=True)
 class PoolingWindow:
-    """Closed-open time range, in seconds, pooled into one row."""
+    """Closed-open time range, in seconds, pooled into one row (repr/backend.py:19-33)."""
 
     start_seconds: float
     end_seconds: float
 
     def __post_init__(self) -> None:
-        if not np.isfinite(self.start_seconds) or not np.isfinite(self.end_seconds):
-            raise ValueError("PoolingWindow bounds must be finite numbers.")
-        if self.start_seconds < 0.0:
-            raise ValueError("PoolingWindow start_seconds must be non-negative.")
-        if self.end_seconds <= self.start_seconds:
-            raise ValueError("PoolingWindow end_seconds must be greater than start_seconds.")
+        lo, hi = self.start_seconds, self.end_seconds
+        _reject((
+            (lambda: not (np.isfinite(lo) and np.isfinite(hi)), "PoolingWindow bounds must be finite numbers."),
+            (lambda: lo < 0.0, "PoolingWindow start_seconds must be non-negative."),
+            (lambda: hi <= lo, "PoolingWindow end_seconds must be greater than start_seconds."),
+        ))
 
 
 @dataclass(frozen=True)
 class EncodedSequence:
-    """Per-window feature rows with their time bounds."""
+    """Per-window feature rows with their time bounds (repr/backend.py:36-78)."""
 
     embeddings: NDArray[np.float32]
     frame_start_seconds: NDArray[np.float64]
@@ -39,31 +48,20 @@ class EncodedSequence:
     backend_id: str
 
     def __post_init__(self) -> None:
-        if not self.backend_id:
-            raise ValueError("EncodedSequence backend_id must be a non-empty string.")
-        if self.embeddings.ndim != 2:
-            raise ValueError("EncodedSequence embeddings must be 2D (frames, features).")
-        if self.frame_start_seconds.ndim != 1 or self.frame_end_seconds.ndim != 1:
-            raise ValueError("Frame timestamp arrays must be 1D.")
-        n_frames = int(self.embeddings.shape[0])
-        if n_frames <= 0:
-            raise ValueError("EncodedSequence must contain at least one frame.")
-        if self.frame_start_seconds.size != n_frames:
-            raise ValueError("frame_start_seconds length must match embeddings frame count.")
-        if self.frame_end_seconds.size != n_frames:
-            raise ValueError("frame_end_seconds length must match embeddings frame count.")
-        if not np.all(np.isfinite(self.embeddings)):
-            raise ValueError("EncodedSequence embeddings contain non-finite values.")
-        if not np.all(np.isfinite(self.frame_start_seconds)):
-            raise ValueError("EncodedSequence frame_start_seconds contain non-finite values.")
-        if not np.all(np.isfinite(self.frame_end_seconds)):
-            raise ValueError("EncodedSequence frame_end_seconds contain non-finite values.")
-        if np.any(np.diff(self.frame_start_seconds) < 0.0):
-            raise ValueError("frame_start_seconds must be non-decreasing.")
-        if np.any(np.diff(self.frame_end_seconds) < 0.0):
-            raise ValueError("frame_end_seconds must be non-decreasing.")
-        if np.any(self.frame_end_seconds <= self.frame_start_seconds):
-            raise ValueError("Each frame must satisfy end_seconds > start_seconds.")
+        rows, t0, t1 = self.embeddings, self.frame_start_seconds, self.frame_end_seconds
+        stamps = (("frame_start_seconds", t0), ("frame_end_seconds", t1))
+        _reject((
+            (lambda: not self.backend_id, "EncodedSequence backend_id must be a non-empty string."),
+            (lambda: rows.ndim != 2, "EncodedSequence embeddings must be 2D (frames, features)."),
+            (lambda: t0.ndim != 1 or t1.ndim != 1, "Frame timestamp arrays must be 1D."),
+            (lambda: rows.shape[0] <= 0, "EncodedSequence must contain at least one frame."),
+            *((lambda v=v: v.size != rows.shape[0], f"{name} length must match embeddings frame count.")
+              for name, v in stamps),
+            *((lambda v=v: not np.isfinite(v).all(), f"EncodedSequence {name} contain non-finite values.")
+              for name, v in (("embeddings", rows), *stamps)),
+            *((lambda v=v: bool((v[1:] < v[:-1]).any()), f"{name} must be non-decreasing.") for name, v in stamps),
+            (lambda: bool((t1 <= t0).any()), "Each frame must satisfy end_seconds > start_seconds."),
+        ))
 
 
 def overlap_frame_mask(encoded: EncodedSequence, window: PoolingWindow) -> NDArray[np.bool_]:
