@@ -32,7 +32,7 @@ struct DevBuf {
     cudaError_t reserve(size_t need) {
         if (need <= bytes) return cudaSuccess;
         if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
-        // grow geometrically so repeated calls with slowly growing sizes do not thrash
+        // exact-size growth (bytes is 0 here: the old block is gone, so want == need); sizes repeat per workload
         size_t want = std::max(need, bytes + bytes / 2);
         cudaError_t e = cudaMalloc(&ptr, want);
         if (e != cudaSuccess) {
