@@ -268,7 +268,7 @@ def run_reference(args) -> None:
 
     flag_tuple, dim = flag_tuple_and_dim()
     sr, n = args.sample_rate, args.clip_samples
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = args.cpu_clips or max(4 * cores, 8)     # four clips per core: the cores drain evenly
     whole_clip = args.config == "c3"
     specs = synth.ravdess_specs(per_step)
