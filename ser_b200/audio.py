@@ -1,7 +1,8 @@
 """Audio file reading for the file-level seams (mirror of ser/_internal/utils/audio_utils.py:28-113).
 
-The reference decodes with librosa/soundfile; this image has neither, so PCM WAV is decoded
-with the standard library and anything else is rejected.  Post-decode preparation is the
+The reference decodes with librosa/soundfile; this image has neither, so WAV (integer PCM of 8 / 16 /
+24 / 32 bits, IEEE float of 32 / 64 bits, plain or WAVE_FORMAT_EXTENSIBLE headers) is decoded here
+and anything else is rejected with ``AudioDecodeError``.  Post-decode preparation is the
 reference's: NaN/Inf -> 0, channel mean, whole-file peak normalisation to [-1, 1].
 
 16-bit PCM WAV -- what RAVDESS and the reference's own synthetic generator ship -- does not need
@@ -12,6 +13,7 @@ that host pass at all: ``read_pcm16_file`` hands the raw int16 samples to the de
 
 from __future__ import annotations
 
+import struct
 import wave
 from pathlib import Path
 
@@ -48,28 +50,79 @@ def prepare_audio_buffer(raw_audio: NDArray) -> NDArray[np.float32]:
     return prepared / peak
 
 
+def _pcm_to_float32(raw: bytes, width: int, path) -> NDArray[np.float32]:
+    """Integer PCM -> float32 in soundfile's convention: ``x / 2^(bits - 1)`` (8-bit WAV is unsigned)."""
+    if width == 2:
+        return np.frombuffer(raw, dtype="<i2").astype(np.float32) / np.float32(32768.0)
+    if width == 1:
+        return (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / np.float32(128.0)
+    if width == 4:
+        return (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    if width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        return (np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float64) / 8388608.0).astype(np.float32)
+    raise AudioDecodeError(f"Unsupported PCM sample width {width} in {path}")
+
+
+_WAVE_FORMAT_PCM, _WAVE_FORMAT_IEEE_FLOAT, _WAVE_FORMAT_EXTENSIBLE = 0x0001, 0x0003, 0xFFFE
+
+
+def _decode_riff(path) -> tuple[NDArray[np.float32], int, int]:
+    """RIFF/WAVE chunk walk for what the standard library's ``wave`` refuses: IEEE-float samples
+    (format tag 3, 32 or 64 bit: handed on as float32 like soundfile's ``dtype="float32"`` read) and
+    WAVE_FORMAT_EXTENSIBLE headers whose sub-format is PCM or IEEE float.  Returns
+    ``(flat samples, channels, sample_rate)``."""
+    blob = Path(path).read_bytes()
+    if len(blob) < 12 or blob[:4] != b"RIFF" or blob[8:12] != b"WAVE":
+        raise AudioDecodeError(f"Could not decode audio file {path}: not a RIFF/WAVE file")
+    fmt = data = None
+    pos = 12
+    while pos + 8 <= len(blob):
+        tag = blob[pos:pos + 4]
+        size = struct.unpack_from("<I", blob, pos + 4)[0]
+        body = blob[pos + 8:pos + 8 + size]
+        if tag == b"fmt " and fmt is None:
+            fmt = body
+        elif tag == b"data" and data is None:
+            data = body                  # a truncated file yields the samples that are there
+        pos += 8 + size + (size & 1)     # chunks are word aligned
+    if fmt is None or data is None or len(fmt) < 16:
+        raise AudioDecodeError(f"Could not decode audio file {path}: missing fmt or data chunk")
+    kind, channels, sample_rate, _rate, block_align, bits = struct.unpack_from("<HHIIHH", fmt, 0)
+    if kind == _WAVE_FORMAT_EXTENSIBLE:
+        if len(fmt) < 26:
+            raise AudioDecodeError(f"Could not decode audio file {path}: short extensible header")
+        kind = struct.unpack_from("<H", fmt, 24)[0]      # first two bytes of the sub-format GUID
+    if channels < 1 or sample_rate < 1 or bits % 8 or block_align != channels * (bits // 8):
+        raise AudioDecodeError(f"Could not decode audio file {path}: inconsistent fmt chunk")
+    width = bits // 8
+    data = data[: len(data) // block_align * block_align]
+    if kind == _WAVE_FORMAT_IEEE_FLOAT and width in (4, 8):
+        samples = np.frombuffer(data, dtype="<f4" if width == 4 else "<f8").astype(np.float32)
+    elif kind == _WAVE_FORMAT_PCM:
+        samples = _pcm_to_float32(data, width, path)
+    else:
+        raise AudioDecodeError(f"Could not decode audio file {path}: unsupported WAVE format tag {kind:#06x}")
+    return samples, int(channels), int(sample_rate)
+
+
 def decode_wav(path: str | Path) -> tuple[NDArray[np.float32], int]:
-    """PCM WAV -> float32 in soundfile's convention (int16 / 32768), shape (frames[, channels])."""
+    """WAV -> float32 in soundfile's convention (int16 / 32768, floats as they are), shape
+    (frames[, channels]).  Integer PCM goes through the standard library's reader; IEEE-float and
+    extensible files, which it refuses, through ``_decode_riff``."""
     try:
         with wave.open(str(path), "rb") as handle:
             sample_rate = handle.getframerate()
             channels = handle.getnchannels()
             width = handle.getsampwidth()
             raw = handle.readframes(handle.getnframes())
-    except (wave.Error, EOFError) as err:
-        raise AudioDecodeError(f"Could not decode audio file {path}: {err}") from err
-    if width == 2:
-        data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / np.float32(32768.0)
-    elif width == 1:
-        data = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / np.float32(128.0)
-    elif width == 4:
-        data = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
-    elif width == 3:
-        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
-        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
-        data = (np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float64) / 8388608.0).astype(np.float32)
-    else:
-        raise AudioDecodeError(f"Unsupported PCM sample width {width} in {path}")
+        data = _pcm_to_float32(raw[: len(raw) // (width * channels) * (width * channels)], width, path)
+    except (wave.Error, EOFError, struct.error):
+        try:
+            data, channels, sample_rate = _decode_riff(path)
+        except (struct.error, ValueError) as err:
+            raise AudioDecodeError(f"Could not decode audio file {path}: {err}") from err
     if channels > 1:
         data = data.reshape(-1, channels)
     return data, int(sample_rate)
