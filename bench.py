@@ -195,10 +195,14 @@ def _cpu_worker(args):
 
 def _cpu_warm(_):
     """Imports the oracle in a pool worker (numpy / scipy pages, FFT plans) before anything is timed."""
+    import warnings
+
     from oracle import ser_oracle
 
-    ser_oracle.extract_feature_from_signal(np.zeros(4096, dtype=np.float32), 16000,
-                                           feature_flags=ser_oracle.FeatureFlags(True, True, True, False, False))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # a silent clip: "empty frequency set" from the tuning estimate
+        ser_oracle.extract_feature_from_signal(np.zeros(4096, dtype=np.float32), 16000,
+                                               feature_flags=ser_oracle.FeatureFlags(True, True, True, False, False))
     time.sleep(0.05)        # keeps the worker busy long enough for every process of the pool to take one
     return os.getpid()
 
