@@ -80,9 +80,12 @@ def weights_from_model(model) -> MlpWeights:
     )
 
 
+_RAMPS: dict[int, np.ndarray] = {}      # position weights of the second checksum, by array length
+
+
 def _fingerprint(model) -> tuple:
-    """Cheap identity of a model's *current* weights: object id plus the data pointers, shapes and a
-    strided sample of every array the kernel reads.  A model re-fitted in place (new ``coefs_``
+    """Cheap identity of a model's *current* weights: object id plus the data pointers, shapes and two
+    checksums of every array the kernel reads.  A model re-fitted in place (new ``coefs_``
     arrays, or the same arrays overwritten) changes it, so stale device weights are never reused."""
     if isinstance(model, MlpWeights):
         arrays = (model.mean, model.scale, model.w1, model.b1, model.w2, model.b2)
@@ -97,8 +100,13 @@ def _fingerprint(model) -> tuple:
     for a in arrays:
         a = np.asarray(a)
         flat = a.reshape(-1)
-        stride = max(1, flat.size // 512)
-        parts.append((a.__array_interface__["data"][0], a.shape, float(np.sum(flat[::stride], dtype=np.float64))))
+        # two full-length sums (58 k doubles for the 193 x 300 layer: ~30 us), the second position-weighted,
+        # so a single overwritten element or two swapped ones change the fingerprint too
+        ramp = _RAMPS.get(flat.size)
+        if ramp is None:
+            ramp = _RAMPS.setdefault(flat.size, np.arange(1, flat.size + 1, dtype=np.float64))
+        flat64 = flat if flat.dtype == np.float64 else flat.astype(np.float64)
+        parts.append((a.__array_interface__["data"][0], a.shape, float(flat64.sum()), float(flat64 @ ramp)))
     return tuple(parts)
 
 
