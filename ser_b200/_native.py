@@ -115,6 +115,32 @@ def _raise(lib, ctx, code: int) -> None:
     raise RuntimeError(text)
 
 
+def _clip_arrays(starts, lengths) -> tuple[np.ndarray, np.ndarray]:
+    """``starts`` / ``lengths`` as the contiguous int64 vectors the C entries read ``n_clips`` items of;
+    a length mismatch would be an out-of-bounds read on the other side, so it is refused here."""
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    if starts.ndim != 1 or lengths.ndim != 1 or starts.size != lengths.size:
+        raise ValueError(f"starts and lengths must be 1-D with one entry per clip, got {starts.shape} and {lengths.shape}")
+    return starts, lengths
+
+
+def _mlp_arrays(mean, scale, w1, b1, w2, b2) -> list[np.ndarray]:
+    """The six weight arrays as contiguous float64 with consistent shapes (serb_mlp_load reads
+    n_in, n_in, n_in x n_hidden, n_hidden, n_hidden x n_out and n_out doubles from them)."""
+    arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, scale, w1, b1, w2, b2)]
+    mean, scale, w1, b1, w2, b2 = arrays
+    if w1.ndim != 2 or w2.ndim != 2:
+        raise ValueError("classifier weight matrices must be 2-D (n_in x n_hidden, n_hidden x n_out)")
+    n_in, n_hidden = w1.shape
+    if mean.shape != (n_in,) or scale.shape != (n_in,) or b1.shape != (n_hidden,) or \
+            w2.shape[0] != n_hidden or b2.shape != (w2.shape[1],):
+        raise ValueError(
+            f"inconsistent classifier shapes: mean {mean.shape}, scale {scale.shape}, w1 {w1.shape}, b1 {b1.shape}, "
+            f"w2 {w2.shape}, b2 {b2.shape}")
+    return arrays
+
+
 class Context:
     """One libser_b200 context (one CUDA device).  Thread-safe; calls are serialised natively."""
 
@@ -127,6 +153,7 @@ class Context:
         self._handle = handle
         self.device = int(device)
         self._mlp_classes: int = 0
+        self._mlp_n_in: int = 0
 
     def close(self) -> None:
         if getattr(self, "_handle", None):
@@ -148,8 +175,7 @@ class Context:
                       sample_rate: int, flag_bits: int) -> np.ndarray:
         """Ragged batch over a host waveform -> (n_clips, dim) float32."""
         wave = np.ascontiguousarray(wave, dtype=np.float32)
-        starts = np.ascontiguousarray(starts, dtype=np.int64)
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        starts, lengths = _clip_arrays(starts, lengths)
         dim = self._lib.serb_feature_dim(flag_bits)
         out = np.empty((starts.size, dim), dtype=np.float32)
         self._check(self._lib.serb_features_host(
@@ -172,8 +198,7 @@ class Context:
     def features_device(self, d_wave_ptr: int, n_wave: int, starts: np.ndarray, lengths: np.ndarray,
                         sample_rate: int, flag_bits: int, d_out_ptr: int, stream: int = 0) -> None:
         """Device pointers in, device pointer out; enqueues on ``stream`` (0 = the context's)."""
-        starts = np.ascontiguousarray(starts, dtype=np.int64)
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        starts, lengths = _clip_arrays(starts, lengths)
         self._check(self._lib.serb_features_device(
             self._handle, c_void_p(d_wave_ptr), int(n_wave), _ptr(starts), _ptr(lengths), starts.size,
             int(sample_rate), int(flag_bits), c_void_p(d_out_ptr), c_void_p(stream)))
@@ -260,12 +285,13 @@ class Context:
 
     # ---- classifier ----------------------------------------------------------------------
     def mlp_load(self, mean, scale, w1, b1, w2, b2, out_activation: int) -> None:
-        arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, scale, w1, b1, w2, b2)]
+        arrays = _mlp_arrays(mean, scale, w1, b1, w2, b2)
         n_in, n_hidden = arrays[2].shape
         n_out = arrays[4].shape[1]
         self._check(self._lib.serb_mlp_load(self._handle, n_in, n_hidden, n_out,
                                             *[_ptr(a) for a in arrays], int(out_activation)))
         self._mlp_classes = self._lib.serb_mlp_n_classes(self._handle)
+        self._mlp_n_in = int(n_in)
 
     @property
     def mlp_n_classes(self) -> int:
@@ -273,6 +299,8 @@ class Context:
 
     def mlp_predict_host(self, x: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
         x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim != 2 or (self._mlp_n_in and x.shape[1] != self._mlp_n_in):
+            raise ValueError(f"X has shape {x.shape}, but the loaded classifier expects (n, {self._mlp_n_in}).")
         n = x.shape[0]
         proba = np.empty((n, max(self._mlp_classes, 1)), dtype=np.float64)
         labels = np.empty(n, dtype=np.int32)
@@ -287,8 +315,7 @@ class Context:
     def infer_host(self, wave: np.ndarray, starts: np.ndarray, lengths: np.ndarray, sample_rate: int,
                    flag_bits: int, *, want_features: bool = True):
         wave = np.ascontiguousarray(wave, dtype=np.float32)
-        starts = np.ascontiguousarray(starts, dtype=np.int64)
-        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        starts, lengths = _clip_arrays(starts, lengths)
         n = starts.size
         dim = self._lib.serb_feature_dim(flag_bits)
         feats = np.empty((n, dim), dtype=np.float32) if want_features else None
@@ -305,6 +332,8 @@ class Context:
         emb = np.ascontiguousarray(embeddings, dtype=np.float32)
         lo = np.ascontiguousarray(lo, dtype=np.int32)
         hi = np.ascontiguousarray(hi, dtype=np.int32)
+        if emb.ndim != 2 or lo.ndim != 1 or lo.shape != hi.shape:
+            raise ValueError(f"embeddings must be 2-D and lo / hi 1-D of one length, got {emb.shape}, {lo.shape}, {hi.shape}")
         n_frames, dim = emb.shape
         out = np.empty((lo.size, 2 * dim if mode == 1 else dim), dtype=np.float64)
         self._check(self._lib.serb_pool_frames_host(self._handle, _ptr(emb), n_frames, dim, _ptr(lo), _ptr(hi),
